@@ -1,0 +1,215 @@
+/*
+ * svd_xtend_b200 — C ABI of the B200-native SVD spatio-temporal UNet hot path.
+ *
+ * Every entry point takes raw device pointers, explicit shapes/strides and a CUDA stream
+ * (passed as void* == cudaStream_t). Contract for ALL functions:
+ *   - return 0 on success, <0 on error (see SVDX_E_*); never throw, never allocate or free
+ *     device memory, never synchronise the device; re-entrant across streams;
+ *   - bf16 = __nv_bfloat16 storage, fp32 accumulation everywhere.
+ *
+ * The reference (pixeli99/SVD_Xtend) is pure Python on top of diffusers; the operator each entry
+ * replaces is therefore the ATen/cuDNN/cuBLAS call reached from the reference's module code.
+ * The replaced interface is cited per function as  <reference file:line> -> <diffusers op [D]>.
+ * "[D]" = code that lives in the un-vendored diffusers dependency.
+ */
+#ifndef SVD_XTEND_B200_H_
+#define SVD_XTEND_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVDX_OK 0
+#define SVDX_E_BADARG (-1)     /* unsupported shape / alignment / null pointer */
+#define SVDX_E_CUDA (-2)       /* CUDA runtime / driver error on launch */
+#define SVDX_E_NODRIVER (-3)   /* cuTensorMapEncodeTiled entry point unavailable */
+
+#define SVDX_MAX_TAPS 27
+
+/* A-operand addressing modes of svdx_tapgemm */
+#define SVDX_A_ROWS 0    /* A is [groups][rows_per_group][K] (a plain matrix when groups==1);
+                            tap t reads rows shifted by tap_d0[t] inside the group, rows outside
+                            the group read as zero (this is the (3,1,1) temporal conv / a linear) */
+#define SVDX_A_CONV2D 1  /* A is [nimg][H][W][K] channels-last; tap t reads pixel (h+tap_d1[t],
+                            w+tap_d0[t]) of image n+tap_d2[t]; out-of-image reads are zero
+                            (3x3 conv padding=1, and the parity-plane form of the stride-2 conv) */
+
+#define SVDX_OUT_BF16 0
+#define SVDX_OUT_F32 1
+#define SVDX_OUT_F32_ATOMIC 2  /* out += result (fp32 red.add), used by split-K weight gradients */
+
+/*
+ * svdx_tapgemm — the one tensor-core contraction of the path (tcgen05.mma, TMEM accumulators,
+ * TMA-fed 128B-swizzled shared memory, warp-specialised persistent CTAs):
+ *
+ *     acc[m, n] = sum_{t < num_taps} sum_{k < K}  A_t[m, k] * B[n, t*K + k]
+ *     v         = acc + bias[n] + rowbias[m / rowbias_div, n]
+ *     v         = geglu ? v[:, :N/2] * gelu_erf(v[:, N/2:]) : v
+ *     out[m, n] = scales[0] * v + scales[1] * res1[m, n] + scales[2] * res2[m, n]
+ *
+ * Replaces, with the epilogue fused:
+ *   F.linear      — Attention.to_q/to_k/to_v/to_out, FeedForward proj/out, proj_in/proj_out,
+ *                   time_emb_proj, TimestepEmbedding  [D]; reached from
+ *                   src/unet_spatio_temporal_condition.py:138-144,170-233
+ *   F.conv2d 3x3  — ResnetBlock2D.conv1/conv2, Downsample2D, Upsample2D.conv [D], conv_in/conv_out
+ *                   (src/unet_spatio_temporal_condition.py:128-133,241-246)
+ *   F.conv2d 1x1  — ResnetBlock2D.conv_shortcut [D]
+ *   F.conv3d (3,1,1) — TemporalResnetBlock.conv1/conv2 [D]
+ *   GEGLU, AlphaBlender, residual adds [D] (epilogue)
+ * and their data/weight gradients (dgrad = same contraction on transposed weights; wgrad =
+ * a_major_mn = b_major_mn = 1 with SVDX_OUT_F32_ATOMIC).
+ */
+typedef struct SvdxTapGemm {
+  /* A operand (bf16) */
+  const void* a;
+  int64_t lda;          /* elements between consecutive rows/pixels */
+  int32_t a_mode;       /* SVDX_A_ROWS / SVDX_A_CONV2D */
+  int32_t a_major_mn;   /* 0: A[m][k] k contiguous. 1 (ROWS, groups==1 only): memory is [k][m], m contiguous */
+  int32_t rows_per_group, groups;      /* ROWS   */
+  int32_t W, H, nimg;                  /* CONV2D: 128 % W == 0 */
+  int32_t num_taps;
+  int32_t tap_d0[SVDX_MAX_TAPS];
+  int32_t tap_d1[SVDX_MAX_TAPS];
+  int32_t tap_d2[SVDX_MAX_TAPS];
+  /* B operand (bf16): [N][num_taps*K] (k contiguous), or if b_major_mn: memory [K][N], n contiguous */
+  const void* b;
+  int64_t ldb;
+  int32_t b_major_mn;
+  /* problem */
+  int32_t M, N, K;      /* M output rows, N = B rows (before GEGLU halving), K = contraction per tap */
+  int32_t block_n;      /* multiple of 32, <= 256 (multiple of 64 when b_major_mn) */
+  int32_t split_k;      /* >= 1; > 1 requires SVDX_OUT_F32_ATOMIC */
+  /* epilogue */
+  void* out;
+  int64_t ldo;
+  int32_t out_dtype;
+  int32_t geglu;        /* out has N/2 columns */
+  const float* bias;    /* [N] or NULL */
+  const float* rowbias; /* [ceil(M/rowbias_div)][ldrb] or NULL */
+  int32_t rowbias_div;
+  int64_t ldrb;
+  const void* res1;     /* bf16 [M][ldr1] or NULL */
+  int64_t ldr1;
+  const void* res2;
+  int64_t ldr2;
+  const float* scales;  /* device float[3] {acc, res1, res2} or NULL (= 1,1,1) */
+  void* pre;            /* geglu: bf16 [M][ldpre] pre-activation (value | gate) saved for backward, or NULL */
+  int64_t ldpre;
+} SvdxTapGemm;
+
+int svdx_tapgemm(const SvdxTapGemm* desc, void* stream);
+
+/* number of SMs the persistent kernels size their grids to (queried once) */
+int svdx_num_sms(void);
+/* sizeof(SvdxTapGemm) (which==0) / sizeof(SvdxAttn) (which==1): lets bindings verify their struct layout */
+int svdx_struct_size(int which);
+/* human-readable last error of this thread */
+const char* svdx_last_error(void);
+
+/* ------------------------------------------------------------------ normalisation
+ * GroupNorm(32)+SiLU over channels-last activations, replaces F.group_norm + F.silu of
+ * ResnetBlock2D.norm1/norm2, TemporalResnetBlock.norm1/norm2 (stats over T*H*W),
+ * TransformerSpatioTemporalModel.norm [D], conv_norm_out (src/unet_spatio_temporal_condition.py:238-239,480-481).
+ * x is [ngroups_outer][rows][C] bf16 where one statistics group spans `rows` rows x (C/32) channels.
+ * A second source x2 (C2 channels) is concatenated along channels (the up-block torch.cat).
+ */
+int svdx_groupnorm_stats(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                         int32_t outer, int32_t rows, int32_t num_groups, float eps,
+                         float* mean, float* rstd, void* stream);
+int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                         int32_t outer, int32_t rows, int32_t num_groups,
+                         const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         int32_t fuse_silu, void* y, int64_t ldy, void* stream);
+/* backward: dx (and optional dgamma/dbeta accumulation, fp32 atomic) */
+int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                       const void* dy, int64_t lddy,
+                       int32_t outer, int32_t rows, int32_t num_groups,
+                       const float* mean, const float* rstd, const float* gamma, const float* beta,
+                       int32_t fuse_silu, void* dx, int64_t lddx, void* dx2, int64_t lddx2,
+                       float* dgamma, float* dbeta, float* workspace, void* stream);
+
+/* LayerNorm over the last dim (C <= 2560, C % 8 == 0), replaces F.layer_norm of
+ * BasicTransformerBlock.norm1-3 / TemporalBasicTransformerBlock.norm_in,norm1-3 [D].
+ * add_vec (optional, [rows/add_div][C] fp32) is added to x before normalisation and the sum is
+ * written to xsum (the "+ time_pos_embed" of TransformerSpatioTemporalModel [D]). */
+int svdx_layernorm_fwd(const void* x, int64_t ldx, int32_t rows, int32_t C, const float* gamma, const float* beta,
+                       float eps, void* y, int64_t ldy, float* mean, float* rstd, void* stream);
+int svdx_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int32_t rows, int32_t C,
+                       const float* gamma, const float* mean, const float* rstd,
+                       void* dx, int64_t lddx, const void* dres, int64_t lddres,
+                       float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------ attention
+ * Scaled-dot-product attention, head_dim 64, no mask, replaces
+ * AttnProcessor2_0 -> F.scaled_dot_product_attention [D].
+ * q/k/v/o are column slices of token-major [tokens][ld] bf16 matrices; head h uses columns
+ * [h*64, h*64+64). A sequence s (0 <= s < nseq) has its i-th token at row  seq_base(s) + i*tok_stride
+ * with seq_base(s) = (s / inner) * outer_stride + (s % inner) * inner_stride:
+ *   spatial  (per frame over H*W):  inner = 1,  outer_stride = HW, tok_stride = 1
+ *   temporal (per pixel over T):    inner = HW, outer_stride = T*HW, inner_stride = 1, tok_stride = HW
+ * lse [nseq][heads][S] fp32 (natural-log sum-exp of the scaled scores) is saved for backward. */
+typedef struct SvdxAttn {
+  const void* q; const void* k; const void* v; void* o;
+  int64_t ldq, ldk, ldv, ldo;
+  int32_t nseq, heads, S;
+  int32_t inner;
+  int64_t outer_stride, inner_stride, tok_stride;
+  float scale;
+  float* lse;
+  /* backward only */
+  const void* dout; int64_t lddo;
+  void* dq; void* dk; void* dv; int64_t lddq, lddk, lddv;
+  float* delta;     /* workspace [nseq][heads][S] */
+} SvdxAttn;
+int svdx_attention_fwd(const SvdxAttn* d, void* stream);
+int svdx_attention_bwd(const SvdxAttn* d, void* stream);
+
+/* ------------------------------------------------------------------ elementwise / layout */
+/* fp32 (or bf16 when src_bf16) weights -> bf16, optionally re-laid-out:
+ *   mode 0: plain copy           dst[n][k]           = src[n][k]
+ *   mode 1: transpose            dst[k][n]           = src[n][k]            (dgrad operand of a linear)
+ *   mode 2: conv OIHW -> O(HW)I  dst[o][t][i(pad)]   = src[o][i][t]         (fwd operand; taps = kh*kw or kt)
+ *   mode 3: conv OIHW -> I(HW)O  dst[i][t][o]        = src[o][i][taps-1-t]  (dgrad operand: flipped taps)
+ * i_pad >= I pads the input-channel axis with zeros (conv_in: 8 -> 64). */
+int svdx_prep_weight(const void* src, int32_t src_bf16, void* dst, int32_t mode,
+                     int32_t O, int32_t I, int32_t taps, int32_t i_pad, void* stream);
+int svdx_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int svdx_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* NCHW (fp32 or bf16) -> [N][H][W][c_pad] bf16 (zero padded channels) and back (to fp32 / bf16 NCHW) */
+int svdx_nchw_to_nhwc(const void* src, int32_t src_bf16, void* dst, int32_t N, int32_t C, int32_t H, int32_t W,
+                      int32_t c_pad, void* stream);
+int svdx_nhwc_to_nchw(const void* src, int64_t lds, void* dst, int32_t dst_bf16, int32_t N, int32_t C, int32_t H,
+                      int32_t W, void* stream);
+/* nearest 2x upsample, channels-last (F.interpolate of Upsample2D [D]) and its adjoint (2x2 sum) */
+int svdx_upsample2x(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int svdx_upsample2x_bwd(const void* dsrc, void* ddst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* parity planes for the stride-2 conv: dst[(p*2+q)*N + n][H/2][W/2][C] = src[n][2h+p][2w+q][C], and adjoint */
+int svdx_space_to_planes(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int svdx_planes_to_space(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* channel concat / split of channels-last tensors (torch.cat(dim=1) of the up blocks) */
+int svdx_concat_channels(const void* a, int32_t Ca, const void* b, int32_t Cb, void* dst, int64_t rows, void* stream);
+int svdx_split_channels(const void* src, void* a, int32_t Ca, void* b, int32_t Cb, int64_t rows, int32_t accumulate_a,
+                        void* stream);
+/* y = a + b (bf16), y = silu(x) for fp32 vectors, column sums (bias gradients) */
+int svdx_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
+int svdx_axpby_bf16(const void* a, const void* b, const float* scales, void* y, int64_t n, void* stream);
+int svdx_silu_f32(const float* x, float* y, int64_t n, void* stream);
+int svdx_colsum(const void* x, int64_t ldx, int64_t rows, int32_t cols, float* out, int32_t accumulate, void* stream);
+/* GEGLU backward: dpre[m][:h] = dout*gelu(gate); dpre[m][h:] = dout*value*gelu'(gate) */
+int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t lddo, void* dpre, int64_t lddpre,
+                   int64_t rows, int32_t h, void* stream);
+/* blend scales {1-alpha, 1, 0}/{...} from mix_factor: out[0]=1-sigmoid(m), out[1]=sigmoid(m), out[2]=sigmoid(m)*(1-sigmoid(m)) */
+int svdx_blend_scales(const float* mix_factor, float* out3, void* stream);
+/* EDM-preconditioned MSE of train_svd.py:1025-1036 fused with its gradient wrt model_pred */
+int svdx_edm_loss(const void* pred, const float* noisy, const float* target, const float* sigma,
+                  int32_t B, int64_t per_sample, float* loss, void* dpred, void* stream);
+/* fused multi-tensor AdamW on a flat fp32 buffer (torch.optim.AdamW of train_svd.py:767-773) */
+int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+               float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVD_XTEND_B200_H_ */

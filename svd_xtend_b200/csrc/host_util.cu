@@ -1,0 +1,76 @@
+#include "host_util.h"
+#include "../../include/svd_xtend_b200.h"
+#include <stdio.h>
+
+static thread_local char g_err[512] = "";
+
+int svdx_fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int svdx_fail_cuda(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return SVDX_E_CUDA;
+}
+extern "C" const char* svdx_last_error(void) { return g_err; }
+
+extern "C" int svdx_num_sms(void) {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    n = v;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int svdx_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                   const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return svdx_fail(SVDX_E_NODRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u stride0 %llu", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+             (unsigned long long)(rank > 1 ? strides[0] : 0));
+    return svdx_fail(SVDX_E_CUDA, buf);
+  }
+  return 0;
+}
+
+extern "C" int svdx_struct_size(int which) {
+  return which == 0 ? (int)sizeof(SvdxTapGemm) : which == 1 ? (int)sizeof(SvdxAttn) : -1;
+}

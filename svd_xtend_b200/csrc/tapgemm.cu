@@ -1,0 +1,479 @@
+// svdx_tapgemm: the tensor-core contraction of the SVD UNet hot path on sm_100a.
+//
+//   acc[m,n] = sum_taps sum_k A_tap[m,k] * B[n, tap*K + k]      (tcgen05.mma, fp32 accum in TMEM)
+//
+// One persistent, warp-specialised kernel:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  : epilogue (tcgen05.ld TMEM->regs, bias/rowbias/GEGLU/residual/blend, global store)
+// Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+//
+// A-operand modes (see include/svd_xtend_b200.h): plain/grouped rows with row-shifted taps
+// (linear, (3,1,1) temporal conv [D: TemporalResnetBlock]) and channels-last images with 2-D
+// shifted taps (3x3 conv [D: ResnetBlock2D/Downsample2D/Upsample2D]); zero padding comes from
+// TMA out-of-bounds fill, so no im2col buffer ever exists.
+#include "common.cuh"
+#include "../../include/svd_xtend_b200.h"
+#include "host_util.h"
+
+namespace svdx {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;      // 32 KB
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+
+struct __align__(64) TapGemmKParams {
+  CUtensorMap tma;
+  CUtensorMap tmb;
+  int a_mode, a_mn, b_mn;
+  int rows_per_group, groups, tiles_per_group;
+  int W, H, nimg;
+  int num_taps;
+  int tap_d0[SVDX_MAX_TAPS], tap_d1[SVDX_MAX_TAPS], tap_d2[SVDX_MAX_TAPS];
+  int M, N, K;
+  int block_n, m_tiles, n_tiles, split_k, kb_total, kb_per_split, kb_per_tap;
+  // epilogue
+  void* out;
+  long long ldo;
+  int out_dtype, geglu;
+  const float* bias;
+  const float* rowbias;
+  int rowbias_div;
+  long long ldrb;
+  const bf16* res1;
+  long long ldr1;
+  const bf16* res2;
+  long long ldr2;
+  const float* scales;
+  bf16* pre;
+  long long ldpre;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t sBar = sB + STAGES * B_STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[ACC], tmem_empty[ACC], then tmem ptr
+  const uint32_t bar_full = sBar;
+  const uint32_t bar_empty = sBar + 8 * STAGES;
+  const uint32_t bar_tfull = sBar + 16 * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 8 * ACC_STAGES;
+  const uint32_t tmem_slot = bar_tempty + 8 * ACC_STAGES;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tma);
+    prefetch_tmap(&p.tmb);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+  const int b_bytes = p.block_n * BLOCK_K * 2;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = (tile / p.n_tiles) % p.m_tiles;
+        const int ks = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int n0 = nt * (p.geglu ? p.block_n / 2 : p.block_n);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, A_STAGE_BYTES + b_bytes);
+          const uint32_t dA = sA + stage * A_STAGE_BYTES;
+          const uint32_t dB = sB + stage * B_STAGE_BYTES;
+          const int tap = kb / p.kb_per_tap;
+          const int kc = (kb - tap * p.kb_per_tap) * BLOCK_K;
+          // ---- A
+          if (p.a_mn) {
+            // memory [k rows][m cols]: two 64x64 boxes
+            tma_load_2d(&p.tma, full, dA, mt * BLOCK_M, kb * BLOCK_K);
+            tma_load_2d(&p.tma, full, dA + 8192, mt * BLOCK_M + 64, kb * BLOCK_K);
+          } else if (p.a_mode == SVDX_A_ROWS) {
+            const int g = mt / p.tiles_per_group;
+            const int t = mt - g * p.tiles_per_group;
+            tma_load_3d(&p.tma, full, dA, kc, t * BLOCK_M + p.tap_d0[tap], g);
+          } else {
+            const int R = BLOCK_M / p.W;
+            const int dw = p.tap_d0[tap], dh = p.tap_d1[tap], dn = p.tap_d2[tap];
+            for (int i = 0; i < R; ++i) {
+              const int rowid = mt * R + i;
+              const int n = rowid / p.H;
+              const int h = rowid - n * p.H;
+              // rows past the last image land out of bounds (n >= nimg) and are zero-filled
+              const int nn = (n < p.nimg) ? n + dn : (1 << 28);
+              tma_load_4d(&p.tma, full, dA + i * p.W * 128, kc, dw, h + dh, nn);
+            }
+          }
+          // ---- B
+          if (p.b_mn) {
+            for (int j = 0; j < p.block_n / 64; ++j)
+              tma_load_2d(&p.tmb, full, dB + j * 8192, n0 + 64 * j, kb * BLOCK_K);
+          } else if (p.geglu) {
+            const int h = p.block_n / 2;
+            tma_load_2d(&p.tmb, full, dB, tap * p.K + kc, n0);
+            tma_load_2d(&p.tmb, full, dB + h * 128, tap * p.K + kc, p.N / 2 + n0);
+          } else {
+            tma_load_2d(&p.tmb, full, dB, tap * p.K + kc, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.block_n, p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t aaddr = sA + stage * A_STAGE_BYTES;
+          const uint32_t baddr = sB + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BLOCK_K / 16; ++j) {
+            const uint64_t ad = p.a_mn ? make_smem_desc_sw128(aaddr + j * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(aaddr + j * 32, 16, 1024);
+            const uint64_t bd = p.b_mn ? make_smem_desc_sw128(baddr + j * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(baddr + j * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float s_acc = 1.f, s_r1 = 1.f, s_r2 = 1.f;
+    if (p.scales) { s_acc = p.scales[0]; s_r1 = p.scales[1]; s_r2 = p.scales[2]; }
+    const int n_out_total = p.geglu ? p.N / 2 : p.N;
+    const int bn_out = p.geglu ? p.block_n / 2 : p.block_n;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int n0 = nt * bn_out;
+      // output row of this thread
+      long long m;
+      bool row_ok;
+      {
+        const int r = q * 32 + lane;
+        if (p.a_mode == SVDX_A_ROWS && !p.a_mn) {
+          const int g = mt / p.tiles_per_group;
+          const int t = mt - g * p.tiles_per_group;
+          const int rin = t * BLOCK_M + r;
+          row_ok = rin < p.rows_per_group;
+          m = (long long)g * p.rows_per_group + rin;
+        } else {
+          m = (long long)mt * BLOCK_M + r;
+          row_ok = m < p.M;
+        }
+      }
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const float* rb = p.rowbias ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
+      for (int c = 0; c < bn_out; c += 32) {
+        uint32_t v[32];
+        uint32_t gte[32];
+        __syncwarp();
+        tmem_ld32(t_base + c, v);
+        if (p.geglu) tmem_ld32(t_base + bn_out + c, gte);
+        tc_wait_ld();
+        const int col0 = n0 + c;
+        if (row_ok && col0 < n_out_total) {
+        const bool full_chunk = (col0 + 32 <= n_out_total);
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.geglu) {
+          float g[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(gte[i]);
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (full_chunk || col0 + i < n_out_total) {
+                f[i] += __ldg(p.bias + col0 + i);
+                g[i] += __ldg(p.bias + p.N / 2 + col0 + i);
+              }
+            }
+          }
+          if (p.pre) {
+            bf16* pv = p.pre + m * p.ldpre + col0;
+            bf16* pg = pv + p.N / 2;
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 a, b;
+                a.x = pack_bf16x2(f[i], f[i + 1]); a.y = pack_bf16x2(f[i + 2], f[i + 3]);
+                a.z = pack_bf16x2(f[i + 4], f[i + 5]); a.w = pack_bf16x2(f[i + 6], f[i + 7]);
+                b.x = pack_bf16x2(g[i], g[i + 1]); b.y = pack_bf16x2(g[i + 2], g[i + 3]);
+                b.z = pack_bf16x2(g[i + 4], g[i + 5]); b.w = pack_bf16x2(g[i + 6], g[i + 7]);
+                *reinterpret_cast<uint4*>(pv + i) = a;
+                *reinterpret_cast<uint4*>(pg + i) = b;
+              }
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < n_out_total) { pv[i] = __float2bfloat16(f[i]); pg[i] = __float2bfloat16(g[i]); }
+            }
+          }
+          // the reference applies GEGLU on the bf16-rounded projection (autocast F.linear output)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float fv = __bfloat162float(__float2bfloat16(f[i]));
+            const float gv = __bfloat162float(__float2bfloat16(g[i]));
+            f[i] = fv * gelu_erf_f(gv);
+          }
+        } else {
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full_chunk || col0 + i < n_out_total) f[i] += __ldg(p.bias + col0 + i);
+          }
+        }
+        if (rb) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full_chunk || col0 + i < n_out_total) f[i] += __ldg(rb + col0 + i);
+        }
+        if (p.scales) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] *= s_acc;
+        }
+        if (p.res1) {
+          const bf16* r1 = p.res1 + m * p.ldr1 + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(r1 + i);
+              float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+              f[i] += s_r1 * a.x; f[i + 1] += s_r1 * a.y; f[i + 2] += s_r1 * b.x; f[i + 3] += s_r1 * b.y;
+              f[i + 4] += s_r1 * c2.x; f[i + 5] += s_r1 * c2.y; f[i + 6] += s_r1 * d.x; f[i + 7] += s_r1 * d.y;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < n_out_total) f[i] += s_r1 * __bfloat162float(r1[i]);
+          }
+        }
+        if (p.res2) {
+          const bf16* r2 = p.res2 + m * p.ldr2 + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(r2 + i);
+              float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+              f[i] += s_r2 * a.x; f[i + 1] += s_r2 * a.y; f[i + 2] += s_r2 * b.x; f[i + 3] += s_r2 * b.y;
+              f[i + 4] += s_r2 * c2.x; f[i + 5] += s_r2 * c2.y; f[i + 6] += s_r2 * d.x; f[i + 7] += s_r2 * d.y;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < n_out_total) f[i] += s_r2 * __bfloat162float(r2[i]);
+          }
+        }
+        // ---- store
+        if (p.out_dtype == SVDX_OUT_BF16) {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + m * p.ldo + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 a;
+              a.x = pack_bf16x2(f[i], f[i + 1]); a.y = pack_bf16x2(f[i + 2], f[i + 3]);
+              a.z = pack_bf16x2(f[i + 4], f[i + 5]); a.w = pack_bf16x2(f[i + 6], f[i + 7]);
+              *reinterpret_cast<uint4*>(o + i) = a;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < n_out_total) o[i] = __float2bfloat16(f[i]);
+          }
+        } else if (p.out_dtype == SVDX_OUT_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < n_out_total) o[i] = f[i];
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col0;
+          for (int i = 0; i < 32; ++i)
+            if (full_chunk || col0 + i < n_out_total) atomicAdd(o + i, f[i]);
+        }
+        }  // row_ok
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace svdx
+
+using namespace svdx;
+
+extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!d || !d->a || !d->b || !d->out) return svdx_fail(SVDX_E_BADARG, "tapgemm: null pointer");
+  if (d->block_n < 32 || d->block_n > 256 || d->block_n % 32) return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n must be a multiple of 32 in [32,256]");
+  if (d->b_major_mn && d->block_n % 64) return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n %% 64 for MN-major B");
+  if (d->num_taps < 1 || d->num_taps > SVDX_MAX_TAPS) return svdx_fail(SVDX_E_BADARG, "tapgemm: num_taps");
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return svdx_fail(SVDX_E_BADARG, "tapgemm: empty problem");
+  if (d->split_k < 1 || (d->split_k > 1 && d->out_dtype != SVDX_OUT_F32_ATOMIC)) return svdx_fail(SVDX_E_BADARG, "tapgemm: split_k needs atomic output");
+  if (d->geglu && (d->N % 2 || d->block_n % 64 || d->b_major_mn || (d->N / 2) % (d->block_n / 2))) return svdx_fail(SVDX_E_BADARG, "tapgemm: geglu shape");
+  if ((d->lda % 8) || (d->ldb % 8)) return svdx_fail(SVDX_E_BADARG, "tapgemm: lda/ldb must be multiples of 8 elements (16 B)");
+  if ((reinterpret_cast<uintptr_t>(d->a) & 15) || (reinterpret_cast<uintptr_t>(d->b) & 15)) return svdx_fail(SVDX_E_BADARG, "tapgemm: operands must be 16 B aligned");
+  if ((d->a_major_mn || d->b_major_mn) && (d->a_mode != SVDX_A_ROWS || d->num_taps != 1)) return svdx_fail(SVDX_E_BADARG, "tapgemm: MN-major operands only in single-tap ROWS mode");
+
+  TapGemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_mode = d->a_mode; p.a_mn = d->a_major_mn; p.b_mn = d->b_major_mn;
+  p.num_taps = d->num_taps;
+  for (int i = 0; i < d->num_taps; ++i) { p.tap_d0[i] = d->tap_d0[i]; p.tap_d1[i] = d->tap_d1[i]; p.tap_d2[i] = d->tap_d2[i]; }
+  p.M = d->M; p.N = d->N; p.K = d->K; p.block_n = d->block_n; p.split_k = d->split_k;
+  p.geglu = d->geglu;
+  const int bn_out = d->geglu ? d->block_n / 2 : d->block_n;
+  const int n_out = d->geglu ? d->N / 2 : d->N;
+  p.n_tiles = (n_out + bn_out - 1) / bn_out;
+
+  int rc;
+  if (d->a_major_mn) {
+    // memory [K rows][M cols]
+    if (d->groups > 1) return svdx_fail(SVDX_E_BADARG, "tapgemm: MN-major A requires groups==1");
+    uint64_t dims[2] = {(uint64_t)d->M, (uint64_t)d->K};
+    uint64_t strides[1] = {(uint64_t)d->lda * 2};
+    uint32_t box[2] = {64, 64};
+    rc = svdx_make_tmap(&p.tma, d->a, 2, dims, strides, box);
+    p.rows_per_group = d->M; p.groups = 1; p.tiles_per_group = (d->M + BLOCK_M - 1) / BLOCK_M;
+    p.m_tiles = p.tiles_per_group;
+  } else if (d->a_mode == SVDX_A_ROWS) {
+    if (d->rows_per_group <= 0 || d->groups <= 0 || (long long)d->rows_per_group * d->groups != d->M) return svdx_fail(SVDX_E_BADARG, "tapgemm: rows_per_group*groups != M");
+    uint64_t dims[3] = {(uint64_t)d->K, (uint64_t)d->rows_per_group, (uint64_t)d->groups};
+    uint64_t strides[2] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * (uint64_t)d->rows_per_group};
+    uint32_t box[3] = {64, 128, 1};
+    rc = svdx_make_tmap(&p.tma, d->a, 3, dims, strides, box);
+    p.rows_per_group = d->rows_per_group; p.groups = d->groups;
+    p.tiles_per_group = (d->rows_per_group + BLOCK_M - 1) / BLOCK_M;
+    p.m_tiles = p.tiles_per_group * d->groups;
+  } else if (d->a_mode == SVDX_A_CONV2D) {
+    if (d->W <= 0 || d->W > 128 || (128 % d->W) || d->H <= 0 || d->nimg <= 0) return svdx_fail(SVDX_E_BADARG, "tapgemm: conv2d needs W | 128");
+    // M counts output pixels of the first `M / (H*W)` images; the tensor may hold more images (parity planes)
+    uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->nimg};
+    uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * d->W, (uint64_t)d->lda * 2 * d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)d->W, 1, 1};
+    rc = svdx_make_tmap(&p.tma, d->a, 4, dims, strides, box);
+    p.W = d->W; p.H = d->H; p.nimg = d->M / (d->H * d->W);
+    if ((long long)p.nimg * d->H * d->W != d->M) return svdx_fail(SVDX_E_BADARG, "tapgemm: conv2d M must be images*H*W");
+    p.m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
+    p.rows_per_group = d->M; p.groups = 1; p.tiles_per_group = p.m_tiles;
+  } else {
+    return svdx_fail(SVDX_E_BADARG, "tapgemm: a_mode");
+  }
+  if (rc) return rc;
+
+  if (d->b_major_mn) {
+    uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->K};
+    uint64_t strides[1] = {(uint64_t)d->ldb * 2};
+    uint32_t box[2] = {64, 64};
+    rc = svdx_make_tmap(&p.tmb, d->b, 2, dims, strides, box);
+  } else {
+    uint64_t dims[2] = {(uint64_t)d->K * d->num_taps, (uint64_t)d->N};
+    uint64_t strides[1] = {(uint64_t)d->ldb * 2};
+    uint32_t box[2] = {64, (uint32_t)(d->geglu ? d->block_n / 2 : d->block_n)};
+    rc = svdx_make_tmap(&p.tmb, d->b, 2, dims, strides, box);
+  }
+  if (rc) return rc;
+
+  p.kb_per_tap = (d->K + BLOCK_K - 1) / BLOCK_K;
+  p.kb_total = p.kb_per_tap * d->num_taps;
+  p.kb_per_split = (p.kb_total + d->split_k - 1) / d->split_k;
+  // drop empty splits
+  p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+
+  p.out = d->out; p.ldo = d->ldo; p.out_dtype = d->out_dtype;
+  p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_div = d->rowbias_div > 0 ? d->rowbias_div : 1; p.ldrb = d->ldrb;
+  p.res1 = reinterpret_cast<const bf16*>(d->res1); p.ldr1 = d->ldr1;
+  p.res2 = reinterpret_cast<const bf16*>(d->res2); p.ldr2 = d->ldr2;
+  p.scales = d->scales; p.pre = reinterpret_cast<bf16*>(d->pre); p.ldpre = d->ldpre;
+  if (p.split_k > 1 && (p.bias || p.rowbias || p.res1 || p.res2 || p.geglu)) return svdx_fail(SVDX_E_BADARG, "tapgemm: split_k with epilogue operands");
+  // vector paths need 16 B alignment of every row start
+  if (d->out_dtype == SVDX_OUT_BF16 && ((d->ldo % 8) || (reinterpret_cast<uintptr_t>(d->out) & 15))) return svdx_fail(SVDX_E_BADARG, "tapgemm: out alignment");
+  if (d->out_dtype != SVDX_OUT_BF16 && ((d->ldo % 4) || (reinterpret_cast<uintptr_t>(d->out) & 15))) return svdx_fail(SVDX_E_BADARG, "tapgemm: out alignment");
+  if (d->res1 && ((d->ldr1 % 8) || (reinterpret_cast<uintptr_t>(d->res1) & 15))) return svdx_fail(SVDX_E_BADARG, "tapgemm: res1 alignment");
+  if (d->res2 && ((d->ldr2 % 8) || (reinterpret_cast<uintptr_t>(d->res2) & 15))) return svdx_fail(SVDX_E_BADARG, "tapgemm: res2 alignment");
+  if (d->pre && ((d->ldpre % 8) || (reinterpret_cast<uintptr_t>(d->pre) & 15))) return svdx_fail(SVDX_E_BADARG, "tapgemm: pre alignment");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm: set smem attribute");
+    attr_set = true;
+  }
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+  int grid = svdx_num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  tapgemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm: launch");
+  return SVDX_OK;
+}

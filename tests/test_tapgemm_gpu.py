@@ -1,0 +1,172 @@
+"""GPU parity of svdx_tapgemm (tcgen05 contraction) against fp32 torch math on the same bf16 inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+bf16 = torch.bfloat16
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(_dev())
+
+
+def _close(got, ref, rtol=1.5e-2, atol=None, what=""):
+    got = got.float()
+    ref = ref.float()
+    if atol is None:
+        atol = 1.5e-2 * ref.abs().max().item()
+    err = (got - ref).abs()
+    bad = err > (atol + rtol * ref.abs())
+    rel = (got - ref).norm() / (ref.norm() + 1e-12)
+    assert not bad.any() and rel < 1e-2, (
+        f"{what}: {bad.sum().item()} / {bad.numel()} mismatches, max err {err.max().item():.4g}, rel-l2 {rel.item():.4g}, "
+        f"first bad idx {bad.nonzero()[:4].tolist()}")
+
+
+@pytest.fixture(scope="module")
+def raw():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from svd_xtend_b200 import raw
+    return raw
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (256, 320, 320), (1000, 640, 1024), (35840, 320, 320), (560, 1280, 2560), (14, 1280, 320)])
+def test_linear_bias(raw, M, N, K):
+    a = _rand(M, K, seed=1).to(bf16)
+    w = _rand(N, K, scale=K ** -0.5, seed=2).to(bf16)
+    bias = _rand(N, seed=3)
+    out = torch.full((M, N), float("nan"), device=_dev(), dtype=bf16)
+    raw.tapgemm(a, w, out, M=M, N=N, K=K, bias=bias)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    _close(out, ref, what=f"linear {M}x{N}x{K}")
+
+
+def test_linear_f32_out_and_strided(raw):
+    M, N, K = 300, 96, 192
+    abig = _rand(M, K + 64, seed=4).to(bf16)
+    a = abig[:, 64:]            # column-sliced view, lda = K + 64
+    w = _rand(N, K, scale=K ** -0.5, seed=5).to(bf16)
+    out = torch.zeros(M, N, device=_dev(), dtype=torch.float32)
+    raw.tapgemm(a, w, out, M=M, N=N, K=K)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ w.float().t(), rtol=1e-3, atol=1e-3, what="f32 out")
+
+
+def test_geglu(raw):
+    M, C = 512, 320
+    a = _rand(M, C, seed=6).to(bf16)
+    w = _rand(8 * C, C, scale=C ** -0.5, seed=7).to(bf16)
+    bias = _rand(8 * C, scale=0.1, seed=8)
+    out = torch.empty(M, 4 * C, device=_dev(), dtype=bf16)
+    pre = torch.empty(M, 8 * C, device=_dev(), dtype=bf16)
+    raw.tapgemm(a, w, out, M=M, N=8 * C, K=C, bias=bias, geglu=True, pre=pre)
+    torch.cuda.synchronize()
+    proj = a.float() @ w.float().t() + bias
+    _close(pre, proj, what="geglu pre")
+    pr = proj.to(bf16).float()
+    ref = pr[:, : 4 * C] * F.gelu(pr[:, 4 * C:])
+    _close(out, ref, what="geglu out")
+
+
+def test_residual_blend(raw):
+    M, N, K = 640, 320, 1280
+    a = _rand(M, K, seed=9).to(bf16)
+    w = _rand(N, K, scale=K ** -0.5, seed=10).to(bf16)
+    bias = _rand(N, seed=11)
+    r1 = _rand(M, N, seed=12).to(bf16)
+    r2 = _rand(M, N, seed=13).to(bf16)
+    scales = torch.tensor([0.378, 0.622, 0.378], device=_dev())
+    out = torch.empty(M, N, device=_dev(), dtype=bf16)
+    raw.tapgemm(a, w, out, M=M, N=N, K=K, bias=bias, res1=r1, res2=r2, scales=scales)
+    torch.cuda.synchronize()
+    ref = scales[0] * (a.float() @ w.float().t() + bias) + scales[1] * r1.float() + scales[2] * r2.float()
+    _close(out, ref, what="residual blend")
+
+
+def test_rowbias(raw):
+    M, N, K, div = 14 * 40, 320, 320, 40
+    a = _rand(M, K, seed=14).to(bf16)
+    w = _rand(N, K, scale=K ** -0.5, seed=15).to(bf16)
+    rb = _rand(M // div, N, seed=16)
+    out = torch.empty(M, N, device=_dev(), dtype=bf16)
+    raw.tapgemm(a, w, out, M=M, N=N, K=K, rowbias=rb, rowbias_div=div)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + rb.repeat_interleave(div, 0)
+    _close(out, ref, what="rowbias")
+
+
+@pytest.mark.parametrize("B,T,HW,C", [(1, 14, 160, 320), (2, 5, 40, 640), (1, 14, 2560, 320)])
+def test_temporal_conv(raw, B, T, HW, C):
+    # TemporalResnetBlock conv (3,1,1): x [B,T,HW,C] channels-last, w [Cout, Cin, 3]
+    Cout = C
+    x = _rand(B, T, HW, C, seed=17).to(bf16)
+    w = _rand(Cout, C, 3, scale=(3 * C) ** -0.5, seed=18).to(bf16)
+    bias = _rand(Cout, seed=19)
+    wk = w.permute(0, 2, 1).contiguous().view(Cout, 3 * C)  # [Cout][tap][Cin]
+    out = torch.empty(B * T * HW, Cout, device=_dev(), dtype=bf16)
+    taps = [(-HW, 0, 0), (0, 0, 0), (HW, 0, 0)]
+    raw.tapgemm(x.view(-1, C), wk, out, M=B * T * HW, N=Cout, K=C, taps=taps, rows_per_group=T * HW, groups=B, bias=bias)
+    torch.cuda.synchronize()
+    x5 = x.float().permute(0, 3, 1, 2).reshape(B, C, T, HW, 1)
+    ref = F.conv3d(x5, w.float().view(Cout, C, 3, 1, 1), bias, padding=(1, 0, 0))
+    ref = ref.reshape(B, Cout, T, HW).permute(0, 2, 3, 1).reshape(-1, Cout)
+    _close(out, ref, what="temporal conv")
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(3, 40, 64, 64, 320), (14, 5, 8, 128, 160), (5, 10, 16, 320, 64), (2, 20, 32, 192, 320)])
+def test_conv3x3(raw, N, H, W, Cin, Cout):
+    x = _rand(N, H, W, Cin, seed=20).to(bf16)   # channels-last
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=21).to(bf16)
+    bias = _rand(Cout, seed=22)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9 * Cin)  # [Cout][kh][kw][Cin]
+    out = torch.empty(N * H * W, Cout, device=_dev(), dtype=bf16)
+    raw.tapgemm(x.view(-1, Cin), wk, out, M=N * H * W, N=Cout, K=Cin, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS,
+                conv_whn=(W, H, N), bias=bias)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    _close(out, ref, what="conv3x3")
+
+
+def test_conv3x3_stride2_planes(raw):
+    # Downsample2D: stride-2 conv as 9 taps over 4 parity planes
+    N, H, W, C, Cout = 3, 20, 32, 128, 128
+    x = _rand(N, H, W, C, seed=23).to(bf16)
+    w = _rand(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=24).to(bf16)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9 * C)
+    Ho, Wo = H // 2, W // 2
+    planes = torch.empty(4 * N, Ho, Wo, C, device=_dev(), dtype=bf16)
+    for p in range(2):
+        for q in range(2):
+            planes[(p * 2 + q) * N:(p * 2 + q + 1) * N] = x[:, p::2, q::2]
+    taps = []
+    for kh in range(3):
+        for kw in range(3):
+            ph, dh = ((1, -1), (0, 0), (1, 0))[kh]
+            pw, dw = ((1, -1), (0, 0), (1, 0))[kw]
+            taps.append((dw, dh, (ph * 2 + pw) * N))
+    out = torch.empty(N * Ho * Wo, Cout, device=_dev(), dtype=bf16)
+    raw.tapgemm(planes.view(-1, C), wk, out, M=N * Ho * Wo, N=Cout, K=C, mode=raw.A_CONV2D, taps=taps, conv_whn=(Wo, Ho, 4 * N))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    _close(out, ref, what="conv stride 2")
+
+
+@pytest.mark.parametrize("Mtok,Nout,Kin,split", [(512, 128, 64, 1), (2240, 320, 1280, 4), (35840, 2560, 320, 8)])
+def test_wgrad_mn_major(raw, Mtok, Nout, Kin, split):
+    # dW[Nout, Kin] = dY[Mtok, Nout]^T @ X[Mtok, Kin]: both operands MN-major
+    dy = _rand(Mtok, Nout, scale=0.1, seed=25).to(bf16)
+    x = _rand(Mtok, Kin, seed=26).to(bf16)
+    dw = torch.zeros(Nout, Kin, device=_dev(), dtype=torch.float32)
+    raw.tapgemm(dy, x, dw, M=Nout, N=Kin, K=Mtok, a_mn=True, b_mn=True, split_k=split, out_dtype=raw.OUT_F32_ATOMIC)
+    torch.cuda.synchronize()
+    ref = dy.float().t() @ x.float()
+    _close(dw, ref, rtol=2e-3, atol=2e-3 * ref.abs().max().item(), what="wgrad")
