@@ -171,7 +171,7 @@ int svdx_attention_bwd(const SvdxAttn* d, void* stream);
  *   mode 0: plain copy           dst[n][k]           = src[n][k]
  *   mode 1: transpose            dst[k][n]           = src[n][k]            (dgrad operand of a linear)
  *   mode 2: conv OIHW -> O(HW)I  dst[o][t][i(pad)]   = src[o][i][t]         (fwd operand; taps = kh*kw or kt)
- *   mode 3: conv OIHW -> I(HW)O  dst[i][t][o]        = src[o][i][taps-1-t]  (dgrad operand: flipped taps)
+ *   mode 3: conv OIHW -> I(HW)O  dst[i][t][o]        = src[o][i][t]         (dgrad operand; the caller negates tap offsets)
  * i_pad >= I pads the input-channel axis with zeros (conv_in: 8 -> 64). */
 int svdx_prep_weight(const void* src, int32_t src_bf16, void* dst, int32_t mode,
                      int32_t O, int32_t I, int32_t taps, int32_t i_pad, void* stream);
@@ -202,9 +202,6 @@ int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t ldd
                    int64_t rows, int32_t h, void* stream);
 /* blend scales {1-alpha, 1, 0}/{...} from mix_factor: out[0]=1-sigmoid(m), out[1]=sigmoid(m), out[2]=sigmoid(m)*(1-sigmoid(m)) */
 int svdx_blend_scales(const float* mix_factor, float* out3, void* stream);
-/* EDM-preconditioned MSE of train_svd.py:1025-1036 fused with its gradient wrt model_pred */
-int svdx_edm_loss(const void* pred, const float* noisy, const float* target, const float* sigma,
-                  int32_t B, int64_t per_sample, float* loss, void* dpred, void* stream);
 /* fused multi-tensor AdamW on a flat fp32 buffer (torch.optim.AdamW of train_svd.py:767-773) */
 int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int32_t step, float grad_scale, void* stream);

@@ -1,0 +1,449 @@
+// Elementwise / layout / reduction kernels of the SVD UNet hot path (HBM-bound, CUDA cores):
+// weight preparation (fp32 master -> bf16 operand layouts), NCHW<->channels-last boundary
+// conversion, nearest-2x upsample, stride-2 parity planes, channel concat/split, GEGLU backward,
+// bias-gradient column sums, AlphaBlender scales, fused AdamW.
+// All 16-byte vectorised where the layout allows; grids are sized from the element count.
+#include "common.cuh"
+#include "../../include/svd_xtend_b200.h"
+#include "host_util.h"
+
+namespace svdx {
+
+SVDX_DEVINL long long gtid() { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
+static inline unsigned nblocks(long long n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------ weight prep
+template <typename T>
+SVDX_DEVINL float ldf(const T* p, long long i);
+template <>
+SVDX_DEVINL float ldf<float>(const float* p, long long i) { return p[i]; }
+template <>
+SVDX_DEVINL float ldf<bf16>(const bf16* p, long long i) { return __bfloat162float(p[i]); }
+
+// mode 0: dst[o][i]            = src[o][i]          (taps == 1)
+// mode 2: dst[o][t][i_pad]     = src[o][i][t]
+// mode 3: dst[i][t][o]         = src[o][i][t]
+template <typename T>
+__global__ void prep_gather_kernel(const T* __restrict__ src, bf16* __restrict__ dst, int mode, int O, int I, int taps, int i_pad) {
+  const long long idx = gtid();
+  if (mode == 0) {
+    if (idx >= (long long)O * I) return;
+    dst[idx] = __float2bfloat16(ldf(src, idx));
+  } else if (mode == 2) {
+    const long long total = (long long)O * taps * i_pad;
+    if (idx >= total) return;
+    const int i = (int)(idx % i_pad);
+    const int t = (int)((idx / i_pad) % taps);
+    const int o = (int)(idx / ((long long)i_pad * taps));
+    dst[idx] = (i < I) ? __float2bfloat16(ldf(src, ((long long)o * I + i) * taps + t)) : __float2bfloat16(0.f);
+  } else {
+    const long long total = (long long)I * taps * O;
+    if (idx >= total) return;
+    const int o = (int)(idx % O);
+    const int t = (int)((idx / O) % taps);
+    const int i = (int)(idx / ((long long)O * taps));
+    dst[idx] = __float2bfloat16(ldf(src, ((long long)o * I + i) * taps + t));
+  }
+}
+
+// mode 1: dst[i][o] = src[o][i]  — 32x32 shared-memory tile transpose
+template <typename T>
+__global__ void prep_transpose_kernel(const T* __restrict__ src, bf16* __restrict__ dst, int O, int I) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int o = o0 + r, i = i0 + threadIdx.x;
+    tile[r][threadIdx.x] = (o < O && i < I) ? ldf(src, (long long)o * I + i) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, o = o0 + threadIdx.x;
+    if (i < I && o < O) dst[(long long)i * O + o] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long i = gtid() * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  } else {
+    for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16(src[k]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = gtid();
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+// ------------------------------------------------------------------ layout boundary
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, bf16* __restrict__ dst, int N, int C, int H, int W, int c_pad) {
+  const long long idx = gtid();
+  const long long total = (long long)N * H * W * c_pad;
+  if (idx >= total) return;
+  const int c = (int)(idx % c_pad);
+  const long long pix = idx / c_pad;
+  const int w = (int)(pix % W);
+  const int h = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  dst[idx] = (c < C) ? __float2bfloat16(ldf(src, (((long long)n * C + c) * H + h) * W + w)) : __float2bfloat16(0.f);
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, long long lds, T* __restrict__ dst, int N, int C, int H, int W) {
+  const long long idx = gtid();
+  const long long total = (long long)N * C * H * W;
+  if (idx >= total) return;
+  const int w = (int)(idx % W);
+  const int h = (int)((idx / W) % H);
+  const int c = (int)((idx / ((long long)W * H)) % C);
+  const int n = (int)(idx / ((long long)W * H * C));
+  const float v = __bfloat162float(src[(((long long)n * H + h) * W + w) * lds + c]);
+  if constexpr (sizeof(T) == 4) dst[idx] = v; else dst[idx] = __float2bfloat16(v);
+}
+
+// nearest 2x: dst[n][2h+a][2w+b][:] = src[n][h][w][:]   (16 B vectors)
+__global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int H, int W, int CV) {
+  const long long idx = gtid();
+  const long long total = (long long)N * 2 * H * 2 * W * CV;
+  if (idx >= total) return;
+  const int cv = (int)(idx % CV);
+  const long long pix = idx / CV;
+  const int w2 = (int)(pix % (2 * W));
+  const int h2 = (int)((pix / (2 * W)) % (2 * H));
+  const int n = (int)(pix / ((long long)4 * W * H));
+  dst[idx] = src[(((long long)n * H + (h2 >> 1)) * W + (w2 >> 1)) * CV + cv];
+}
+SVDX_DEVINL uint32_t add_bf16x2_f32(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  const float2 x = unpack_bf16x2(a), y = unpack_bf16x2(b), z = unpack_bf16x2(c), w = unpack_bf16x2(d);
+  return pack_bf16x2(x.x + y.x + z.x + w.x, x.y + y.y + z.y + w.y);
+}
+// adjoint: ddst[n][h][w] = sum of the 2x2 block of dsrc
+__global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dsrc, uint4* __restrict__ ddst, int N, int H, int W, int CV) {
+  const long long idx = gtid();
+  const long long total = (long long)N * H * W * CV;
+  if (idx >= total) return;
+  const int cv = (int)(idx % CV);
+  const long long pix = idx / CV;
+  const int w = (int)(pix % W);
+  const int h = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const long long base = (((long long)n * 2 * H + 2 * h) * 2 * W + 2 * w) * CV + cv;
+  const uint4 a = dsrc[base], b = dsrc[base + CV], c = dsrc[base + (long long)2 * W * CV], d = dsrc[base + (long long)2 * W * CV + CV];
+  uint4 o;
+  o.x = add_bf16x2_f32(a.x, b.x, c.x, d.x); o.y = add_bf16x2_f32(a.y, b.y, c.y, d.y);
+  o.z = add_bf16x2_f32(a.z, b.z, c.z, d.z); o.w = add_bf16x2_f32(a.w, b.w, c.w, d.w);
+  ddst[idx] = o;
+}
+
+// parity planes: dst[(p*2+q)*N + n][h][w][:] = src[n][2h+p][2w+q][:]; to_planes=0 runs the inverse copy
+__global__ void planes_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int H, int W, int CV, int to_planes) {
+  const long long idx = gtid();  // index over the full-resolution tensor [N][H][W][CV]
+  const long long total = (long long)N * H * W * CV;
+  if (idx >= total) return;
+  const int cv = (int)(idx % CV);
+  const long long pix = idx / CV;
+  const int w = (int)(pix % W);
+  const int h = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const int Ho = H / 2, Wo = W / 2;
+  const long long pidx = ((((long long)((h & 1) * 2 + (w & 1)) * N + n) * Ho + (h >> 1)) * Wo + (w >> 1)) * CV + cv;
+  if (to_planes) dst[pidx] = src[idx]; else dst[idx] = src[pidx];
+}
+
+__global__ void concat_kernel(const uint4* __restrict__ a, int CVa, const uint4* __restrict__ b, int CVb, uint4* __restrict__ dst, long long rows) {
+  const long long idx = gtid();
+  const int CV = CVa + CVb;
+  if (idx >= rows * CV) return;
+  const long long r = idx / CV;
+  const int c = (int)(idx - r * CV);
+  dst[idx] = (c < CVa) ? a[r * CVa + c] : b[r * CVb + (c - CVa)];
+}
+__global__ void split_kernel(const uint4* __restrict__ src, uint4* __restrict__ a, int CVa, uint4* __restrict__ b, int CVb, long long rows,
+                             int accumulate_a) {
+  const long long idx = gtid();
+  const int CV = CVa + CVb;
+  if (idx >= rows * CV) return;
+  const long long r = idx / CV;
+  const int c = (int)(idx - r * CV);
+  const uint4 v = src[idx];
+  if (c < CVa) {
+    uint4* p = a + r * CVa + c;
+    if (accumulate_a) {
+      const uint4 o = *p;
+      uint4 s;
+      float2 x, y;
+      x = unpack_bf16x2(o.x); y = unpack_bf16x2(v.x); s.x = pack_bf16x2(x.x + y.x, x.y + y.y);
+      x = unpack_bf16x2(o.y); y = unpack_bf16x2(v.y); s.y = pack_bf16x2(x.x + y.x, x.y + y.y);
+      x = unpack_bf16x2(o.z); y = unpack_bf16x2(v.z); s.z = pack_bf16x2(x.x + y.x, x.y + y.y);
+      x = unpack_bf16x2(o.w); y = unpack_bf16x2(v.w); s.w = pack_bf16x2(x.x + y.x, x.y + y.y);
+      *p = s;
+    } else {
+      *p = v;
+    }
+  } else if (b) {
+    b[r * CVb + (c - CVa)] = v;
+  }
+}
+
+// y = s0*a + s1*b (scales == NULL -> 1,1)
+__global__ void axpby_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const float* __restrict__ scales, uint4* __restrict__ y,
+                             long long nvec) {
+  const long long idx = gtid();
+  if (idx >= nvec) return;
+  const float s0 = scales ? scales[0] : 1.f, s1 = scales ? scales[1] : 1.f;
+  const uint4 u = a[idx], v = b[idx];
+  uint4 o;
+  float2 x, z;
+  x = unpack_bf16x2(u.x); z = unpack_bf16x2(v.x); o.x = pack_bf16x2(s0 * x.x + s1 * z.x, s0 * x.y + s1 * z.y);
+  x = unpack_bf16x2(u.y); z = unpack_bf16x2(v.y); o.y = pack_bf16x2(s0 * x.x + s1 * z.x, s0 * x.y + s1 * z.y);
+  x = unpack_bf16x2(u.z); z = unpack_bf16x2(v.z); o.z = pack_bf16x2(s0 * x.x + s1 * z.x, s0 * x.y + s1 * z.y);
+  x = unpack_bf16x2(u.w); z = unpack_bf16x2(v.w); o.w = pack_bf16x2(s0 * x.x + s1 * z.x, s0 * x.y + s1 * z.y);
+  y[idx] = o;
+}
+
+__global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long i = gtid();
+  if (i < n) y[i] = silu_f(x[i]);
+}
+
+// column sums of a bf16 [rows][ldx] matrix: grid (col blocks of 64, row chunks); 256 threads =
+// 32 column pairs x 8 row lanes; fp32 atomics into out
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int cols, long long rows_per_cta,
+                                                     float* __restrict__ out) {
+  __shared__ float sh[8][64];
+  const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * cp;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, rows);
+  float a = 0.f, b = 0.f;
+  if (c < cols) {
+    for (long long r = r0 + rl; r < r1; r += 8) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ldx + c));
+      a += v.x; b += v.y;
+    }
+  }
+  sh[rl][2 * cp] = a; sh[rl][2 * cp + 1] = b;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sh[k][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < cols) atomicAdd(out + cc, s);
+  }
+}
+
+// GEGLU backward. pre = [value | gate] (bf16, the saved projection), dout [rows][h]
+__global__ void geglu_bwd_kernel(const bf16* __restrict__ pre, long long ldpre, const bf16* __restrict__ dout, long long lddo,
+                                 bf16* __restrict__ dpre, long long lddpre, long long rows, int h) {
+  const long long idx = gtid();  // one thread per 8 columns
+  const int hv = h / 8;
+  if (idx >= rows * hv) return;
+  const long long r = idx / hv;
+  const int c = (int)(idx - r * hv) * 8;
+  const uint4 uv = *reinterpret_cast<const uint4*>(pre + r * ldpre + c);
+  const uint4 ug = *reinterpret_cast<const uint4*>(pre + r * ldpre + h + c);
+  const uint4 ud = *reinterpret_cast<const uint4*>(dout + r * lddo + c);
+  const uint32_t v[4] = {uv.x, uv.y, uv.z, uv.w}, g[4] = {ug.x, ug.y, ug.z, ug.w}, d[4] = {ud.x, ud.y, ud.z, ud.w};
+  uint32_t ov[4], og[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 fv = unpack_bf16x2(v[k]), fg = unpack_bf16x2(g[k]), fd = unpack_bf16x2(d[k]);
+    ov[k] = pack_bf16x2(fd.x * gelu_erf_f(fg.x), fd.y * gelu_erf_f(fg.y));
+    og[k] = pack_bf16x2(fd.x * fv.x * gelu_erf_grad_f(fg.x), fd.y * fv.y * gelu_erf_grad_f(fg.y));
+  }
+  *reinterpret_cast<uint4*>(dpre + r * lddpre + c) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+  *reinterpret_cast<uint4*>(dpre + r * lddpre + h + c) = make_uint4(og[0], og[1], og[2], og[3]);
+}
+
+__global__ void blend_scales_kernel(const float* mix, float* out) {
+  const float a = 1.f / (1.f + __expf(-mix[0]));
+  out[0] = 1.f - a;
+  out[1] = a;
+  out[2] = a * (1.f - a);
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) {
+  const long long i = gtid();
+  if (i >= n) return;
+  const float gi = g[i] * gscale;
+  float pi = p[i] * (1.f - lr * wd);
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  pi -= (lr / bc1) * mi / denom;
+  p[i] = pi;
+}
+
+}  // namespace svdx
+
+using namespace svdx;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int svdx_prep_weight(const void* src, int32_t src_bf16, void* dst, int32_t mode, int32_t O, int32_t I, int32_t taps,
+                                int32_t i_pad, void* stream) {
+  if (!src || !dst || O <= 0 || I <= 0 || taps <= 0 || mode < 0 || mode > 3) return svdx_fail(SVDX_E_BADARG, "prep_weight: bad arguments");
+  if ((mode == 0 || mode == 1) && taps != 1) return svdx_fail(SVDX_E_BADARG, "prep_weight: modes 0/1 need taps == 1");
+  if (mode == 2 && i_pad < I) return svdx_fail(SVDX_E_BADARG, "prep_weight: i_pad < I");
+  bf16* d = reinterpret_cast<bf16*>(dst);
+  if (mode == 1) {
+    dim3 grid((I + 31) / 32, (O + 31) / 32), block(32, 8);
+    if (src_bf16) prep_transpose_kernel<bf16><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), d, O, I);
+    else prep_transpose_kernel<float><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), d, O, I);
+  } else {
+    const long long total = mode == 0 ? (long long)O * I : mode == 2 ? (long long)O * taps * i_pad : (long long)I * taps * O;
+    if (src_bf16) prep_gather_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), d, mode, O, I, taps, i_pad);
+    else prep_gather_kernel<float><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), d, mode, O, I, taps, i_pad);
+  }
+  SVDX_CHECK_LAUNCH("prep_weight");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst || n <= 0 || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 7))
+    return svdx_fail(SVDX_E_BADARG, "cast_f32_bf16: bad arguments");
+  cast_f32_bf16_kernel<<<nblocks((n + 3) / 4), 256, 0, ST(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+  SVDX_CHECK_LAUNCH("cast_f32_bf16");
+  return SVDX_OK;
+}
+extern "C" int svdx_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
+  if (!src || !dst || n <= 0) return svdx_fail(SVDX_E_BADARG, "cast_bf16_f32: bad arguments");
+  cast_bf16_f32_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), dst, n);
+  SVDX_CHECK_LAUNCH("cast_bf16_f32");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_nchw_to_nhwc(const void* src, int32_t src_bf16, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, int32_t c_pad,
+                                 void* stream) {
+  if (!src || !dst || N <= 0 || C <= 0 || H <= 0 || W <= 0 || c_pad < C) return svdx_fail(SVDX_E_BADARG, "nchw_to_nhwc: bad arguments");
+  const long long total = (long long)N * H * W * c_pad;
+  if (src_bf16) nchw_to_nhwc_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(dst), N, C, H, W, c_pad);
+  else nchw_to_nhwc_kernel<float><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), reinterpret_cast<bf16*>(dst), N, C, H, W, c_pad);
+  SVDX_CHECK_LAUNCH("nchw_to_nhwc");
+  return SVDX_OK;
+}
+extern "C" int svdx_nhwc_to_nchw(const void* src, int64_t lds, void* dst, int32_t dst_bf16, int32_t N, int32_t C, int32_t H, int32_t W,
+                                 void* stream) {
+  if (!src || !dst || N <= 0 || C <= 0 || H <= 0 || W <= 0 || lds < C) return svdx_fail(SVDX_E_BADARG, "nhwc_to_nchw: bad arguments");
+  const long long total = (long long)N * C * H * W;
+  if (dst_bf16) nhwc_to_nchw_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<bf16*>(dst), N, C, H, W);
+  else nhwc_to_nchw_kernel<float><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<float*>(dst), N, C, H, W);
+  SVDX_CHECK_LAUNCH("nhwc_to_nchw");
+  return SVDX_OK;
+}
+
+static int vec_ok(const void* a, const void* b, int C) {
+  return a && b && C > 0 && C % 8 == 0 && !(reinterpret_cast<uintptr_t>(a) & 15) && !(reinterpret_cast<uintptr_t>(b) & 15);
+}
+
+extern "C" int svdx_upsample2x(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!vec_ok(src, dst, C) || N <= 0 || H <= 0 || W <= 0) return svdx_fail(SVDX_E_BADARG, "upsample2x: bad arguments");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), N, H, W, C / 8);
+  SVDX_CHECK_LAUNCH("upsample2x");
+  return SVDX_OK;
+}
+extern "C" int svdx_upsample2x_bwd(const void* dsrc, void* ddst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!vec_ok(dsrc, ddst, C) || N <= 0 || H <= 0 || W <= 0) return svdx_fail(SVDX_E_BADARG, "upsample2x_bwd: bad arguments");
+  const long long total = (long long)N * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(dsrc), reinterpret_cast<uint4*>(ddst), N, H, W, C / 8);
+  SVDX_CHECK_LAUNCH("upsample2x_bwd");
+  return SVDX_OK;
+}
+extern "C" int svdx_space_to_planes(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!vec_ok(src, dst, C) || N <= 0 || H <= 0 || W <= 0 || H % 2 || W % 2) return svdx_fail(SVDX_E_BADARG, "space_to_planes: bad arguments");
+  const long long total = (long long)N * H * W * (C / 8);
+  planes_kernel<<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), N, H, W, C / 8, 1);
+  SVDX_CHECK_LAUNCH("space_to_planes");
+  return SVDX_OK;
+}
+extern "C" int svdx_planes_to_space(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!vec_ok(src, dst, C) || N <= 0 || H <= 0 || W <= 0 || H % 2 || W % 2) return svdx_fail(SVDX_E_BADARG, "planes_to_space: bad arguments");
+  const long long total = (long long)N * H * W * (C / 8);
+  planes_kernel<<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), N, H, W, C / 8, 0);
+  SVDX_CHECK_LAUNCH("planes_to_space");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_concat_channels(const void* a, int32_t Ca, const void* b, int32_t Cb, void* dst, int64_t rows, void* stream) {
+  if (!vec_ok(a, dst, Ca) || !vec_ok(b, dst, Cb) || rows <= 0) return svdx_fail(SVDX_E_BADARG, "concat_channels: bad arguments");
+  const long long total = rows * ((Ca + Cb) / 8);
+  concat_kernel<<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(a), Ca / 8, reinterpret_cast<const uint4*>(b), Cb / 8,
+                                                        reinterpret_cast<uint4*>(dst), rows);
+  SVDX_CHECK_LAUNCH("concat_channels");
+  return SVDX_OK;
+}
+extern "C" int svdx_split_channels(const void* src, void* a, int32_t Ca, void* b, int32_t Cb, int64_t rows, int32_t accumulate_a, void* stream) {
+  if (!vec_ok(src, a, Ca) || Cb <= 0 || Cb % 8 || rows <= 0 || (b && (reinterpret_cast<uintptr_t>(b) & 15)))
+    return svdx_fail(SVDX_E_BADARG, "split_channels: bad arguments");
+  const long long total = rows * ((Ca + Cb) / 8);
+  split_kernel<<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(a), Ca / 8,
+                                                       reinterpret_cast<uint4*>(b), Cb / 8, rows, accumulate_a);
+  SVDX_CHECK_LAUNCH("split_channels");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_axpby_bf16(const void* a, const void* b, const float* scales, void* y, int64_t n, void* stream) {
+  if (!a || !b || !y || n <= 0 || n % 8 || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) ||
+      (reinterpret_cast<uintptr_t>(y) & 15))
+    return svdx_fail(SVDX_E_BADARG, "axpby_bf16: bad arguments (n %% 8, 16 B alignment)");
+  axpby_kernel<<<nblocks(n / 8), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), scales,
+                                                       reinterpret_cast<uint4*>(y), n / 8);
+  SVDX_CHECK_LAUNCH("axpby_bf16");
+  return SVDX_OK;
+}
+extern "C" int svdx_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream) { return svdx_axpby_bf16(a, b, nullptr, y, n, stream); }
+
+extern "C" int svdx_silu_f32(const float* x, float* y, int64_t n, void* stream) {
+  if (!x || !y || n <= 0) return svdx_fail(SVDX_E_BADARG, "silu_f32: bad arguments");
+  silu_f32_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(x, y, n);
+  SVDX_CHECK_LAUNCH("silu_f32");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_colsum(const void* x, int64_t ldx, int64_t rows, int32_t cols, float* out, int32_t accumulate, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0 || cols % 2 || ldx % 2) return svdx_fail(SVDX_E_BADARG, "colsum: bad arguments");
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * cols, ST(stream));
+  const int col_blocks = (cols + 63) / 64;
+  long long chunks = (2LL * svdx_num_sms() + col_blocks - 1) / col_blocks;
+  if (chunks < 1) chunks = 1;
+  long long rows_per_cta = (rows + chunks - 1) / chunks;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  chunks = (rows + rows_per_cta - 1) / rows_per_cta;
+  colsum_kernel<<<dim3(col_blocks, (unsigned)chunks), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, rows, cols, rows_per_cta, out);
+  SVDX_CHECK_LAUNCH("colsum");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t lddo, void* dpre, int64_t lddpre, int64_t rows,
+                              int32_t h, void* stream) {
+  if (!pre || !dout || !dpre || rows <= 0 || h <= 0 || h % 8 || ldpre % 8 || lddo % 8 || lddpre % 8)
+    return svdx_fail(SVDX_E_BADARG, "geglu_bwd: bad arguments");
+  geglu_bwd_kernel<<<nblocks(rows * (h / 8)), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), ldpre, reinterpret_cast<const bf16*>(dout),
+                                                                    lddo, reinterpret_cast<bf16*>(dpre), lddpre, rows, h);
+  SVDX_CHECK_LAUNCH("geglu_bwd");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_blend_scales(const float* mix_factor, float* out3, void* stream) {
+  if (!mix_factor || !out3) return svdx_fail(SVDX_E_BADARG, "blend_scales: null");
+  blend_scales_kernel<<<1, 1, 0, ST(stream)>>>(mix_factor, out3);
+  SVDX_CHECK_LAUNCH("blend_scales");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int32_t step, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || step < 1) return svdx_fail(SVDX_E_BADARG, "adamw: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adamw_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  SVDX_CHECK_LAUNCH("adamw");
+  return SVDX_OK;
+}
