@@ -1,0 +1,692 @@
+// Scaled-dot-product attention (head_dim 64, no mask), forward and backward, on tcgen05.
+//
+// Replaces AttnProcessor2_0 -> F.scaled_dot_product_attention [D: diffusers models/attention_processor.py]
+// for BasicTransformerBlock.attn1 (spatial, S = H*W per frame) and
+// TemporalBasicTransformerBlock.attn1 (temporal, S = T per pixel) of the SVD UNet
+// (reached from /root/reference/src/unet_spatio_temporal_condition.py:170-233).
+//
+// Layout: q/k/v/o are column slices of token-major [tokens][ld] bf16 matrices (channels-last
+// activations), head h = columns [64h, 64h+64). One 128-row MMA tile holds G interleaved sequences
+// x RT = 128/G tokens (tile row r -> sequence r % G, token r / G); spatial attention uses G = 1,
+// temporal attention packs G = 8 neighbouring pixels (T <= 16) so the tensor-core tile is full and
+// the strided token rows are gathered by ONE 4-D TMA box. Cross-sequence score entries are masked.
+//
+//   forward  : S = Q K^T (TMEM) -> online softmax in registers (exp2) -> P (bf16, swizzled smem)
+//              -> O_j = P V (TMEM, V as MN-major B operand) -> fp32 register accumulation.
+//   backward : bwd_dq  (CTA per query tile, loops key tiles):  dQ += dS K
+//              bwd_dkv (CTA per key tile, loops query tiles):  dV += P^T dO, dK += dS^T Q
+//              with P = exp(scale*S - lse) recomputed, dS = P o (dP - delta) * scale.
+#include "common.cuh"
+#include "../../include/svd_xtend_b200.h"
+#include "host_util.h"
+
+namespace svdx {
+
+constexpr int AT_THREADS = 192;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // one [128 rows][64 cols] bf16 operand tile, 16 KB
+constexpr int PT_BYTES = 2 * TILE_BYTES;  // one [128][128] bf16 score tile (two 64-column halves)
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnKParams {
+  CUtensorMap tq, tk, tv, tdo;  // 4-D maps: (col, inner, token, outer), box (64, G, RT, 1)
+  int heads, S, G, RT, inner_groups, tiles;
+  long long outer_stride, inner_stride, tok_stride;
+  float scale;
+  bf16* o; long long ldo;
+  float* lse;     // [tokens][heads]
+  float* delta;   // [tokens][heads]
+  bf16* dq; long long lddq;
+  bf16* dk; long long lddk;
+  bf16* dv; long long lddv;
+};
+
+struct RowInfo {
+  long long token;  // global token row
+  int g;            // sequence slot inside the tile
+  bool valid;
+};
+
+SVDX_DEVINL RowInfo row_info(const AttnKParams& p, int r, int tile, int outer, int inner0) {
+  RowInfo ri;
+  const int t = tile * p.RT + r / p.G;
+  ri.g = r % p.G;
+  ri.valid = t < p.S;
+  ri.token = (long long)outer * p.outer_stride + (long long)(inner0 + ri.g) * p.inner_stride + (long long)t * p.tok_stride;
+  return ri;
+}
+
+// store 32 consecutive bf16 score values of tile row r, columns [c0, c0+32), into a K-major
+// 128B-swizzled [128][128] tile (two [128][64] halves)
+SVDX_DEVINL void store_score_chunk(uint32_t tile_base, int r, int c0, const float (&f)[32]) {
+  const uint32_t half_base = tile_base + (c0 >> 6) * TILE_BYTES + r * 128;
+  const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t addr = half_base + (((chunk0 + k) ^ (r & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(f[8 * k], f[8 * k + 1])),
+                 "r"(pack_bf16x2(f[8 * k + 2], f[8 * k + 3])), "r"(pack_bf16x2(f[8 * k + 4], f[8 * k + 5])),
+                 "r"(pack_bf16x2(f[8 * k + 6], f[8 * k + 7]))
+                 : "memory");
+  }
+}
+
+SVDX_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// acc[128 x N] (+)= A[128 x 64] (K-major tile) * B[N x 64]^T (K-major tile)
+SVDX_DEVINL void mma_kk64(uint32_t d_tmem, uint32_t a, uint32_t b, uint32_t idesc, bool acc_first) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    umma_bf16(d_tmem, make_smem_desc_sw128(a + ks * 32, 16, 1024), make_smem_desc_sw128(b + ks * 32, 16, 1024), idesc,
+              (acc_first || ks > 0) ? 1u : 0u);
+}
+// acc[128 x 64] (+)= P[128 x 128] (K-major score tile, 2 halves) * V[128 keys x 64] (MN-major B tile)
+SVDX_DEVINL void mma_pv(uint32_t d_tmem, uint32_t pbase, uint32_t v, uint32_t idesc, bool acc_first) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks)
+    umma_bf16(d_tmem, make_smem_desc_sw128(pbase + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024),
+              make_smem_desc_sw128(v + ks * 2048, 8192, 1024), idesc, (acc_first || ks > 0) ? 1u : 0u);
+}
+
+SVDX_DEVINL void decode_block(const AttnKParams& p, int& tile, int& head, int& outer, int& inner0) {
+  tile = blockIdx.x;
+  head = blockIdx.y;
+  outer = blockIdx.z / p.inner_groups;
+  inner0 = (blockIdx.z % p.inner_groups) * p.G;
+}
+
+// =====================================================================================
+// forward
+// smem: Q | KV ring 3 x (K,V) | P x 2 | barriers
+constexpr int FWD_KV_STAGES = 3;
+constexpr int FWD_SMEM = 1024 + TILE_BYTES + FWD_KV_STAGES * 2 * TILE_BYTES + 2 * PT_BYTES + 256;
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sKV = sQ + TILE_BYTES;
+  const uint32_t sP = sKV + FWD_KV_STAGES * 2 * TILE_BYTES;
+  const uint32_t sBar = sP + 2 * PT_BYTES;
+  const uint32_t b_qfull = sBar;
+  const uint32_t b_kvfull = sBar + 8;          // [3]
+  const uint32_t b_kvempty = sBar + 8 * 4;     // [3]
+  const uint32_t b_sfull = sBar + 8 * 7;       // [2]
+  const uint32_t b_sempty = sBar + 8 * 9;      // [2]
+  const uint32_t b_pfull = sBar + 8 * 11;      // [2]
+  const uint32_t b_pempty = sBar + 8 * 13;     // [2]
+  const uint32_t b_ofull = sBar + 8 * 15;      // [2]
+  const uint32_t b_oempty = sBar + 8 * 17;     // [2]
+  const uint32_t tmem_slot = sBar + 8 * 19;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile, head, outer, inner0;
+  decode_block(p, tile, head, outer, inner0);
+  const int nkv = p.tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv);
+    mbar_init(b_qfull, 1);
+    for (int i = 0; i < FWD_KV_STAGES; ++i) { mbar_init(b_kvfull + 8 * i, 1); mbar_init(b_kvempty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_sfull + 8 * i, 1); mbar_init(b_sempty + 8 * i, 128);
+      mbar_init(b_pfull + 8 * i, 128); mbar_init(b_pempty + 8 * i, 1);
+      mbar_init(b_ofull + 8 * i, 1); mbar_init(b_oempty + 8 * i, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem, tO = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_qfull, TILE_BYTES);
+      tma_load_4d(&p.tq, b_qfull, sQ, head * 64, inner0, tile * p.RT, outer);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % FWD_KV_STAGES;
+        mbar_wait(b_kvempty + 8 * st, ((j / FWD_KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(b_kvfull + 8 * st, 2 * TILE_BYTES);
+        tma_load_4d(&p.tk, b_kvfull + 8 * st, sKV + st * 2 * TILE_BYTES, head * 64, inner0, j * p.RT, outer);
+        tma_load_4d(&p.tv, b_kvfull + 8 * st, sKV + st * 2 * TILE_BYTES + TILE_BYTES, head * 64, inner0, j * p.RT, outer);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      mbar_wait(b_qfull, 0);
+      for (int j = 0; j <= nkv; ++j) {
+        if (j < nkv) {
+          const int st = j % FWD_KV_STAGES;
+          mbar_wait(b_kvfull + 8 * st, (j / FWD_KV_STAGES) & 1);
+          mbar_wait(b_sempty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);
+          tc_fence_after();
+          mma_kk64(tS + (j & 1) * 128, sQ, sKV + st * 2 * TILE_BYTES, idesc_s, false);
+          umma_commit(b_sfull + 8 * (j & 1));
+        }
+        if (j >= 1) {
+          const int k = j - 1;
+          const int st = k % FWD_KV_STAGES;
+          mbar_wait(b_pfull + 8 * (k & 1), (k >> 1) & 1);
+          mbar_wait(b_oempty + 8 * (k & 1), ((k >> 1) & 1) ^ 1);
+          tc_fence_after();
+          mma_pv(tO + (k & 1) * 64, sP + (k & 1) * PT_BYTES, sKV + st * 2 * TILE_BYTES + TILE_BYTES, idesc_o, false);
+          umma_commit(b_ofull + 8 * (k & 1));
+          umma_commit(b_pempty + 8 * (k & 1));
+          umma_commit(b_kvempty + 8 * st);
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax / accumulate threads: one thread per tile row
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const RowInfo ri = row_info(p, r, tile, outer, inner0);
+    const float sc = p.scale * LOG2E;
+    float m_run = -INFINITY, l_run = 0.f, alpha_pend = 1.f;
+    float o_acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+
+    auto absorb = [&](int k, float alpha) {
+      mbar_wait(b_ofull + 8 * (k & 1), (k >> 1) & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tO + (k & 1) * 64 + lane_off, v0);
+      tmem_ld32(tO + (k & 1) * 64 + 32 + lane_off, v1);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        o_acc[i] = o_acc[i] * alpha + __uint_as_float(v0[i]);
+        o_acc[32 + i] = o_acc[32 + i] * alpha + __uint_as_float(v1[i]);
+      }
+      tc_fence_before();
+      mbar_arrive(b_oempty + 8 * (k & 1));
+    };
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(b_sfull + 8 * (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tS + (j & 1) * 128 + lane_off;
+      // pass 1: masked row max of this block
+      float bmax = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(ts + c0, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = c0 + i;
+          const bool ok = ((c % p.G) == ri.g) && (j * p.RT + c / p.G < p.S);
+          if (ok) bmax = fmaxf(bmax, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, bmax);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_use) * sc);
+      // pass 2: probabilities -> smem
+      mbar_wait(b_pempty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);
+      float rsum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(ts + c0, v);
+        tc_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = c0 + i;
+          const bool ok = ((c % p.G) == ri.g) && (j * p.RT + c / p.G < p.S);
+          const float e = ok ? exp2f((__uint_as_float(v[i]) - m_use) * sc) : 0.f;
+          // the PV product consumes bf16 probabilities; sum the rounded values so the row normaliser matches
+          const float eb = __bfloat162float(__float2bfloat16(e));
+          f[i] = eb;
+          rsum += eb;
+        }
+        store_score_chunk(sP + (j & 1) * PT_BYTES, r, c0, f);
+      }
+      l_run = l_run * alpha + rsum;
+      m_run = m_new;
+      tc_fence_before();
+      mbar_arrive(b_sempty + 8 * (j & 1));
+      fence_proxy_async_smem();
+      mbar_arrive(b_pfull + 8 * (j & 1));
+      if (j >= 1) absorb(j - 1, alpha_pend);
+      alpha_pend = alpha;
+    }
+    absorb(nkv - 1, alpha_pend);
+
+    if (ri.valid) {
+      const float inv = 1.f / l_run;
+      bf16* orow = p.o + ri.token * p.ldo + head * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
+        u.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+        u.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+        u.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+        *reinterpret_cast<uint4*>(orow + i) = u;
+      }
+      if (p.lse) p.lse[ri.token * p.heads + head] = m_run * p.scale + __logf(l_run);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// =====================================================================================
+// backward, dQ:  CTA owns a query tile, loops key tiles.
+// smem: Q | dO | KV ring 2 x (K,V) | dS | barriers.  TMEM: S [0,128) dP [128,256) dQ [256,320)
+constexpr int BWD_STAGES = 2;
+constexpr int BDQ_SMEM = 1024 + 2 * TILE_BYTES + BWD_STAGES * 2 * TILE_BYTES + PT_BYTES + 256;
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sDO = sQ + TILE_BYTES;
+  const uint32_t sKV = sDO + TILE_BYTES;
+  const uint32_t sDS = sKV + BWD_STAGES * 2 * TILE_BYTES;
+  const uint32_t sBar = sDS + PT_BYTES;
+  const uint32_t b_qfull = sBar;
+  const uint32_t b_kvfull = sBar + 8;        // [2]
+  const uint32_t b_kvempty = sBar + 8 * 3;   // [2]
+  const uint32_t b_sfull = sBar + 8 * 5;
+  const uint32_t b_sempty = sBar + 8 * 6;
+  const uint32_t b_dsfull = sBar + 8 * 7;
+  const uint32_t b_dsempty = sBar + 8 * 8;
+  const uint32_t b_done = sBar + 8 * 9;
+  const uint32_t tmem_slot = sBar + 8 * 10;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile, head, outer, inner0;
+  decode_block(p, tile, head, outer, inner0);
+  const int nkv = p.tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv); prefetch_tmap(&p.tdo);
+    mbar_init(b_qfull, 1);
+    for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(b_kvfull + 8 * i, 1); mbar_init(b_kvempty + 8 * i, 1); }
+    mbar_init(b_sfull, 1); mbar_init(b_sempty, 128);
+    mbar_init(b_dsfull, 128); mbar_init(b_dsempty, 1);
+    mbar_init(b_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_qfull, 2 * TILE_BYTES);
+      tma_load_4d(&p.tq, b_qfull, sQ, head * 64, inner0, tile * p.RT, outer);
+      tma_load_4d(&p.tdo, b_qfull, sDO, head * 64, inner0, tile * p.RT, outer);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % BWD_STAGES;
+        mbar_wait(b_kvempty + 8 * st, ((j / BWD_STAGES) & 1) ^ 1);
+        mbar_expect_tx(b_kvfull + 8 * st, 2 * TILE_BYTES);
+        tma_load_4d(&p.tk, b_kvfull + 8 * st, sKV + st * 2 * TILE_BYTES, head * 64, inner0, j * p.RT, outer);
+        tma_load_4d(&p.tv, b_kvfull + 8 * st, sKV + st * 2 * TILE_BYTES + TILE_BYTES, head * 64, inner0, j * p.RT, outer);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      mbar_wait(b_qfull, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % BWD_STAGES;
+        const uint32_t sK = sKV + st * 2 * TILE_BYTES, sV = sK + TILE_BYTES;
+        mbar_wait(b_kvfull + 8 * st, (j / BWD_STAGES) & 1);
+        mbar_wait(b_sempty, (j & 1) ^ 1);
+        tc_fence_after();
+        mma_kk64(tS, sQ, sK, idesc_s, false);     // S  = Q K^T
+        mma_kk64(tDP, sDO, sV, idesc_s, false);   // dP = dO V^T
+        umma_commit(b_sfull);
+        mbar_wait(b_dsfull, j & 1);
+        tc_fence_after();
+        mma_pv(tDQ, sDS, sK, idesc_o, j > 0);     // dQ += dS K   (K tile as MN-major B)
+        umma_commit(b_dsempty);
+        umma_commit(b_kvempty + 8 * st);
+      }
+      umma_commit(b_done);
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const RowInfo ri = row_info(p, r, tile, outer, inner0);
+    const float sc = p.scale * LOG2E;
+    const float lse2 = ri.valid ? p.lse[ri.token * p.heads + head] * LOG2E : 0.f;
+    const float dlt = ri.valid ? p.delta[ri.token * p.heads + head] : 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(b_sfull, j & 1);
+      tc_fence_after();
+      mbar_wait(b_dsempty, (j & 1) ^ 1);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t vs[32], vd[32];
+        tmem_ld32(tS + lane_off + c0, vs);
+        tmem_ld32(tDP + lane_off + c0, vd);
+        tc_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = c0 + i;
+          const bool ok = ri.valid && ((c % p.G) == ri.g) && (j * p.RT + c / p.G < p.S);
+          const float pr = ok ? exp2f(__uint_as_float(vs[i]) * sc - lse2) : 0.f;
+          f[i] = pr * (__uint_as_float(vd[i]) - dlt) * p.scale;
+        }
+        store_score_chunk(sDS, r, c0, f);
+      }
+      tc_fence_before();
+      mbar_arrive(b_sempty);
+      fence_proxy_async_smem();
+      mbar_arrive(b_dsfull);
+    }
+    mbar_wait(b_done, 0);
+    tc_fence_after();
+    uint32_t v0[32], v1[32];
+    tmem_ld32(tDQ + lane_off, v0);
+    tmem_ld32(tDQ + lane_off + 32, v1);
+    tc_wait_ld();
+    if (ri.valid) {
+      bf16* orow = p.dq + ri.token * p.lddq + head * 64;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+        u.y = pack_bf16x2(__uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3]));
+        u.z = pack_bf16x2(__uint_as_float(v0[i + 4]), __uint_as_float(v0[i + 5]));
+        u.w = pack_bf16x2(__uint_as_float(v0[i + 6]), __uint_as_float(v0[i + 7]));
+        *reinterpret_cast<uint4*>(orow + i) = u;
+        u.x = pack_bf16x2(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+        u.y = pack_bf16x2(__uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3]));
+        u.z = pack_bf16x2(__uint_as_float(v1[i + 4]), __uint_as_float(v1[i + 5]));
+        u.w = pack_bf16x2(__uint_as_float(v1[i + 6]), __uint_as_float(v1[i + 7]));
+        *reinterpret_cast<uint4*>(orow + 32 + i) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// =====================================================================================
+// backward, dK/dV: CTA owns a key tile, loops query tiles. Scores are computed transposed
+// (S^T = K Q^T, dP^T = V dO^T) so that P^T / dS^T land row-major-in-keys = K-major A operands.
+// smem: K | V | Q/dO ring 2 | P^T | dS^T | lse/delta | barriers
+// TMEM: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384)
+constexpr int BKV_SMEM = 1024 + 2 * TILE_BYTES + BWD_STAGES * 2 * TILE_BYTES + 2 * PT_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = sK + TILE_BYTES;
+  const uint32_t sQD = sV + TILE_BYTES;
+  const uint32_t sPT = sQD + BWD_STAGES * 2 * TILE_BYTES;
+  const uint32_t sDST = sPT + PT_BYTES;
+  const uint32_t sVec = sDST + PT_BYTES;  // float lse2[128], delta[128]
+  const uint32_t sBar = sVec + 1024;
+  const uint32_t b_kvfull = sBar;
+  const uint32_t b_qfull = sBar + 8;        // [2]
+  const uint32_t b_qempty = sBar + 8 * 3;   // [2]
+  const uint32_t b_sfull = sBar + 8 * 5;
+  const uint32_t b_sempty = sBar + 8 * 6;
+  const uint32_t b_pfull = sBar + 8 * 7;
+  const uint32_t b_pempty = sBar + 8 * 8;
+  const uint32_t b_done = sBar + 8 * 9;
+  const uint32_t tmem_slot = sBar + 8 * 10;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* vec = reinterpret_cast<float*>(smem_raw + (sVec - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile, head, outer, inner0;
+  decode_block(p, tile, head, outer, inner0);
+  const int nq = p.tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv); prefetch_tmap(&p.tdo);
+    mbar_init(b_kvfull, 1);
+    for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, 1); }
+    mbar_init(b_sfull, 1); mbar_init(b_sempty, 128);
+    mbar_init(b_pfull, 128); mbar_init(b_pempty, 1);
+    mbar_init(b_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_kvfull, 2 * TILE_BYTES);
+      tma_load_4d(&p.tk, b_kvfull, sK, head * 64, inner0, tile * p.RT, outer);
+      tma_load_4d(&p.tv, b_kvfull, sV, head * 64, inner0, tile * p.RT, outer);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i % BWD_STAGES;
+        mbar_wait(b_qempty + 8 * st, ((i / BWD_STAGES) & 1) ^ 1);
+        mbar_expect_tx(b_qfull + 8 * st, 2 * TILE_BYTES);
+        tma_load_4d(&p.tq, b_qfull + 8 * st, sQD + st * 2 * TILE_BYTES, head * 64, inner0, i * p.RT, outer);
+        tma_load_4d(&p.tdo, b_qfull + 8 * st, sQD + st * 2 * TILE_BYTES + TILE_BYTES, head * 64, inner0, i * p.RT, outer);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      mbar_wait(b_kvfull, 0);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i % BWD_STAGES;
+        const uint32_t sQ = sQD + st * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES;
+        mbar_wait(b_qfull + 8 * st, (i / BWD_STAGES) & 1);
+        mbar_wait(b_sempty, (i & 1) ^ 1);
+        tc_fence_after();
+        mma_kk64(tST, sK, sQ, idesc_s, false);     // S^T  = K Q^T
+        mma_kk64(tDPT, sV, sDO, idesc_s, false);   // dP^T = V dO^T
+        umma_commit(b_sfull);
+        mbar_wait(b_pfull, i & 1);
+        tc_fence_after();
+        mma_pv(tDV, sPT, sDO, idesc_o, i > 0);     // dV += P^T dO
+        mma_pv(tDK, sDST, sQ, idesc_o, i > 0);     // dK += dS^T Q
+        umma_commit(b_pempty);
+        umma_commit(b_qempty + 8 * st);
+      }
+      umma_commit(b_done);
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;          // key row of this thread
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const RowInfo ki = row_info(p, r, tile, outer, inner0);
+    const float sc = p.scale * LOG2E;
+    for (int i = 0; i < nq; ++i) {
+      // stage lse/delta of the 128 queries of tile i (column vectors of the transposed scores)
+      const RowInfo qi = row_info(p, r, i, outer, inner0);
+      named_bar_sync(1, 128);  // previous iteration finished reading vec[]
+      vec[r] = qi.valid ? p.lse[qi.token * p.heads + head] * LOG2E : INFINITY;  // +inf -> p = 0
+      vec[128 + r] = qi.valid ? p.delta[qi.token * p.heads + head] : 0.f;
+      named_bar_sync(1, 128);
+      mbar_wait(b_sfull, i & 1);
+      tc_fence_after();
+      mbar_wait(b_pempty, (i & 1) ^ 1);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t vs[32], vd[32];
+        tmem_ld32(tST + lane_off + c0, vs);
+        tmem_ld32(tDPT + lane_off + c0, vd);
+        tc_wait_ld();
+        float fp[32], fd[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int c = c0 + k;  // query column
+          const bool ok = ki.valid && ((c % p.G) == ki.g);
+          const float pr = ok ? exp2f(__uint_as_float(vs[k]) * sc - vec[c]) : 0.f;
+          fp[k] = pr;
+          fd[k] = pr * (__uint_as_float(vd[k]) - vec[128 + c]) * p.scale;
+        }
+        store_score_chunk(sPT, r, c0, fp);
+        store_score_chunk(sDST, r, c0, fd);
+      }
+      tc_fence_before();
+      mbar_arrive(b_sempty);
+      fence_proxy_async_smem();
+      mbar_arrive(b_pfull);
+    }
+    mbar_wait(b_done, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      uint32_t v0[32], v1[32];
+      const uint32_t t = which == 0 ? tDV : tDK;
+      tmem_ld32(t + lane_off, v0);
+      tmem_ld32(t + lane_off + 32, v1);
+      tc_wait_ld();
+      if (ki.valid) {
+        bf16* orow = which == 0 ? (p.dv + ki.token * p.lddv + head * 64) : (p.dk + ki.token * p.lddk + head * 64);
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v0[k]), __uint_as_float(v0[k + 1]));
+          u.y = pack_bf16x2(__uint_as_float(v0[k + 2]), __uint_as_float(v0[k + 3]));
+          u.z = pack_bf16x2(__uint_as_float(v0[k + 4]), __uint_as_float(v0[k + 5]));
+          u.w = pack_bf16x2(__uint_as_float(v0[k + 6]), __uint_as_float(v0[k + 7]));
+          *reinterpret_cast<uint4*>(orow + k) = u;
+          u.x = pack_bf16x2(__uint_as_float(v1[k]), __uint_as_float(v1[k + 1]));
+          u.y = pack_bf16x2(__uint_as_float(v1[k + 2]), __uint_as_float(v1[k + 3]));
+          u.z = pack_bf16x2(__uint_as_float(v1[k + 4]), __uint_as_float(v1[k + 5]));
+          u.w = pack_bf16x2(__uint_as_float(v1[k + 6]), __uint_as_float(v1[k + 7]));
+          *reinterpret_cast<uint4*>(orow + 32 + k) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// delta[token][head] = sum_d dO * O   — one warp per (token, head)
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ dout, long long lddo, long long tokens,
+                                  int heads, float* __restrict__ delta) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= tokens * heads) return;
+  const long long tok = w / heads;
+  const int h = (int)(w - tok * heads);
+  const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + tok * ldo + h * 64 + 2 * lane));
+  const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + tok * lddo + h * 64 + 2 * lane));
+  const float s = warp_sum(a.x * b.x + a.y * b.y);
+  if (lane == 0) delta[w] = s;
+}
+
+}  // namespace svdx
+
+using namespace svdx;
+
+static int attn_make_map(CUtensorMap* m, const void* ptr, int64_t ld, int cols, const SvdxAttn* d, int G, int RT) {
+  const int outer = d->nseq / d->inner;
+  uint64_t dims[4] = {(uint64_t)cols, (uint64_t)d->inner, (uint64_t)d->S, (uint64_t)outer};
+  uint64_t strides[3] = {(uint64_t)(d->inner_stride * ld * 2), (uint64_t)(d->tok_stride * ld * 2), (uint64_t)(d->outer_stride * ld * 2)};
+  if (d->inner == 1) strides[0] = (uint64_t)ld * 2;  // extent-1 dimension: any legal stride
+  uint32_t box[4] = {64, (uint32_t)G, (uint32_t)RT, 1};
+  return svdx_make_tmap(m, ptr, 4, dims, strides, box);
+}
+
+static int attn_setup(const SvdxAttn* d, AttnKParams& p, bool bwd, dim3& grid) {
+  if (!d || !d->q || !d->k || !d->v) return svdx_fail(SVDX_E_BADARG, "attention: null pointer");
+  if (d->heads <= 0 || d->S <= 0 || d->nseq <= 0 || d->inner <= 0 || d->nseq % d->inner) return svdx_fail(SVDX_E_BADARG, "attention: bad sequence geometry");
+  if ((d->ldq % 8) || (d->ldk % 8) || (d->ldv % 8)) return svdx_fail(SVDX_E_BADARG, "attention: leading dims must be multiples of 8");
+  memset(&p, 0, sizeof(p));
+  int G = 1;
+  if (d->inner > 1) {
+    // pack G sequences per tile: largest power of two with G * S <= 128 that divides inner
+    G = 1;
+    while (G * 2 * d->S <= 128 && d->inner % (G * 2) == 0 && G < 64) G *= 2;
+  }
+  const int RT = 128 / G;
+  if (d->inner > 1 && d->S > RT) return svdx_fail(SVDX_E_BADARG, "attention: strided sequences longer than 128 tokens are not supported");
+  p.G = G; p.RT = RT; p.S = d->S; p.heads = d->heads;
+  p.inner_groups = d->inner / G;
+  p.tiles = (d->S + RT - 1) / RT;
+  p.outer_stride = d->outer_stride; p.inner_stride = d->inner_stride; p.tok_stride = d->tok_stride;
+  p.scale = d->scale;
+  const int cols = d->heads * 64;
+  int rc;
+  if ((rc = attn_make_map(&p.tq, d->q, d->ldq, cols, d, G, RT))) return rc;
+  if ((rc = attn_make_map(&p.tk, d->k, d->ldk, cols, d, G, RT))) return rc;
+  if ((rc = attn_make_map(&p.tv, d->v, d->ldv, cols, d, G, RT))) return rc;
+  if (bwd) {
+    if (!d->dout || !d->dq || !d->dk || !d->dv || !d->lse || !d->delta || !d->o) return svdx_fail(SVDX_E_BADARG, "attention_bwd: null pointer");
+    if ((d->lddo % 8) || (d->lddq % 8) || (d->lddk % 8) || (d->lddv % 8) || (d->ldo % 8)) return svdx_fail(SVDX_E_BADARG, "attention_bwd: leading dims");
+    if ((rc = attn_make_map(&p.tdo, d->dout, d->lddo, cols, d, G, RT))) return rc;
+  } else {
+    if (!d->o || (d->ldo % 8)) return svdx_fail(SVDX_E_BADARG, "attention_fwd: output");
+  }
+  p.o = reinterpret_cast<bf16*>(d->o); p.ldo = d->ldo;
+  p.lse = d->lse; p.delta = d->delta;
+  p.dq = reinterpret_cast<bf16*>(d->dq); p.lddq = d->lddq;
+  p.dk = reinterpret_cast<bf16*>(d->dk); p.lddk = d->lddk;
+  p.dv = reinterpret_cast<bf16*>(d->dv); p.lddv = d->lddv;
+  const long long gz = (long long)(d->nseq / d->inner) * p.inner_groups;
+  if (gz > 65535 || d->heads > 65535) return svdx_fail(SVDX_E_BADARG, "attention: grid too large");
+  grid = dim3(p.tiles, d->heads, (unsigned)gz);
+  return 0;
+}
+
+extern "C" int svdx_attention_fwd(const SvdxAttn* d, void* stream_v) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  AttnKParams p;
+  dim3 grid;
+  int rc = attn_setup(d, p, false, grid);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    if (e != cudaSuccess) return svdx_fail_cuda(e, "attention_fwd: smem attribute");
+    attr = true;
+  }
+  attn_fwd_kernel<<<grid, AT_THREADS, FWD_SMEM, st>>>(p);
+  SVDX_CHECK_LAUNCH("attention_fwd");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_attention_bwd(const SvdxAttn* d, void* stream_v) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  AttnKParams p;
+  dim3 grid;
+  int rc = attn_setup(d, p, true, grid);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BDQ_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BKV_SMEM);
+    if (e != cudaSuccess) return svdx_fail_cuda(e, "attention_bwd: smem attribute");
+    attr = true;
+  }
+  // tokens covered = nseq * S (dense token-major matrices)
+  const long long tokens = (long long)d->nseq * d->S;
+  const long long warps = tokens * d->heads;
+  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(d->o), d->ldo,
+                                                                         reinterpret_cast<const bf16*>(d->dout), d->lddo, tokens, d->heads, d->delta);
+  attn_bwd_dq_kernel<<<grid, AT_THREADS, BDQ_SMEM, st>>>(p);
+  attn_bwd_dkv_kernel<<<grid, AT_THREADS, BKV_SMEM, st>>>(p);
+  SVDX_CHECK_LAUNCH("attention_bwd");
+  return SVDX_OK;
+}

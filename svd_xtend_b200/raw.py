@@ -128,3 +128,179 @@ def tapgemm(
 
 
 CONV3x3_TAPS = tuple((kw - 1, kh - 1, 0) for kh in range(3) for kw in range(3))
+
+
+# ----------------------------------------------------------------------------- attention
+def _attn_desc(q, k, v, o, heads, S, nseq, inner, outer_stride, inner_stride, tok_stride, scale, lse):
+    d = SvdxAttn()
+    d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    d.ldq, d.ldk, d.ldv, d.ldo = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v"), _rowmajor(o, "o")
+    d.nseq, d.heads, d.S, d.inner = nseq, heads, S, inner
+    d.outer_stride, d.inner_stride, d.tok_stride = outer_stride, inner_stride, tok_stride
+    d.scale = scale
+    d.lse = _ptr(lse)
+    return d
+
+
+def attention_fwd(q, k, v, o, *, heads, S, nseq, inner=1, outer_stride=None, inner_stride=0, tok_stride=1,
+                  scale=0.125, lse=None):
+    """q/k/v/o: [tokens, >=heads*64] bf16 (column slices allowed). Spatial: inner=1, outer_stride=S."""
+    if outer_stride is None:
+        outer_stride = S
+    d = _attn_desc(q, k, v, o, heads, S, nseq, inner, outer_stride, inner_stride, tok_stride, scale, lse)
+    check(load().svdx_attention_fwd(C.byref(d), _stream()), "svdx_attention_fwd")
+    return o
+
+
+def attention_bwd(q, k, v, o, dout, dq, dk, dv, lse, delta, *, heads, S, nseq, inner=1, outer_stride=None,
+                  inner_stride=0, tok_stride=1, scale=0.125):
+    if outer_stride is None:
+        outer_stride = S
+    d = _attn_desc(q, k, v, o, heads, S, nseq, inner, outer_stride, inner_stride, tok_stride, scale, lse)
+    d.dout, d.lddo = dout.data_ptr(), _rowmajor(dout, "dout")
+    d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    d.lddq, d.lddk, d.lddv = _rowmajor(dq, "dq"), _rowmajor(dk, "dk"), _rowmajor(dv, "dv")
+    d.delta = delta.data_ptr()
+    check(load().svdx_attention_bwd(C.byref(d), _stream()), "svdx_attention_bwd")
+
+
+# ----------------------------------------------------------------------------- norms
+def groupnorm_stats(x, x2, outer, rows, eps, groups=32):
+    C1 = x.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    mean = torch.empty(outer * groups, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    check(load().svdx_groupnorm_stats(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0,
+                                      C2, outer, rows, groups, eps, mean.data_ptr(), rstd.data_ptr(), _stream()), "groupnorm_stats")
+    return mean, rstd
+
+
+def groupnorm_apply(x, x2, outer, rows, mean, rstd, gamma, beta, silu, y, groups=32):
+    C1 = x.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    check(load().svdx_groupnorm_apply(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0,
+                                      C2, outer, rows, groups, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                      int(silu), y.data_ptr(), _rowmajor(y, "y"), _stream()), "groupnorm_apply")
+    return y
+
+
+def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2, dgamma=None, dbeta=None, groups=32):
+    C1 = x.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    ws = torch.empty(outer * groups * 2, device=x.device, dtype=torch.float32)
+    check(load().svdx_groupnorm_bwd(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0, C2,
+                                    dy.data_ptr(), _rowmajor(dy, "dy"), outer, rows, groups, mean.data_ptr(), rstd.data_ptr(),
+                                    gamma.data_ptr(), beta.data_ptr(), int(silu), dx.data_ptr(), _rowmajor(dx, "dx"),
+                                    _ptr(dx2), _rowmajor(dx2, "dx2") if dx2 is not None else 0, _ptr(dgamma), _ptr(dbeta),
+                                    ws.data_ptr(), _stream()), "groupnorm_bwd")
+
+
+def layernorm_fwd(x, gamma, beta, eps, y):
+    rows, Cc = x.shape
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    check(load().svdx_layernorm_fwd(x.data_ptr(), _rowmajor(x, "x"), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps,
+                                    y.data_ptr(), _rowmajor(y, "y"), mean.data_ptr(), rstd.data_ptr(), _stream()), "layernorm_fwd")
+    return mean, rstd
+
+
+def layernorm_bwd(x, dy, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=None):
+    rows, Cc = x.shape
+    check(load().svdx_layernorm_bwd(x.data_ptr(), _rowmajor(x, "x"), dy.data_ptr(), _rowmajor(dy, "dy"), rows, Cc, gamma.data_ptr(),
+                                    mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), _rowmajor(dx, "dx"), _ptr(dres),
+                                    _rowmajor(dres, "dres") if dres is not None else 0, _ptr(dgamma), _ptr(dbeta), _stream()),
+          "layernorm_bwd")
+
+
+# ----------------------------------------------------------------------------- elementwise / layout
+def prep_weight(src, dst, mode, O, I, taps=1, i_pad=None):
+    check(load().svdx_prep_weight(src.data_ptr(), int(src.dtype == bf16), dst.data_ptr(), mode, O, I, taps,
+                                  i_pad if i_pad is not None else I, _stream()), "prep_weight")
+    return dst
+
+
+def cast_f32_bf16(src, dst):
+    check(load().svdx_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast_f32_bf16")
+    return dst
+
+
+def cast_bf16_f32(src, dst):
+    check(load().svdx_cast_bf16_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast_bf16_f32")
+    return dst
+
+
+def nchw_to_nhwc(src, dst, N, Cc, H, W, c_pad):
+    check(load().svdx_nchw_to_nhwc(src.data_ptr(), int(src.dtype == bf16), dst.data_ptr(), N, Cc, H, W, c_pad, _stream()), "nchw_to_nhwc")
+    return dst
+
+
+def nhwc_to_nchw(src, dst, N, Cc, H, W):
+    check(load().svdx_nhwc_to_nchw(src.data_ptr(), _rowmajor(src, "src"), dst.data_ptr(), int(dst.dtype == bf16), N, Cc, H, W, _stream()),
+          "nhwc_to_nchw")
+    return dst
+
+
+def upsample2x(src, dst, N, H, W, Cc):
+    check(load().svdx_upsample2x(src.data_ptr(), dst.data_ptr(), N, H, W, Cc, _stream()), "upsample2x")
+    return dst
+
+
+def upsample2x_bwd(dsrc, ddst, N, H, W, Cc):
+    check(load().svdx_upsample2x_bwd(dsrc.data_ptr(), ddst.data_ptr(), N, H, W, Cc, _stream()), "upsample2x_bwd")
+    return ddst
+
+
+def space_to_planes(src, dst, N, H, W, Cc):
+    check(load().svdx_space_to_planes(src.data_ptr(), dst.data_ptr(), N, H, W, Cc, _stream()), "space_to_planes")
+    return dst
+
+
+def planes_to_space(src, dst, N, H, W, Cc):
+    check(load().svdx_planes_to_space(src.data_ptr(), dst.data_ptr(), N, H, W, Cc, _stream()), "planes_to_space")
+    return dst
+
+
+def concat_channels(a, b, dst):
+    check(load().svdx_concat_channels(a.data_ptr(), a.shape[-1], b.data_ptr(), b.shape[-1], dst.data_ptr(), a.numel() // a.shape[-1],
+                                      _stream()), "concat_channels")
+    return dst
+
+
+def split_channels(src, a, b, accumulate_a=False):
+    Ca = a.shape[-1]
+    Cb = src.shape[-1] - Ca
+    check(load().svdx_split_channels(src.data_ptr(), a.data_ptr(), Ca, _ptr(b), Cb, src.numel() // src.shape[-1], int(accumulate_a),
+                                     _stream()), "split_channels")
+
+
+def axpby(a, b, y, scales=None):
+    check(load().svdx_axpby_bf16(a.data_ptr(), b.data_ptr(), _ptr(scales), y.data_ptr(), a.numel(), _stream()), "axpby_bf16")
+    return y
+
+
+def silu_f32(x, y):
+    check(load().svdx_silu_f32(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "silu_f32")
+    return y
+
+
+def colsum(x, out, accumulate=False):
+    rows, cols = x.shape
+    check(load().svdx_colsum(x.data_ptr(), _rowmajor(x, "x"), rows, cols, out.data_ptr(), int(accumulate), _stream()), "colsum")
+    return out
+
+
+def geglu_bwd(pre, dout, dpre):
+    rows, h2 = pre.shape
+    check(load().svdx_geglu_bwd(pre.data_ptr(), _rowmajor(pre, "pre"), dout.data_ptr(), _rowmajor(dout, "dout"), dpre.data_ptr(),
+                                _rowmajor(dpre, "dpre"), rows, h2 // 2, _stream()), "geglu_bwd")
+    return dpre
+
+
+def blend_scales(mix_factor, out3):
+    check(load().svdx_blend_scales(mix_factor.data_ptr(), out3.data_ptr(), _stream()), "blend_scales")
+    return out3
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(load().svdx_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, weight_decay,
+                            step, grad_scale, _stream()), "adamw")

@@ -1,0 +1,252 @@
+"""GPU parity of the attention / normalisation / elementwise kernels against fp32 torch math."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+DEV = "cuda:0"
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _close(got, ref, tol=2e-2, what=""):
+    got, ref = got.float(), ref.float()
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    rel = ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+    mx = (got - ref).abs().max().item()
+    assert rel < tol and mx < 8 * tol * max(ref.abs().max().item(), 1e-6), (
+        f"{what}: rel-l2 {rel:.4g} max-abs {mx:.4g} (ref max {ref.abs().max().item():.4g})")
+
+
+@pytest.fixture(scope="module")
+def raw():
+    from svd_xtend_b200 import raw
+    return raw
+
+
+def _sdpa_ref(q, k, v, scale):
+    # q,k,v: [nseq, S, heads, 64] fp32
+    qh, kh, vh = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    att = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return (att @ vh).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("nseq,S,heads", [(2, 256, 2), (3, 640, 5), (2, 160, 3), (4, 40, 2), (1, 2560, 1)])
+def test_attention_spatial_fwd_bwd(raw, nseq, S, heads):
+    C = heads * 64
+    qkv = _rand(nseq * S, 3 * C, seed=1).to(bf16)          # fused projection buffer: q|k|v column slices
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    o = torch.zeros(nseq * S, C, device=DEV, dtype=bf16)
+    lse = torch.zeros(nseq * S, heads, device=DEV)
+    raw.attention_fwd(q, k, v, o, heads=heads, S=S, nseq=nseq, lse=lse)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().reshape(nseq, S, heads, 64).requires_grad_(True) for t in (q, k, v))
+    ref = _sdpa_ref(qf, kf, vf, 0.125)
+    _close(o.view(nseq, S, heads, 64), ref, what="attn fwd")
+    sc = torch.einsum("nqhd,nkhd->nhqk", qf, kf) * 0.125
+    _close(lse.view(nseq, S, heads), torch.logsumexp(sc, -1).permute(0, 2, 1), tol=2e-3, what="lse")
+    dout = _rand(nseq * S, C, seed=2).to(bf16)
+    dqkv = torch.zeros_like(qkv)
+    delta = torch.zeros_like(lse)
+    raw.attention_bwd(q, k, v, o, dout, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], lse, delta, heads=heads, S=S, nseq=nseq)
+    torch.cuda.synchronize()
+    ref.backward(dout.float().view(nseq, S, heads, 64))
+    _close(dqkv[:, :C].reshape(nseq, S, heads, 64), qf.grad, tol=3e-2, what="dq")
+    _close(dqkv[:, C:2 * C].reshape(nseq, S, heads, 64), kf.grad, tol=3e-2, what="dk")
+    _close(dqkv[:, 2 * C:].reshape(nseq, S, heads, 64), vf.grad, tol=3e-2, what="dv")
+
+
+@pytest.mark.parametrize("B,T,HW,heads", [(1, 14, 160, 2), (2, 14, 40, 3), (1, 25, 144, 2), (1, 4, 64, 1)])
+def test_attention_temporal_fwd_bwd(raw, B, T, HW, heads):
+    # tokens are [B, T, HW] row-major; a sequence = fixed (b, pixel), tokens strided by HW
+    C = heads * 64
+    M = B * T * HW
+    qkv = _rand(M, 3 * C, seed=3).to(bf16)
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    o = torch.zeros(M, C, device=DEV, dtype=bf16)
+    lse = torch.zeros(M, heads, device=DEV)
+    geo = dict(heads=heads, S=T, nseq=B * HW, inner=HW, outer_stride=T * HW, inner_stride=1, tok_stride=HW)
+    raw.attention_fwd(q, k, v, o, lse=lse, **geo)
+    torch.cuda.synchronize()
+
+    def to_seq(t):  # [M, C] -> [B*HW, T, heads, 64]
+        return t.float().reshape(B, T, HW, heads, 64).permute(0, 2, 1, 3, 4).reshape(B * HW, T, heads, 64)
+
+    qf, kf, vf = (to_seq(t).requires_grad_(True) for t in (q, k, v))
+    ref = _sdpa_ref(qf, kf, vf, 0.125)
+    _close(to_seq(o), ref, what="temporal attn fwd")
+    dout = _rand(M, C, seed=4).to(bf16)
+    dqkv = torch.zeros_like(qkv)
+    delta = torch.zeros_like(lse)
+    raw.attention_bwd(q, k, v, o, dout, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], lse, delta, **geo)
+    torch.cuda.synchronize()
+    ref.backward(to_seq(dout))
+    _close(to_seq(dqkv[:, :C]), qf.grad, tol=3e-2, what="temporal dq")
+    _close(to_seq(dqkv[:, C:2 * C]), kf.grad, tol=3e-2, what="temporal dk")
+    _close(to_seq(dqkv[:, 2 * C:]), vf.grad, tol=3e-2, what="temporal dv")
+
+
+@pytest.mark.parametrize("outer,rows,C1,C2,silu", [(14, 160, 320, 0, True), (3, 640, 1280, 640, True), (2, 14 * 40, 640, 0, False), (2, 100, 640, 320, True)])
+def test_groupnorm_fwd_bwd(raw, outer, rows, C1, C2, silu):
+    C = C1 + C2
+    x1 = _rand(outer * rows, C1, seed=5).to(bf16) + 0.5
+    x2 = _rand(outer * rows, C2, seed=6).to(bf16) if C2 else None
+    gamma = _rand(C, seed=7) * 0.2 + 1.0
+    beta = _rand(C, seed=8) * 0.1
+    mean, rstd = raw.groupnorm_stats(x1, x2, outer, rows, 1e-5)
+    y = torch.empty(outer * rows, C, device=DEV, dtype=bf16)
+    raw.groupnorm_apply(x1, x2, outer, rows, mean, rstd, gamma, beta, silu, y)
+    torch.cuda.synchronize()
+    xcat = torch.cat([x1, x2], 1) if C2 else x1
+    xr = xcat.float().reshape(outer, rows, C).permute(0, 2, 1).requires_grad_(True)  # [outer, C, rows]
+    g = gamma.clone().requires_grad_(True)
+    b = beta.clone().requires_grad_(True)
+    ref = F.group_norm(xr, 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    _close(y.view(outer, rows, C), ref.permute(0, 2, 1), what="groupnorm fwd")
+    dy = _rand(outer * rows, C, seed=9).to(bf16)
+    dx1 = torch.zeros_like(x1)
+    dx2 = torch.zeros_like(x2) if C2 else None
+    dgamma = torch.zeros(C, device=DEV)
+    dbeta = torch.zeros(C, device=DEV)
+    raw.groupnorm_bwd(x1, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx1, dx2, dgamma, dbeta)
+    torch.cuda.synchronize()
+    ref.backward(dy.float().view(outer, rows, C).permute(0, 2, 1))
+    dxr = xr.grad.permute(0, 2, 1).reshape(outer * rows, C)
+    _close(dx1, dxr[:, :C1], what="groupnorm dx")
+    if C2:
+        _close(dx2, dxr[:, C1:], what="groupnorm dx2")
+    _close(dgamma, g.grad, what="groupnorm dgamma")
+    _close(dbeta, b.grad, what="groupnorm dbeta")
+
+
+@pytest.mark.parametrize("rows,C", [(1000, 320), (560, 1280), (77, 64), (300, 640)])
+def test_layernorm_fwd_bwd(raw, rows, C):
+    x = (_rand(rows, C, seed=10) + 0.3).to(bf16)
+    gamma = _rand(C, seed=11) * 0.2 + 1.0
+    beta = _rand(C, seed=12) * 0.1
+    y = torch.empty_like(x)
+    mean, rstd = raw.layernorm_fwd(x, gamma, beta, 1e-5, y)
+    torch.cuda.synchronize()
+    xr = x.float().requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    b = beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (C,), g, b, 1e-5)
+    _close(y, ref, what="layernorm fwd")
+    dy = _rand(rows, C, seed=13).to(bf16)
+    dres = _rand(rows, C, seed=14).to(bf16)
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros(C, device=DEV)
+    dbeta = torch.zeros(C, device=DEV)
+    raw.layernorm_bwd(x, dy, gamma, mean, rstd, dx, dres, dgamma, dbeta)
+    torch.cuda.synchronize()
+    ref.backward(dy.float())
+    _close(dx, xr.grad + dres.float(), what="layernorm dx")
+    _close(dgamma, g.grad, what="layernorm dgamma")
+    _close(dbeta, b.grad, what="layernorm dbeta")
+
+
+def test_prep_weight_layouts(raw):
+    O, I, T = 96, 40, 9
+    w = _rand(O, I, T, seed=15)
+    d2 = torch.empty(O, T, 64, device=DEV, dtype=bf16)
+    raw.prep_weight(w, d2, 2, O, I, T, 64)
+    d3 = torch.empty(I, T, O, device=DEV, dtype=bf16)
+    raw.prep_weight(w, d3, 3, O, I, T)
+    wl = _rand(O, I, seed=16)
+    d0 = torch.empty(O, I, device=DEV, dtype=bf16)
+    d1 = torch.empty(I, O, device=DEV, dtype=bf16)
+    raw.prep_weight(wl, d0, 0, O, I)
+    raw.prep_weight(wl.to(bf16), d1, 1, O, I)
+    torch.cuda.synchronize()
+    ref2 = torch.zeros(O, T, 64, device=DEV)
+    ref2[:, :, :I] = w.permute(0, 2, 1)
+    assert torch.equal(d2, ref2.to(bf16))
+    assert torch.equal(d3, w.permute(1, 2, 0).contiguous().to(bf16))
+    assert torch.equal(d0, wl.to(bf16))
+    assert torch.equal(d1, wl.to(bf16).t().contiguous())
+
+
+def test_layout_kernels(raw):
+    N, C, H, W = 3, 8, 10, 16
+    x = _rand(N, C, H, W, seed=17)
+    nhwc = torch.empty(N, H, W, 64, device=DEV, dtype=bf16)
+    raw.nchw_to_nhwc(x, nhwc, N, C, H, W, 64)
+    back = torch.empty(N, C, H, W, device=DEV)
+    raw.nhwc_to_nchw(nhwc.view(-1, 64), back, N, C, H, W)
+    torch.cuda.synchronize()
+    assert torch.equal(nhwc[..., :C], x.permute(0, 2, 3, 1).to(bf16)) and (nhwc[..., C:] == 0).all()
+    assert torch.equal(back, x.to(bf16).float())
+    a = _rand(N, H, W, 64, seed=18).to(bf16)
+    up = torch.empty(N, 2 * H, 2 * W, 64, device=DEV, dtype=bf16)
+    raw.upsample2x(a, up, N, H, W, 64)
+    torch.cuda.synchronize()
+    ref = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    dup = _rand(N, 2 * H, 2 * W, 64, seed=19).to(bf16)
+    da = torch.empty_like(a)
+    raw.upsample2x_bwd(dup, da, N, H, W, 64)
+    torch.cuda.synchronize()
+    refd = dup.float().view(N, H, 2, W, 2, 64).sum((2, 4))
+    _close(da, refd, tol=1e-2, what="upsample bwd")
+    planes = torch.empty(4 * N, H // 2, W // 2, 64, device=DEV, dtype=bf16)
+    raw.space_to_planes(a, planes, N, H, W, 64)
+    a2 = torch.empty_like(a)
+    raw.planes_to_space(planes, a2, N, H, W, 64)
+    torch.cuda.synchronize()
+    for p in range(2):
+        for q in range(2):
+            assert torch.equal(planes[(p * 2 + q) * N:(p * 2 + q + 1) * N], a[:, p::2, q::2])
+    assert torch.equal(a2, a)
+    b = _rand(N, H, W, 128, seed=20).to(bf16)
+    cat = torch.empty(N, H, W, 192, device=DEV, dtype=bf16)
+    raw.concat_channels(a, b, cat)
+    a3, b3 = torch.empty_like(a), torch.empty_like(b)
+    raw.split_channels(cat, a3, b3)
+    torch.cuda.synchronize()
+    assert torch.equal(cat, torch.cat([a, b], -1)) and torch.equal(a3, a) and torch.equal(b3, b)
+
+
+def test_misc_elementwise(raw):
+    rows, h = 333, 256
+    pre = _rand(rows, 2 * h, seed=21).to(bf16)
+    dout = _rand(rows, h, seed=22).to(bf16)
+    dpre = torch.empty_like(pre)
+    raw.geglu_bwd(pre, dout, dpre)
+    pr = pre.float().requires_grad_(True)
+    (pr[:, :h] * F.gelu(pr[:, h:])).backward(dout.float())
+    torch.cuda.synchronize()
+    _close(dpre, pr.grad, what="geglu bwd")
+    x = _rand(5000, 320, seed=23).to(bf16)
+    out = torch.empty(320, device=DEV)
+    raw.colsum(x, out)
+    torch.cuda.synchronize()
+    _close(out, x.float().sum(0), tol=1e-3, what="colsum")
+    mix = torch.tensor([0.5], device=DEV)
+    s3 = torch.empty(3, device=DEV)
+    raw.blend_scales(mix, s3)
+    a = torch.sigmoid(mix)
+    torch.cuda.synchronize()
+    assert torch.allclose(s3, torch.stack([1 - a, a, a * (1 - a)]).flatten(), atol=1e-6)
+    y = torch.empty_like(x)
+    raw.axpby(x, x, y, s3)
+    torch.cuda.synchronize()
+    _close(y, x.float() * (s3[0] + s3[1]), tol=1e-2, what="axpby")
+    # AdamW vs torch
+    p = _rand(1000, seed=24)
+    g = _rand(1000, seed=25)
+    pt = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pt], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in (1, 2, 3):
+        pt.grad = g.clone()
+        opt.step()
+        raw.adamw(p, g, m, v, 1e-2, 0.9, 0.999, 1e-8, 1e-2, step)
+    torch.cuda.synchronize()
+    assert torch.allclose(p, pt.detach(), atol=1e-5, rtol=1e-5)
