@@ -132,10 +132,11 @@ int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const void* x2, i
 
 /* LayerNorm over the last dim (C <= 2560, C % 8 == 0), replaces F.layer_norm of
  * BasicTransformerBlock.norm1-3 / TemporalBasicTransformerBlock.norm_in,norm1-3 [D].
- * add_vec (optional, [rows/add_div][C] fp32) is added to x before normalisation and the sum is
- * written to xsum (the "+ time_pos_embed" of TransformerSpatioTemporalModel [D]). */
+ * addvec (optional, [ceil(rows/add_div)][C] fp32): row r gets addvec[r / add_div] added before normalisation and
+ * the bf16 sum is written to xsum (the "hidden_states + emb" of TransformerSpatioTemporalModel [D]). */
 int svdx_layernorm_fwd(const void* x, int64_t ldx, int32_t rows, int32_t C, const float* gamma, const float* beta,
-                       float eps, void* y, int64_t ldy, float* mean, float* rstd, void* stream);
+                       float eps, void* y, int64_t ldy, float* mean, float* rstd,
+                       const float* addvec, int32_t add_div, void* xsum, int64_t ldxs, void* stream);
 int svdx_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int32_t rows, int32_t C,
                        const float* gamma, const float* mean, const float* rstd,
                        void* dx, int64_t lddx, const void* dres, int64_t lddres,
@@ -200,8 +201,10 @@ int svdx_colsum(const void* x, int64_t ldx, int64_t rows, int32_t cols, float* o
 /* GEGLU backward: dpre[m][:h] = dout*gelu(gate); dpre[m][h:] = dout*value*gelu'(gate) */
 int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t lddo, void* dpre, int64_t lddpre,
                    int64_t rows, int32_t h, void* stream);
-/* blend scales {1-alpha, 1, 0}/{...} from mix_factor: out[0]=1-sigmoid(m), out[1]=sigmoid(m), out[2]=sigmoid(m)*(1-sigmoid(m)) */
-int svdx_blend_scales(const float* mix_factor, float* out3, void* stream);
+/* AlphaBlender epilogue scale triples from mix_factor, a = sigmoid(mix_factor); writes float[8]:
+ *   out[0..3] = {1-a, a, 1-a, 0}      transformer blend  out = a*x_spatial + (1-a)*(acc + residual)
+ *   out[4..7] = {1-a, 1, 0, a*(1-a)}  resnet blend       out = x_spatial + (1-a)*acc */
+int svdx_blend_scales(const float* mix_factor, float* out8, void* stream);
 /* fused multi-tensor AdamW on a flat fp32 buffer (torch.optim.AdamW of train_svd.py:767-773) */
 int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int32_t step, float grad_scale, void* stream);

@@ -63,7 +63,7 @@ _PROTOS = {
                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p, c_i64,
                            c_void_p, c_void_p, c_void_p, c_void_p],
     "svdx_layernorm_fwd": [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_i64,
-                           c_void_p, c_void_p, c_void_p],
+                           c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p],
     "svdx_layernorm_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p],
     "svdx_attention_fwd": [C.POINTER(SvdxAttn), c_void_p],

@@ -262,9 +262,8 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ pre, long long ldpre, 
 
 __global__ void blend_scales_kernel(const float* mix, float* out) {
   const float a = 1.f / (1.f + __expf(-mix[0]));
-  out[0] = 1.f - a;
-  out[1] = a;
-  out[2] = a * (1.f - a);
+  out[0] = 1.f - a; out[1] = a; out[2] = 1.f - a; out[3] = 0.f;
+  out[4] = 1.f - a; out[5] = 1.f; out[6] = 0.f; out[7] = a * (1.f - a);
 }
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,

@@ -201,11 +201,13 @@ constexpr int LN_MAXJ = 40;  // C <= 2560
 template <int NJ>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int rows, int C,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                     bf16* __restrict__ y, long long ldy, float* __restrict__ mean, float* __restrict__ rstd) {
+                                                     bf16* __restrict__ y, long long ldy, float* __restrict__ mean, float* __restrict__ rstd,
+                                                     const float* __restrict__ addvec, int add_div, bf16* __restrict__ xsum, long long ldxs) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const bf16* xr = x + (long long)warp * ldx;
+  const float* av = addvec ? addvec + (long long)(warp / add_div) * C : nullptr;
   float2 v[NJ];
   float sum = 0.f;
 #pragma unroll
@@ -213,6 +215,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
     const int c = 2 * lane + 64 * j;
     if (c < C) {
       v[j] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
+      if (av) {
+        // x + addvec is rounded to bf16 (it is the residual stream value the reference materialises)
+        const uint32_t pk = pack_bf16x2(v[j].x + av[c], v[j].y + av[c + 1]);
+        *reinterpret_cast<uint32_t*>(xsum + (long long)warp * ldxs + c) = pk;
+        v[j] = unpack_bf16x2(pk);
+      }
       sum += v[j].x + v[j].y;
     } else {
       v[j] = make_float2(0.f, 0.f);
@@ -385,22 +393,25 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
 
 template <int NJ>
 static void ln_fwd_launch(const void* x, int64_t ldx, int rows, int C, const float* g, const float* b, float eps, void* y, int64_t ldy,
-                          float* mean, float* rstd, cudaStream_t st) {
+                          float* mean, float* rstd, const float* addvec, int add_div, void* xsum, int64_t ldxs, cudaStream_t st) {
   const int warps_per_cta = 8;
   ln_fwd_kernel<NJ><<<(rows + warps_per_cta - 1) / warps_per_cta, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, rows, C, g, b, eps,
-                                                                              reinterpret_cast<bf16*>(y), ldy, mean, rstd);
+                                                                              reinterpret_cast<bf16*>(y), ldy, mean, rstd, addvec, add_div,
+                                                                              reinterpret_cast<bf16*>(xsum), ldxs);
 }
 
 extern "C" int svdx_layernorm_fwd(const void* x, int64_t ldx, int32_t rows, int32_t C, const float* gamma, const float* beta, float eps,
-                                  void* y, int64_t ldy, float* mean, float* rstd, void* stream_v) {
+                                  void* y, int64_t ldy, float* mean, float* rstd, const float* addvec, int32_t add_div, void* xsum,
+                                  int64_t ldxs, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
-  if (!x || !y || !gamma || !beta || !mean || !rstd || rows <= 0 || C <= 0 || C % 2 || C > 64 * LN_MAXJ || ldx % 2 || ldy % 2)
+  if (!x || !y || !gamma || !beta || !mean || !rstd || rows <= 0 || C <= 0 || C % 2 || C > 64 * LN_MAXJ || ldx % 2 || ldy % 2 ||
+      (addvec && (!xsum || add_div <= 0 || ldxs % 2)))
     return svdx_fail(SVDX_E_BADARG, "layernorm_fwd: bad arguments");
   const int nj = (C + 63) / 64;
-  if (nj <= 5) ln_fwd_launch<5>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, st);
-  else if (nj <= 10) ln_fwd_launch<10>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, st);
-  else if (nj <= 20) ln_fwd_launch<20>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, st);
-  else ln_fwd_launch<40>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, st);
+  if (nj <= 5) ln_fwd_launch<5>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  else if (nj <= 10) ln_fwd_launch<10>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  else if (nj <= 20) ln_fwd_launch<20>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  else ln_fwd_launch<40>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
   SVDX_CHECK_LAUNCH("layernorm_fwd");
   return SVDX_OK;
 }

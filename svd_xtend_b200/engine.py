@@ -1,0 +1,557 @@
+"""Execution engine of the B200 SVD-UNet step: a hand-rolled tape over the C-ABI kernels.
+
+Design (B200-first, not a translation of diffusers' module-by-module autograd graph):
+  * activations live as token-major channels-last bf16 matrices ``[B*T*H*W, C]`` for the WHOLE
+    network — the (BT,C,H,W)<->(BT,HW,C)<->(B*HW,T,C) permutes of the reference
+     never happen: linears are row-permutation invariant, the temporal conv and
+    temporal attention address frames through strides (TMA tensor maps);
+  * every op is one or two kernel launches through ``raw`` (ctypes -> extern "C"); the forward
+    pushes a backward closure on a tape, the backward pops them — no torch autograd graph, no
+    torch kernels on the path, so the whole step can be captured in one CUDA graph;
+  * fan-out gradient accumulation, parameter-gradient accumulation (fp32) and the weight-operand
+    cache (fp32 master -> bf16 forward / transposed dgrad layouts) are explicit.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import raw
+from .raw import A_CONV2D, A_ROWS, OUT_F32_ATOMIC, bf16
+
+F32 = torch.float32
+
+
+class Var:
+    """An activation on the tape: bf16 ``[rows, C]`` data plus (lazily) its gradient."""
+
+    __slots__ = ("data", "grad", "needs_grad")
+
+    def __init__(self, data: torch.Tensor, needs_grad: bool = False):
+        self.data = data
+        self.grad: Optional[torch.Tensor] = None
+        self.needs_grad = needs_grad
+
+    @property
+    def rows(self) -> int:
+        return self.data.shape[0]
+
+    @property
+    def cols(self) -> int:
+        return self.data.shape[1]
+
+
+class Geom:
+    """Clip geometry of the token matrix: rows = B*T*H*W in (b, t, h, w) order."""
+
+    __slots__ = ("B", "T", "H", "W")
+
+    def __init__(self, B, T, H, W):
+        self.B, self.T, self.H, self.W = B, T, H, W
+
+    @property
+    def HW(self):
+        return self.H * self.W
+
+    @property
+    def M(self):
+        return self.B * self.T * self.H * self.W
+
+    def down(self):
+        return Geom(self.B, self.T, self.H // 2, self.W // 2)
+
+    def up(self):
+        return Geom(self.B, self.T, self.H * 2, self.W * 2)
+
+
+CONV3x3_TAPS = tuple((kw - 1, kh - 1, 0) for kh in range(3) for kw in range(3))
+
+
+def _neg_taps(taps):
+    return tuple((-a, -b, -c) for a, b, c in taps)
+
+
+class WeightCache:
+    """bf16 operand layouts of the (fp32 or bf16) master parameters.
+
+    kinds: 'lin' [N,K]; 'linT' [K,N]; 'conv' [O,taps,Ipad]; 'convT' [I,taps,O];
+           'cat:<kind>' for fused projections (q|k|v); 'f32' fp32 copy of a bf16 vector.
+    Entries are refreshed when the source parameter's version counter changes (optimizer step,
+    load_state_dict), or unconditionally for trainable parameters when ``refresh_trainable`` is
+    called (CUDA-graph capture of a full train step re-prepares them inside the graph)."""
+
+    def __init__(self):
+        self._store: Dict[Tuple, Tuple[torch.Tensor, Tuple, Callable[[], None], bool]] = {}
+
+    @staticmethod
+    def _ver(params):
+        return tuple((p._version, p.data_ptr()) for p in params)
+
+    def get(self, key, params: Sequence[torch.Tensor], shape, build: Callable[[torch.Tensor], None], dtype=bf16):
+        ent = self._store.get(key)
+        ver = self._ver(params)
+        if ent is None or ent[0].shape != torch.Size(shape) or ent[0].device != params[0].device:
+            buf = torch.empty(shape, device=params[0].device, dtype=dtype)
+            fn = lambda buf=buf: build(buf)
+            fn()
+            self._store[key] = (buf, ver, fn, any(p.requires_grad for p in params))
+            return buf
+        if ent[1] != ver:
+            ent[2]()
+            self._store[key] = (ent[0], ver, ent[2], ent[3])
+        return ent[0]
+
+    def refresh_trainable(self):
+        for key, (buf, ver, fn, trainable) in self._store.items():
+            if trainable:
+                fn()
+
+    def clear(self):
+        self._store.clear()
+
+
+class Engine:
+    """Per-model execution state: weight cache, tape, parameter-gradient arena."""
+
+    def __init__(self):
+        self.wc = WeightCache()
+        self.tape: List[Callable[[], None]] = []
+        self.recording = False
+        self.pgrads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self.launches = 0
+        self.grad_ready_hook: Optional[Callable[[List[torch.nn.Parameter]], None]] = None
+
+    # ------------------------------------------------------------------ tape
+    def begin(self, recording: bool):
+        self.tape = []
+        self.recording = recording
+        self.pgrads = {}
+
+    def record(self, fn: Callable[[], None]):
+        if self.recording:
+            self.tape.append(fn)
+
+    def run_backward(self):
+        tape, self.tape = self.tape, []
+        while tape:
+            tape.pop()()
+
+    def add_grad(self, v: Var, g: torch.Tensor, owned: bool = True):
+        """Accumulate gradient g into v. `owned`: g is a fresh tensor this call may keep / overwrite."""
+        if not v.needs_grad:
+            return
+        if v.grad is None:
+            v.grad = g
+        else:
+            raw.axpby(v.grad, g, v.grad)
+
+    def pgrad(self, p: torch.nn.Parameter) -> torch.Tensor:
+        """fp32 accumulation buffer for the gradient of p (zero-initialised once per backward)."""
+        g = self.pgrads.get(p)
+        if g is None:
+            g = torch.zeros(p.shape, device=p.device, dtype=F32)
+            self.pgrads[p] = g
+        return g
+
+    # ------------------------------------------------------------------ operand preparation
+    def w_lin(self, p: torch.Tensor, transposed: bool) -> torch.Tensor:
+        w2 = p.detach()
+        O, I = w2.shape[0], w2[0].numel()
+        w2 = w2.reshape(O, I)
+        if transposed:
+            return self.wc.get(("linT", id(p)), [p], (I, O), lambda buf: raw.prep_weight(w2, buf, 1, O, I))
+        return self.wc.get(("lin", id(p)), [p], (O, I), lambda buf: raw.prep_weight(w2, buf, 0, O, I))
+
+    def w_lin_cat(self, ps: Sequence[torch.Tensor], transposed: bool) -> torch.Tensor:
+        """concatenated projection weights [sum O_i, I] (fused q|k|v)."""
+        I = ps[0].shape[1]
+        Os = [p.shape[0] for p in ps]
+        key = ("catT" if transposed else "cat",) + tuple(id(p) for p in ps)
+        if transposed:
+            def build(buf):
+                tmp = torch.empty(sum(Os), I, device=buf.device, dtype=bf16)
+                o0 = 0
+                for p, O in zip(ps, Os):
+                    raw.prep_weight(p.detach(), tmp[o0:o0 + O], 0, O, I)
+                    o0 += O
+                raw.prep_weight(tmp, buf, 1, sum(Os), I)
+            return self.wc.get(key, list(ps), (I, sum(Os)), build)
+
+        def build(buf):
+            o0 = 0
+            for p, O in zip(ps, Os):
+                raw.prep_weight(p.detach(), buf[o0:o0 + O], 0, O, I)
+                o0 += O
+        return self.wc.get(key, list(ps), (sum(Os), I), build)
+
+    def w_conv(self, p: torch.Tensor, transposed: bool, i_pad: Optional[int] = None) -> torch.Tensor:
+        w = p.detach()
+        O, I = w.shape[0], w.shape[1]
+        taps = w[0, 0].numel()
+        if transposed:
+            return self.wc.get(("convT", id(p)), [p], (I, taps * O), lambda buf: raw.prep_weight(w, buf, 3, O, I, taps))
+        ip = i_pad if i_pad is not None else I
+        return self.wc.get(("conv", id(p), ip), [p], (O, taps * ip), lambda buf: raw.prep_weight(w, buf, 2, O, I, taps, ip))
+
+    def vec_f32(self, p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if p is None:
+            return None
+        if p.dtype == F32:
+            return p.detach()
+        return self.wc.get(("f32", id(p)), [p], tuple(p.shape), lambda buf: raw.cast_bf16_f32(p.detach(), buf), dtype=F32)
+
+    # ------------------------------------------------------------------ small helpers
+    @staticmethod
+    def empty(rows, cols, like: torch.Tensor, dtype=bf16):
+        return torch.empty(rows, cols, device=like.device, dtype=dtype)
+
+    def _bias_grad(self, bias_p, dy: torch.Tensor, scale: Optional[torch.Tensor] = None):
+        if bias_p is None or not bias_p.requires_grad:
+            return
+        g = self.pgrad(bias_p)
+        if scale is None:
+            raw.colsum(dy, g, accumulate=True)
+        else:
+            tmp = torch.empty_like(g)
+            raw.colsum(dy, tmp)
+            g.add_(tmp * scale)
+
+    # ------------------------------------------------------------------ linear family
+    def linear(self, x: Var, weight, bias=None, *, res1: Optional[Var] = None, res2: Optional[Var] = None,
+               scales: Optional[torch.Tensor] = None, geglu: bool = False, rowbias: Optional[torch.Tensor] = None,
+               rowbias_div: int = 1, out_f32: bool = False, fused: Optional[Sequence] = None,
+               rowbias_grad: Optional[Callable[[torch.Tensor], None]] = None) -> Var:
+        """y = epilogue(x @ W^T). `weight` is a parameter [N,K] (or conv 1x1 [N,K,1,1]); `fused` = list of
+        parameters whose rows are concatenated (q|k|v). scales (device float[>=3]) = {acc, res1, res2}."""
+        ws = list(fused) if fused is not None else [weight]
+        wf = self.w_lin_cat(ws, False) if fused is not None else self.w_lin(weight, False)
+        N, K = wf.shape
+        M = x.rows
+        n_out = N // 2 if geglu else N
+        out = self.empty(M, n_out, x.data, F32 if out_f32 else bf16)
+        pre = self.empty(M, N, x.data) if (geglu and self.recording) else None
+        b32 = self.vec_f32(bias)
+        raw.tapgemm(x.data, wf, out, M=M, N=N, K=K, bias=b32, res1=None if res1 is None else res1.data,
+                    res2=None if res2 is None else res2.data, scales=scales, geglu=geglu, pre=pre,
+                    rowbias=rowbias, rowbias_div=rowbias_div)
+        w_train = any(p.requires_grad for p in ws) or (bias is not None and bias.requires_grad)
+        need = x.needs_grad or w_train or (res1 is not None and res1.needs_grad) or (res2 is not None and res2.needs_grad) \
+            or rowbias_grad is not None
+        y = Var(out, need)
+        if need and self.recording:
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                if dy is None:
+                    return
+                s_acc = None if scales is None else scales[0:3]
+                if res1 is not None and res1.needs_grad:
+                    self.add_grad(res1, dy if scales is None else self._scaled(dy, scales[1:2]))
+                if res2 is not None and res2.needs_grad:
+                    self.add_grad(res2, dy if scales is None else self._scaled(dy, scales[2:3]))
+                if geglu:
+                    dpre = torch.empty_like(pre)
+                    raw.geglu_bwd(pre, dy, dpre)
+                    dyl = dpre
+                else:
+                    dyl = dy
+                if rowbias_grad is not None:
+                    rowbias_grad(dyl)
+                if x.needs_grad:
+                    wt = self.w_lin_cat(ws, True) if fused is not None else self.w_lin(weight, True)
+                    dx = self.empty(M, K, x.data)
+                    raw.tapgemm(dyl, wt, dx, M=M, N=K, K=N, scales=self._acc_only(s_acc))
+                    self.add_grad(x, dx)
+                if any(p.requires_grad for p in ws):
+                    self._wgrad(dyl, x.data, ws, N, K, M, self._acc_only(s_acc))
+                if bias is not None and bias.requires_grad:
+                    self._bias_grad(bias, dyl, None if scales is None else scales[0])
+            self.record(bwd)
+        return y
+
+    def _acc_only(self, s3):
+        """scales triple {s_acc, 0, 0} for gradient GEMMs of a scaled forward."""
+        if s3 is None:
+            return None
+        t = torch.zeros(3, device=s3.device, dtype=F32)
+        t[0:1].copy_(s3[0:1])
+        return t
+
+    def _scaled(self, t: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+        """fresh tensor s*t (s: device scalar tensor [1])."""
+        out = torch.empty_like(t)
+        sc = torch.zeros(2, device=t.device, dtype=F32)
+        sc[0:1].copy_(s)
+        raw.axpby(t.reshape(-1), t.reshape(-1), out.reshape(-1), sc)
+        return out
+
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, ws, N, K, M, scales3):
+        """dW[N,K] += dy[M,N]^T @ x[M,K] — both operands MN-major, split-K over tokens, fp32 atomics."""
+        if len(ws) == 1:
+            targets = [(ws[0], 0, N)]
+        else:
+            targets, o0 = [], 0
+            for p in ws:
+                targets.append((p, o0, p.shape[0]))
+                o0 += p.shape[0]
+        for p, o0, O in targets:
+            if not p.requires_grad:
+                continue
+            g = self.pgrad(p).view(O, -1)
+            dyp = dy[:, o0:o0 + O]
+            bn = raw.pick_block_n(K, True)
+            tiles = ((O + 127) // 128) * ((K + bn - 1) // bn)
+            kb = (M + 63) // 64
+            split = max(1, min(kb, (2 * raw.load().svdx_num_sms()) // max(tiles, 1), 32))
+            raw.tapgemm(dyp, x, g, M=O, N=K, K=M, a_mn=True, b_mn=True, split_k=split, out_dtype=OUT_F32_ATOMIC,
+                        block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
+
+    # ------------------------------------------------------------------ convolutions
+    def conv2d_3x3(self, x: Var, g: Geom, conv, *, rowbias=None, rowbias_div=1, res1: Optional[Var] = None,
+                   scales=None, i_pad=None, n_pad=None, planes: bool = False) -> Var:
+        """3x3 conv, padding 1, on channels-last [N*H*W, Cin]. planes=True: x holds the 4 stride-2 parity planes
+        of a [N,2H,2W] image and the result is the stride-2 conv at geometry g (= output geometry)."""
+        w = conv.weight
+        O, I = w.shape[0], w.shape[1]
+        ip = i_pad if i_pad is not None else I
+        wf = self.w_conv(w, False, ip)
+        nimg = g.B * g.T
+        M = nimg * g.H * g.W
+        n_alloc = n_pad if n_pad is not None else O
+        out = self.empty(M, n_alloc, x.data)
+        if planes:
+            taps = []
+            for kh in range(3):
+                for kw in range(3):
+                    ph, dh = ((1, -1), (0, 0), (1, 0))[kh]
+                    pw, dw = ((1, -1), (0, 0), (1, 0))[kw]
+                    taps.append((dw, dh, (ph * 2 + pw) * nimg))
+            taps = tuple(taps)
+            whn = (g.W, g.H, 4 * nimg)
+        else:
+            taps = CONV3x3_TAPS
+            whn = (g.W, g.H, nimg)
+        raw.tapgemm(x.data, wf, out, M=M, N=O, K=ip, mode=A_CONV2D, taps=taps, conv_whn=whn, bias=self.vec_f32(conv.bias),
+                    rowbias=rowbias, rowbias_div=rowbias_div, res1=None if res1 is None else res1.data, scales=scales,
+                    block_n=raw.pick_block_n(O) if O >= 32 else 32)
+        w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad)
+        need = x.needs_grad or w_train or (res1 is not None and res1.needs_grad)
+        y = Var(out, need)
+        if need and self.recording:
+            if w.requires_grad:
+                raise NotImplementedError("svd_xtend_b200: weight gradient of spatial convolutions is not implemented yet "
+                                          "(train_svd.py:761-766 trains only temporal_transformer_block parameters)")
+
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                if dy is None:
+                    return
+                if res1 is not None and res1.needs_grad:
+                    self.add_grad(res1, dy if scales is None else self._scaled(dy, scales[1:2]))
+                if conv.bias is not None and conv.bias.requires_grad:
+                    self._bias_grad(conv.bias, dy, None if scales is None else scales[0])
+                if x.needs_grad:
+                    wt = self.w_conv(w, True)  # [I, 9*O]
+                    sc = self._acc_only(None if scales is None else scales[0:3])
+                    if not planes:
+                        dx = self.empty(M, I, x.data)
+                        raw.tapgemm(dy, wt, dx, M=M, N=I, K=O, mode=A_CONV2D, taps=_neg_taps(CONV3x3_TAPS),
+                                    conv_whn=(g.W, g.H, nimg), scales=sc)
+                    else:
+                        # gradient w.r.t. each parity plane: the taps that read that plane, shifts negated
+                        dx = self.empty(4 * M, I, x.data)
+                        wt3 = wt.view(I, 9, O)
+                        for pl in range(4):
+                            sel = [t for t in range(9) if taps[t][2] == pl * nimg]
+                            wsub = self.wc.get(("convT_plane", id(w), pl), [w], (I, len(sel) * O),
+                                               lambda buf, sel=sel: buf.view(I, len(sel), O).copy_(wt3[:, sel, :]))
+                            tp = tuple((-taps[t][0], -taps[t][1], 0) for t in sel)
+                            raw.tapgemm(dy, wsub, dx[pl * M:(pl + 1) * M], M=M, N=I, K=O, mode=A_CONV2D, taps=tp,
+                                        conv_whn=(g.W, g.H, nimg), scales=sc)
+                    self.add_grad(x, dx)
+            self.record(bwd)
+        return y
+
+    def conv_temporal(self, x: Var, g: Geom, conv, *, rowbias=None, rowbias_div=1, res1: Optional[Var] = None, scales=None) -> Var:
+        """Conv3d kernel (3,1,1), padding (1,0,0): frames are HW rows apart in the token matrix."""
+        w = conv.weight
+        O, I = w.shape[0], w.shape[1]
+        wf = self.w_conv(w, False)
+        M = g.M
+        HW = g.HW
+        taps = ((-HW, 0, 0), (0, 0, 0), (HW, 0, 0))
+        out = self.empty(M, O, x.data)
+        raw.tapgemm(x.data, wf, out, M=M, N=O, K=I, taps=taps, rows_per_group=g.T * HW, groups=g.B, bias=self.vec_f32(conv.bias),
+                    rowbias=rowbias, rowbias_div=rowbias_div, res1=None if res1 is None else res1.data, scales=scales)
+        need = x.needs_grad or w.requires_grad or (res1 is not None and res1.needs_grad)
+        y = Var(out, need)
+        if need and self.recording:
+            if w.requires_grad:
+                raise NotImplementedError("svd_xtend_b200: weight gradient of temporal convolutions is not implemented yet")
+
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                if dy is None:
+                    return
+                if res1 is not None and res1.needs_grad:
+                    self.add_grad(res1, dy if scales is None else self._scaled(dy, scales[1:2]))
+                if x.needs_grad:
+                    wt = self.w_conv(w, True)
+                    dx = self.empty(M, I, x.data)
+                    raw.tapgemm(dy, wt, dx, M=M, N=I, K=O, taps=_neg_taps(taps), rows_per_group=g.T * HW, groups=g.B,
+                                scales=self._acc_only(None if scales is None else scales[0:3]))
+                    self.add_grad(x, dx)
+            self.record(bwd)
+        return y
+
+    # ------------------------------------------------------------------ normalisation
+    def groupnorm(self, x: Var, gn, outer: int, rows: int, silu: bool) -> Var:
+        """GroupNorm(32) (+SiLU); one statistics group spans `rows` rows (H*W per frame, or T*H*W per clip)."""
+        C = x.cols
+        gamma, beta = self.vec_f32(gn.weight), self.vec_f32(gn.bias)
+        mean, rstd = raw.groupnorm_stats(x.data, None, outer, rows, gn.eps, gn.num_groups)
+        out = self.empty(x.rows, C, x.data)
+        raw.groupnorm_apply(x.data, None, outer, rows, mean, rstd, gamma, beta, silu, out, gn.num_groups)
+        p_train = gn.weight.requires_grad
+        need = x.needs_grad or p_train
+        y = Var(out, need)
+        if need and self.recording:
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                if dy is None:
+                    return
+                dx = self.empty(x.rows, C, x.data)
+                dg = self.pgrad(gn.weight) if p_train else None
+                db = self.pgrad(gn.bias) if p_train else None
+                raw.groupnorm_bwd(x.data, None, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, None, dg, db, gn.num_groups)
+                self.add_grad(x, dx)
+            self.record(bwd)
+        return y
+
+    def layernorm(self, x: Var, ln, *, addvec: Optional[torch.Tensor] = None, add_div: int = 1) -> Tuple[Var, Var]:
+        """returns (xs, LN(xs)) with xs = x + addvec[row / add_div] (xs is x itself when addvec is None).
+        Backward folds the gradient already accumulated on xs (its residual uses) into dx."""
+        C = x.cols
+        gamma, beta = self.vec_f32(ln.weight), self.vec_f32(ln.bias)
+        out = self.empty(x.rows, C, x.data)
+        if addvec is not None:
+            xs_data = self.empty(x.rows, C, x.data)
+            mean, rstd = raw.layernorm_fwd(x.data, gamma, beta, ln.eps, out, addvec, add_div, xs_data)
+        else:
+            xs_data = x.data
+            mean, rstd = raw.layernorm_fwd(x.data, gamma, beta, ln.eps, out)
+        p_train = ln.weight.requires_grad
+        need = x.needs_grad or p_train
+        xs = x if addvec is None else Var(xs_data, x.needs_grad)
+        y = Var(out, need)
+        if need and self.recording:
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                dres = xs.grad
+                if dy is None:
+                    if addvec is not None and dres is not None:
+                        xs.grad = None
+                        self.add_grad(x, dres)
+                    return
+                dg = self.pgrad(ln.weight) if p_train else None
+                db = self.pgrad(ln.bias) if p_train else None
+                if x.needs_grad:
+                    dx = self.empty(x.rows, C, x.data)
+                    raw.layernorm_bwd(xs_data, dy, gamma, mean, rstd, dx, dres, dg, db)
+                    xs.grad = None
+                    if addvec is None:
+                        x.grad = dx          # dres (the old x.grad) is folded in
+                    else:
+                        self.add_grad(x, dx)
+                elif p_train:
+                    dx = self.empty(x.rows, C, x.data)  # still needed to produce dgamma/dbeta
+                    raw.layernorm_bwd(xs_data, dy, gamma, mean, rstd, dx, None, dg, db)
+            self.record(bwd)
+        return xs, y
+
+    # ------------------------------------------------------------------ attention
+    def attention(self, qkv: Var, heads: int, g: Geom, temporal: bool) -> Var:
+        """self-attention over H*W per frame (spatial) or over T per pixel (temporal) on a fused q|k|v matrix."""
+        C = heads * 64
+        M = qkv.rows
+        q, k, v = qkv.data[:, :C], qkv.data[:, C:2 * C], qkv.data[:, 2 * C:3 * C]
+        out = self.empty(M, C, qkv.data)
+        need = qkv.needs_grad
+        lse = torch.empty(M, heads, device=out.device, dtype=F32) if (need and self.recording) else None
+        if temporal:
+            geo = dict(heads=heads, S=g.T, nseq=g.B * g.HW, inner=g.HW, outer_stride=g.T * g.HW, inner_stride=1, tok_stride=g.HW)
+        else:
+            geo = dict(heads=heads, S=g.HW, nseq=g.B * g.T, inner=1, outer_stride=g.HW, inner_stride=0, tok_stride=1)
+        raw.attention_fwd(q, k, v, out, lse=lse, **geo)
+        y = Var(out, need)
+        if need and self.recording:
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                if dy is None:
+                    return
+                dqkv = self.empty(M, 3 * C, out)
+                delta = torch.empty_like(lse)
+                raw.attention_bwd(q, k, v, out, dy, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], lse, delta, **geo)
+                self.add_grad(qkv, dqkv)
+            self.record(bwd)
+        return y
+
+    # ------------------------------------------------------------------ layout ops
+    def concat(self, a: Var, b: Var) -> Var:
+        out = self.empty(a.rows, a.cols + b.cols, a.data)
+        raw.concat_channels(a.data, b.data, out)
+        need = a.needs_grad or b.needs_grad
+        y = Var(out, need)
+        if need and self.recording:
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                if dy is None:
+                    return
+                da = torch.empty_like(a.data)
+                db = torch.empty_like(b.data)
+                raw.split_channels(dy, da, db)
+                self.add_grad(a, da)
+                self.add_grad(b, db)
+            self.record(bwd)
+        return y
+
+    def upsample2x(self, x: Var, g: Geom) -> Var:
+        N = g.B * g.T
+        out = self.empty(4 * x.rows, x.cols, x.data)
+        raw.upsample2x(x.data, out, N, g.H, g.W, x.cols)
+        y = Var(out, x.needs_grad)
+        if x.needs_grad and self.recording:
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                if dy is None:
+                    return
+                dx = torch.empty_like(x.data)
+                raw.upsample2x_bwd(dy, dx, N, g.H, g.W, x.cols)
+                self.add_grad(x, dx)
+            self.record(bwd)
+        return y
+
+    def space_to_planes(self, x: Var, g: Geom) -> Var:
+        N = g.B * g.T
+        out = torch.empty_like(x.data)
+        raw.space_to_planes(x.data, out, N, g.H, g.W, x.cols)
+        y = Var(out, x.needs_grad)
+        if x.needs_grad and self.recording:
+            def bwd():
+                dy = y.grad
+                y.grad = None
+                if dy is None:
+                    return
+                dx = torch.empty_like(x.data)
+                raw.planes_to_space(dy, dx, N, g.H, g.W, x.cols)
+                self.add_grad(x, dx)
+            self.record(bwd)
+        return y

@@ -195,12 +195,13 @@ def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2
                                     ws.data_ptr(), _stream()), "groupnorm_bwd")
 
 
-def layernorm_fwd(x, gamma, beta, eps, y):
+def layernorm_fwd(x, gamma, beta, eps, y, addvec=None, add_div=1, xsum=None):
     rows, Cc = x.shape
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty_like(mean)
     check(load().svdx_layernorm_fwd(x.data_ptr(), _rowmajor(x, "x"), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps,
-                                    y.data_ptr(), _rowmajor(y, "y"), mean.data_ptr(), rstd.data_ptr(), _stream()), "layernorm_fwd")
+                                    y.data_ptr(), _rowmajor(y, "y"), mean.data_ptr(), rstd.data_ptr(), _ptr(addvec), add_div,
+                                    _ptr(xsum), _rowmajor(xsum, "xsum") if xsum is not None else 0, _stream()), "layernorm_fwd")
     return mean, rstd
 
 
@@ -296,7 +297,7 @@ def geglu_bwd(pre, dout, dpre):
     return dpre
 
 
-def blend_scales(mix_factor, out3):
+def blend_scales(mix_factor, out3):  # out3: float[8]
     check(load().svdx_blend_scales(mix_factor.data_ptr(), out3.data_ptr(), _stream()), "blend_scales")
     return out3
 
