@@ -26,12 +26,17 @@ F32 = torch.float32
 class Var:
     """An activation on the tape: bf16 ``[rows, C]`` data plus (lazily) its gradient."""
 
-    __slots__ = ("data", "grad", "needs_grad")
+    __slots__ = ("data", "grad", "needs_grad", "owned")
 
     def __init__(self, data: torch.Tensor, needs_grad: bool = False):
         self.data = data
         self.grad: Optional[torch.Tensor] = None
         self.needs_grad = needs_grad
+        self.owned = False  # True when .grad is a tensor no other Var can see (safe to accumulate in place)
+
+    def take_grad(self) -> Optional[torch.Tensor]:
+        g, self.grad, self.owned = self.grad, None, False
+        return g
 
     @property
     def rows(self) -> int:
@@ -120,6 +125,7 @@ class Engine:
         self.recording = False
         self.pgrads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         self.launches = 0
+        self.keep: List[torch.Tensor] = []   # small device scalars referenced by in-flight launches
         self.grad_ready_hook: Optional[Callable[[List[torch.nn.Parameter]], None]] = None
 
     # ------------------------------------------------------------------ tape
@@ -136,15 +142,24 @@ class Engine:
         tape, self.tape = self.tape, []
         while tape:
             tape.pop()()
+        self.keep.clear()
 
     def add_grad(self, v: Var, g: torch.Tensor, owned: bool = True):
-        """Accumulate gradient g into v. `owned`: g is a fresh tensor this call may keep / overwrite."""
+        """Accumulate gradient g into v. `owned`: g is a fresh tensor nobody else references (it may be
+        kept and later overwritten in place); pass owned=False when g aliases another Var's gradient."""
         if not v.needs_grad:
             return
         if v.grad is None:
-            v.grad = g
-        else:
+            v.grad, v.owned = g, owned
+        elif v.grad.dtype != bf16:
+            v.grad = v.grad + g
+            v.owned = True
+        elif v.owned:
             raw.axpby(v.grad, g, v.grad)
+        else:
+            out = torch.empty_like(v.grad)
+            raw.axpby(v.grad, g, out)
+            v.grad, v.owned = out, True
 
     def pgrad(self, p: torch.nn.Parameter) -> torch.Tensor:
         """fp32 accumulation buffer for the gradient of p (zero-initialised once per backward)."""
@@ -190,6 +205,13 @@ class Engine:
         O, I = w.shape[0], w.shape[1]
         taps = w[0, 0].numel()
         if transposed:
+            Op = (O + 7) // 8 * 8
+            if Op != O:  # conv_out (O = 4): zero-pad the output-channel axis so rows stay 16-byte aligned
+                def build(buf):
+                    wp = torch.zeros(Op, I, taps, device=w.device, dtype=w.dtype)
+                    wp[:O] = w.reshape(O, I, taps)
+                    raw.prep_weight(wp, buf, 3, Op, I, taps)
+                return self.wc.get(("convT", id(p)), [p], (I, taps * Op), build)
             return self.wc.get(("convT", id(p)), [p], (I, taps * O), lambda buf: raw.prep_weight(w, buf, 3, O, I, taps))
         ip = i_pad if i_pad is not None else I
         return self.wc.get(("conv", id(p), ip), [p], (O, taps * ip), lambda buf: raw.prep_weight(w, buf, 2, O, I, taps, ip))
@@ -218,12 +240,34 @@ class Engine:
             g.add_(tmp * scale)
 
     # ------------------------------------------------------------------ linear family
+    def _res_grad(self, r: Optional[Var], dy: torch.Tensor, scale: Optional[torch.Tensor]):
+        """gradient of a residual epilogue operand: scale * dy (scale None = 1: dy is passed on by alias)."""
+        if r is None or not r.needs_grad:
+            return
+        if scale is None:
+            self.add_grad(r, dy, owned=False)
+        else:
+            self.add_grad(r, self._scaled(dy, scale))
+
+    def _rowbias_grad(self, rb: Optional[Var], dy: torch.Tensor, div: int, scale: Optional[torch.Tensor]):
+        """rowbias[b] is added to rows [b*div, (b+1)*div): its gradient is the per-block column sum of dy."""
+        if rb is None or not rb.needs_grad:
+            return
+        nb = rb.rows
+        g = torch.empty(nb, dy.shape[1], device=dy.device, dtype=F32)
+        for b in range(nb):
+            raw.colsum(dy[b * div:(b + 1) * div], g[b])
+        if scale is not None:
+            g = g * scale
+        self.add_grad(rb, g)
+
     def linear(self, x: Var, weight, bias=None, *, res1: Optional[Var] = None, res2: Optional[Var] = None,
-               scales: Optional[torch.Tensor] = None, geglu: bool = False, rowbias: Optional[torch.Tensor] = None,
-               rowbias_div: int = 1, out_f32: bool = False, fused: Optional[Sequence] = None,
-               rowbias_grad: Optional[Callable[[torch.Tensor], None]] = None) -> Var:
+               scales: Optional[torch.Tensor] = None, res1_unit: bool = False, geglu: bool = False,
+               rowbias: Optional[Var] = None, rowbias_div: int = 1, out_f32: bool = False,
+               fused: Optional[Sequence] = None) -> Var:
         """y = epilogue(x @ W^T). `weight` is a parameter [N,K] (or conv 1x1 [N,K,1,1]); `fused` = list of
-        parameters whose rows are concatenated (q|k|v). scales (device float[>=3]) = {acc, res1, res2}."""
+        parameters whose rows are concatenated (q|k|v). scales (device float[>=3]) = {acc, res1, res2};
+        res1_unit: scales[1] is known to be exactly 1. rowbias: Var with fp32 data [ceil(M/div), N]."""
         ws = list(fused) if fused is not None else [weight]
         wf = self.w_lin_cat(ws, False) if fused is not None else self.w_lin(weight, False)
         N, K = wf.shape
@@ -234,39 +278,35 @@ class Engine:
         b32 = self.vec_f32(bias)
         raw.tapgemm(x.data, wf, out, M=M, N=N, K=K, bias=b32, res1=None if res1 is None else res1.data,
                     res2=None if res2 is None else res2.data, scales=scales, geglu=geglu, pre=pre,
-                    rowbias=rowbias, rowbias_div=rowbias_div)
+                    rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div)
         w_train = any(p.requires_grad for p in ws) or (bias is not None and bias.requires_grad)
-        need = x.needs_grad or w_train or (res1 is not None and res1.needs_grad) or (res2 is not None and res2.needs_grad) \
-            or rowbias_grad is not None
+        need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, res2, rowbias))
         y = Var(out, need)
         if need and self.recording:
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 if dy is None:
                     return
-                s_acc = None if scales is None else scales[0:3]
-                if res1 is not None and res1.needs_grad:
-                    self.add_grad(res1, dy if scales is None else self._scaled(dy, scales[1:2]))
-                if res2 is not None and res2.needs_grad:
-                    self.add_grad(res2, dy if scales is None else self._scaled(dy, scales[2:3]))
+                if dy.dtype != bf16:
+                    dy = raw.cast_f32_bf16(dy.contiguous(), torch.empty(dy.shape, device=dy.device, dtype=bf16))
+                s_acc = None if scales is None else scales[0:1]
+                self._res_grad(res1, dy, None if (scales is None or res1_unit) else scales[1:2])
+                self._res_grad(res2, dy, None if scales is None else scales[2:3])
                 if geglu:
-                    dpre = torch.empty_like(pre)
-                    raw.geglu_bwd(pre, dy, dpre)
-                    dyl = dpre
+                    dyl = raw.geglu_bwd(pre, dy, torch.empty_like(pre))
                 else:
                     dyl = dy
-                if rowbias_grad is not None:
-                    rowbias_grad(dyl)
+                self._rowbias_grad(rowbias, dyl, rowbias_div, s_acc)
+                sc3 = self._acc_only(s_acc)
                 if x.needs_grad:
                     wt = self.w_lin_cat(ws, True) if fused is not None else self.w_lin(weight, True)
                     dx = self.empty(M, K, x.data)
-                    raw.tapgemm(dyl, wt, dx, M=M, N=K, K=N, scales=self._acc_only(s_acc))
+                    raw.tapgemm(dyl, wt, dx, M=M, N=K, K=N, scales=sc3)
                     self.add_grad(x, dx)
                 if any(p.requires_grad for p in ws):
-                    self._wgrad(dyl, x.data, ws, N, K, M, self._acc_only(s_acc))
+                    self._wgrad(dyl, x.data, ws, N, K, M, sc3)
                 if bias is not None and bias.requires_grad:
-                    self._bias_grad(bias, dyl, None if scales is None else scales[0])
+                    self._bias_grad(bias, dyl, s_acc)
             self.record(bwd)
         return y
 
@@ -276,6 +316,7 @@ class Engine:
             return None
         t = torch.zeros(3, device=s3.device, dtype=F32)
         t[0:1].copy_(s3[0:1])
+        self.keep.append(t)
         return t
 
     def _scaled(self, t: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
@@ -284,6 +325,7 @@ class Engine:
         sc = torch.zeros(2, device=t.device, dtype=F32)
         sc[0:1].copy_(s)
         raw.axpby(t.reshape(-1), t.reshape(-1), out.reshape(-1), sc)
+        self.keep.append(sc)
         return out
 
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, ws, N, K, M, scales3):
@@ -308,8 +350,8 @@ class Engine:
                         block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
 
     # ------------------------------------------------------------------ convolutions
-    def conv2d_3x3(self, x: Var, g: Geom, conv, *, rowbias=None, rowbias_div=1, res1: Optional[Var] = None,
-                   scales=None, i_pad=None, n_pad=None, planes: bool = False) -> Var:
+    def conv2d_3x3(self, x: Var, g: Geom, conv, *, rowbias: Optional[Var] = None, rowbias_div=1, res1: Optional[Var] = None,
+                   scales=None, res1_unit: bool = False, i_pad=None, n_pad=None, planes: bool = False) -> Var:
         """3x3 conv, padding 1, on channels-last [N*H*W, Cin]. planes=True: x holds the 4 stride-2 parity planes
         of a [N,2H,2W] image and the result is the stride-2 conv at geometry g (= output geometry)."""
         w = conv.weight
@@ -333,8 +375,11 @@ class Engine:
             taps = CONV3x3_TAPS
             whn = (g.W, g.H, nimg)
         raw.tapgemm(x.data, wf, out, M=M, N=O, K=ip, mode=A_CONV2D, taps=taps, conv_whn=whn, bias=self.vec_f32(conv.bias),
-                    rowbias=rowbias, rowbias_div=rowbias_div, res1=None if res1 is None else res1.data, scales=scales,
+                    rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
+                    res1=None if res1 is None else res1.data, scales=scales,
                     block_n=raw.pick_block_n(O) if O >= 32 else 32)
+        if rowbias is not None and rowbias.needs_grad:
+            raise NotImplementedError("svd_xtend_b200: gradient of the time-embedding projection is not implemented yet")
         w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad)
         need = x.needs_grad or w_train or (res1 is not None and res1.needs_grad)
         y = Var(out, need)
@@ -344,20 +389,19 @@ class Engine:
                                           "(train_svd.py:761-766 trains only temporal_transformer_block parameters)")
 
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 if dy is None:
                     return
-                if res1 is not None and res1.needs_grad:
-                    self.add_grad(res1, dy if scales is None else self._scaled(dy, scales[1:2]))
+                self._res_grad(res1, dy, None if (scales is None or res1_unit) else scales[1:2])
                 if conv.bias is not None and conv.bias.requires_grad:
-                    self._bias_grad(conv.bias, dy, None if scales is None else scales[0])
+                    self._bias_grad(conv.bias, dy[:, :O], None if scales is None else scales[0:1])
                 if x.needs_grad:
-                    wt = self.w_conv(w, True)  # [I, 9*O]
-                    sc = self._acc_only(None if scales is None else scales[0:3])
+                    wt = self.w_conv(w, True)  # [I, 9*Opad]
+                    Op = wt.shape[1] // 9
+                    sc = self._acc_only(None if scales is None else scales[0:1])
                     if not planes:
                         dx = self.empty(M, I, x.data)
-                        raw.tapgemm(dy, wt, dx, M=M, N=I, K=O, mode=A_CONV2D, taps=_neg_taps(CONV3x3_TAPS),
+                        raw.tapgemm(dy, wt, dx, M=M, N=I, K=Op, mode=A_CONV2D, taps=_neg_taps(CONV3x3_TAPS),
                                     conv_whn=(g.W, g.H, nimg), scales=sc)
                     else:
                         # gradient w.r.t. each parity plane: the taps that read that plane, shifts negated
@@ -374,7 +418,8 @@ class Engine:
             self.record(bwd)
         return y
 
-    def conv_temporal(self, x: Var, g: Geom, conv, *, rowbias=None, rowbias_div=1, res1: Optional[Var] = None, scales=None) -> Var:
+    def conv_temporal(self, x: Var, g: Geom, conv, *, rowbias: Optional[Var] = None, rowbias_div=1, res1: Optional[Var] = None,
+                      scales=None, res1_unit: bool = False) -> Var:
         """Conv3d kernel (3,1,1), padding (1,0,0): frames are HW rows apart in the token matrix."""
         w = conv.weight
         O, I = w.shape[0], w.shape[1]
@@ -384,7 +429,10 @@ class Engine:
         taps = ((-HW, 0, 0), (0, 0, 0), (HW, 0, 0))
         out = self.empty(M, O, x.data)
         raw.tapgemm(x.data, wf, out, M=M, N=O, K=I, taps=taps, rows_per_group=g.T * HW, groups=g.B, bias=self.vec_f32(conv.bias),
-                    rowbias=rowbias, rowbias_div=rowbias_div, res1=None if res1 is None else res1.data, scales=scales)
+                    rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
+                    res1=None if res1 is None else res1.data, scales=scales)
+        if (rowbias is not None and rowbias.needs_grad) or (conv.bias is not None and conv.bias.requires_grad):
+            raise NotImplementedError("svd_xtend_b200: bias / time-embedding gradients of temporal convolutions are not implemented yet")
         need = x.needs_grad or w.requires_grad or (res1 is not None and res1.needs_grad)
         y = Var(out, need)
         if need and self.recording:
@@ -392,17 +440,15 @@ class Engine:
                 raise NotImplementedError("svd_xtend_b200: weight gradient of temporal convolutions is not implemented yet")
 
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 if dy is None:
                     return
-                if res1 is not None and res1.needs_grad:
-                    self.add_grad(res1, dy if scales is None else self._scaled(dy, scales[1:2]))
+                self._res_grad(res1, dy, None if (scales is None or res1_unit) else scales[1:2])
                 if x.needs_grad:
                     wt = self.w_conv(w, True)
                     dx = self.empty(M, I, x.data)
                     raw.tapgemm(dy, wt, dx, M=M, N=I, K=O, taps=_neg_taps(taps), rows_per_group=g.T * HW, groups=g.B,
-                                scales=self._acc_only(None if scales is None else scales[0:3]))
+                                scales=self._acc_only(None if scales is None else scales[0:1]))
                     self.add_grad(x, dx)
             self.record(bwd)
         return y
@@ -420,8 +466,7 @@ class Engine:
         y = Var(out, need)
         if need and self.recording:
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 if dy is None:
                     return
                 dx = self.empty(x.rows, C, x.data)
@@ -450,22 +495,20 @@ class Engine:
         y = Var(out, need)
         if need and self.recording:
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 dres = xs.grad
                 if dy is None:
                     if addvec is not None and dres is not None:
-                        xs.grad = None
-                        self.add_grad(x, dres)
+                        self.add_grad(x, xs.take_grad(), owned=False)
                     return
                 dg = self.pgrad(ln.weight) if p_train else None
                 db = self.pgrad(ln.bias) if p_train else None
                 if x.needs_grad:
                     dx = self.empty(x.rows, C, x.data)
                     raw.layernorm_bwd(xs_data, dy, gamma, mean, rstd, dx, dres, dg, db)
-                    xs.grad = None
+                    xs.take_grad()
                     if addvec is None:
-                        x.grad = dx          # dres (the old x.grad) is folded in
+                        x.grad, x.owned = dx, True   # dres (the old x.grad) is folded in
                     else:
                         self.add_grad(x, dx)
                 elif p_train:
@@ -491,8 +534,7 @@ class Engine:
         y = Var(out, need)
         if need and self.recording:
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 if dy is None:
                     return
                 dqkv = self.empty(M, 3 * C, out)
@@ -510,8 +552,7 @@ class Engine:
         y = Var(out, need)
         if need and self.recording:
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 if dy is None:
                     return
                 da = torch.empty_like(a.data)
@@ -529,8 +570,7 @@ class Engine:
         y = Var(out, x.needs_grad)
         if x.needs_grad and self.recording:
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 if dy is None:
                     return
                 dx = torch.empty_like(x.data)
@@ -546,8 +586,7 @@ class Engine:
         y = Var(out, x.needs_grad)
         if x.needs_grad and self.recording:
             def bwd():
-                dy = y.grad
-                y.grad = None
+                dy = y.take_grad()
                 if dy is None:
                     return
                 dx = torch.empty_like(x.data)
