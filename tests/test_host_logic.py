@@ -1,0 +1,84 @@
+"""CPU tests of the host-side mirror: construction, naming contract, helper API, no-CPU-fallback."""
+import os
+
+import pytest
+import torch
+
+from oracle.svd_unet_oracle import SVD_CONFIG, TINY_CONFIG
+from oracle.svd_unet_oracle import UNetSpatioTemporalConditionModel as Oracle
+from svd_xtend_b200.engine import Geom
+from svd_xtend_b200.raw import pick_block_n
+from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel as Ours
+
+
+def test_same_parameter_names_and_shapes_as_oracle():
+    with torch.device("meta"):
+        a, b = Ours(**SVD_CONFIG), Oracle(**SVD_CONFIG)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    assert all(sa[k].shape == sb[k].shape for k in sa)
+    assert sum(p.numel() for p in a.parameters()) == 1_524_623_082
+
+
+def test_trainable_filter_of_train_svd():
+    """train_svd.py:761-766 selects parameters by name substring."""
+    with torch.device("meta"):
+        m = Ours(**SVD_CONFIG)
+    n = sum(p.numel() for k, p in m.named_parameters() if "temporal_transformer_block" in k)
+    assert n == 397_620_480
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(ValueError, match="down_block_types"):
+        Ours(**{**TINY_CONFIG, "up_block_types": ("UpBlockSpatioTemporal",)})
+    with pytest.raises(ValueError, match="block_out_channels"):
+        Ours(**{**TINY_CONFIG, "block_out_channels": (64,)})
+    with pytest.raises(ValueError, match="num_attention_heads"):
+        Ours(**{**TINY_CONFIG, "num_attention_heads": (1, 2, 3)})
+    with pytest.raises(ValueError):
+        Ours(**{**TINY_CONFIG, "down_block_types": ("Nope", "DownBlockSpatioTemporal")})
+
+
+def test_helper_api_surface():
+    m = Ours(**TINY_CONFIG)
+    assert m.config.addition_time_embed_dim == 32 and m.config["in_channels"] == 8   # train_svd.py:887-889
+    assert m.add_embedding.linear_1.in_features == 96
+    procs = m.attn_processors
+    assert len(procs) == 16 and all(k.endswith(".processor") for k in procs)
+    assert "down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor" in procs
+    m.set_attn_processor(dict(procs))
+    with pytest.raises(ValueError, match="number of processors"):
+        m.set_attn_processor({"x": 1})
+    m.set_default_attn_processor()
+    assert not m.is_gradient_checkpointing
+    m.enable_gradient_checkpointing()
+    assert m.is_gradient_checkpointing
+    with pytest.raises(ValueError):
+        m.enable_forward_chunking(dim=2)
+    m.enable_forward_chunking(2, dim=1)
+    m.enable_xformers_memory_efficient_attention()
+
+
+def test_no_cpu_fallback():
+    m = Ours(**TINY_CONFIG)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 2, 8, 16, 16), torch.zeros(1), torch.zeros(1, 1, 64), torch.zeros(1, 3))
+
+
+def test_save_load_roundtrip(tmp_path):
+    torch.manual_seed(1)
+    m = Ours(**TINY_CONFIG)
+    m.save_pretrained(os.path.join(tmp_path, "unet"))
+    m2 = Ours.from_pretrained(str(tmp_path), subfolder="unet", low_cpu_mem_usage=True, variant="fp16")
+    for (ka, va), (kb, vb) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    oracle = Oracle(**TINY_CONFIG)
+    oracle.load_state_dict(m.state_dict())       # same key contract both ways
+
+
+def test_tile_selection_and_geometry():
+    assert pick_block_n(320) == 160 and pick_block_n(1280) == 256 and pick_block_n(960) == 160
+    assert pick_block_n(320, True) == 64 and pick_block_n(1280, True) == 256
+    assert pick_block_n(4) == 32
+    g = Geom(2, 14, 40, 64)
+    assert g.M == 2 * 14 * 2560 and g.down().HW == 640 and g.down().up().W == 64
