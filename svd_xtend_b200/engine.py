@@ -108,7 +108,7 @@ class WeightCache:
         return ent[0]
 
     def refresh_trainable(self):
-        for key, (buf, ver, fn, trainable) in self._store.items():
+        for key, (buf, ver, fn, trainable) in list(self._store.items()):
             if trainable:
                 fn()
 
@@ -125,6 +125,7 @@ class Engine:
         self.recording = False
         self.pgrads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         self.launches = 0
+        self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}   # optional flat gradient arena (train.ParamArena)
         self.keep: List[torch.Tensor] = []   # small device scalars referenced by in-flight launches
         self.grad_ready_hook: Optional[Callable[[List[torch.nn.Parameter]], None]] = None
 
@@ -165,7 +166,9 @@ class Engine:
         """fp32 accumulation buffer for the gradient of p (zero-initialised once per backward)."""
         g = self.pgrads.get(p)
         if g is None:
-            g = torch.zeros(p.shape, device=p.device, dtype=F32)
+            g = self.grad_views.get(p)
+            if g is None:
+                g = torch.zeros(p.shape, device=p.device, dtype=F32)
             self.pgrads[p] = g
         return g
 

@@ -7,9 +7,18 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import A_CONV2D, A_ROWS, OUT_BF16, OUT_F32, OUT_F32_ATOMIC, SvdxAttn, SvdxTapGemm, check, load
+from ._lib import A_CONV2D, A_ROWS, OUT_BF16, OUT_F32, OUT_F32_ATOMIC, SvdxAttn, SvdxTapGemm, load
 
 bf16 = torch.bfloat16
+
+# number of kernels launched through the C ABI since import (each wrapper adds what its entry point launches)
+LAUNCHES = [0]
+_KERNELS_PER_CALL = {"svdx_groupnorm_stats": 2, "svdx_groupnorm_bwd": 2, "svdx_attention_bwd": 3}
+
+
+def check(rc: int, what: str = "") -> None:
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 1)
+    _lib.check(rc, what)
 
 
 def _stream() -> int:
@@ -171,7 +180,7 @@ def groupnorm_stats(x, x2, outer, rows, eps, groups=32):
     mean = torch.empty(outer * groups, device=x.device, dtype=torch.float32)
     rstd = torch.empty_like(mean)
     check(load().svdx_groupnorm_stats(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0,
-                                      C2, outer, rows, groups, eps, mean.data_ptr(), rstd.data_ptr(), _stream()), "groupnorm_stats")
+                                      C2, outer, rows, groups, eps, mean.data_ptr(), rstd.data_ptr(), _stream()), "svdx_groupnorm_stats")
     return mean, rstd
 
 
@@ -192,7 +201,7 @@ def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2
                                     dy.data_ptr(), _rowmajor(dy, "dy"), outer, rows, groups, mean.data_ptr(), rstd.data_ptr(),
                                     gamma.data_ptr(), beta.data_ptr(), int(silu), dx.data_ptr(), _rowmajor(dx, "dx"),
                                     _ptr(dx2), _rowmajor(dx2, "dx2") if dx2 is not None else 0, _ptr(dgamma), _ptr(dbeta),
-                                    ws.data_ptr(), _stream()), "groupnorm_bwd")
+                                    ws.data_ptr(), _stream()), "svdx_groupnorm_bwd")
 
 
 def layernorm_fwd(x, gamma, beta, eps, y, addvec=None, add_div=1, xsum=None):

@@ -1,0 +1,155 @@
+"""Training-step plumbing around the UNet hot path: flat parameter/gradient arenas, the fused AdamW
+kernel, and the data-parallel gradient all-reduce the build owns.
+
+Why the build owns the all-reduce: train_svd.py strips accelerate's DDP wrapper right after
+`prepare()` (`unet = unet.module`, /root/reference/train_svd.py:823-824) and then calls the bare module
+(:1021), so torch DDP's reducer is never armed. The path shards on clips (one
+clip per rank, §8e); the only exchange is one gradient all-reduce per step over NCCL/NVLink.
+
+    arena = ParamArena(unet)            # trainable fp32 parameters re-homed into ONE flat buffer
+    unet.attach_arena(arena)            # kernels accumulate parameter gradients straight into arena.grad
+    reducer = GradReducer(arena)        # bucketed ncclAllReduce on a side stream, overlapped with backward
+    opt = FusedAdamW(arena, lr=...)     # one kernel over the flat buffers (torch.optim.AdamW semantics)
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import raw
+
+F32 = torch.float32
+
+
+class ParamArena:
+    """Flattens the trainable parameters (in registration order) into one fp32 buffer; every parameter's
+    `.data` becomes a view, and a same-shaped gradient arena provides `.grad` views."""
+
+    def __init__(self, module: torch.nn.Module, params: Optional[Iterable[torch.nn.Parameter]] = None):
+        ps = [p for p in (params if params is not None else module.parameters()) if p.requires_grad]
+        if not ps:
+            raise ValueError("ParamArena: no trainable parameters")
+        dev = ps[0].device
+        if any(p.dtype != F32 for p in ps):
+            raise ValueError("ParamArena expects fp32 master parameters (train_svd.py loads the UNet in fp32)")
+        self.params: List[torch.nn.Parameter] = ps
+        # 64-element alignment keeps every view 256-byte aligned (vector loads, TMA-friendly)
+        self.offsets: List[int] = []
+        off = 0
+        for p in ps:
+            self.offsets.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        self.numel = off
+        self.data = torch.zeros(off, device=dev, dtype=F32)
+        self.grad = torch.zeros(off, device=dev, dtype=F32)
+        self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        with torch.no_grad():
+            for p, o in zip(ps, self.offsets):
+                view = self.data[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self.grad_views[p] = self.grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def attach_grads(self):
+        for p in self.params:
+            p.grad = self.grad_views[p]
+
+
+class FusedAdamW:
+    """torch.optim.AdamW semantics (train_svd.py:767-773) as ONE elementwise kernel over the arena."""
+
+    def __init__(self, arena: ParamArena, lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8):
+        self.arena = arena
+        self.lr, self.betas, self.weight_decay, self.eps = lr, betas, weight_decay, eps
+        self.m = torch.zeros_like(arena.data)
+        self.v = torch.zeros_like(arena.data)
+        self.t = 0
+        # called after every update; wire it to `unet.refresh_trainable_operands` so the bf16 operand copies of
+        # the trainable weights are re-prepared (the flat in-place update does not bump tensor version counters)
+        self.on_updated = None
+
+    def step(self, grad_scale: float = 1.0):
+        self.t += 1
+        a = self.arena
+        raw.adamw(a.data, a.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                  self.t, grad_scale)
+        if self.on_updated is not None:
+            self.on_updated()
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.arena.zero_grad()
+
+
+class GradReducer:
+    """Bucketed gradient all-reduce (mean) over the flat gradient arena on a side stream.
+
+    `on_grads_ready(params)` may be called from the backward as parameter gradients become final; buckets whose
+    parameters are all ready are reduced immediately so NCCL overlaps the rest of the backward.
+    `finish()` reduces what is left and makes the compute stream wait for the communication stream."""
+
+    def __init__(self, arena: ParamArena, bucket_mb: float = 64.0, group=None):
+        self.arena = arena
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.stream = torch.cuda.Stream() if arena.data.is_cuda else None
+        per = int(bucket_mb * (1 << 20) // 4)
+        self.buckets: List[tuple] = []       # (start, end) element ranges over arena.grad
+        self.bucket_of: Dict[torch.nn.Parameter, int] = {}
+        start, cur = 0, 0
+        for p, o in zip(arena.params, arena.offsets):
+            end = o + (p.numel() + 63) // 64 * 64
+            self.bucket_of[p] = len(self.buckets)
+            cur = end
+            if cur - start >= per:
+                self.buckets.append((start, cur))
+                start = cur
+        if cur > start:
+            self.buckets.append((start, cur))
+        # parameters of the tail bucket were assigned index len(buckets) before it was appended: consistent
+        self._pending = [0] * len(self.buckets)
+        self._members = [0] * len(self.buckets)
+        for p in arena.params:
+            self._members[self.bucket_of[p]] += 1
+        self.reset()
+
+    def reset(self):
+        self._pending = list(self._members)
+        self._done = [False] * len(self.buckets)
+
+    def _launch(self, i: int):
+        if self._done[i] or self.world == 1:
+            self._done[i] = True
+            return
+        s, e = self.buckets[i]
+        buf = self.arena.grad[s:e]
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                buf.mul_(1.0 / self.world)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.mul_(1.0 / self.world)
+        self._done[i] = True
+
+    def on_grads_ready(self, params: Iterable[torch.nn.Parameter]):
+        for p in params:
+            i = self.bucket_of.get(p)
+            if i is None:
+                continue
+            self._pending[i] -= 1
+            if self._pending[i] == 0:
+                self._launch(i)
+
+    def finish(self):
+        for i in range(len(self.buckets)):
+            if not self._done[i]:
+                self._launch(i)
+        if self.stream is not None and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.reset()

@@ -394,7 +394,23 @@ class UNetSpatioTemporalConditionModel(nn.Module):
 
         self._engine = Engine()
         self._resblocks: List[SpatioTemporalResBlock] = [m for m in self.modules() if isinstance(m, SpatioTemporalResBlock)]
-        self.grad_hook = None   # callable(list_of_params) invoked as soon as a parameter's gradient is final (DDP overlap)
+        self.grad_hook = None   # callable(list_of_params) invoked as soon as parameter gradients are final (DDP overlap)
+        self._arena = None
+
+    # ------------------------------------------------------------------ training plumbing (svd_xtend_b200.train)
+    def attach_arena(self, arena):
+        """Accumulate parameter gradients directly into `arena.grad` views (see train.ParamArena)."""
+        self._arena = arena
+        self._engine.grad_views = arena.grad_views if arena is not None else {}
+        self._engine.wc.clear()
+
+    def refresh_trainable_operands(self):
+        """Re-prepare the bf16 operand layouts of all trainable parameters (after an out-of-band update)."""
+        self._engine.wc.refresh_trainable()
+
+    @property
+    def kernel_launches(self) -> int:
+        return raw.LAUNCHES[0]
 
     # ------------------------------------------------------------------ reference helper API
     @property
@@ -563,7 +579,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         projs = []
         for rb in self._resblocks:
             projs += [rb.spatial_res_block.time_emb_proj, rb.temporal_res_block.time_emb_proj]
-        if any(p.weight.requires_grad or p.bias.requires_grad for p in projs):
+        if E.recording and any(p.weight.requires_grad or p.bias.requires_grad for p in projs):
             raise NotImplementedError("svd_xtend_b200: gradients of time_emb_proj are not implemented yet")
         w_all = E.w_lin_cat([p.weight for p in projs], False)
         b_all = E.wc.get(("tembbias",) + tuple(id(p.bias) for p in projs), [p.bias for p in projs], (w_all.shape[0],),
@@ -630,7 +646,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
     def _mlp(self, E: Engine, x32: torch.Tensor, mlp: TimestepEmbedding) -> torch.Tensor:
         """TimestepEmbedding on a few rows: Linear -> SiLU -> Linear, fp32 in/out, bf16 operands."""
         for lin in (mlp.linear_1, mlp.linear_2):
-            if lin.weight.requires_grad or lin.bias.requires_grad:
+            if E.recording and (lin.weight.requires_grad or lin.bias.requires_grad):
                 raise NotImplementedError("svd_xtend_b200: gradients of the time-embedding MLPs are not implemented yet")
         dev = x32.device
         xb = raw.cast_f32_bf16(x32.contiguous().float(), torch.empty(x32.shape, device=dev, dtype=bf16))
@@ -639,7 +655,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         return E.linear(Var(hb), mlp.linear_2.weight, mlp.linear_2.bias, out_f32=True).data
 
     def _blend(self, E: Engine, mixer: AlphaBlender) -> torch.Tensor:
-        if mixer.mix_factor.requires_grad:
+        if E.recording and mixer.mix_factor.requires_grad:
             raise NotImplementedError("svd_xtend_b200: gradient of AlphaBlender.mix_factor is not implemented yet")
         mf = E.vec_f32(mixer.mix_factor)
         return E.wc.get(("blend", id(mixer.mix_factor)), [mixer.mix_factor], (8,), lambda buf: raw.blend_scales(mf, buf), dtype=F32)
@@ -685,6 +701,10 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         per_clip = g.T * g.HW
         heads = tr.heads
         sb, tb = tr.transformer_blocks[0], tr.temporal_transformer_blocks[0]
+        if self.grad_hook is not None and E.recording:
+            ready = [p for p in tr.parameters() if p.requires_grad]
+            if ready:  # recorded first => runs last in this block's backward: its parameter gradients are final
+                E.record(lambda ready=ready: self.grad_hook(ready))
         h = E.groupnorm(x_in, tr.norm, outer=N, rows=g.HW, silu=False)
         x0 = E.linear(h, tr.proj_in.weight, tr.proj_in.bias)
         # spatial BasicTransformerBlock
@@ -740,7 +760,11 @@ class _UNetFn(torch.autograd.Function):
         raw.nchw_to_nhwc(d, dy, N, ctx.n_out, g.H, g.W, y.data.shape[1])
         E.add_grad(y, dy)
         E.run_backward()
+        views = E.grad_views
         for p in params:
+            if p in views:
+                p.grad = views[p]        # the kernels accumulated straight into the arena
+                continue
             gp = E.pgrads.get(p)
             if gp is None:
                 gp = torch.zeros(p.shape, device=p.device, dtype=F32)   # e.g. attn2.to_q/to_k/norm2: exactly zero
@@ -751,5 +775,5 @@ class _UNetFn(torch.autograd.Function):
                 p.grad.add_(gp)
         E.pgrads = {}
         if model.grad_hook is not None:
-            model.grad_hook(list(params))
+            model.grad_hook(None)       # None = everything is final
         return (None,) * (6 + len(params))
