@@ -206,6 +206,7 @@ def main():
     torch.manual_seed(1234)
     with torch.device(dev):
         unet = UNetSpatioTemporalConditionModel(**SVD_CONFIG)
+    unet.to(dev)
     unet.requires_grad_(False)
     n_train = 0
     for n, p in unet.named_parameters():

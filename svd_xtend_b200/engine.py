@@ -381,7 +381,7 @@ class Engine:
                     rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
                     res1=None if res1 is None else res1.data, scales=scales,
                     block_n=raw.pick_block_n(O) if O >= 32 else 32)
-        if rowbias is not None and rowbias.needs_grad:
+        if self.recording and rowbias is not None and rowbias.needs_grad:
             raise NotImplementedError("svd_xtend_b200: gradient of the time-embedding projection is not implemented yet")
         w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad)
         need = x.needs_grad or w_train or (res1 is not None and res1.needs_grad)
@@ -434,7 +434,7 @@ class Engine:
         raw.tapgemm(x.data, wf, out, M=M, N=O, K=I, taps=taps, rows_per_group=g.T * HW, groups=g.B, bias=self.vec_f32(conv.bias),
                     rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
                     res1=None if res1 is None else res1.data, scales=scales)
-        if (rowbias is not None and rowbias.needs_grad) or (conv.bias is not None and conv.bias.requires_grad):
+        if self.recording and ((rowbias is not None and rowbias.needs_grad) or (conv.bias is not None and conv.bias.requires_grad)):
             raise NotImplementedError("svd_xtend_b200: bias / time-embedding gradients of temporal convolutions are not implemented yet")
         need = x.needs_grad or w.requires_grad or (res1 is not None and res1.needs_grad)
         y = Var(out, need)

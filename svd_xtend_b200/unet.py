@@ -118,7 +118,7 @@ class TemporalBasicTransformerBlock(nn.Module):
 class AlphaBlender(nn.Module):
     def __init__(self, alpha: float):
         super().__init__()
-        self.register_parameter("mix_factor", nn.Parameter(torch.Tensor([alpha])))
+        self.register_parameter("mix_factor", nn.Parameter(torch.tensor([float(alpha)])))
 
 
 class ResnetBlock2D(nn.Module):
@@ -545,6 +545,8 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         """Same contract as src/unet_spatio_temporal_condition.py:357-490."""
         if not sample.is_cuda:
             raise RuntimeError("svd_xtend_b200: the UNet hot path only runs on a CUDA (sm_100a) device; there is no CPU fallback")
+        if any(p.device != sample.device for p in self.parameters()):
+            raise RuntimeError("svd_xtend_b200: all parameters must live on the device of `sample`")
         timesteps = timestep
         if not torch.is_tensor(timesteps):
             dtype = torch.float64 if isinstance(timestep, float) else torch.int64
