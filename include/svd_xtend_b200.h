@@ -77,6 +77,12 @@ typedef struct SvdxTapGemm {
   const void* b;
   int64_t ldb;
   int32_t b_major_mn;
+  int32_t b_mode;       /* weight-gradient forms (a_major_mn = b_major_mn = 1): 0 plain [K][N];
+                           1: B is a channels-last image tensor [nimg][H][W][N], contraction row p (an output
+                              pixel) reads pixel shifted by (tap_d0[0], tap_d1[0]) of image +tap_d2[0], zero outside
+                              (dW of a 3x3 conv tap); K = images*H*W output pixels;
+                           2: B is [groups][rows_per_group][N], contraction row reads row + tap_d0[0] of its
+                              group, zero outside (dW of a (3,1,1) temporal conv tap) */
   /* problem */
   int32_t M, N, K;      /* M output rows, N = B rows (before GEGLU halving), K = contraction per tap */
   int32_t block_n;      /* multiple of 32, <= 256 (multiple of 64 when b_major_mn) */
@@ -176,6 +182,12 @@ int svdx_attention_bwd(const SvdxAttn* d, void* stream);
  * i_pad >= I pads the input-channel axis with zeros (conv_in: 8 -> 64). */
 int svdx_prep_weight(const void* src, int32_t src_bf16, void* dst, int32_t mode,
                      int32_t O, int32_t I, int32_t taps, int32_t i_pad, void* stream);
+/* adjoint of svdx_prep_weight mode 2: dst[o][i][t] += src[o][t][i] (fp32; src row = taps*i_pad, dst = OIHW gradient) */
+int svdx_unprep_conv_grad(const float* src, float* dst, int32_t O, int32_t I, int32_t taps, int32_t i_pad, void* stream);
+/* sum over all elements of dy * (a - b) (bf16 inputs) accumulated into out[0] (fp32): AlphaBlender mix_factor gradient */
+int svdx_dot_diff(const void* dy, const void* a, const void* b, int64_t n, float* out, void* stream);
+/* y = dy * silu'(x) on fp32 vectors (time-embedding MLP backward) */
+int svdx_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, void* stream);
 int svdx_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int svdx_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
 /* NCHW (fp32 or bf16) -> [N][H][W][c_pad] bf16 (zero padded channels) and back (to fp32 / bf16 NCHW) */

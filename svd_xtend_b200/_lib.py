@@ -27,7 +27,7 @@ class SvdxTapGemm(C.Structure):
         ("W", c_int), ("H", c_int), ("nimg", c_int),
         ("num_taps", c_int),
         ("tap_d0", c_int * SVDX_MAX_TAPS), ("tap_d1", c_int * SVDX_MAX_TAPS), ("tap_d2", c_int * SVDX_MAX_TAPS),
-        ("b", c_void_p), ("ldb", c_i64), ("b_major_mn", c_int),
+        ("b", c_void_p), ("ldb", c_i64), ("b_major_mn", c_int), ("b_mode", c_int),
         ("M", c_int), ("N", c_int), ("K", c_int),
         ("block_n", c_int), ("split_k", c_int),
         ("out", c_void_p), ("ldo", c_i64), ("out_dtype", c_int), ("geglu", c_int),
@@ -69,6 +69,9 @@ _PROTOS = {
     "svdx_attention_fwd": [C.POINTER(SvdxAttn), c_void_p],
     "svdx_attention_bwd": [C.POINTER(SvdxAttn), c_void_p],
     "svdx_prep_weight": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "svdx_unprep_conv_grad": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "svdx_dot_diff": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p],
+    "svdx_silu_bwd_f32": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
     "svdx_cast_f32_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "svdx_cast_bf16_f32": [c_void_p, c_void_p, c_i64, c_void_p],
     "svdx_nchw_to_nhwc": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

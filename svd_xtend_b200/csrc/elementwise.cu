@@ -260,6 +260,43 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ pre, long long ldpre, 
   *reinterpret_cast<uint4*>(dpre + r * lddpre + h + c) = make_uint4(og[0], og[1], og[2], og[3]);
 }
 
+__global__ void unprep_conv_grad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int taps, int i_pad) {
+  const long long idx = gtid();  // over dst [O][I][taps]
+  if (idx >= (long long)O * I * taps) return;
+  const int t = (int)(idx % taps);
+  const int i = (int)((idx / taps) % I);
+  const int o = (int)(idx / ((long long)taps * I));
+  dst[idx] += src[((long long)o * taps + t) * i_pad + i];
+}
+
+__global__ void __launch_bounds__(256) dot_diff_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                       long long nvec, float* out) {
+  float acc = 0.f;
+  for (long long i = gtid(); i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 d = dy[i], x = a[i], y = b[i];
+    const uint32_t dd[4] = {d.x, d.y, d.z, d.w}, xx[4] = {x.x, x.y, x.z, x.w}, yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fd = unpack_bf16x2(dd[k]), fx = unpack_bf16x2(xx[k]), fy = unpack_bf16x2(yy[k]);
+      acc += fd.x * (fx.x - fy.x) + fd.y * (fx.y - fy.y);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += sh[k];
+    atomicAdd(out, s);
+  }
+}
+
+__global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
+  const long long i = gtid();
+  if (i < n) dx[i] = dy[i] * silu_grad_f(x[i]);
+}
+
 __global__ void blend_scales_kernel(const float* mix, float* out) {
   const float a = 1.f / (1.f + __expf(-mix[0]));
   out[0] = 1.f - a; out[1] = a; out[2] = 1.f - a; out[3] = 0.f;
@@ -444,5 +481,31 @@ extern "C" int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t 
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
   SVDX_CHECK_LAUNCH("adamw");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_unprep_conv_grad(const float* src, float* dst, int32_t O, int32_t I, int32_t taps, int32_t i_pad, void* stream) {
+  if (!src || !dst || O <= 0 || I <= 0 || taps <= 0 || i_pad < I) return svdx_fail(SVDX_E_BADARG, "unprep_conv_grad: bad arguments");
+  unprep_conv_grad_kernel<<<nblocks((long long)O * I * taps), 256, 0, ST(stream)>>>(src, dst, O, I, taps, i_pad);
+  SVDX_CHECK_LAUNCH("unprep_conv_grad");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_dot_diff(const void* dy, const void* a, const void* b, int64_t n, float* out, void* stream) {
+  if (!dy || !a || !b || !out || n <= 0 || n % 8) return svdx_fail(SVDX_E_BADARG, "dot_diff: bad arguments");
+  long long nvec = n / 8;
+  unsigned grid = nblocks(nvec);
+  const unsigned cap = 4u * (unsigned)svdx_num_sms();
+  if (grid > cap) grid = cap;
+  dot_diff_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(a),
+                                              reinterpret_cast<const uint4*>(b), nvec, out);
+  SVDX_CHECK_LAUNCH("dot_diff");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, void* stream) {
+  if (!x || !dy || !dx || n <= 0) return svdx_fail(SVDX_E_BADARG, "silu_bwd_f32: bad arguments");
+  silu_bwd_f32_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(x, dy, dx, n);
+  SVDX_CHECK_LAUNCH("silu_bwd_f32");
   return SVDX_OK;
 }

@@ -32,7 +32,7 @@ constexpr int SMEM_BYTES = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256
 struct __align__(64) TapGemmKParams {
   CUtensorMap tma;
   CUtensorMap tmb;
-  int a_mode, a_mn, b_mn;
+  int a_mode, a_mn, b_mn, b_mode, kb_per_group;
   int rows_per_group, groups, tiles_per_group;
   int W, H, nimg;
   int num_taps;
@@ -120,9 +120,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
           const int kc = (kb - tap * p.kb_per_tap) * BLOCK_K;
           // ---- A
           if (p.a_mn) {
-            // memory [k rows][m cols]: two 64x64 boxes
-            tma_load_2d(&p.tma, full, dA, mt * BLOCK_M, kb * BLOCK_K);
-            tma_load_2d(&p.tma, full, dA + 8192, mt * BLOCK_M + 64, kb * BLOCK_K);
+            // memory [k rows][m cols]: two 64x64 boxes. b_mode 2 walks the k rows group by group.
+            int arow = kb * BLOCK_K;
+            if (p.b_mode == 2) {
+              const int g = kb / p.kb_per_group;
+              arow = g * p.rows_per_group + (kb - g * p.kb_per_group) * BLOCK_K;
+            }
+            tma_load_2d(&p.tma, full, dA, mt * BLOCK_M, arow);
+            tma_load_2d(&p.tma, full, dA + 8192, mt * BLOCK_M + 64, arow);
           } else if (p.a_mode == SVDX_A_ROWS) {
             const int g = mt / p.tiles_per_group;
             const int t = mt - g * p.tiles_per_group;
@@ -140,7 +145,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
             }
           }
           // ---- B
-          if (p.b_mn) {
+          if (p.b_mn && p.b_mode == 1) {
+            // B rows are the pixels of a channels-last image tensor read at a fixed 2-D shift (conv weight gradient):
+            // a k-block = 64 consecutive output pixels; out-of-image reads are zero-filled by TMA
+            const int dw = p.tap_d0[0], dh = p.tap_d1[0], dn = p.tap_d2[0];
+            const int pix0 = kb * BLOCK_K;
+            for (int j = 0; j < p.block_n / 64; ++j) {
+              if (p.W >= 64) {
+                const int row = pix0 / p.W;
+                const int n = row / p.H;
+                const int nn = (n < p.nimg) ? n + dn : (1 << 28);
+                tma_load_4d(&p.tmb, full, dB + j * 8192, n0 + 64 * j, pix0 - row * p.W + dw, row - n * p.H + dh, nn);
+              } else {
+                const int R = 64 / p.W;
+                for (int i = 0; i < R; ++i) {
+                  const int row = pix0 / p.W + i;
+                  const int n = row / p.H;
+                  const int nn = (n < p.nimg) ? n + dn : (1 << 28);
+                  tma_load_4d(&p.tmb, full, dB + j * 8192 + i * p.W * 128, n0 + 64 * j, dw, row - n * p.H + dh, nn);
+                }
+              }
+            }
+          } else if (p.b_mn && p.b_mode == 2) {
+            // B rows shifted by tap_d0[0] rows inside their group (temporal conv weight gradient)
+            const int g = kb / p.kb_per_group;
+            const int k0 = (kb - g * p.kb_per_group) * BLOCK_K;
+            for (int j = 0; j < p.block_n / 64; ++j)
+              tma_load_3d(&p.tmb, full, dB + j * 8192, n0 + 64 * j, k0 + p.tap_d0[0], g);
+          } else if (p.b_mn) {
             for (int j = 0; j < p.block_n / 64; ++j)
               tma_load_2d(&p.tmb, full, dB + j * 8192, n0 + 64 * j, kb * BLOCK_K);
           } else if (p.geglu) {
@@ -384,6 +416,7 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
   if ((d->lda % 8) || (d->ldb % 8)) return svdx_fail(SVDX_E_BADARG, "tapgemm: lda/ldb must be multiples of 8 elements (16 B)");
   if ((reinterpret_cast<uintptr_t>(d->a) & 15) || (reinterpret_cast<uintptr_t>(d->b) & 15)) return svdx_fail(SVDX_E_BADARG, "tapgemm: operands must be 16 B aligned");
   if ((d->a_major_mn || d->b_major_mn) && (d->a_mode != SVDX_A_ROWS || d->num_taps != 1)) return svdx_fail(SVDX_E_BADARG, "tapgemm: MN-major operands only in single-tap ROWS mode");
+  if (d->b_mode != 0 && !(d->a_major_mn && d->b_major_mn)) return svdx_fail(SVDX_E_BADARG, "tapgemm: b_mode needs MN-major A and B (weight-gradient form)");
 
   TapGemmKParams p;
   memset(&p, 0, sizeof(p));
@@ -397,9 +430,10 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
   p.n_tiles = (n_out + bn_out - 1) / bn_out;
 
   int rc;
+  p.b_mode = d->b_mode;
   if (d->a_major_mn) {
     // memory [K rows][M cols]
-    if (d->groups > 1) return svdx_fail(SVDX_E_BADARG, "tapgemm: MN-major A requires groups==1");
+    if (d->groups > 1 && d->b_mode != 2) return svdx_fail(SVDX_E_BADARG, "tapgemm: MN-major A requires groups==1");
     uint64_t dims[2] = {(uint64_t)d->M, (uint64_t)d->K};
     uint64_t strides[1] = {(uint64_t)d->lda * 2};
     uint32_t box[2] = {64, 64};
@@ -431,7 +465,22 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
   }
   if (rc) return rc;
 
-  if (d->b_major_mn) {
+  if (d->b_major_mn && d->b_mode == 1) {
+    if (d->W <= 0 || d->H <= 0 || d->nimg <= 0 || (d->W < 64 && 64 % d->W) || (d->W >= 64 && d->W % 64)) return svdx_fail(SVDX_E_BADARG, "tapgemm: b_mode 1 needs W | 64 or 64 | W");
+    uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->nimg};
+    uint64_t strides[3] = {(uint64_t)d->ldb * 2, (uint64_t)d->ldb * 2 * d->W, (uint64_t)d->ldb * 2 * d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)(d->W >= 64 ? 64 : d->W), 1, 1};
+    rc = svdx_make_tmap(&p.tmb, d->b, 4, dims, strides, box);
+    p.W = d->W; p.H = d->H; p.nimg = d->K / (d->W * d->H);   // K = output pixels = images * H * W
+    if ((long long)p.nimg * d->W * d->H != d->K) return svdx_fail(SVDX_E_BADARG, "tapgemm: b_mode 1 K must be images*H*W");
+  } else if (d->b_major_mn && d->b_mode == 2) {
+    if (d->rows_per_group <= 0 || d->groups <= 0 || (long long)d->rows_per_group * d->groups != d->K) return svdx_fail(SVDX_E_BADARG, "tapgemm: b_mode 2 rows_per_group*groups != K");
+    uint64_t dims[3] = {(uint64_t)d->N, (uint64_t)d->rows_per_group, (uint64_t)d->groups};
+    uint64_t strides[2] = {(uint64_t)d->ldb * 2, (uint64_t)d->ldb * 2 * (uint64_t)d->rows_per_group};
+    uint32_t box[3] = {64, 64, 1};
+    rc = svdx_make_tmap(&p.tmb, d->b, 3, dims, strides, box);
+    p.rows_per_group = d->rows_per_group; p.groups = d->groups;
+  } else if (d->b_major_mn) {
     uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->K};
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
     uint32_t box[2] = {64, 64};
@@ -446,6 +495,12 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
 
   p.kb_per_tap = (d->K + BLOCK_K - 1) / BLOCK_K;
   p.kb_total = p.kb_per_tap * d->num_taps;
+  p.kb_per_group = p.kb_per_tap;
+  if (d->b_mode == 2) {
+    p.kb_per_group = (d->rows_per_group + BLOCK_K - 1) / BLOCK_K;
+    p.kb_per_tap = p.kb_per_group * d->groups;
+    p.kb_total = p.kb_per_tap;
+  }
   p.kb_per_split = (p.kb_total + d->split_k - 1) / d->split_k;
   // drop empty splits
   p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;

@@ -174,12 +174,11 @@ class Engine:
 
     # ------------------------------------------------------------------ operand preparation
     def w_lin(self, p: torch.Tensor, transposed: bool) -> torch.Tensor:
-        w2 = p.detach()
-        O, I = w2.shape[0], w2[0].numel()
-        w2 = w2.reshape(O, I)
+        O, I = p.shape[0], p[0].numel()
+        src = lambda: p.detach().reshape(O, I)      # re-read at build time: p.data may have been re-homed
         if transposed:
-            return self.wc.get(("linT", id(p)), [p], (I, O), lambda buf: raw.prep_weight(w2, buf, 1, O, I))
-        return self.wc.get(("lin", id(p)), [p], (O, I), lambda buf: raw.prep_weight(w2, buf, 0, O, I))
+            return self.wc.get(("linT", id(p)), [p], (I, O), lambda buf: raw.prep_weight(src(), buf, 1, O, I))
+        return self.wc.get(("lin", id(p)), [p], (O, I), lambda buf: raw.prep_weight(src(), buf, 0, O, I))
 
     def w_lin_cat(self, ps: Sequence[torch.Tensor], transposed: bool) -> torch.Tensor:
         """concatenated projection weights [sum O_i, I] (fused q|k|v)."""
@@ -204,20 +203,20 @@ class Engine:
         return self.wc.get(key, list(ps), (sum(Os), I), build)
 
     def w_conv(self, p: torch.Tensor, transposed: bool, i_pad: Optional[int] = None) -> torch.Tensor:
-        w = p.detach()
-        O, I = w.shape[0], w.shape[1]
-        taps = w[0, 0].numel()
+        O, I = p.shape[0], p.shape[1]
+        taps = p[0, 0].numel()
         if transposed:
             Op = (O + 7) // 8 * 8
             if Op != O:  # conv_out (O = 4): zero-pad the output-channel axis so rows stay 16-byte aligned
                 def build(buf):
+                    w = p.detach()
                     wp = torch.zeros(Op, I, taps, device=w.device, dtype=w.dtype)
                     wp[:O] = w.reshape(O, I, taps)
                     raw.prep_weight(wp, buf, 3, Op, I, taps)
                 return self.wc.get(("convT", id(p)), [p], (I, taps * Op), build)
-            return self.wc.get(("convT", id(p)), [p], (I, taps * O), lambda buf: raw.prep_weight(w, buf, 3, O, I, taps))
+            return self.wc.get(("convT", id(p)), [p], (I, taps * O), lambda buf: raw.prep_weight(p.detach(), buf, 3, O, I, taps))
         ip = i_pad if i_pad is not None else I
-        return self.wc.get(("conv", id(p), ip), [p], (O, taps * ip), lambda buf: raw.prep_weight(w, buf, 2, O, I, taps, ip))
+        return self.wc.get(("conv", id(p), ip), [p], (O, taps * ip), lambda buf: raw.prep_weight(p.detach(), buf, 2, O, I, taps, ip))
 
     def vec_f32(self, p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         if p is None:
@@ -267,7 +266,7 @@ class Engine:
     def linear(self, x: Var, weight, bias=None, *, res1: Optional[Var] = None, res2: Optional[Var] = None,
                scales: Optional[torch.Tensor] = None, res1_unit: bool = False, geglu: bool = False,
                rowbias: Optional[Var] = None, rowbias_div: int = 1, out_f32: bool = False,
-               fused: Optional[Sequence] = None) -> Var:
+               fused: Optional[Sequence] = None, blend=None) -> Var:
         """y = epilogue(x @ W^T). `weight` is a parameter [N,K] (or conv 1x1 [N,K,1,1]); `fused` = list of
         parameters whose rows are concatenated (q|k|v). scales (device float[>=3]) = {acc, res1, res2};
         res1_unit: scales[1] is known to be exactly 1. rowbias: Var with fp32 data [ceil(M/div), N]."""
@@ -282,7 +281,8 @@ class Engine:
         raw.tapgemm(x.data, wf, out, M=M, N=N, K=K, bias=b32, res1=None if res1 is None else res1.data,
                     res2=None if res2 is None else res2.data, scales=scales, geglu=geglu, pre=pre,
                     rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div)
-        w_train = any(p.requires_grad for p in ws) or (bias is not None and bias.requires_grad)
+        w_train = any(p.requires_grad for p in ws) or (bias is not None and bias.requires_grad) \
+            or (blend is not None and blend[0].requires_grad)
         need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, res2, rowbias))
         y = Var(out, need)
         if need and self.recording:
@@ -293,6 +293,7 @@ class Engine:
                 if dy.dtype != bf16:
                     dy = raw.cast_f32_bf16(dy.contiguous(), torch.empty(dy.shape, device=dy.device, dtype=bf16))
                 s_acc = None if scales is None else scales[0:1]
+                self._mix_grad(blend, dy, res1, out)
                 self._res_grad(res1, dy, None if (scales is None or res1_unit) else scales[1:2])
                 self._res_grad(res2, dy, None if scales is None else scales[2:3])
                 if geglu:
@@ -353,6 +354,33 @@ class Engine:
                         block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
 
     # ------------------------------------------------------------------ convolutions
+    def _conv_wgrad(self, dy: torch.Tensor, x: torch.Tensor, w: torch.nn.Parameter, taps, *, b_mode: int, Opad: int, ip: int,
+                    K: int, conv_whn=None, rows_per_group=None, groups=1, scales3=None):
+        """dW[o][tap][i] = sum_p dy[p, o] * x[p + tap, i]: one MN-major split-K launch per tap (fp32 atomics into a
+        [O][taps][ip] workspace), then the adjoint of the weight re-layout accumulates into the OIHW gradient."""
+        O, I = w.shape[0], w.shape[1]
+        nt = len(taps)
+        ws = torch.zeros(Opad, nt * ip, device=dy.device, dtype=F32)
+        bn = raw.pick_block_n(ip, True)
+        tiles = ((Opad + 127) // 128) * ((ip + bn - 1) // bn)
+        kb = (K + 63) // 64
+        split = max(1, min(kb, (2 * raw.load().svdx_num_sms()) // max(tiles, 1), 64))
+        for t, tap in enumerate(taps):
+            raw.tapgemm(dy, x, ws[:, t * ip:(t + 1) * ip], M=Opad, N=ip, K=K, a_mn=True, b_mn=True, b_mode=b_mode, taps=(tap,),
+                        conv_whn=conv_whn, rows_per_group=rows_per_group if rows_per_group is not None else K, groups=groups,
+                        split_k=split, out_dtype=OUT_F32_ATOMIC, block_n=bn, lda=dy.stride(0), ldb=x.stride(0), ldo=nt * ip,
+                        scales=scales3)
+        raw.unprep_conv_grad(ws, self.pgrad(w).view(O, I, nt), O, I, nt, ip)
+
+    def _mix_grad(self, blend, dy: torch.Tensor, res1: Var, out: torch.Tensor):
+        """AlphaBlender.mix_factor gradient: d mix = alpha * sum(dy * (x_spatial - out))  (see DESIGN.md)."""
+        if blend is None or not blend[0].requires_grad:
+            return
+        mix, alpha = blend
+        acc = torch.zeros(1, device=dy.device, dtype=F32)
+        raw.dot_diff(dy.reshape(-1), res1.data.reshape(-1), out.reshape(-1), acc)
+        self.pgrad(mix).add_((acc * alpha).to(F32).view(mix.shape))
+
     def conv2d_3x3(self, x: Var, g: Geom, conv, *, rowbias: Optional[Var] = None, rowbias_div=1, res1: Optional[Var] = None,
                    scales=None, res1_unit: bool = False, i_pad=None, n_pad=None, planes: bool = False) -> Var:
         """3x3 conv, padding 1, on channels-last [N*H*W, Cin]. planes=True: x holds the 4 stride-2 parity planes
@@ -381,27 +409,25 @@ class Engine:
                     rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
                     res1=None if res1 is None else res1.data, scales=scales,
                     block_n=raw.pick_block_n(O) if O >= 32 else 32)
-        if self.recording and rowbias is not None and rowbias.needs_grad:
-            raise NotImplementedError("svd_xtend_b200: gradient of the time-embedding projection is not implemented yet")
         w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad)
-        need = x.needs_grad or w_train or (res1 is not None and res1.needs_grad)
+        need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, rowbias))
         y = Var(out, need)
         if need and self.recording:
-            if w.requires_grad:
-                raise NotImplementedError("svd_xtend_b200: weight gradient of spatial convolutions is not implemented yet "
-                                          "(train_svd.py:761-766 trains only temporal_transformer_block parameters)")
-
             def bwd():
                 dy = y.take_grad()
                 if dy is None:
                     return
+                s_acc = None if scales is None else scales[0:1]
                 self._res_grad(res1, dy, None if (scales is None or res1_unit) else scales[1:2])
                 if conv.bias is not None and conv.bias.requires_grad:
-                    self._bias_grad(conv.bias, dy[:, :O], None if scales is None else scales[0:1])
+                    self._bias_grad(conv.bias, dy[:, :O], s_acc)
+                self._rowbias_grad(rowbias, dy, rowbias_div, s_acc)
+                sc = self._acc_only(s_acc)
+                if w.requires_grad:
+                    self._conv_wgrad(dy, x.data, w, taps, b_mode=1, Opad=dy.shape[1], ip=ip, K=M, conv_whn=whn, scales3=sc)
                 if x.needs_grad:
                     wt = self.w_conv(w, True)  # [I, 9*Opad]
                     Op = wt.shape[1] // 9
-                    sc = self._acc_only(None if scales is None else scales[0:1])
                     if not planes:
                         dx = self.empty(M, I, x.data)
                         raw.tapgemm(dy, wt, dx, M=M, N=I, K=Op, mode=A_CONV2D, taps=_neg_taps(CONV3x3_TAPS),
@@ -422,8 +448,9 @@ class Engine:
         return y
 
     def conv_temporal(self, x: Var, g: Geom, conv, *, rowbias: Optional[Var] = None, rowbias_div=1, res1: Optional[Var] = None,
-                      scales=None, res1_unit: bool = False) -> Var:
-        """Conv3d kernel (3,1,1), padding (1,0,0): frames are HW rows apart in the token matrix."""
+                      scales=None, res1_unit: bool = False, blend=None) -> Var:
+        """Conv3d kernel (3,1,1), padding (1,0,0): frames are HW rows apart in the token matrix.
+        blend = (mix_factor parameter, device alpha[1]) when this conv carries the AlphaBlender epilogue."""
         w = conv.weight
         O, I = w.shape[0], w.shape[1]
         wf = self.w_conv(w, False)
@@ -434,25 +461,55 @@ class Engine:
         raw.tapgemm(x.data, wf, out, M=M, N=O, K=I, taps=taps, rows_per_group=g.T * HW, groups=g.B, bias=self.vec_f32(conv.bias),
                     rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
                     res1=None if res1 is None else res1.data, scales=scales)
-        if self.recording and ((rowbias is not None and rowbias.needs_grad) or (conv.bias is not None and conv.bias.requires_grad)):
-            raise NotImplementedError("svd_xtend_b200: bias / time-embedding gradients of temporal convolutions are not implemented yet")
-        need = x.needs_grad or w.requires_grad or (res1 is not None and res1.needs_grad)
+        w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad) or (blend is not None and blend[0].requires_grad)
+        need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, rowbias))
         y = Var(out, need)
         if need and self.recording:
-            if w.requires_grad:
-                raise NotImplementedError("svd_xtend_b200: weight gradient of temporal convolutions is not implemented yet")
-
             def bwd():
                 dy = y.take_grad()
                 if dy is None:
                     return
+                s_acc = None if scales is None else scales[0:1]
+                self._mix_grad(blend, dy, res1, out)
                 self._res_grad(res1, dy, None if (scales is None or res1_unit) else scales[1:2])
+                if conv.bias is not None and conv.bias.requires_grad:
+                    self._bias_grad(conv.bias, dy, s_acc)
+                self._rowbias_grad(rowbias, dy, rowbias_div, s_acc)
+                sc = self._acc_only(s_acc)
+                if w.requires_grad:
+                    self._conv_wgrad(dy, x.data, w, taps, b_mode=2, Opad=O, ip=I, K=M, rows_per_group=g.T * HW, groups=g.B, scales3=sc)
                 if x.needs_grad:
                     wt = self.w_conv(w, True)
                     dx = self.empty(M, I, x.data)
-                    raw.tapgemm(dy, wt, dx, M=M, N=I, K=O, taps=_neg_taps(taps), rows_per_group=g.T * HW, groups=g.B,
-                                scales=self._acc_only(None if scales is None else scales[0:1]))
+                    raw.tapgemm(dy, wt, dx, M=M, N=I, K=O, taps=_neg_taps(taps), rows_per_group=g.T * HW, groups=g.B, scales=sc)
                     self.add_grad(x, dx)
+            self.record(bwd)
+        return y
+
+    # ------------------------------------------------------------------ small fp32 ops of the embedding MLPs
+    def silu_cast(self, x: Var) -> Var:
+        """bf16(silu(x)) for an fp32 Var (TimestepEmbedding.act / nonlinearity(temb) feeding a GEMM)."""
+        h = raw.silu_f32(x.data, torch.empty_like(x.data))
+        y = Var(raw.cast_f32_bf16(h, torch.empty(h.shape, device=h.device, dtype=bf16)), x.needs_grad)
+        if x.needs_grad and self.recording:
+            def bwd():
+                dy = y.take_grad()
+                if dy is None:
+                    return
+                d32 = raw.cast_bf16_f32(dy.contiguous(), torch.empty(dy.shape, device=dy.device, dtype=F32)) if dy.dtype == bf16 else dy
+                self.add_grad(x, raw.silu_bwd_f32(x.data, d32.contiguous(), torch.empty_like(x.data)))
+            self.record(bwd)
+        return y
+
+    def add_f32(self, a: Var, b: Var) -> Var:
+        y = Var(a.data + b.data, a.needs_grad or b.needs_grad)
+        if y.needs_grad and self.recording:
+            def bwd():
+                dy = y.take_grad()
+                if dy is None:
+                    return
+                self.add_grad(a, dy, owned=False)
+                self.add_grad(b, dy, owned=False)
             self.record(bwd)
         return y
 
@@ -480,7 +537,8 @@ class Engine:
             self.record(bwd)
         return y
 
-    def layernorm(self, x: Var, ln, *, addvec: Optional[torch.Tensor] = None, add_div: int = 1) -> Tuple[Var, Var]:
+    def layernorm(self, x: Var, ln, *, addvec: Optional[torch.Tensor] = None, add_div: int = 1,
+                  addvec_var: Optional[Var] = None) -> Tuple[Var, Var]:
         """returns (xs, LN(xs)) with xs = x + addvec[row / add_div] (xs is x itself when addvec is None).
         Backward folds the gradient already accumulated on xs (its residual uses) into dx."""
         C = x.cols
@@ -513,6 +571,7 @@ class Engine:
                     if addvec is None:
                         x.grad, x.owned = dx, True   # dres (the old x.grad) is folded in
                     else:
+                        self._rowbias_grad(addvec_var, dx, add_div, None)   # d(frame embedding) = per-frame sums of d(x + emb)
                         self.add_grad(x, dx)
                 elif p_train:
                     dx = self.empty(x.rows, C, x.data)  # still needed to produce dgamma/dbeta

@@ -66,6 +66,7 @@ def tapgemm(
     ldo: Optional[int] = None,
     a_mn: bool = False,
     b_mn: bool = False,
+    b_mode: int = 0,
     block_n: Optional[int] = None,
     split_k: int = 1,
     out_dtype: Optional[int] = None,
@@ -95,6 +96,7 @@ def tapgemm(
     d.b = b.data_ptr()
     d.ldb = ldb if ldb is not None else _rowmajor(b, "b")
     d.b_major_mn = int(b_mn)
+    d.b_mode = b_mode
     d.M, d.N, d.K = M, N, K
     n_out = N // 2 if geglu else N
     if block_n is None:
@@ -314,3 +316,18 @@ def blend_scales(mix_factor, out3):  # out3: float[8]
 def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     check(load().svdx_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, weight_decay,
                             step, grad_scale, _stream()), "adamw")
+
+
+def unprep_conv_grad(src, dst, O, I, taps, i_pad):
+    check(load().svdx_unprep_conv_grad(src.data_ptr(), dst.data_ptr(), O, I, taps, i_pad, _stream()), "svdx_unprep_conv_grad")
+    return dst
+
+
+def dot_diff(dy, a, b, out):
+    check(load().svdx_dot_diff(dy.data_ptr(), a.data_ptr(), b.data_ptr(), dy.numel(), out.data_ptr(), _stream()), "svdx_dot_diff")
+    return out
+
+
+def silu_bwd_f32(x, dy, dx):
+    check(load().svdx_silu_bwd_f32(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "svdx_silu_bwd_f32")
+    return dx

@@ -573,25 +573,28 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         cfg = self.config
 
         # ---- 1. time embeddings (:403-416): tiny; sinusoid in torch, MLPs through the GEMM kernel
-        emb = self._mlp(E, _sinusoid(timesteps.to(dev), cfg.block_out_channels[0]), self.time_embedding)
+        emb1 = self._mlp(E, _sinusoid(timesteps.to(dev), cfg.block_out_channels[0]), self.time_embedding)
         t_ids = _sinusoid(added_time_ids.flatten().to(dev), cfg.addition_time_embed_dim).reshape(B, -1)
-        emb = emb + self._mlp(E, t_ids, self.add_embedding)                      # [B, 1280] fp32
-        semb = Var(raw.cast_f32_bf16(raw.silu_f32(emb, torch.empty_like(emb)), torch.empty(emb.shape, device=dev, dtype=bf16)))
-        # every resnet's time_emb_proj in ONE GEMM (44 projections of the same silu(emb))
+        emb = E.add_f32(emb1, self._mlp(E, t_ids, self.add_embedding))            # [B, 1280] fp32
+        semb = E.silu_cast(emb)                                                   # nonlinearity(temb), shared by all resnets
         projs = []
         for rb in self._resblocks:
             projs += [rb.spatial_res_block.time_emb_proj, rb.temporal_res_block.time_emb_proj]
-        if E.recording and any(p.weight.requires_grad or p.bias.requires_grad for p in projs):
-            raise NotImplementedError("svd_xtend_b200: gradients of time_emb_proj are not implemented yet")
-        w_all = E.w_lin_cat([p.weight for p in projs], False)
-        b_all = E.wc.get(("tembbias",) + tuple(id(p.bias) for p in projs), [p.bias for p in projs], (w_all.shape[0],),
-                         lambda buf: buf.copy_(torch.cat([p.bias.detach().float() for p in projs])), dtype=F32)
-        temb_all = torch.empty(B, w_all.shape[0], device=dev, dtype=F32)
-        raw.tapgemm(semb.data, w_all, temb_all, M=B, N=w_all.shape[0], K=w_all.shape[1], bias=b_all)
-        temb_slices, o0 = {}, 0
-        for p in projs:
-            temb_slices[p] = Var(temb_all[:, o0:o0 + p.out_features])
-            o0 += p.out_features
+        temb_slices = {}
+        if semb.needs_grad or any(p.weight.requires_grad or p.bias.requires_grad for p in projs):
+            for p in projs:      # differentiable path: one small GEMM per projection
+                temb_slices[p] = E.linear(semb, p.weight, p.bias, out_f32=True)
+        else:
+            # frozen (the scripted configuration): every resnet's time_emb_proj in ONE GEMM
+            w_all = E.w_lin_cat([p.weight for p in projs], False)
+            b_all = E.wc.get(("tembbias",) + tuple(id(p.bias) for p in projs), [p.bias for p in projs], (w_all.shape[0],),
+                             lambda buf: buf.copy_(torch.cat([p.bias.detach().float() for p in projs])), dtype=F32)
+            temb_all = torch.empty(B, w_all.shape[0], device=dev, dtype=F32)
+            raw.tapgemm(semb.data, w_all, temb_all, M=B, N=w_all.shape[0], K=w_all.shape[1], bias=b_all)
+            o0 = 0
+            for p in projs:
+                temb_slices[p] = Var(temb_all[:, o0:o0 + p.out_features])
+                o0 += p.out_features
         self._temb = temb_slices
 
         # image embedding per clip (encoder_hidden_states is [B,1,1024]; :425 repeats it per frame)
@@ -645,22 +648,17 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         raw.nhwc_to_nchw(y.data, out, N, Cout, H, W)
         return out, y, g
 
-    def _mlp(self, E: Engine, x32: torch.Tensor, mlp: TimestepEmbedding) -> torch.Tensor:
+    def _mlp(self, E: Engine, x32: torch.Tensor, mlp: TimestepEmbedding) -> Var:
         """TimestepEmbedding on a few rows: Linear -> SiLU -> Linear, fp32 in/out, bf16 operands."""
-        for lin in (mlp.linear_1, mlp.linear_2):
-            if E.recording and (lin.weight.requires_grad or lin.bias.requires_grad):
-                raise NotImplementedError("svd_xtend_b200: gradients of the time-embedding MLPs are not implemented yet")
         dev = x32.device
         xb = raw.cast_f32_bf16(x32.contiguous().float(), torch.empty(x32.shape, device=dev, dtype=bf16))
-        h = E.linear(Var(xb), mlp.linear_1.weight, mlp.linear_1.bias, out_f32=True).data
-        hb = raw.cast_f32_bf16(raw.silu_f32(h, torch.empty_like(h)), torch.empty(h.shape, device=dev, dtype=bf16))
-        return E.linear(Var(hb), mlp.linear_2.weight, mlp.linear_2.bias, out_f32=True).data
+        h = E.linear(Var(xb), mlp.linear_1.weight, mlp.linear_1.bias, out_f32=True)
+        return E.linear(E.silu_cast(h), mlp.linear_2.weight, mlp.linear_2.bias, out_f32=True)
 
     def _blend(self, E: Engine, mixer: AlphaBlender) -> torch.Tensor:
-        if E.recording and mixer.mix_factor.requires_grad:
-            raise NotImplementedError("svd_xtend_b200: gradient of AlphaBlender.mix_factor is not implemented yet")
-        mf = E.vec_f32(mixer.mix_factor)
-        return E.wc.get(("blend", id(mixer.mix_factor)), [mixer.mix_factor], (8,), lambda buf: raw.blend_scales(mf, buf), dtype=F32)
+        """device float[8] epilogue scale triples of an AlphaBlender (image_only_indicator is all zeros, :430)."""
+        mix = mixer.mix_factor
+        return E.wc.get(("blend", id(mix)), [mix], (8,), lambda buf: raw.blend_scales(E.vec_f32(mix), buf), dtype=F32)
 
     def _resblock(self, E: Engine, blk: SpatioTemporalResBlock, x: Var, g: Geom) -> Var:
         """SpatioTemporalResBlock [D: resnet.py]: spatial ResnetBlock2D -> TemporalResnetBlock -> AlphaBlender."""
@@ -677,7 +675,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         t = E.groupnorm(t, tp.norm2, outer=g.B, rows=per_clip, silu=True)
         s8 = self._blend(E, blk.time_mixer)
         # alpha*hs + (1-alpha)*(hs + conv) = hs + (1-alpha)*conv
-        return E.conv_temporal(t, g, tp.conv2, res1=hs, scales=s8[4:7], res1_unit=True)
+        return E.conv_temporal(t, g, tp.conv2, res1=hs, scales=s8[4:7], res1_unit=True, blend=(blk.time_mixer.mix_factor, s8[1:2]))
 
     def _cross_vec(self, E: Engine, attn2: Attention, enc: Var) -> Var:
         """Image cross-attention has ONE key/value token (train_svd.py:1000-1001), so softmax == 1 and the
@@ -686,16 +684,20 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         v = E.linear(enc, attn2.to_v.weight)
         return E.linear(v, attn2.to_out[0].weight, attn2.to_out[0].bias, out_f32=True)
 
-    def _frame_emb(self, E: Engine, tr: TransformerSpatioTemporalModel, g: Geom) -> torch.Tensor:
-        """time_pos_embed(Timesteps(arange(T))) [D: transformer_temporal.py] -> fp32 [B*T, C]; input independent."""
+    def _frame_emb(self, E: Engine, tr: TransformerSpatioTemporalModel, g: Geom):
+        """time_pos_embed(Timesteps(arange(T))) [D: transformer_temporal.py] -> fp32 [B*T, C]; input independent, so it
+        is cached while its MLP is frozen. Returns (tensor, Var-or-None for the gradient path)."""
         mlp = tr.time_pos_embed
         params = [mlp.linear_1.weight, mlp.linear_1.bias, mlp.linear_2.weight, mlp.linear_2.bias]
         C = tr.in_channels
 
-        def build(buf):
-            t = torch.arange(g.T, device=buf.device).repeat(g.B)
-            buf.copy_(self._mlp(E, _sinusoid(t, C), mlp))
-        return E.wc.get(("frame_emb", id(tr), g.B, g.T), params, (g.B * g.T, C), build, dtype=F32)
+        def sinus(dev):
+            return _sinusoid(torch.arange(g.T, device=dev).repeat(g.B), C)
+        if E.recording and any(p.requires_grad for p in params):
+            v = self._mlp(E, sinus(params[0].device), mlp)
+            return v.data, v
+        return E.wc.get(("frame_emb", id(tr), g.B, g.T), params, (g.B * g.T, C),
+                        lambda buf: buf.copy_(self._mlp(E, sinus(buf.device), mlp).data), dtype=F32), None
 
     def _transformer(self, E: Engine, tr: TransformerSpatioTemporalModel, x_in: Var, g: Geom, enc: Var) -> Var:
         """TransformerSpatioTemporalModel [D]: GN -> proj_in -> spatial block -> temporal block -> blend -> proj_out -> +x."""
@@ -719,7 +721,8 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         ff = E.linear(n3, sb.ff.net[0].proj.weight, sb.ff.net[0].proj.bias, geglu=True)
         x2 = E.linear(ff, sb.ff.net[2].weight, sb.ff.net[2].bias, res1=x1)
         # TemporalBasicTransformerBlock on the same token layout (frames are HW rows apart)
-        xm, ni = E.layernorm(x2, tb.norm_in, addvec=self._frame_emb(E, tr, g), add_div=g.HW)
+        femb, femb_var = self._frame_emb(E, tr, g)
+        xm, ni = E.layernorm(x2, tb.norm_in, addvec=femb, add_div=g.HW, addvec_var=femb_var)
         ff = E.linear(ni, tb.ff_in.net[0].proj.weight, tb.ff_in.net[0].proj.bias, geglu=True)
         y1 = E.linear(ff, tb.ff_in.net[2].weight, tb.ff_in.net[2].bias, res1=xm)
         _, n1 = E.layernorm(y1, tb.norm1)
@@ -731,7 +734,8 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         ff = E.linear(n3, tb.ff.net[0].proj.weight, tb.ff.net[0].proj.bias, geglu=True)
         s8 = self._blend(E, tr.time_mixer)
         # alpha*x_spatial + (1-alpha)*(ff + y2)
-        xb = E.linear(ff, tb.ff.net[2].weight, tb.ff.net[2].bias, res1=x2, res2=y2, scales=s8[0:3])
+        xb = E.linear(ff, tb.ff.net[2].weight, tb.ff.net[2].bias, res1=x2, res2=y2, scales=s8[0:3],
+                      blend=(tr.time_mixer.mix_factor, s8[1:2]))
         return E.linear(xb, tr.proj_out.weight, tr.proj_out.bias, res1=x_in)
 
 

@@ -170,3 +170,84 @@ def test_wgrad_mn_major(raw, Mtok, Nout, Kin, split):
     torch.cuda.synchronize()
     ref = dy.float().t() @ x.float()
     _close(dw, ref, rtol=2e-3, atol=2e-3 * ref.abs().max().item(), what="wgrad")
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,split", [(3, 40, 64, 64, 128, 4), (14, 5, 8, 128, 192, 2), (2, 10, 16, 320, 64, 1), (1, 4, 128, 64, 64, 1)])
+def test_conv3x3_weight_gradient(raw, N, H, W, Cin, Cout, split):
+    x = _rand(N, H, W, Cin, seed=30).to(bf16)
+    dy = _rand(N, H, W, Cout, scale=0.1, seed=31).to(bf16)
+    M = N * H * W
+    ws = torch.zeros(Cout, 9 * Cin, device=_dev(), dtype=torch.float32)
+    for t, tap in enumerate(raw.CONV3x3_TAPS):
+        raw.tapgemm(dy.view(M, Cout), x.view(M, Cin), ws[:, t * Cin:(t + 1) * Cin], M=Cout, N=Cin, K=M, a_mn=True, b_mn=True, b_mode=1,
+                    taps=(tap,), conv_whn=(W, H, N), split_k=split, out_dtype=raw.OUT_F32_ATOMIC, ldo=9 * Cin)
+    gw = torch.zeros(Cout, Cin, 3, 3, device=_dev())
+    raw.unprep_conv_grad(ws, gw, Cout, Cin, 9, Cin)
+    torch.cuda.synchronize()
+    w = torch.zeros(Cout, Cin, 3, 3, device=_dev(), requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), w, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    _close(gw, w.grad, rtol=3e-3, atol=3e-3 * w.grad.abs().max().item(), what="conv wgrad")
+
+
+def test_conv_stride2_planes_weight_gradient(raw):
+    N, H, W, C, Cout = 3, 20, 32, 128, 64
+    x = _rand(N, H, W, C, seed=32).to(bf16)
+    Ho, Wo = H // 2, W // 2
+    dy = _rand(N, Ho, Wo, Cout, scale=0.1, seed=33).to(bf16)
+    planes = torch.empty(4 * N, Ho, Wo, C, device=_dev(), dtype=bf16)
+    for p in range(2):
+        for q in range(2):
+            planes[(p * 2 + q) * N:(p * 2 + q + 1) * N] = x[:, p::2, q::2]
+    M = N * Ho * Wo
+    ws = torch.zeros(Cout, 9 * C, device=_dev(), dtype=torch.float32)
+    t = 0
+    for kh in range(3):
+        for kw in range(3):
+            ph, dh = ((1, -1), (0, 0), (1, 0))[kh]
+            pw, dw = ((1, -1), (0, 0), (1, 0))[kw]
+            raw.tapgemm(dy.view(M, Cout), planes.view(-1, C), ws[:, t * C:(t + 1) * C], M=Cout, N=C, K=M, a_mn=True, b_mn=True, b_mode=1,
+                        taps=((dw, dh, (ph * 2 + pw) * N),), conv_whn=(Wo, Ho, 4 * N), split_k=2, out_dtype=raw.OUT_F32_ATOMIC, ldo=9 * C)
+            t += 1
+    gw = torch.zeros(Cout, C, 3, 3, device=_dev())
+    raw.unprep_conv_grad(ws, gw, Cout, C, 9, C)
+    torch.cuda.synchronize()
+    w = torch.zeros(Cout, C, 3, 3, device=_dev(), requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), w, stride=2, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    _close(gw, w.grad, rtol=3e-3, atol=3e-3 * w.grad.abs().max().item(), what="stride-2 conv wgrad")
+
+
+@pytest.mark.parametrize("B,T,HW,C,split", [(1, 14, 160, 128, 4), (2, 5, 40, 64, 1), (2, 14, 40, 192, 2)])
+def test_temporal_conv_weight_gradient(raw, B, T, HW, C, split):
+    Cout = C
+    x = _rand(B, T, HW, C, seed=34).to(bf16)
+    dy = _rand(B, T, HW, Cout, scale=0.1, seed=35).to(bf16)
+    M = B * T * HW
+    ws = torch.zeros(Cout, 3 * C, device=_dev(), dtype=torch.float32)
+    for t, sh in enumerate((-HW, 0, HW)):
+        raw.tapgemm(dy.view(M, Cout), x.view(M, C), ws[:, t * C:(t + 1) * C], M=Cout, N=C, K=M, a_mn=True, b_mn=True, b_mode=2,
+                    taps=((sh, 0, 0),), rows_per_group=T * HW, groups=B, split_k=split, out_dtype=raw.OUT_F32_ATOMIC, ldo=3 * C)
+    gw = torch.zeros(Cout, C, 3, device=_dev())
+    raw.unprep_conv_grad(ws, gw, Cout, C, 3, C)
+    torch.cuda.synchronize()
+    w = torch.zeros(Cout, C, 3, 1, 1, device=_dev(), requires_grad=True)
+    x5 = x.float().permute(0, 3, 1, 2).reshape(B, C, T, HW, 1)
+    d5 = dy.float().permute(0, 3, 1, 2).reshape(B, Cout, T, HW, 1)
+    F.conv3d(x5, w, padding=(1, 0, 0)).backward(d5)
+    _close(gw, w.grad.view(Cout, C, 3), rtol=3e-3, atol=3e-3 * w.grad.abs().max().item(), what="temporal conv wgrad")
+
+
+def test_dot_diff_and_silu_bwd(raw):
+    n = 8 * 12345
+    dy, a, b = (_rand(n, seed=s).to(bf16) for s in (36, 37, 38))
+    out = torch.zeros(1, device=_dev())
+    raw.dot_diff(dy, a, b, out)
+    x = _rand(1000, seed=39)
+    g = _rand(1000, seed=40)
+    dx = torch.empty_like(x)
+    raw.silu_bwd_f32(x, g, dx)
+    torch.cuda.synchronize()
+    ref = (dy.float() * (a.float() - b.float())).sum()
+    assert abs(out.item() - ref.item()) < 2e-3 * dy.float().abs().sum().item() ** 0.5 + 1e-2 * abs(ref.item())
+    xr = x.clone().requires_grad_(True)
+    F.silu(xr).backward(g)
+    assert torch.allclose(dx, xr.grad, atol=1e-5, rtol=1e-4)

@@ -129,3 +129,37 @@ def test_svd_config_forward_matches_oracle():
     print("svd forward rel-l2", e, "torch autocast bf16", ea)
     assert torch.isfinite(out).all()
     assert e <= max(2 * ea, 2e-2), f"rel-l2 {e:.4g} vs autocast {ea:.4g}"
+
+
+def test_tiny_full_finetune_all_gradients():
+    """README.md:41 'all parameters trainable': every parameter gradient (conv wgrad, norms, embeddings, mix factors)."""
+    from oracle.svd_unet_oracle import TINY_CONFIG, synthetic_batch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, ours = _build(TINY_CONFIG, seed=5)
+    for m in (oracle, ours):
+        m.requires_grad_(True)
+        m.train()
+    batch = synthetic_batch(2, 4, 16, 16, seed=4321, device=DEV, cross_dim=TINY_CONFIG["cross_attention_dim"])
+    pred_ref, loss_ref = _loss(oracle, batch)
+    loss_ref.backward()
+    g_ref = {n: p.grad.clone() for n, p in oracle.named_parameters()}
+    oracle.zero_grad(set_to_none=True)
+    _, loss_ac = _loss(oracle, batch, autocast=True)
+    loss_ac.backward()
+    g_ac = {n: p.grad.clone() for n, p in oracle.named_parameters()}
+    pred, loss = _loss(ours, batch)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _rel(pred, pred_ref) < 2e-2
+    bad = []
+    for n, p in ours.named_parameters():
+        assert p.grad is not None, n
+        ref = g_ref[n]
+        if ref.abs().max() == 0:
+            assert p.grad.abs().max() == 0, n
+            continue
+        e, ea = _rel(p.grad, ref), _rel(g_ac[n], ref)
+        if e > max(3 * ea, 6e-2):
+            bad.append((n, round(e, 4), round(ea, 4)))
+    assert not bad, bad[:10]
