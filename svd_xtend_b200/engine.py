@@ -127,6 +127,7 @@ class Engine:
         self.launches = 0
         self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}   # optional flat gradient arena (train.ParamArena)
         self.keep: List[torch.Tensor] = []   # small device scalars referenced by in-flight launches
+        self._consts: Dict[Tuple, torch.Tensor] = {}
         self.grad_ready_hook: Optional[Callable[[List[torch.nn.Parameter]], None]] = None
 
     # ------------------------------------------------------------------ tape
@@ -266,7 +267,7 @@ class Engine:
     def linear(self, x: Var, weight, bias=None, *, res1: Optional[Var] = None, res2: Optional[Var] = None,
                scales: Optional[torch.Tensor] = None, res1_unit: bool = False, geglu: bool = False,
                rowbias: Optional[Var] = None, rowbias_div: int = 1, out_f32: bool = False,
-               fused: Optional[Sequence] = None, blend=None) -> Var:
+               fused: Optional[Sequence] = None, blend=None, lora: Optional[Sequence] = None) -> Var:
         """y = epilogue(x @ W^T). `weight` is a parameter [N,K] (or conv 1x1 [N,K,1,1]); `fused` = list of
         parameters whose rows are concatenated (q|k|v). scales (device float[>=3]) = {acc, res1, res2};
         res1_unit: scales[1] is known to be exactly 1. rowbias: Var with fp32 data [ceil(M/div), N]."""
@@ -281,8 +282,17 @@ class Engine:
         raw.tapgemm(x.data, wf, out, M=M, N=N, K=K, bias=b32, res1=None if res1 is None else res1.data,
                     res2=None if res2 is None else res2.data, scales=scales, geglu=geglu, pre=pre,
                     rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div)
+        lora = [l for l in (lora or []) if l is not None]
+        lora_t = []
+        for (off, n, A, Bm, sc) in lora:
+            # LoRA side path (train_svd_lora.py:659-671): out[:, off:off+n] += scale * (x A^T) B^T, accumulated in place
+            t = self.empty(M, A.shape[0], x.data)
+            raw.tapgemm(x.data, self.w_lin(A, False), t, M=M, N=A.shape[0], K=K)
+            ov = out[:, off:off + n]
+            raw.tapgemm(t, self.w_lin(Bm, False), ov, M=M, N=n, K=A.shape[0], res1=ov, scales=self._lora_scales(sc, out.device))
+            lora_t.append(t)
         w_train = any(p.requires_grad for p in ws) or (bias is not None and bias.requires_grad) \
-            or (blend is not None and blend[0].requires_grad)
+            or (blend is not None and blend[0].requires_grad) or any(l[2].requires_grad or l[3].requires_grad for l in lora)
         need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, res2, rowbias))
         y = Var(out, need)
         if need and self.recording:
@@ -311,8 +321,30 @@ class Engine:
                     self._wgrad(dyl, x.data, ws, N, K, M, sc3)
                 if bias is not None and bias.requires_grad:
                     self._bias_grad(bias, dyl, s_acc)
+                for (off, n, A, Bm, sc), t in zip(lora, lora_t):
+                    r = A.shape[0]
+                    dys = dyl[:, off:off + n]
+                    s3 = self._lora_scales(sc, dyl.device, acc_only=True)
+                    dt = self.empty(M, r, x.data)
+                    raw.tapgemm(dys, self.w_lin(Bm, True), dt, M=M, N=r, K=n, scales=s3)      # dt = scale * dy B
+                    if Bm.requires_grad:
+                        self._wgrad(dys, t, [Bm], n, r, M, s3)                                  # dB += scale * dy^T t
+                    if A.requires_grad:
+                        self._wgrad(dt, x.data, [A], r, K, M, None)                             # dA += dt^T x
+                    if x.needs_grad:
+                        dxl = self.empty(M, K, x.data)
+                        raw.tapgemm(dt, self.w_lin(A, True), dxl, M=M, N=K, K=r)
+                        self.add_grad(x, dxl)
             self.record(bwd)
         return y
+
+    def _lora_scales(self, scale: float, device, acc_only: bool = False) -> torch.Tensor:
+        key = ("lora_scale", float(scale), acc_only, str(device))
+        t = self._consts.get(key)
+        if t is None:
+            t = torch.tensor([float(scale), 0.0 if acc_only else 1.0, 0.0], device=device, dtype=F32)
+            self._consts[key] = t
+        return t
 
     def _acc_only(self, s3):
         """scales triple {s_acc, 0, 0} for gradient GEMMs of a scaled forward."""
@@ -498,6 +530,17 @@ class Engine:
                     return
                 d32 = raw.cast_bf16_f32(dy.contiguous(), torch.empty(dy.shape, device=dy.device, dtype=F32)) if dy.dtype == bf16 else dy
                 self.add_grad(x, raw.silu_bwd_f32(x.data, d32.contiguous(), torch.empty_like(x.data)))
+            self.record(bwd)
+        return y
+
+    def cast_to_f32(self, x: Var) -> Var:
+        y = Var(raw.cast_bf16_f32(x.data.contiguous(), torch.empty(x.data.shape, device=x.data.device, dtype=F32)), x.needs_grad)
+        if x.needs_grad and self.recording:
+            def bwd():
+                dy = y.take_grad()
+                if dy is None:
+                    return
+                self.add_grad(x, raw.cast_f32_bf16(dy.contiguous(), torch.empty(dy.shape, device=dy.device, dtype=bf16)))
             self.record(bwd)
         return y
 

@@ -270,6 +270,54 @@ class UNetSpatioTemporalConditionOutput:
         return (self.sample,)[i]
 
 
+class LoraLinear(nn.Module):
+    """PEFT-compatible LoRA wrapper layout (base_layer + lora_A/lora_B ModuleDicts keyed by adapter name), so that
+    parameter names match what `unet.add_adapter(LoraConfig)` of train_svd_lora.py:659-671 produces:
+    `<linear>.base_layer.weight`, `<linear>.lora_A.default.weight` [r,in], `<linear>.lora_B.default.weight` [out,r]."""
+
+    def __init__(self, base: nn.Linear, r: int, lora_alpha: float, adapter_name: str = "default", init: str = "gaussian"):
+        super().__init__()
+        self.base_layer = base
+        self.in_features, self.out_features = base.in_features, base.out_features
+        self.lora_A = nn.ModuleDict({adapter_name: nn.Linear(base.in_features, r, bias=False)})
+        self.lora_B = nn.ModuleDict({adapter_name: nn.Linear(r, base.out_features, bias=False)})
+        self.scaling = {adapter_name: lora_alpha / r}
+        self.active_adapters = [adapter_name]
+        self.r = {adapter_name: r}
+        with torch.no_grad():
+            if init == "gaussian":
+                nn.init.normal_(self.lora_A[adapter_name].weight, std=1.0 / r)
+            else:
+                nn.init.kaiming_uniform_(self.lora_A[adapter_name].weight, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_B[adapter_name].weight)
+        dev, dt = base.weight.device, base.weight.dtype
+        self.lora_A.to(device=dev, dtype=dt)
+        self.lora_B.to(device=dev, dtype=dt)
+
+    @property
+    def weight(self):
+        return self.base_layer.weight
+
+    @property
+    def bias(self):
+        return self.base_layer.bias
+
+
+def _lora_of(lin: nn.Module, off: int = 0):
+    """(col_offset, out_features, A, B, scale) of a LoRA-wrapped linear (ours or PEFT's), else None."""
+    if not hasattr(lin, "lora_A") or not hasattr(lin, "base_layer"):
+        return None
+    names = [n for n in getattr(lin, "active_adapters", list(lin.lora_A.keys())) if n in lin.lora_A]
+    if not names:
+        return None
+    if len(names) > 1:
+        raise NotImplementedError("svd_xtend_b200: one active LoRA adapter per layer is supported")
+    n = names[0]
+    if getattr(lin, "merged", False):
+        return None
+    return (off, lin.lora_B[n].weight.shape[0], lin.lora_A[n].weight, lin.lora_B[n].weight, float(lin.scaling[n]))
+
+
 def _sinusoid(t: torch.Tensor, dim: int) -> torch.Tensor:
     """Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0) [D: embeddings.py]; fp32, tiny."""
     half = dim // 2
@@ -487,6 +535,27 @@ class UNetSpatioTemporalConditionModel(nn.Module):
             if hasattr(m, "set_chunk_feed_forward"):
                 m.set_chunk_feed_forward(chunk_size=chunk_size, dim=dim)
 
+    def add_adapter(self, adapter_config, adapter_name: str = "default"):
+        """LoRA injection with the surface of diffusers' PeftAdapterMixin.add_adapter (train_svd_lora.py:671): wraps
+        every nn.Linear whose name ends with one of `target_modules` (to_k, to_q, to_v, to_out.0 at :659-664),
+        freezes the base model and leaves only lora_A / lora_B trainable."""
+        targets = list(getattr(adapter_config, "target_modules"))
+        r = int(getattr(adapter_config, "r"))
+        alpha = float(getattr(adapter_config, "lora_alpha", r))
+        init = getattr(adapter_config, "init_lora_weights", True)
+        self.requires_grad_(False)
+        n = 0
+        for parent_name, parent in list(self.named_modules()):
+            for child_name, child in list(parent.named_children()):
+                full = f"{parent_name}.{child_name}" if parent_name else child_name
+                if isinstance(child, nn.Linear) and any(full == t or full.endswith("." + t) for t in targets):
+                    setattr(parent, child_name, LoraLinear(child, r, alpha, adapter_name, "gaussian" if init == "gaussian" else "kaiming"))
+                    n += 1
+        if n == 0:
+            raise ValueError(f"add_adapter: no module matched target_modules={targets}")
+        self._engine.wc.clear()
+        return n
+
     def register_to_config(self, **kwargs):
         for k, v in kwargs.items():
             setattr(self.config, k, v)
@@ -677,12 +746,18 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         # alpha*hs + (1-alpha)*(hs + conv) = hs + (1-alpha)*conv
         return E.conv_temporal(t, g, tp.conv2, res1=hs, scales=s8[4:7], res1_unit=True, blend=(blk.time_mixer.mix_factor, s8[1:2]))
 
+    @staticmethod
+    def _qkv_lora(attn: Attention):
+        C = attn.inner_dim
+        return [_lora_of(attn.to_q, 0), _lora_of(attn.to_k, C), _lora_of(attn.to_v, 2 * C)]
+
     def _cross_vec(self, E: Engine, attn2: Attention, enc: Var) -> Var:
         """Image cross-attention has ONE key/value token (train_svd.py:1000-1001), so softmax == 1 and the
         attention output is to_out(to_v(e)) for every query of the clip: a [B, C]
         vector, added through the row-bias epilogue. to_q / to_k / norm2 receive exactly zero gradient."""
-        v = E.linear(enc, attn2.to_v.weight)
-        return E.linear(v, attn2.to_out[0].weight, attn2.to_out[0].bias, out_f32=True)
+        v = E.linear(enc, attn2.to_v.weight, lora=[_lora_of(attn2.to_v)])
+        c = E.linear(v, attn2.to_out[0].weight, attn2.to_out[0].bias, lora=[_lora_of(attn2.to_out[0])])
+        return E.cast_to_f32(c)
 
     def _frame_emb(self, E: Engine, tr: TransformerSpatioTemporalModel, g: Geom):
         """time_pos_embed(Timesteps(arange(T))) [D: transformer_temporal.py] -> fp32 [B*T, C]; input independent, so it
@@ -713,10 +788,10 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         x0 = E.linear(h, tr.proj_in.weight, tr.proj_in.bias)
         # spatial BasicTransformerBlock
         _, n1 = E.layernorm(x0, sb.norm1)
-        qkv = E.linear(n1, None, fused=[sb.attn1.to_q.weight, sb.attn1.to_k.weight, sb.attn1.to_v.weight])
+        qkv = E.linear(n1, None, fused=[sb.attn1.to_q.weight, sb.attn1.to_k.weight, sb.attn1.to_v.weight], lora=self._qkv_lora(sb.attn1))
         a = E.attention(qkv, heads, g, temporal=False)
         x1 = E.linear(a, sb.attn1.to_out[0].weight, sb.attn1.to_out[0].bias, res1=x0,
-                      rowbias=self._cross_vec(E, sb.attn2, enc), rowbias_div=per_clip)
+                      rowbias=self._cross_vec(E, sb.attn2, enc), rowbias_div=per_clip, lora=[_lora_of(sb.attn1.to_out[0])])
         _, n3 = E.layernorm(x1, sb.norm3)
         ff = E.linear(n3, sb.ff.net[0].proj.weight, sb.ff.net[0].proj.bias, geglu=True)
         x2 = E.linear(ff, sb.ff.net[2].weight, sb.ff.net[2].bias, res1=x1)
@@ -726,10 +801,10 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         ff = E.linear(ni, tb.ff_in.net[0].proj.weight, tb.ff_in.net[0].proj.bias, geglu=True)
         y1 = E.linear(ff, tb.ff_in.net[2].weight, tb.ff_in.net[2].bias, res1=xm)
         _, n1 = E.layernorm(y1, tb.norm1)
-        qkv = E.linear(n1, None, fused=[tb.attn1.to_q.weight, tb.attn1.to_k.weight, tb.attn1.to_v.weight])
+        qkv = E.linear(n1, None, fused=[tb.attn1.to_q.weight, tb.attn1.to_k.weight, tb.attn1.to_v.weight], lora=self._qkv_lora(tb.attn1))
         a = E.attention(qkv, heads, g, temporal=True)
         y2 = E.linear(a, tb.attn1.to_out[0].weight, tb.attn1.to_out[0].bias, res1=y1,
-                      rowbias=self._cross_vec(E, tb.attn2, enc), rowbias_div=per_clip)
+                      rowbias=self._cross_vec(E, tb.attn2, enc), rowbias_div=per_clip, lora=[_lora_of(tb.attn1.to_out[0])])
         _, n3 = E.layernorm(y2, tb.norm3)
         ff = E.linear(n3, tb.ff.net[0].proj.weight, tb.ff.net[0].proj.bias, geglu=True)
         s8 = self._blend(E, tr.time_mixer)

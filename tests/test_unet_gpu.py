@@ -163,3 +163,57 @@ def test_tiny_full_finetune_all_gradients():
         if e > max(3 * ea, 6e-2):
             bad.append((n, round(e, 4), round(ea, 4)))
     assert not bad, bad[:10]
+
+
+def test_tiny_lora_matches_merged_weight_oracle():
+    """config 5 (train_svd_lora.py:659-671): y = W x + (alpha/r) B A x on to_q/to_k/to_v/to_out.0.
+    Reference = the oracle with merged weights W' = W + s*B@A; dA = s*B^T dW', dB = s*dW' A^T."""
+    from types import SimpleNamespace
+    from oracle.svd_unet_oracle import TINY_CONFIG, synthetic_batch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    oracle, ours = _build(TINY_CONFIG, seed=21)
+    r = 16
+    n = ours.add_adapter(SimpleNamespace(r=r, lora_alpha=r, init_lora_weights="gaussian",
+                                         target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+    assert n == 64
+    torch.manual_seed(5)
+    merged = {}
+    with torch.no_grad():
+        for name, mod in ours.named_modules():
+            if hasattr(mod, "lora_B"):
+                mod.lora_B["default"].weight.normal_(0, 0.05)
+                A, B = mod.lora_A["default"].weight, mod.lora_B["default"].weight
+                merged[name + ".weight"] = mod.base_layer.weight + (B @ A)
+    sd = oracle.state_dict()
+    for k, v in merged.items():
+        sd[k].copy_(v)
+    oracle.requires_grad_(False)
+    for k in merged:
+        dict(oracle.named_parameters())[k].requires_grad_(True)
+    oracle.train()
+    ours.train()
+    trainable = [k for k, p in ours.named_parameters() if p.requires_grad]
+    assert all("lora_" in k for k in trainable) and len(trainable) == 128
+    batch = synthetic_batch(1, 4, 16, 16, seed=99, device=DEV, cross_dim=TINY_CONFIG["cross_attention_dim"])
+    pred_ref, loss_ref = _loss(oracle, batch)
+    loss_ref.backward()
+    pred, loss = _loss(ours, batch)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _rel(pred, pred_ref) < 2e-2
+    gw = dict(oracle.named_parameters())
+    bad = []
+    for name, mod in ours.named_modules():
+        if not hasattr(mod, "lora_B"):
+            continue
+        dW = gw[name + ".weight"].grad
+        A, B = mod.lora_A["default"].weight, mod.lora_B["default"].weight
+        refA, refB = B.detach().t() @ dW, dW @ A.detach().t()
+        for g, ref, tag in ((A.grad, refA, "A"), (B.grad, refB, "B")):
+            if ref.abs().max() == 0:
+                assert g.abs().max() == 0
+                continue
+            e = _rel(g, ref)
+            if e > 8e-2:
+                bad.append((name, tag, round(e, 4)))
+    assert not bad, bad[:8]
