@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 : > gpurun_out/bench_dev.log
-for k in "tiny_inference" "lora" "full_finetune" "tiny_forward_backward" "svd_config_forward"; do
+for k in "tiny_inference" "checkpointing" "lora" "full_finetune" "tiny_forward_backward" "svd_config_forward"; do
   echo "=== $k" >> gpurun_out/bench_dev.log
   timeout 900 python -m pytest tests/test_unet_gpu.py -q -s -k "$k" --no-header -p no:cacheprovider 2>&1 | tail -30 >> gpurun_out/bench_dev.log
 done

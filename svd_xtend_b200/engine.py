@@ -146,6 +146,38 @@ class Engine:
             tape.pop()()
         self.keep.clear()
 
+    def checkpoint(self, fn: Callable[..., Var], *inputs: Var) -> Var:
+        """Gradient checkpointing on the tape (the contract of src/unet_spatio_temporal_condition.py:323-325 and
+        torch.utils.checkpoint in the diffusers blocks): run `fn` without recording, and re-run it with recording
+        inside the backward to rebuild the saved activations just before they are consumed."""
+        if not self.recording:
+            return fn(*inputs)
+        self.recording = False
+        try:
+            out = fn(*inputs)
+        finally:
+            self.recording = True
+        if not out.needs_grad:
+            return out
+
+        def bwd():
+            dy = out.take_grad()
+            if dy is None:
+                return
+            outer, self.tape = self.tape, []
+            ins2 = [Var(v.data, v.needs_grad) for v in inputs]
+            out2 = fn(*ins2)
+            self.add_grad(out2, dy, owned=False)
+            sub, self.tape = self.tape, outer
+            while sub:
+                sub.pop()()
+            for v, v2 in zip(inputs, ins2):
+                g = v2.take_grad()
+                if g is not None:
+                    self.add_grad(v, g)
+        self.record(bwd)
+        return out
+
     def add_grad(self, v: Var, g: torch.Tensor, owned: bool = True):
         """Accumulate gradient g into v. `owned`: g is a fresh tensor nobody else references (it may be
         kept and later overwritten in place); pass owned=False when g aliases another Var's gradient."""

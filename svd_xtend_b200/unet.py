@@ -680,7 +680,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         skips = [(x, g)]
         for blk in self.down_blocks:
             for j, res in enumerate(blk.resnets):
-                x = self._resblock(E, res, x, g)
+                x = self._res(E, blk, res, x, g)
                 if blk.has_cross_attention:
                     x = self._transformer(E, blk.attentions[j], x, g, enc)
                 skips.append((x, g))
@@ -691,17 +691,17 @@ class UNetSpatioTemporalConditionModel(nn.Module):
                 skips.append((x, g))
 
         # ---- 4. mid (:451-456)
-        x = self._resblock(E, self.mid_block.resnets[0], x, g)
+        x = self._resblock(E, self.mid_block.resnets[0], x, g)     # [D]: the first mid resnet is never checkpointed
         for attn, res in zip(self.mid_block.attentions, self.mid_block.resnets[1:]):
             x = self._transformer(E, attn, x, g, enc)
-            x = self._resblock(E, res, x, g)
+            x = self._res(E, self.mid_block, res, x, g)
 
         # ---- 5. up (:459-477)
         for blk in self.up_blocks:
             for j, res in enumerate(blk.resnets):
                 skip, _ = skips.pop()
                 x = E.concat(x, skip)
-                x = self._resblock(E, res, x, g)
+                x = self._res(E, blk, res, x, g)
                 if blk.has_cross_attention:
                     x = self._transformer(E, blk.attentions[j], x, g, enc)
             if blk.upsamplers is not None:
@@ -728,6 +728,12 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         """device float[8] epilogue scale triples of an AlphaBlender (image_only_indicator is all zeros, :430)."""
         mix = mixer.mix_factor
         return E.wc.get(("blend", id(mix)), [mix], (8,), lambda buf: raw.blend_scales(E.vec_f32(mix), buf), dtype=F32)
+
+    def _res(self, E: Engine, owner: nn.Module, res: SpatioTemporalResBlock, x: Var, g: Geom) -> Var:
+        """a resnet of a down/mid/up block, gradient-checkpointed when the owner's flag is set ([D] unet_3d_blocks.py)."""
+        if self.training and getattr(owner, "gradient_checkpointing", False):
+            return E.checkpoint(lambda v: self._resblock(E, res, v, g), x)
+        return self._resblock(E, res, x, g)
 
     def _resblock(self, E: Engine, blk: SpatioTemporalResBlock, x: Var, g: Geom) -> Var:
         """SpatioTemporalResBlock [D: resnet.py]: spatial ResnetBlock2D -> TemporalResnetBlock -> AlphaBlender."""
@@ -786,15 +792,21 @@ class UNetSpatioTemporalConditionModel(nn.Module):
                 E.record(lambda ready=ready: self.grad_hook(ready))
         h = E.groupnorm(x_in, tr.norm, outer=N, rows=g.HW, silu=False)
         x0 = E.linear(h, tr.proj_in.weight, tr.proj_in.bias)
-        # spatial BasicTransformerBlock
-        _, n1 = E.layernorm(x0, sb.norm1)
-        qkv = E.linear(n1, None, fused=[sb.attn1.to_q.weight, sb.attn1.to_k.weight, sb.attn1.to_v.weight], lora=self._qkv_lora(sb.attn1))
-        a = E.attention(qkv, heads, g, temporal=False)
-        x1 = E.linear(a, sb.attn1.to_out[0].weight, sb.attn1.to_out[0].bias, res1=x0,
-                      rowbias=self._cross_vec(E, sb.attn2, enc), rowbias_div=per_clip, lora=[_lora_of(sb.attn1.to_out[0])])
-        _, n3 = E.layernorm(x1, sb.norm3)
-        ff = E.linear(n3, sb.ff.net[0].proj.weight, sb.ff.net[0].proj.bias, geglu=True)
-        x2 = E.linear(ff, sb.ff.net[2].weight, sb.ff.net[2].bias, res1=x1)
+        # spatial BasicTransformerBlock ([D] transformer_temporal.py checkpoints only this block)
+        def spatial(x0: Var) -> Var:
+            _, n1 = E.layernorm(x0, sb.norm1)
+            qkv = E.linear(n1, None, fused=[sb.attn1.to_q.weight, sb.attn1.to_k.weight, sb.attn1.to_v.weight], lora=self._qkv_lora(sb.attn1))
+            a = E.attention(qkv, heads, g, temporal=False)
+            x1 = E.linear(a, sb.attn1.to_out[0].weight, sb.attn1.to_out[0].bias, res1=x0,
+                          rowbias=self._cross_vec(E, sb.attn2, enc), rowbias_div=per_clip, lora=[_lora_of(sb.attn1.to_out[0])])
+            _, n3 = E.layernorm(x1, sb.norm3)
+            ff = E.linear(n3, sb.ff.net[0].proj.weight, sb.ff.net[0].proj.bias, geglu=True)
+            return E.linear(ff, sb.ff.net[2].weight, sb.ff.net[2].bias, res1=x1)
+
+        if self.training and tr.gradient_checkpointing:
+            x2 = E.checkpoint(spatial, x0)
+        else:
+            x2 = spatial(x0)
         # TemporalBasicTransformerBlock on the same token layout (frames are HW rows apart)
         femb, femb_var = self._frame_emb(E, tr, g)
         xm, ni = E.layernorm(x2, tb.norm_in, addvec=femb, add_div=g.HW, addvec_var=femb_var)

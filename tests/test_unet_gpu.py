@@ -217,3 +217,30 @@ def test_tiny_lora_matches_merged_weight_oracle():
             if e > 8e-2:
                 bad.append((name, tag, round(e, 4)))
     assert not bad, bad[:8]
+
+
+def test_tiny_gradient_checkpointing_equivalence():
+    """--gradient_checkpointing (train_svd.py:731-732): same loss and gradients with the flag on and off."""
+    from oracle.svd_unet_oracle import TINY_CONFIG, synthetic_batch
+    _, ours = _build(TINY_CONFIG, seed=8)
+    _train_filter(ours)
+    ours.train()
+    batch = synthetic_batch(1, 4, 16, 16, seed=77, device=DEV, cross_dim=TINY_CONFIG["cross_attention_dim"])
+
+    def run():
+        ours.zero_grad(set_to_none=True)
+        pred, loss = _loss(ours, batch)
+        loss.backward()
+        torch.cuda.synchronize()
+        return pred.detach().clone(), {n: p.grad.clone() for n, p in ours.named_parameters() if p.requires_grad}
+
+    p0, g0 = run()
+    ours.enable_gradient_checkpointing()
+    assert ours.is_gradient_checkpointing
+    p1, g1 = run()
+    assert torch.equal(p0, p1)
+    for n in g0:
+        if g0[n].abs().max() == 0:
+            assert g1[n].abs().max() == 0
+        else:
+            assert _rel(g1[n], g0[n]) < 2e-3, (n, _rel(g1[n], g0[n]))
