@@ -332,7 +332,9 @@ def main():
         s.record()
         r = orig(a, b, out, M=M, N=N, K=K, **kw)
         e.record()
-        recs.append((s, e, 2.0 * M * N * K * len(kw.get("taps", ((0, 0, 0),)))))
+        ntaps = len(kw.get("taps", ((0, 0, 0),)))
+        recs.append((s, e, 2.0 * M * N * K * ntaps, (M, N, K, ntaps, int(kw.get("mode", 0)), bool(kw.get("geglu", False)),
+                                                      bool(kw.get("a_mn", False)), int(kw.get("split_k", 1)))))
         return r
 
     raw.tapgemm = timed_tapgemm
@@ -341,8 +343,20 @@ def main():
         torch.cuda.synchronize()
     finally:
         raw.tapgemm = orig
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-    gemm_flops = sum(f for _, _, f in recs)
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
+    gemm_flops = sum(f for _, _, f, _ in recs)
+    if rank == 0 and os.environ.get("SVDX_GEMM_TABLE"):
+        agg = {}
+        for s_, e_, f_, key in recs:
+            a = agg.setdefault(key, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += s_.elapsed_time(e_)
+            a[2] += f_
+        table = [{"M": k[0], "N": k[1], "K": k[2], "taps": k[3], "mode": k[4], "geglu": k[5], "wgrad": k[6], "split_k": k[7], "n": v[0],
+                  "ms": v[1], "tflops": v[2] / v[1] / 1e9 if v[1] > 0 else 0.0} for k, v in agg.items()]
+        table.sort(key=lambda r_: -r_["ms"])
+        with open(os.environ["SVDX_GEMM_TABLE"], "w") as fh:
+            json.dump(table, fh, indent=0)
     sustained, burst, hbm, src = peaks()
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "svdx::tapgemm_kernel (tcgen05)", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",

@@ -29,7 +29,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnKParams {
   CUtensorMap tq, tk, tv, tdo;  // 4-D maps: (col, inner, token, outer), box (64, G, RT, 1)
-  int heads, S, G, RT, inner_groups, tiles;
+  int heads, S, G, RT, inner_groups, tiles, gshift, gmask;
   long long outer_stride, inner_stride, tok_stride;
   float scale;
   bf16* o; long long ldo;
@@ -48,8 +48,8 @@ struct RowInfo {
 
 SVDX_DEVINL RowInfo row_info(const AttnKParams& p, int r, int tile, int outer, int inner0) {
   RowInfo ri;
-  const int t = tile * p.RT + r / p.G;
-  ri.g = r % p.G;
+  const int t = tile * p.RT + (r >> p.gshift);
+  ri.g = r & p.gmask;
   ri.valid = t < p.S;
   ri.token = (long long)outer * p.outer_stride + (long long)(inner0 + ri.g) * p.inner_stride + (long long)t * p.tok_stride;
   return ri;
@@ -68,6 +68,12 @@ SVDX_DEVINL void store_score_chunk(uint32_t tile_base, int r, int c0, const floa
                  "r"(pack_bf16x2(f[8 * k + 6], f[8 * k + 7]))
                  : "memory");
   }
+}
+
+SVDX_DEVINL float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 SVDX_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -213,6 +219,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       mbar_wait(b_sfull + 8 * (j & 1), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t ts = tS + (j & 1) * 128 + lane_off;
+      const int kvalid = p.S - j * p.RT;                 // valid key tokens in this block
+      const bool nomask = (p.G == 1) && (kvalid >= 128);  // warp-uniform fast path: nothing to mask
       // pass 1: masked row max of this block
       float bmax = -INFINITY;
 #pragma unroll 1
@@ -223,13 +231,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int c = c0 + i;
-          const bool ok = ((c % p.G) == ri.g) && (j * p.RT + c / p.G < p.S);
+          const bool ok = nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid));
           if (ok) bmax = fmaxf(bmax, __uint_as_float(v[i]));
         }
       }
       const float m_new = fmaxf(m_run, bmax);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_use) * sc);
+      const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_use) * sc);
       // pass 2: probabilities -> smem
       mbar_wait(b_pempty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);
       float rsum = 0.f;
@@ -242,8 +250,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int c = c0 + i;
-          const bool ok = ((c % p.G) == ri.g) && (j * p.RT + c / p.G < p.S);
-          const float e = ok ? exp2f((__uint_as_float(v[i]) - m_use) * sc) : 0.f;
+          const bool ok = nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid));
+          const float e = ok ? fast_exp2((__uint_as_float(v[i]) - m_use) * sc) : 0.f;
           // the PV product consumes bf16 probabilities; sum the rounded values so the row normaliser matches
           const float eb = __bfloat162float(__float2bfloat16(e));
           f[i] = eb;
@@ -375,6 +383,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
       mbar_wait(b_sfull, j & 1);
       tc_fence_after();
       mbar_wait(b_dsempty, (j & 1) ^ 1);
+      const int kvalid = p.S - j * p.RT;
+      const bool nomask = (p.G == 1) && (kvalid >= 128);
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t vs[32], vd[32];
@@ -385,8 +395,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int c = c0 + i;
-          const bool ok = ri.valid && ((c % p.G) == ri.g) && (j * p.RT + c / p.G < p.S);
-          const float pr = ok ? exp2f(__uint_as_float(vs[i]) * sc - lse2) : 0.f;
+          const bool ok = ri.valid && (nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid)));
+          const float pr = ok ? fast_exp2(__uint_as_float(vs[i]) * sc - lse2) : 0.f;
           f[i] = pr * (__uint_as_float(vd[i]) - dlt) * p.scale;
         }
         store_score_chunk(sDS, r, c0, f);
@@ -536,8 +546,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __gri
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const int c = c0 + k;  // query column
-          const bool ok = ki.valid && ((c % p.G) == ki.g);
-          const float pr = ok ? exp2f(__uint_as_float(vs[k]) * sc - vec[c]) : 0.f;
+          const bool ok = ki.valid && ((c & p.gmask) == ki.g);
+          const float pr = ok ? fast_exp2(__uint_as_float(vs[k]) * sc - vec[c]) : 0.f;
           fp[k] = pr;
           fd[k] = pr * (__uint_as_float(vd[k]) - vec[128 + c]) * p.scale;
         }
@@ -623,6 +633,8 @@ static int attn_setup(const SvdxAttn* d, AttnKParams& p, bool bwd, dim3& grid) {
   const int RT = 128 / G;
   if (d->inner > 1 && d->S > RT) return svdx_fail(SVDX_E_BADARG, "attention: strided sequences longer than 128 tokens are not supported");
   p.G = G; p.RT = RT; p.S = d->S; p.heads = d->heads;
+  p.gmask = G - 1; p.gshift = 0;
+  while ((1 << p.gshift) < G) ++p.gshift;
   p.inner_groups = d->inner / G;
   p.tiles = (d->S + RT - 1) / RT;
   p.outer_stride = d->outer_stride; p.inner_stride = d->inner_stride; p.tok_stride = d->tok_stride;

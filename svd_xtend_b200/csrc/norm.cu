@@ -45,8 +45,11 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_partial(GnSrc s, int rows
   for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sh_s[i] = 0.f;
   __syncthreads();
   // a lane owns channel pairs c = 2*lane + 64*j; accumulate per pair over the warp's rows, flush per j
-  for (int c = 2 * lane; c < C; c += 64) {
+  // blockIdx.z selects a 64-channel slab; a lane owns the channel pair c = slab*64 + 2*lane over the warp's rows
+  const int c = blockIdx.z * 64 + 2 * lane;
+  if (c < C) {
     float a = 0.f, b = 0.f;
+#pragma unroll 4
     for (int r = r0 + warp; r < r1; r += GN_WARPS) {
       const float2 v = load_pair(s, (long long)n * rows + r, c);
       a += v.x + v.y;
@@ -57,7 +60,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_partial(GnSrc s, int rows
     atomicAdd(&sh_s[G + g], b);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < G; i += GN_THREADS) {
+  const int g_lo = (blockIdx.z * 64) / cpg, g_hi = min(C - 1, blockIdx.z * 64 + 63) / cpg;
+  for (int i = g_lo + threadIdx.x; i <= g_hi; i += GN_THREADS) {
     atomicAdd(&sum[n * G + i], sh_s[i]);
     atomicAdd(&sumsq[n * G + i], sh_s[G + i]);
   }
@@ -118,12 +122,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(GnSrc s, const bf16
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sh_s[i] = 0.f;
   __syncthreads();
-  for (int c = 2 * lane; c < C; c += 64) {
+  const int c = blockIdx.z * 64 + 2 * lane;
+  if (c < C) {
     const int g = c / cpg;
     const float m = mean[n * G + g], rs = rstd[n * G + g];
     const float g0 = gamma[c], g1 = gamma[c + 1], b0 = beta[c], b1 = beta[c + 1];
     float a1 = 0.f, a2 = 0.f;          // group sums
     float dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
+#pragma unroll 4
     for (int r = r0 + warp; r < r1; r += GN_WARPS) {
       const long long row = (long long)n * rows + r;
       const float2 v = load_pair(s, row, c);
@@ -146,7 +152,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(GnSrc s, const bf16
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < G; i += GN_THREADS) {
+  const int g_lo = (blockIdx.z * 64) / cpg, g_hi = min(C - 1, blockIdx.z * 64 + 63) / cpg;
+  for (int i = g_lo + threadIdx.x; i <= g_hi; i += GN_THREADS) {
     atomicAdd(&ws[(n * G + i) * 2 + 0], sh_s[i]);
     atomicAdd(&ws[(n * G + i) * 2 + 1], sh_s[G + i]);
   }
@@ -311,13 +318,22 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
     }
   }
   if (dgamma) {
+    // block-level reduction through shared memory, then one atomic per channel per CTA
+    __shared__ float sh_g[64 * NJ], sh_b[64 * NJ];
+    for (int i = threadIdx.x; i < 64 * NJ; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int c = 2 * lane + 64 * j;
       if (c < C) {
-        atomicAdd(&dgamma[c], dg[j].x); atomicAdd(&dgamma[c + 1], dg[j].y);
-        atomicAdd(&dbeta[c], db[j].x); atomicAdd(&dbeta[c + 1], db[j].y);
+        atomicAdd(&sh_g[c], dg[j].x); atomicAdd(&sh_g[c + 1], dg[j].y);
+        atomicAdd(&sh_b[c], db[j].x); atomicAdd(&sh_b[c + 1], db[j].y);
       }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      atomicAdd(&dgamma[i], sh_g[i]);
+      atomicAdd(&dbeta[i], sh_b[i]);
     }
   }
 }
@@ -344,7 +360,7 @@ extern "C" int svdx_groupnorm_stats(const void* x, int64_t ldx, int32_t C1, cons
   const int total = outer * num_groups;
   cudaMemsetAsync(mean, 0, sizeof(float) * total, st);
   cudaMemsetAsync(rstd, 0, sizeof(float) * total, st);
-  dim3 grid((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, outer);
+  dim3 grid((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, outer, (C1 + C2 + 63) / 64);
   gn_stats_partial<<<grid, GN_THREADS, 0, st>>>(s, rows, num_groups, mean, rstd);
   const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
   gn_stats_finalize<<<(total + 127) / 128, 128, 0, st>>>(mean, rstd, total, inv, eps);
@@ -378,7 +394,7 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
   const int total = outer * num_groups;
   cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * total, st);
-  dim3 grid((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, outer);
+  dim3 grid((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, outer, (C1 + C2 + 63) / 64);
   gn_bwd_partial<<<grid, GN_THREADS, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, num_groups, mean, rstd, gamma, beta,
                                               fuse_silu, workspace, dgamma, dbeta);
   const long long total_rows = (long long)outer * rows;
@@ -421,7 +437,7 @@ static void ln_bwd_launch(const void* x, int64_t ldx, const void* dy, int64_t ld
                           const float* rstd, void* dx, int64_t lddx, const void* dres, int64_t lddres, float* dgamma, float* dbeta,
                           cudaStream_t st) {
   int ctas = (rows + 7) / 8;
-  const int cap = svdx_num_sms() * 8;
+  const int cap = svdx_num_sms() * 4;
   if (ctas > cap) ctas = cap;
   ln_bwd_kernel<NJ><<<ctas, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(dy), lddy, rows, C, g, mean,
                                           rstd, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<const bf16*>(dres), lddres, dgamma, dbeta);

@@ -410,10 +410,10 @@ class Engine:
                 continue
             g = self.pgrad(p).view(O, -1)
             dyp = dy[:, o0:o0 + O]
-            bn = raw.pick_block_n(K, True)
+            bn = raw.choose_block_n(O, K, mn_major=True)
             tiles = ((O + 127) // 128) * ((K + bn - 1) // bn)
             kb = (M + 63) // 64
-            split = max(1, min(kb, (2 * raw.load().svdx_num_sms()) // max(tiles, 1), 32))
+            split = max(1, min(kb, (2 * raw.num_sms()) // max(tiles, 1), 32))
             raw.tapgemm(dyp, x, g, M=O, N=K, K=M, a_mn=True, b_mn=True, split_k=split, out_dtype=OUT_F32_ATOMIC,
                         block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
 
@@ -425,10 +425,10 @@ class Engine:
         O, I = w.shape[0], w.shape[1]
         nt = len(taps)
         ws = torch.zeros(Opad, nt * ip, device=dy.device, dtype=F32)
-        bn = raw.pick_block_n(ip, True)
+        bn = raw.choose_block_n(Opad, ip, mn_major=True)
         tiles = ((Opad + 127) // 128) * ((ip + bn - 1) // bn)
         kb = (K + 63) // 64
-        split = max(1, min(kb, (2 * raw.load().svdx_num_sms()) // max(tiles, 1), 64))
+        split = max(1, min(kb, (2 * raw.num_sms()) // max(tiles, 1), 64))
         for t, tap in enumerate(taps):
             raw.tapgemm(dy, x, ws[:, t * ip:(t + 1) * ip], M=Opad, N=ip, K=K, a_mn=True, b_mn=True, b_mode=b_mode, taps=(tap,),
                         conv_whn=conv_whn, rows_per_group=rows_per_group if rows_per_group is not None else K, groups=groups,
@@ -472,7 +472,7 @@ class Engine:
         raw.tapgemm(x.data, wf, out, M=M, N=O, K=ip, mode=A_CONV2D, taps=taps, conv_whn=whn, bias=self.vec_f32(conv.bias),
                     rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
                     res1=None if res1 is None else res1.data, scales=scales,
-                    block_n=raw.pick_block_n(O) if O >= 32 else 32)
+                    block_n=None if O >= 32 else 32)
         w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad)
         need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, rowbias))
         y = Var(out, need)

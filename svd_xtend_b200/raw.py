@@ -48,6 +48,46 @@ def pick_block_n(n_out: int, mn_major: bool = False) -> int:
     return 256 if n_out > 256 else ((n_out + 31) // 32) * 32
 
 
+_NUM_SMS = [0]
+
+
+def num_sms() -> int:
+    if _NUM_SMS[0] == 0:
+        _NUM_SMS[0] = int(load().svdx_num_sms())
+    return _NUM_SMS[0]
+
+
+def _kstep_cycles(bn: int) -> float:
+    """model of one 128 x bn x 16 tcgen05 step: tensor pipe bn/2 clk vs smem operand reads (4 KB + 32*bn B at 128 B/clk)"""
+    return max(bn / 2.0, 32.0 + bn / 4.0)
+
+
+def choose_block_n(M: int, n_out: int, geglu: bool = False, mn_major: bool = False) -> int:
+    """tile width minimising (waves over the SMs) x (cycles per k-step), so small-M levels (5x8, 10x16 latents)
+    spread over all 148 SMs instead of running 25-90 fat tiles. Returns the block_n of the C ABI (2x for GEGLU)."""
+    sms = num_sms()
+    m_tiles = (M + 127) // 128
+    if mn_major:
+        cands = [256, 192, 128, 64]
+    elif geglu:
+        cands = [128, 64, 32]          # output columns per tile; block_n = 2x
+    else:
+        cands = [256, 160, 128, 96, 64, 32]
+    best, best_cost = None, None
+    for bn in cands:
+        n_tiles = (n_out + bn - 1) // bn
+        if (not mn_major) and n_out % bn and n_out > bn:
+            continue                    # K-major path: keep exact tilings (TMA boxes of partial tiles are fine, but wasteful)
+        tiles = m_tiles * n_tiles
+        step = _kstep_cycles(2 * bn if geglu else bn)
+        cost = (tiles * step) if mn_major else (((tiles + sms - 1) // sms) * step)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = bn, cost
+    if best is None:
+        best = pick_block_n(n_out, mn_major)
+    return 2 * best if geglu else best
+
+
 def tapgemm(
     a: torch.Tensor,
     b: torch.Tensor,
@@ -100,9 +140,7 @@ def tapgemm(
     d.M, d.N, d.K = M, N, K
     n_out = N // 2 if geglu else N
     if block_n is None:
-        block_n = 2 * pick_block_n(n_out) if geglu else pick_block_n(n_out, b_mn)
-        if geglu and block_n > 256:
-            block_n = 256 if n_out % 128 == 0 else 128
+        block_n = choose_block_n(M, n_out, geglu, b_mn)
     d.block_n = block_n
     d.split_k = split_k
     d.out = out.data_ptr()
