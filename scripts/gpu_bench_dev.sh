@@ -8,7 +8,7 @@ done
 echo "=== kernels" >> gpurun_out/bench_dev.log
 timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_tapgemm_gpu.py -q --no-header -p no:cacheprovider 2>&1 | tail -30 >> gpurun_out/bench_dev.log
 echo "=== graph debug" >> gpurun_out/bench_dev.log
-timeout 600 python scripts/graph_debug.py >> gpurun_out/bench_dev.log 2>&1
+timeout 900 python scripts/graph_debug.py --full >> gpurun_out/bench_dev.log 2>&1
 echo "=== bench eager" >> gpurun_out/bench_dev.log
 SVDX_GEMM_TABLE=gpurun_out/gemm_table.json timeout 900 python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/bench_eager.json 2>> gpurun_out/bench_dev.log
 cat gpurun_out/bench_eager.json >> gpurun_out/bench_dev.log

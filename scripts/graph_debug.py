@@ -5,10 +5,13 @@ import torch
 from oracle.svd_unet_oracle import TINY_CONFIG, edm_loss, synthetic_batch
 from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel
 from svd_xtend_b200.train import ParamArena, FusedAdamW
+from oracle.svd_unet_oracle import SVD_CONFIG
+FULL = "--full" in sys.argv
 
 dev = "cuda:0"
 torch.manual_seed(0)
-unet = UNetSpatioTemporalConditionModel(**TINY_CONFIG).to(dev)
+CFG = SVD_CONFIG if FULL else TINY_CONFIG
+unet = UNetSpatioTemporalConditionModel(**CFG).to(dev)
 unet.requires_grad_(False)
 for n, p in unet.named_parameters():
     if "temporal_transformer_block" in n:
@@ -16,7 +19,7 @@ for n, p in unet.named_parameters():
 unet.train()
 arena = ParamArena(unet); unet.attach_arena(arena)
 opt = FusedAdamW(arena, lr=1e-5); opt.on_updated = unet.refresh_trainable_operands
-b = synthetic_batch(1, 4, 16, 16, seed=1, device=dev, cross_dim=TINY_CONFIG["cross_attention_dim"])
+b = synthetic_batch(1, 14, 40, 64, seed=1, device=dev) if FULL else synthetic_batch(1, 4, 16, 16, seed=1, device=dev, cross_dim=TINY_CONFIG["cross_attention_dim"])
 
 def fwd():
     with torch.no_grad():

@@ -26,12 +26,15 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;      // 32 KB
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int SMEM_BYTES = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
 
 struct __align__(64) TapGemmKParams {
   CUtensorMap tma;
   CUtensorMap tmb;
+  CUtensorMap tma_bh[4];  // CONV2D: boxes of 2, 4, 8, 16 image rows (tma itself = 1 row)
+  int max_bh_log2;
   int a_mode, a_mn, b_mn, b_mode, kb_per_group;
   int rows_per_group, groups, tiles_per_group;
   int W, H, nimg;
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * i, NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -121,27 +124,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
           // ---- A
           if (p.a_mn) {
             // memory [k rows][m cols]: two 64x64 boxes. b_mode 2 walks the k rows group by group.
-            int arow = kb * BLOCK_K;
             if (p.b_mode == 2) {
+              // group-bounded rows (3-D map): rows past the end of the group read as zero, like the shifted B rows
               const int g = kb / p.kb_per_group;
-              arow = g * p.rows_per_group + (kb - g * p.kb_per_group) * BLOCK_K;
+              const int k0 = (kb - g * p.kb_per_group) * BLOCK_K;
+              tma_load_3d(&p.tma, full, dA, mt * BLOCK_M, k0, g);
+              tma_load_3d(&p.tma, full, dA + 8192, mt * BLOCK_M + 64, k0, g);
+            } else {
+              tma_load_2d(&p.tma, full, dA, mt * BLOCK_M, kb * BLOCK_K);
+              tma_load_2d(&p.tma, full, dA + 8192, mt * BLOCK_M + 64, kb * BLOCK_K);
             }
-            tma_load_2d(&p.tma, full, dA, mt * BLOCK_M, arow);
-            tma_load_2d(&p.tma, full, dA + 8192, mt * BLOCK_M + 64, arow);
           } else if (p.a_mode == SVDX_A_ROWS) {
             const int g = mt / p.tiles_per_group;
             const int t = mt - g * p.tiles_per_group;
             tma_load_3d(&p.tma, full, dA, kc, t * BLOCK_M + p.tap_d0[tap], g);
           } else {
+            // the tile's 128 pixels = R consecutive image rows; walk them image by image and cover each run with
+            // the largest power-of-two row boxes available (few big TMA requests instead of R one-row requests)
             const int R = BLOCK_M / p.W;
             const int dw = p.tap_d0[tap], dh = p.tap_d1[tap], dn = p.tap_d2[tap];
-            for (int i = 0; i < R; ++i) {
-              const int rowid = mt * R + i;
+            int rowid = mt * R, left = R;
+            uint32_t dst = dA;
+            while (left > 0) {
               const int n = rowid / p.H;
               const int h = rowid - n * p.H;
               // rows past the last image land out of bounds (n >= nimg) and are zero-filled
               const int nn = (n < p.nimg) ? n + dn : (1 << 28);
-              tma_load_4d(&p.tma, full, dA + i * p.W * 128, kc, dw, h + dh, nn);
+              int run = min(left, p.H - h);
+              int hh = h;
+              while (run > 0) {
+                int lg = min(p.max_bh_log2, 31 - __clz(run));
+                const int bh = 1 << lg;
+                tma_load_4d(lg == 0 ? &p.tma : &p.tma_bh[lg - 1], full, dst, kc, dw, hh + dh, nn);
+                dst += bh * p.W * 128;
+                hh += bh; run -= bh; left -= bh; rowid += bh;
+              }
             }
           }
           // ---- B
@@ -223,7 +240,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
     }
   } else {
     // =========================== epilogue warps ===========================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which of the two warps of the quarter: takes chunks half, half+2, ...
     int acc = 0;
     uint32_t acc_phase = 0;
     float s_acc = 1.f, s_r1 = 1.f, s_r2 = 1.f;
@@ -254,16 +272,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       const float* rb = p.rowbias ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
-      for (int c = 0; c < bn_out; c += 32) {
+      for (int c = half * 32; c < bn_out; c += 64) {
         uint32_t v[32];
         uint32_t gte[32];
+        const int col0 = n0 + c;
+        const bool full_chunk = (col0 + 32 <= n_out_total);
+        const bool active = row_ok && col0 < n_out_total;
+        // issue the global reads of this chunk before waiting on TMEM so their latency overlaps
+        uint4 rr1[4], rr2[4];
+        if (active && full_chunk) {
+          if (p.res1) {
+            const uint4* r1p = reinterpret_cast<const uint4*>(p.res1 + m * p.ldr1 + col0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rr1[k] = r1p[k];
+          }
+          if (p.res2) {
+            const uint4* r2p = reinterpret_cast<const uint4*>(p.res2 + m * p.ldr2 + col0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rr2[k] = r2p[k];
+          }
+        }
         __syncwarp();
         tmem_ld32(t_base + c, v);
         if (p.geglu) tmem_ld32(t_base + bn_out + c, gte);
         tc_wait_ld();
-        const int col0 = n0 + c;
-        if (row_ok && col0 < n_out_total) {
-        const bool full_chunk = (col0 + 32 <= n_out_total);
+        if (active) {
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -308,15 +341,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
           }
         } else {
           if (p.bias) {
+            if (full_chunk) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (full_chunk || col0 + i < n_out_total) f[i] += __ldg(p.bias + col0 + i);
+              for (int k = 0; k < 8; ++k) {
+                const float4 b4 = __ldg(bp + k);
+                f[4 * k] += b4.x; f[4 * k + 1] += b4.y; f[4 * k + 2] += b4.z; f[4 * k + 3] += b4.w;
+              }
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < n_out_total) f[i] += __ldg(p.bias + col0 + i);
+            }
           }
         }
         if (rb) {
+          if (full_chunk && (reinterpret_cast<uintptr_t>(rb + col0) & 15) == 0) {
+            const float4* bp = reinterpret_cast<const float4*>(rb + col0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full_chunk || col0 + i < n_out_total) f[i] += __ldg(rb + col0 + i);
+            for (int k = 0; k < 8; ++k) {
+              const float4 b4 = __ldg(bp + k);
+              f[4 * k] += b4.x; f[4 * k + 1] += b4.y; f[4 * k + 2] += b4.z; f[4 * k + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full_chunk || col0 + i < n_out_total) f[i] += __ldg(rb + col0 + i);
+          }
         }
         if (p.scales) {
 #pragma unroll
@@ -327,7 +377,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
           if (full_chunk) {
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(r1 + i);
+              const uint4 u = rr1[i >> 3];
               float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
               f[i] += s_r1 * a.x; f[i + 1] += s_r1 * a.y; f[i + 2] += s_r1 * b.x; f[i + 3] += s_r1 * b.y;
               f[i + 4] += s_r1 * c2.x; f[i + 5] += s_r1 * c2.y; f[i + 6] += s_r1 * d.x; f[i + 7] += s_r1 * d.y;
@@ -342,7 +392,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
           if (full_chunk) {
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(r2 + i);
+              const uint4 u = rr2[i >> 3];
               float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
               f[i] += s_r2 * a.x; f[i + 1] += s_r2 * a.y; f[i + 2] += s_r2 * b.x; f[i + 3] += s_r2 * b.y;
               f[i + 4] += s_r2 * c2.x; f[i + 5] += s_r2 * c2.y; f[i + 6] += s_r2 * d.x; f[i + 7] += s_r2 * d.y;
@@ -434,10 +484,17 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
   if (d->a_major_mn) {
     // memory [K rows][M cols]
     if (d->groups > 1 && d->b_mode != 2) return svdx_fail(SVDX_E_BADARG, "tapgemm: MN-major A requires groups==1");
-    uint64_t dims[2] = {(uint64_t)d->M, (uint64_t)d->K};
-    uint64_t strides[1] = {(uint64_t)d->lda * 2};
-    uint32_t box[2] = {64, 64};
-    rc = svdx_make_tmap(&p.tma, d->a, 2, dims, strides, box);
+    if (d->b_mode == 2) {
+      uint64_t dims[3] = {(uint64_t)d->M, (uint64_t)d->rows_per_group, (uint64_t)d->groups};
+      uint64_t strides[2] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * (uint64_t)d->rows_per_group};
+      uint32_t box[3] = {64, 64, 1};
+      rc = svdx_make_tmap(&p.tma, d->a, 3, dims, strides, box);
+    } else {
+      uint64_t dims[2] = {(uint64_t)d->M, (uint64_t)d->K};
+      uint64_t strides[1] = {(uint64_t)d->lda * 2};
+      uint32_t box[2] = {64, 64};
+      rc = svdx_make_tmap(&p.tma, d->a, 2, dims, strides, box);
+    }
     p.rows_per_group = d->M; p.groups = 1; p.tiles_per_group = (d->M + BLOCK_M - 1) / BLOCK_M;
     p.m_tiles = p.tiles_per_group;
   } else if (d->a_mode == SVDX_A_ROWS) {
@@ -456,6 +513,14 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
     uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * d->W, (uint64_t)d->lda * 2 * d->W * d->H};
     uint32_t box[4] = {64, (uint32_t)d->W, 1, 1};
     rc = svdx_make_tmap(&p.tma, d->a, 4, dims, strides, box);
+    p.max_bh_log2 = 0;
+    for (int lg = 1; lg <= 4 && !rc; ++lg) {
+      const int bh = 1 << lg;
+      if (bh * d->W > BLOCK_M || bh > d->H) break;
+      uint32_t boxh[4] = {64, (uint32_t)d->W, (uint32_t)bh, 1};
+      rc = svdx_make_tmap(&p.tma_bh[lg - 1], d->a, 4, dims, strides, boxh);
+      p.max_bh_log2 = lg;
+    }
     p.W = d->W; p.H = d->H; p.nimg = d->M / (d->H * d->W);
     if ((long long)p.nimg * d->H * d->W != d->M) return svdx_fail(SVDX_E_BADARG, "tapgemm: conv2d M must be images*H*W");
     p.m_tiles = (d->M + BLOCK_M - 1) / BLOCK_M;
