@@ -271,6 +271,8 @@ def main():
             graph.replay()
             torch.cuda.synchronize()
         except Exception as e:  # fall back to eager launches, say so
+            import traceback
+            traceback.print_exc()
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
             graph = None
             torch.cuda.synchronize()

@@ -107,6 +107,13 @@ typedef struct SvdxTapGemm {
 
 int svdx_tapgemm(const SvdxTapGemm* desc, void* stream);
 
+/* Second half of a split-K svdx_tapgemm (fp32 partial sums accumulated with SVDX_OUT_F32_ATOMIC into ws): applies the
+ * same epilogue  out = scales[0]*(ws + bias + rowbias[m / rowbias_div]) + scales[1]*res1 + scales[2]*res2  -> bf16.
+ * Used for the 5x8 / 10x16 latent levels where M gives too few output tiles to fill 148 SMs. */
+int svdx_splitk_epilogue(const float* ws, int64_t ldw, void* out, int64_t ldo, int64_t rows, int32_t cols, const float* bias,
+                         const float* rowbias, int32_t rowbias_div, int64_t ldrb, const void* res1, int64_t ldr1,
+                         const void* res2, int64_t ldr2, const float* scales, void* stream);
+
 /* number of SMs the persistent kernels size their grids to (queried once) */
 int svdx_num_sms(void);
 /* sizeof(SvdxTapGemm) (which==0) / sizeof(SvdxAttn) (which==1): lets bindings verify their struct layout */

@@ -53,6 +53,8 @@ class SvdxAttn(C.Structure):
 
 _PROTOS = {
     "svdx_tapgemm": [C.POINTER(SvdxTapGemm), c_void_p],
+    "svdx_splitk_epilogue": [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_int, c_i64, c_void_p, c_i64,
+                             c_void_p, c_i64, c_void_p, c_void_p],
     "svdx_num_sms": [],
     "svdx_struct_size": [c_int],
     "svdx_groupnorm_stats": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_float,

@@ -297,6 +297,49 @@ __global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __
   if (i < n) dx[i] = dy[i] * silu_grad_f(x[i]);
 }
 
+// epilogue of a split-K contraction: out = s0*(ws + bias + rowbias[m/div]) + s1*res1 + s2*res2  (bf16), 8 columns per thread
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __restrict__ ws, long long ldw, bf16* __restrict__ out, long long ldo,
+                                                              long long rows, int cols, const float* __restrict__ bias,
+                                                              const float* __restrict__ rowbias, int rb_div, long long ldrb,
+                                                              const bf16* __restrict__ res1, long long ldr1, const bf16* __restrict__ res2,
+                                                              long long ldr2, const float* __restrict__ scales) {
+  const int cv = cols / 8;
+  const long long idx = gtid();
+  if (idx >= rows * cv) return;
+  const long long r = idx / cv;
+  const int c = (int)(idx - r * cv) * 8;
+  float s0 = 1.f, s1 = 1.f, s2 = 1.f;
+  if (scales) { s0 = scales[0]; s1 = scales[1]; s2 = scales[2]; }
+  const float4 a = *reinterpret_cast<const float4*>(ws + r * ldw + c);
+  const float4 b = *reinterpret_cast<const float4*>(ws + r * ldw + c + 4);
+  float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (bias) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += bias[c + k];
+  }
+  if (rowbias) {
+    const float* rb = rowbias + (r / rb_div) * ldrb + c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += rb[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] *= s0;
+  if (res1) {
+    const uint4 u = *reinterpret_cast<const uint4*>(res1 + r * ldr1 + c);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 v = unpack_bf16x2(w[k]); f[2 * k] += s1 * v.x; f[2 * k + 1] += s1 * v.y; }
+  }
+  if (res2) {
+    const uint4 u = *reinterpret_cast<const uint4*>(res2 + r * ldr2 + c);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 v = unpack_bf16x2(w[k]); f[2 * k] += s2 * v.x; f[2 * k + 1] += s2 * v.y; }
+  }
+  *reinterpret_cast<uint4*>(out + r * ldo + c) =
+      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
 __global__ void blend_scales_kernel(const float* mix, float* out) {
   const float a = 1.f / (1.f + __expf(-mix[0]));
   out[0] = 1.f - a; out[1] = a; out[2] = 1.f - a; out[3] = 0.f;
@@ -507,5 +550,18 @@ extern "C" int svdx_silu_bwd_f32(const float* x, const float* dy, float* dx, int
   if (!x || !dy || !dx || n <= 0) return svdx_fail(SVDX_E_BADARG, "silu_bwd_f32: bad arguments");
   silu_bwd_f32_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(x, dy, dx, n);
   SVDX_CHECK_LAUNCH("silu_bwd_f32");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_splitk_epilogue(const float* ws, int64_t ldw, void* out, int64_t ldo, int64_t rows, int32_t cols, const float* bias,
+                                    const float* rowbias, int32_t rowbias_div, int64_t ldrb, const void* res1, int64_t ldr1,
+                                    const void* res2, int64_t ldr2, const float* scales, void* stream) {
+  if (!ws || !out || rows <= 0 || cols <= 0 || cols % 8 || ldw % 4 || ldo % 8 || (res1 && ldr1 % 8) || (res2 && ldr2 % 8) ||
+      (rowbias && rowbias_div <= 0))
+    return svdx_fail(SVDX_E_BADARG, "splitk_epilogue: bad arguments");
+  splitk_epilogue_kernel<<<nblocks(rows * (cols / 8)), 256, 0, ST(stream)>>>(ws, ldw, reinterpret_cast<bf16*>(out), ldo, rows, cols, bias, rowbias,
+                                                                            rowbias_div, ldrb, reinterpret_cast<const bf16*>(res1), ldr1,
+                                                                            reinterpret_cast<const bf16*>(res2), ldr2, scales);
+  SVDX_CHECK_LAUNCH("splitk_epilogue");
   return SVDX_OK;
 }

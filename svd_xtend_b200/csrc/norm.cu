@@ -437,7 +437,7 @@ static void ln_bwd_launch(const void* x, int64_t ldx, const void* dy, int64_t ld
                           const float* rstd, void* dx, int64_t lddx, const void* dres, int64_t lddres, float* dgamma, float* dbeta,
                           cudaStream_t st) {
   int ctas = (rows + 7) / 8;
-  const int cap = svdx_num_sms() * 4;
+  const int cap = svdx_num_sms() * 2;   // few CTAs: the dgamma/dbeta atomics contend per address
   if (ctas > cap) ctas = cap;
   ln_bwd_kernel<NJ><<<ctas, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(dy), lddy, rows, C, g, mean,
                                           rstd, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<const bf16*>(dres), lddres, dgamma, dbeta);

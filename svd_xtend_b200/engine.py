@@ -311,9 +311,9 @@ class Engine:
         out = self.empty(M, n_out, x.data, F32 if out_f32 else bf16)
         pre = self.empty(M, N, x.data) if (geglu and self.recording) else None
         b32 = self.vec_f32(bias)
-        raw.tapgemm(x.data, wf, out, M=M, N=N, K=K, bias=b32, res1=None if res1 is None else res1.data,
-                    res2=None if res2 is None else res2.data, scales=scales, geglu=geglu, pre=pre,
-                    rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div)
+        raw.tapgemm_auto(x.data, wf, out, M=M, N=N, K=K, bias=b32, res1=None if res1 is None else res1.data,
+                         res2=None if res2 is None else res2.data, scales=scales, geglu=geglu, pre=pre,
+                         rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div)
         lora = [l for l in (lora or []) if l is not None]
         lora_t = []
         for (off, n, A, Bm, sc) in lora:
@@ -347,7 +347,7 @@ class Engine:
                 if x.needs_grad:
                     wt = self.w_lin_cat(ws, True) if fused is not None else self.w_lin(weight, True)
                     dx = self.empty(M, K, x.data)
-                    raw.tapgemm(dyl, wt, dx, M=M, N=K, K=N, scales=sc3)
+                    raw.tapgemm_auto(dyl, wt, dx, M=M, N=K, K=N, scales=sc3)
                     self.add_grad(x, dx)
                 if any(p.requires_grad for p in ws):
                     self._wgrad(dyl, x.data, ws, N, K, M, sc3)
@@ -469,10 +469,10 @@ class Engine:
         else:
             taps = CONV3x3_TAPS
             whn = (g.W, g.H, nimg)
-        raw.tapgemm(x.data, wf, out, M=M, N=O, K=ip, mode=A_CONV2D, taps=taps, conv_whn=whn, bias=self.vec_f32(conv.bias),
-                    rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
-                    res1=None if res1 is None else res1.data, scales=scales,
-                    block_n=None if O >= 32 else 32)
+        raw.tapgemm_auto(x.data, wf, out, M=M, N=O, K=ip, mode=A_CONV2D, taps=taps, conv_whn=whn, bias=self.vec_f32(conv.bias),
+                         rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
+                         res1=None if res1 is None else res1.data, scales=scales,
+                         block_n=None if O >= 32 else 32)
         w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad)
         need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, rowbias))
         y = Var(out, need)
@@ -494,8 +494,8 @@ class Engine:
                     Op = wt.shape[1] // 9
                     if not planes:
                         dx = self.empty(M, I, x.data)
-                        raw.tapgemm(dy, wt, dx, M=M, N=I, K=Op, mode=A_CONV2D, taps=_neg_taps(CONV3x3_TAPS),
-                                    conv_whn=(g.W, g.H, nimg), scales=sc)
+                        raw.tapgemm_auto(dy, wt, dx, M=M, N=I, K=Op, mode=A_CONV2D, taps=_neg_taps(CONV3x3_TAPS),
+                                         conv_whn=(g.W, g.H, nimg), scales=sc)
                     else:
                         # gradient w.r.t. each parity plane: the taps that read that plane, shifts negated
                         dx = self.empty(4 * M, I, x.data)
@@ -522,9 +522,9 @@ class Engine:
         HW = g.HW
         taps = ((-HW, 0, 0), (0, 0, 0), (HW, 0, 0))
         out = self.empty(M, O, x.data)
-        raw.tapgemm(x.data, wf, out, M=M, N=O, K=I, taps=taps, rows_per_group=g.T * HW, groups=g.B, bias=self.vec_f32(conv.bias),
-                    rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
-                    res1=None if res1 is None else res1.data, scales=scales)
+        raw.tapgemm_auto(x.data, wf, out, M=M, N=O, K=I, taps=taps, rows_per_group=g.T * HW, groups=g.B, bias=self.vec_f32(conv.bias),
+                         rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
+                         res1=None if res1 is None else res1.data, scales=scales)
         w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad) or (blend is not None and blend[0].requires_grad)
         need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, rowbias))
         y = Var(out, need)
@@ -545,7 +545,7 @@ class Engine:
                 if x.needs_grad:
                     wt = self.w_conv(w, True)
                     dx = self.empty(M, I, x.data)
-                    raw.tapgemm(dy, wt, dx, M=M, N=I, K=O, taps=_neg_taps(taps), rows_per_group=g.T * HW, groups=g.B, scales=sc)
+                    raw.tapgemm_auto(dy, wt, dx, M=M, N=I, K=O, taps=_neg_taps(taps), rows_per_group=g.T * HW, groups=g.B, scales=sc)
                     self.add_grad(x, dx)
             self.record(bwd)
         return y

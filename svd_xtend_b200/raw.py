@@ -176,6 +176,35 @@ def tapgemm(
     return out
 
 
+def tapgemm_auto(a, b, out, *, M, N, K, taps=((0, 0, 0),), bias=None, rowbias=None, rowbias_div=1, res1=None, res2=None,
+                 scales=None, **kw):
+    """svdx_tapgemm with automatic split-K for small-M / long-K problems (bf16 output, K-major operands, no GEGLU):
+    when 128x256 tiles cannot fill the SMs, the contraction is split over CTAs (fp32 atomics into a workspace) and
+    svdx_splitk_epilogue applies bias / row-bias / residuals / scales."""
+    kb = ((K + 63) // 64) * len(taps)
+    m_tiles = (M + 127) // 128
+    kw = dict(kw)
+    if kw.get("block_n") is None:
+        kw.pop("block_n", None)
+    if (out.dtype == bf16 and not kw.get("geglu") and not kw.get("a_mn") and not kw.get("b_mn") and kw.get("block_n") is None
+            and N % 8 == 0 and N >= 256):
+        bn = 256 if N % 256 == 0 else (160 if N % 160 == 0 else 0)
+        if bn:
+            tiles = m_tiles * (N // bn)
+            split = min(num_sms() // max(tiles, 1), kb // 8)
+            if tiles <= num_sms() // 3 and split >= 2:
+                ws = torch.zeros(M, N, device=out.device, dtype=torch.float32)
+                tapgemm(a, b, ws, M=M, N=N, K=K, taps=taps, block_n=bn, split_k=split, out_dtype=OUT_F32_ATOMIC, **kw)
+                check(load().svdx_splitk_epilogue(ws.data_ptr(), N, out.data_ptr(), _rowmajor(out, "out"), M, N, _ptr(bias), _ptr(rowbias),
+                                                  rowbias_div, _rowmajor(rowbias, "rowbias") if rowbias is not None else 0,
+                                                  _ptr(res1), _rowmajor(res1, "res1") if res1 is not None else 0,
+                                                  _ptr(res2), _rowmajor(res2, "res2") if res2 is not None else 0,
+                                                  _ptr(scales), _stream()), "svdx_splitk_epilogue")
+                return out
+    return tapgemm(a, b, out, M=M, N=N, K=K, taps=taps, bias=bias, rowbias=rowbias, rowbias_div=rowbias_div, res1=res1, res2=res2,
+                   scales=scales, **kw)
+
+
 CONV3x3_TAPS = tuple((kw - 1, kh - 1, 0) for kh in range(3) for kw in range(3))
 
 

@@ -251,3 +251,23 @@ def test_dot_diff_and_silu_bwd(raw):
     xr = x.clone().requires_grad_(True)
     F.silu(xr).backward(g)
     assert torch.allclose(dx, xr.grad, atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(14, 5, 8, 256, 512), (14, 10, 16, 128, 320)])
+def test_conv3x3_auto_split_k(raw, N, H, W, Cin, Cout):
+    """small-M convs (5x8 / 10x16 latents) take the split-K + svdx_splitk_epilogue path with the full epilogue"""
+    x = _rand(N, H, W, Cin, seed=41).to(bf16)
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=42).to(bf16)
+    bias = _rand(Cout, seed=43)
+    M = N * H * W
+    rb = _rand(2, Cout, seed=44)
+    res = _rand(M, Cout, seed=45).to(bf16)
+    scales = torch.tensor([0.4, 1.0, 0.0], device=_dev())
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9 * Cin)
+    out = torch.empty(M, Cout, device=_dev(), dtype=bf16)
+    raw.tapgemm_auto(x.view(-1, Cin), wk, out, M=M, N=Cout, K=Cin, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, N),
+                     bias=bias, rowbias=rb, rowbias_div=M // 2, res1=res, scales=scales)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    ref = 0.4 * (ref + rb.repeat_interleave(M // 2, 0)) + res.float()
+    _close(out, ref, what="conv split-k")
