@@ -13,51 +13,9 @@
 // (linear, (3,1,1) temporal conv [D: TemporalResnetBlock]) and channels-last images with 2-D
 // shifted taps (3x3 conv [D: ResnetBlock2D/Downsample2D/Upsample2D]); zero padding comes from
 // TMA out-of-bounds fill, so no im2col buffer ever exists.
-#include "common.cuh"
-#include "../../include/svd_xtend_b200.h"
-#include "host_util.h"
+#include "tapgemm_common.cuh"
 
 namespace svdx {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;      // 32 KB
-constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = 512;
-constexpr int NUM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes every other 32-column chunk
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr int SMEM_BYTES = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
-
-struct __align__(64) TapGemmKParams {
-  CUtensorMap tma;
-  CUtensorMap tmb;
-  CUtensorMap tma_bh[4];  // CONV2D: boxes of 2, 4, 8, 16 image rows (tma itself = 1 row)
-  int max_bh_log2;
-  int a_mode, a_mn, b_mn, b_mode, kb_per_group;
-  int rows_per_group, groups, tiles_per_group;
-  int W, H, nimg;
-  int num_taps;
-  int tap_d0[SVDX_MAX_TAPS], tap_d1[SVDX_MAX_TAPS], tap_d2[SVDX_MAX_TAPS];
-  int M, N, K;
-  int block_n, m_tiles, n_tiles, split_k, kb_total, kb_per_split, kb_per_tap;
-  // epilogue
-  void* out;
-  long long ldo;
-  int out_dtype, geglu;
-  const float* bias;
-  const float* rowbias;
-  int rowbias_div;
-  long long ldrb;
-  const bf16* res1;
-  long long ldr1;
-  const bf16* res2;
-  long long ldr2;
-  const float* scales;
-  bf16* pre;
-  long long ldpre;
-};
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_constant__ TapGemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -252,188 +210,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) % p.m_tiles;
       const int n0 = nt * bn_out;
-      // output row of this thread
       long long m;
       bool row_ok;
-      {
-        const int r = q * 32 + lane;
-        if (p.a_mode == SVDX_A_ROWS && !p.a_mn) {
-          const int g = mt / p.tiles_per_group;
-          const int t = mt - g * p.tiles_per_group;
-          const int rin = t * BLOCK_M + r;
-          row_ok = rin < p.rows_per_group;
-          m = (long long)g * p.rows_per_group + rin;
-        } else {
-          m = (long long)mt * BLOCK_M + r;
-          row_ok = m < p.M;
-        }
-      }
+      tile_row(p, mt, q * 32 + lane, m, row_ok);
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      const float* rb = p.rowbias ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
-      for (int c = half * 32; c < bn_out; c += 64) {
-        uint32_t v[32];
-        uint32_t gte[32];
-        const int col0 = n0 + c;
-        const bool full_chunk = (col0 + 32 <= n_out_total);
-        const bool active = row_ok && col0 < n_out_total;
-        // issue the global reads of this chunk before waiting on TMEM so their latency overlaps
-        uint4 rr1[4], rr2[4];
-        if (active && full_chunk) {
-          if (p.res1) {
-            const uint4* r1p = reinterpret_cast<const uint4*>(p.res1 + m * p.ldr1 + col0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) rr1[k] = r1p[k];
-          }
-          if (p.res2) {
-            const uint4* r2p = reinterpret_cast<const uint4*>(p.res2 + m * p.ldr2 + col0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) rr2[k] = r2p[k];
-          }
-        }
-        __syncwarp();
-        tmem_ld32(t_base + c, v);
-        if (p.geglu) tmem_ld32(t_base + bn_out + c, gte);
-        tc_wait_ld();
-        if (active) {
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.geglu) {
-          float g[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(gte[i]);
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (full_chunk || col0 + i < n_out_total) {
-                f[i] += __ldg(p.bias + col0 + i);
-                g[i] += __ldg(p.bias + p.N / 2 + col0 + i);
-              }
-            }
-          }
-          if (p.pre) {
-            bf16* pv = p.pre + m * p.ldpre + col0;
-            bf16* pg = pv + p.N / 2;
-            if (full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 a, b;
-                a.x = pack_bf16x2(f[i], f[i + 1]); a.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                a.z = pack_bf16x2(f[i + 4], f[i + 5]); a.w = pack_bf16x2(f[i + 6], f[i + 7]);
-                b.x = pack_bf16x2(g[i], g[i + 1]); b.y = pack_bf16x2(g[i + 2], g[i + 3]);
-                b.z = pack_bf16x2(g[i + 4], g[i + 5]); b.w = pack_bf16x2(g[i + 6], g[i + 7]);
-                *reinterpret_cast<uint4*>(pv + i) = a;
-                *reinterpret_cast<uint4*>(pg + i) = b;
-              }
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < n_out_total) { pv[i] = __float2bfloat16(f[i]); pg[i] = __float2bfloat16(g[i]); }
-            }
-          }
-          // the reference applies GEGLU on the bf16-rounded projection (autocast F.linear output)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float fv = __bfloat162float(__float2bfloat16(f[i]));
-            const float gv = __bfloat162float(__float2bfloat16(g[i]));
-            f[i] = fv * gelu_erf_f(gv);
-          }
-        } else {
-          if (p.bias) {
-            if (full_chunk) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float4 b4 = __ldg(bp + k);
-                f[4 * k] += b4.x; f[4 * k + 1] += b4.y; f[4 * k + 2] += b4.z; f[4 * k + 3] += b4.w;
-              }
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < n_out_total) f[i] += __ldg(p.bias + col0 + i);
-            }
-          }
-        }
-        if (rb) {
-          if (full_chunk && (reinterpret_cast<uintptr_t>(rb + col0) & 15) == 0) {
-            const float4* bp = reinterpret_cast<const float4*>(rb + col0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 b4 = __ldg(bp + k);
-              f[4 * k] += b4.x; f[4 * k + 1] += b4.y; f[4 * k + 2] += b4.z; f[4 * k + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (full_chunk || col0 + i < n_out_total) f[i] += __ldg(rb + col0 + i);
-          }
-        }
-        if (p.scales) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] *= s_acc;
-        }
-        if (p.res1) {
-          const bf16* r1 = p.res1 + m * p.ldr1 + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 u = rr1[i >> 3];
-              float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-              f[i] += s_r1 * a.x; f[i + 1] += s_r1 * a.y; f[i + 2] += s_r1 * b.x; f[i + 3] += s_r1 * b.y;
-              f[i + 4] += s_r1 * c2.x; f[i + 5] += s_r1 * c2.y; f[i + 6] += s_r1 * d.x; f[i + 7] += s_r1 * d.y;
-            }
-          } else {
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < n_out_total) f[i] += s_r1 * __bfloat162float(r1[i]);
-          }
-        }
-        if (p.res2) {
-          const bf16* r2 = p.res2 + m * p.ldr2 + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 u = rr2[i >> 3];
-              float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-              f[i] += s_r2 * a.x; f[i + 1] += s_r2 * a.y; f[i + 2] += s_r2 * b.x; f[i + 3] += s_r2 * b.y;
-              f[i + 4] += s_r2 * c2.x; f[i + 5] += s_r2 * c2.y; f[i + 6] += s_r2 * d.x; f[i + 7] += s_r2 * d.y;
-            }
-          } else {
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < n_out_total) f[i] += s_r2 * __bfloat162float(r2[i]);
-          }
-        }
-        // ---- store
-        if (p.out_dtype == SVDX_OUT_BF16) {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + m * p.ldo + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 a;
-              a.x = pack_bf16x2(f[i], f[i + 1]); a.y = pack_bf16x2(f[i + 2], f[i + 3]);
-              a.z = pack_bf16x2(f[i + 4], f[i + 5]); a.w = pack_bf16x2(f[i + 6], f[i + 7]);
-              *reinterpret_cast<uint4*>(o + i) = a;
-            }
-          } else {
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < n_out_total) o[i] = __float2bfloat16(f[i]);
-          }
-        } else if (p.out_dtype == SVDX_OUT_F32) {
-          float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < n_out_total) o[i] = f[i];
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col0;
-          for (int i = 0; i < 32; ++i)
-            if (full_chunk || col0 + i < n_out_total) atomicAdd(o + i, f[i]);
-        }
-        }  // row_ok
-      }
+      epilogue_tile(p, t_base, m, row_ok, n0, half, bn_out, n_out_total, s_acc, s_r1, s_r2);
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -454,8 +237,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
 
 using namespace svdx;
 
-extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+int svdx_tapgemm_fill(const SvdxTapGemm* d, TapGemmKParams& p, int cg) {
   if (!d || !d->a || !d->b || !d->out) return svdx_fail(SVDX_E_BADARG, "tapgemm: null pointer");
   if (d->block_n < 32 || d->block_n > 256 || d->block_n % 32) return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n must be a multiple of 32 in [32,256]");
   if (d->b_major_mn && d->block_n % 64) return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n %% 64 for MN-major B");
@@ -468,7 +250,6 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
   if ((d->a_major_mn || d->b_major_mn) && (d->a_mode != SVDX_A_ROWS || d->num_taps != 1)) return svdx_fail(SVDX_E_BADARG, "tapgemm: MN-major operands only in single-tap ROWS mode");
   if (d->b_mode != 0 && !(d->a_major_mn && d->b_major_mn)) return svdx_fail(SVDX_E_BADARG, "tapgemm: b_mode needs MN-major A and B (weight-gradient form)");
 
-  TapGemmKParams p;
   memset(&p, 0, sizeof(p));
   p.a_mode = d->a_mode; p.a_mn = d->a_major_mn; p.b_mn = d->b_major_mn;
   p.num_taps = d->num_taps;
@@ -553,10 +334,13 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
   } else {
     uint64_t dims[2] = {(uint64_t)d->K * d->num_taps, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
-    uint32_t box[2] = {64, (uint32_t)(d->geglu ? d->block_n / 2 : d->block_n)};
+    // a CTA of a pair fetches half of the B tile; a GEGLU tile is already fetched as two halves (value | gate)
+    uint32_t box[2] = {64, (uint32_t)((d->geglu || cg == 2) ? d->block_n / 2 : d->block_n)};
     rc = svdx_make_tmap(&p.tmb, d->b, 2, dims, strides, box);
   }
   if (rc) return rc;
+  p.tiles_per_group_pairs = (p.tiles_per_group + 1) / 2;
+  p.pair_m_tiles = p.tiles_per_group_pairs * p.groups;
 
   p.kb_per_tap = (d->K + BLOCK_K - 1) / BLOCK_K;
   p.kb_total = p.kb_per_tap * d->num_taps;
@@ -583,6 +367,19 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
   if (d->res2 && ((d->ldr2 % 8) || (reinterpret_cast<uintptr_t>(d->res2) & 15))) return svdx_fail(SVDX_E_BADARG, "tapgemm: res2 alignment");
   if (d->pre && ((d->ldpre % 8) || (reinterpret_cast<uintptr_t>(d->pre) & 15))) return svdx_fail(SVDX_E_BADARG, "tapgemm: pre alignment");
 
+  return SVDX_OK;
+}
+
+int svdx_tapgemm2_launch(const TapGemmKParams& p, cudaStream_t stream);   // tapgemm2.cu
+bool svdx_tapgemm2_eligible(const SvdxTapGemm* d);
+
+extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  TapGemmKParams p;
+  const bool pair = svdx_tapgemm2_eligible(d);
+  int rc = svdx_tapgemm_fill(d, p, pair ? 2 : 1);
+  if (rc) return rc;
+  if (pair) return svdx_tapgemm2_launch(p, stream);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
