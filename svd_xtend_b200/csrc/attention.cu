@@ -221,48 +221,49 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       const uint32_t ts = tS + (j & 1) * 128 + lane_off;
       const int kvalid = p.S - j * p.RT;                 // valid key tokens in this block
       const bool nomask = (p.G == 1) && (kvalid >= 128);  // warp-uniform fast path: nothing to mask
-      // pass 1: masked row max of this block
+      // single TMEM pass: the 128 scores of this row stay in registers (TMEM reads are the scarce resource here)
+      uint32_t sv[4][32];
+      tmem_ld32(ts, sv[0]);
+      tmem_ld32(ts + 32, sv[1]);
+      tmem_ld32(ts + 64, sv[2]);
+      tmem_ld32(ts + 96, sv[3]);
+      tc_wait_ld();
+      // the S buffer can be overwritten by the next QK^T as soon as the values are in registers
+      tc_fence_before();
+      mbar_arrive(b_sempty + 8 * (j & 1));
       float bmax = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(ts + c0, v);
-        tc_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int c = c0 + i;
+          const int c = q * 32 + i;
           const bool ok = nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid));
-          if (ok) bmax = fmaxf(bmax, __uint_as_float(v[i]));
+          if (ok) bmax = fmaxf(bmax, __uint_as_float(sv[q][i]));
         }
       }
       const float m_new = fmaxf(m_run, bmax);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_use) * sc);
-      // pass 2: probabilities -> smem
+      const float msc = m_use * sc;
       mbar_wait(b_pempty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);
       float rsum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(ts + c0, v);
-        tc_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int c = c0 + i;
+          const int c = q * 32 + i;
           const bool ok = nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid));
-          const float e = ok ? fast_exp2((__uint_as_float(v[i]) - m_use) * sc) : 0.f;
+          const float e = ok ? fast_exp2(fmaf(__uint_as_float(sv[q][i]), sc, -msc)) : 0.f;
           // the PV product consumes bf16 probabilities; sum the rounded values so the row normaliser matches
           const float eb = __bfloat162float(__float2bfloat16(e));
           f[i] = eb;
           rsum += eb;
         }
-        store_score_chunk(sP + (j & 1) * PT_BYTES, r, c0, f);
+        store_score_chunk(sP + (j & 1) * PT_BYTES, r, q * 32, f);
       }
       l_run = l_run * alpha + rsum;
       m_run = m_new;
-      tc_fence_before();
-      mbar_arrive(b_sempty + 8 * (j & 1));
       fence_proxy_async_smem();
       mbar_arrive(b_pfull + 8 * (j & 1));
       if (j >= 1) absorb(j - 1, alpha_pend);

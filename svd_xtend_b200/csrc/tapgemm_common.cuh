@@ -7,7 +7,7 @@
 
 // default of the SVDX_2CTA switch (env SVDX_2CTA=0/1 overrides): use the CTA-pair kernel where eligible
 #ifndef SVDX_2CTA_DEFAULT
-#define SVDX_2CTA_DEFAULT 0
+#define SVDX_2CTA_DEFAULT 1
 #endif
 
 namespace svdx {
@@ -230,8 +230,15 @@ SVDX_DEVINL void epilogue_tile(const TapGemmKParams& p, uint32_t t_base, long lo
           }
         } else {
           float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col0;
-          for (int i = 0; i < 32; ++i)
-            if (full_chunk || col0 + i < n_out_total) atomicAdd(o + i, f[i]);
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)   // 16-byte vector reductions: 4x fewer L2 atomic requests
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(f[i]), "f"(f[i + 1]), "f"(f[i + 2]), "f"(f[i + 3])
+                           : "memory");
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < n_out_total) atomicAdd(o + i, f[i]);
+          }
         }
         }  // row_ok
       }

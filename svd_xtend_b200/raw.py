@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -57,34 +58,59 @@ def num_sms() -> int:
     return _NUM_SMS[0]
 
 
-def _kstep_cycles(bn: int) -> float:
-    """model of one 128 x bn x 16 tcgen05 step: tensor pipe bn/2 clk vs smem operand reads (4 KB + 32*bn B at 128 B/clk)"""
-    return max(bn / 2.0, 32.0 + bn / 4.0)
+PAIR_MODE = os.environ.get("SVDX_2CTA", "1") != "0"     # mirrors SVDX_2CTA_DEFAULT of tapgemm_common.cuh
+_L2_BYTES_PER_CLK = 4500.0                                # ~8.5 TB/s L2->SM at 1.9 GHz (measured, profiles/)
+
+
+def pair_eligible(M: int, n_out: int, bn_out: int, geglu: bool) -> bool:
+    """same rule as svdx_tapgemm2_eligible (tapgemm2.cu) for K-major problems without split-K"""
+    bn = 2 * bn_out if geglu else bn_out
+    return PAIR_MODE and M >= 512 and bn >= 64 and bn % 32 == 0 and (bn // 2) % 8 == 0 and n_out % bn_out == 0
+
+
+def _tile_cost(M: int, n_out: int, bn_out: int, geglu: bool, sms: int) -> float:
+    """relative time of the whole problem with output tiles 128 x bn_out (256 x bn_out for a CTA pair):
+    waves over the SMs x per-k-block time = max(tensor pipe, L2->SM bytes at the measured chip bandwidth)."""
+    bn = 2 * bn_out if geglu else bn_out
+    m_tiles = (M + 127) // 128
+    n_tiles = (n_out + bn_out - 1) // bn_out
+    pair = pair_eligible(M, n_out, bn_out, geglu)
+    if pair:
+        ctas = 2 * ((m_tiles + 1) // 2) * n_tiles
+        bytes_kb = 16384 + 64 * bn
+    else:
+        ctas = m_tiles * n_tiles
+        bytes_kb = 16384 + 128 * bn
+    active = min(ctas, sms)
+    mma = 4 * max(bn / 2.0, 32.0 + bn / 4.0 if not pair else bn / 2.0)
+    l2 = bytes_kb * active / _L2_BYTES_PER_CLK
+    waves = (ctas + sms - 1) // sms
+    return waves * max(mma, l2)
 
 
 def choose_block_n(M: int, n_out: int, geglu: bool = False, mn_major: bool = False) -> int:
-    """tile width minimising (waves over the SMs) x (cycles per k-step), so small-M levels (5x8, 10x16 latents)
-    spread over all 148 SMs instead of running 25-90 fat tiles. Returns the block_n of the C ABI (2x for GEGLU)."""
+    """tile width for svdx_tapgemm: minimises the modelled time (see _tile_cost) over the widths that tile n_out
+    exactly. Small-M levels get narrow tiles that fill the SMs; large-M levels get the widest tile (fewest L2 bytes per
+    FLOP). Returns the block_n of the C ABI (2x the output width for GEGLU)."""
     sms = num_sms()
-    m_tiles = (M + 127) // 128
     if mn_major:
-        cands = [256, 192, 128, 64]
-    elif geglu:
-        cands = [128, 64, 32]          # output columns per tile; block_n = 2x
-    else:
-        cands = [256, 160, 128, 96, 64, 32]
+        best, best_cost = None, None
+        m_tiles = (M + 127) // 128
+        for bn in (256, 192, 128, 64):
+            cost = m_tiles * ((n_out + bn - 1) // bn) * max(bn / 2.0, 32.0 + bn / 4.0)
+            if best_cost is None or cost < best_cost - 1e-9:
+                best, best_cost = bn, cost
+        return best
+    cands = [128, 64, 32] if geglu else [256, 160, 128, 96, 64, 32]
     best, best_cost = None, None
     for bn in cands:
-        n_tiles = (n_out + bn - 1) // bn
-        if (not mn_major) and n_out % bn and n_out > bn:
-            continue                    # K-major path: keep exact tilings (TMA boxes of partial tiles are fine, but wasteful)
-        tiles = m_tiles * n_tiles
-        step = _kstep_cycles(2 * bn if geglu else bn)
-        cost = (tiles * step) if mn_major else (((tiles + sms - 1) // sms) * step)
-        if best_cost is None or cost < best_cost - 1e-9:
+        if n_out % bn and n_out > bn:
+            continue
+        cost = _tile_cost(M, n_out, bn, geglu, sms)
+        if best_cost is None or cost < best_cost * 0.98:
             best, best_cost = bn, cost
     if best is None:
-        best = pick_block_n(n_out, mn_major)
+        best = pick_block_n(n_out, False)
     return 2 * best if geglu else best
 
 
