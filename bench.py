@@ -243,28 +243,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also fills the weight-operand cache)
+    # ---- warm-up (also fills the weight-operand cache). With CUDA-graph capture ahead, warm up on a side stream and
+    # keep no reference to the autograd graph: AccumulateGrad nodes remember the stream they were created on, and a
+    # node born on the default stream would make the captured backward depend on uncaptured work.
+    use_graph = (not args.no_graph) and world == 1 and not args.profile_one
     lps = 0
-    for _ in range(max(args.warmup, 3)):
-        l_before = raw.LAUNCHES[0]
-        loss = step(devb)
-        lps = raw.LAUNCHES[0] - l_before      # kernels of OUR library launched by one step
+    side = torch.cuda.Stream() if use_graph else None
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side) if side is not None else torch.cuda.stream(torch.cuda.current_stream()):
+        for _ in range(max(args.warmup, 3)):
+            l_before = raw.LAUNCHES[0]
+            step(devb)
+            lps = raw.LAUNCHES[0] - l_before      # kernels of OUR library launched by one step
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
     barrier()
     if args.profile_one:
         step(devb)
         torch.cuda.synchronize()
         return
 
-    # ---- optional CUDA-graph capture of the whole step (kills ~4 k launch overheads per step)
+    # ---- optional CUDA-graph capture of the whole step (kills ~7 k launch overheads per step)
     graph, static_loss = None, None
-    if not args.no_graph and world == 1:
+    if use_graph:
         try:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                step(devb)
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_loss = step(devb)

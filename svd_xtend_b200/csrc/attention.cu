@@ -231,14 +231,30 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       // the S buffer can be overwritten by the next QK^T as soon as the values are in registers
       tc_fence_before();
       mbar_arrive(b_sempty + 8 * (j & 1));
-      float bmax = -INFINITY;
+      float bmax;
+      if (nomask) {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4; ++q) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = q * 32 + i;
-          const bool ok = nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid));
-          if (ok) bmax = fmaxf(bmax, __uint_as_float(sv[q][i]));
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(sv[q][i]));
+            m1 = fmaxf(m1, __uint_as_float(sv[q][i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(sv[q][i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(sv[q][i + 3]));
+          }
+        }
+        bmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {
+        bmax = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = q * 32 + i;
+            const bool ok = (((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid);
+            if (ok) bmax = fmaxf(bmax, __uint_as_float(sv[q][i]));
+          }
         }
       }
       const float m_new = fmaxf(m_run, bmax);
@@ -246,22 +262,32 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_use) * sc);
       const float msc = m_use * sc;
       mbar_wait(b_pempty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);
-      float rsum = 0.f;
+      // probabilities: the row sum uses the fp32 values (the bf16 rounding of P averages out, as in flash-attention)
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float f[32];
+        if (nomask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = q * 32 + i;
-          const bool ok = nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid));
-          const float e = ok ? fast_exp2(fmaf(__uint_as_float(sv[q][i]), sc, -msc)) : 0.f;
-          // the PV product consumes bf16 probabilities; sum the rounded values so the row normaliser matches
-          const float eb = __bfloat162float(__float2bfloat16(e));
-          f[i] = eb;
-          rsum += eb;
+          for (int i = 0; i < 32; i += 4) {
+            f[i] = fast_exp2(fmaf(__uint_as_float(sv[q][i]), sc, -msc));
+            f[i + 1] = fast_exp2(fmaf(__uint_as_float(sv[q][i + 1]), sc, -msc));
+            f[i + 2] = fast_exp2(fmaf(__uint_as_float(sv[q][i + 2]), sc, -msc));
+            f[i + 3] = fast_exp2(fmaf(__uint_as_float(sv[q][i + 3]), sc, -msc));
+            r0 += f[i]; r1 += f[i + 1]; r2 += f[i + 2]; r3 += f[i + 3];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = q * 32 + i;
+            const bool ok = (((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid);
+            f[i] = ok ? fast_exp2(fmaf(__uint_as_float(sv[q][i]), sc, -msc)) : 0.f;
+            r0 += f[i];
+          }
         }
         store_score_chunk(sP + (j & 1) * PT_BYTES, r, q * 32, f);
       }
+      const float rsum = (r0 + r1) + (r2 + r3);
       l_run = l_run * alpha + rsum;
       m_run = m_new;
       fence_proxy_async_smem();
@@ -393,12 +419,20 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
         tmem_ld32(tDP + lane_off + c0, vd);
         tc_wait_ld();
         float f[32];
+        if (nomask && ri.valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = c0 + i;
-          const bool ok = ri.valid && (nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid)));
-          const float pr = ok ? fast_exp2(__uint_as_float(vs[i]) * sc - lse2) : 0.f;
-          f[i] = pr * (__uint_as_float(vd[i]) - dlt) * p.scale;
+          for (int i = 0; i < 32; ++i) {
+            const float pr = fast_exp2(fmaf(__uint_as_float(vs[i]), sc, -lse2)) * p.scale;
+            f[i] = pr * (__uint_as_float(vd[i]) - dlt);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = c0 + i;
+            const bool ok = ri.valid && (nomask || ((((c & p.gmask) == ri.g)) && ((c >> p.gshift) < kvalid)));
+            const float pr = ok ? fast_exp2(fmaf(__uint_as_float(vs[i]), sc, -lse2)) * p.scale : 0.f;
+            f[i] = pr * (__uint_as_float(vd[i]) - dlt);
+          }
         }
         store_score_chunk(sDS, r, c0, f);
       }
@@ -544,13 +578,21 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         tmem_ld32(tDPT + lane_off + c0, vd);
         tc_wait_ld();
         float fp[32], fd[32];
+        const float4* l4 = reinterpret_cast<const float4*>(vec + c0);
+        const float4* d4 = reinterpret_cast<const float4*>(vec + 128 + c0);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int c = c0 + k;  // query column
-          const bool ok = ki.valid && ((c & p.gmask) == ki.g);
-          const float pr = ok ? fast_exp2(__uint_as_float(vs[k]) * sc - vec[c]) : 0.f;
-          fp[k] = pr;
-          fd[k] = pr * (__uint_as_float(vd[k]) - vec[128 + c]) * p.scale;
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 ls = l4[k4], dl = d4[k4];   // broadcast 16-byte shared loads: lse / delta of 4 query columns
+          const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = 4 * k4 + u;
+            const int c = c0 + k;  // query column
+            const bool ok = ki.valid && (p.G == 1 || (c & p.gmask) == ki.g);
+            const float pr = ok ? fast_exp2(fmaf(__uint_as_float(vs[k]), sc, -lsv[u])) : 0.f;
+            fp[k] = pr;
+            fd[k] = pr * p.scale * (__uint_as_float(vd[k]) - dlv[u]);
+          }
         }
         store_score_chunk(sPT, r, c0, fp);
         store_score_chunk(sDST, r, c0, fd);

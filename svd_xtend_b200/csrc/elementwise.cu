@@ -210,30 +210,48 @@ __global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__
   if (i < n) y[i] = silu_f(x[i]);
 }
 
-// column sums of a bf16 [rows][ldx] matrix: grid (col blocks of 64, row chunks); 256 threads =
-// 32 column pairs x 8 row lanes; fp32 atomics into out
+// column sums of a bf16 [rows][ldx] matrix: grid (blocks of 32 column vectors = 256 columns, row chunks); 256 threads =
+// 32 column vectors (16 B each, 512 B contiguous per warp) x 8 row lanes, 4 loads in flight; fp32 atomics into out
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int cols, long long rows_per_cta,
                                                      float* __restrict__ out) {
-  __shared__ float sh[8][64];
-  const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 64 + 2 * cp;
+  __shared__ float sh[8][256 + 8];
+  const int cvl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + cvl) * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, rows);
-  float a = 0.f, b = 0.f;
-  if (c < cols) {
-    for (long long r = r0 + rl; r < r1; r += 8) {
-      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ldx + c));
-      a += v.x; b += v.y;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  if (c0 < cols) {
+    long long r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {
+      uint4 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(x + (r + 8 * q) * ldx + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 v = unpack_bf16x2(w[k]); a[2 * k] += v.x; a[2 * k + 1] += v.y; }
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + r * ldx + c0);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 v = unpack_bf16x2(w[k]); a[2 * k] += v.x; a[2 * k + 1] += v.y; }
     }
   }
-  sh[rl][2 * cp] = a; sh[rl][2 * cp + 1] = b;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += sh[k][threadIdx.x];
-    const int cc = blockIdx.x * 64 + threadIdx.x;
-    if (cc < cols) atomicAdd(out + cc, s);
+  for (int k = 0; k < 8; ++k) sh[rl][cvl * 8 + k] = a[k];
+  __syncthreads();
+  {
+    const int c = threadIdx.x;  // 256 columns of this block
+    float sacc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc += sh[k][c];
+    const int cc = blockIdx.x * 256 + c;
+    if (cc < cols) atomicAdd(out + cc, sacc);
   }
 }
 
@@ -488,10 +506,11 @@ extern "C" int svdx_silu_f32(const float* x, float* y, int64_t n, void* stream) 
 }
 
 extern "C" int svdx_colsum(const void* x, int64_t ldx, int64_t rows, int32_t cols, float* out, int32_t accumulate, void* stream) {
-  if (!x || !out || rows <= 0 || cols <= 0 || cols % 2 || ldx % 2) return svdx_fail(SVDX_E_BADARG, "colsum: bad arguments");
+  if (!x || !out || rows <= 0 || cols <= 0 || cols % 8 || ldx % 8 || (reinterpret_cast<uintptr_t>(x) & 15))
+    return svdx_fail(SVDX_E_BADARG, "colsum: bad arguments (cols, ldx multiples of 8; 16 B aligned)");
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * cols, ST(stream));
-  const int col_blocks = (cols + 63) / 64;
-  long long chunks = (2LL * svdx_num_sms() + col_blocks - 1) / col_blocks;
+  const int col_blocks = (cols + 255) / 256;
+  long long chunks = (4LL * svdx_num_sms() + col_blocks - 1) / col_blocks;
   if (chunks < 1) chunks = 1;
   long long rows_per_cta = (rows + chunks - 1) / chunks;
   if (rows_per_cta < 64) rows_per_cta = 64;

@@ -33,35 +33,72 @@ SVDX_DEVINL float2 load_pair(const GnSrc& s, long long row, int c) {
 }
 
 // ------------------------------------------------------------------ GroupNorm statistics
-// grid (row_chunks, outer). Accumulates sum / sumsq into mean[] / rstd[] (pre-zeroed), finalised below.
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_partial(GnSrc s, int rows, int G, float* sum, float* sumsq) {
+// Vectorised: a thread owns ONE 8-channel vector (16 B) and walks rows, keeping 4 loads in flight; the block is
+// (C/8 channel vectors) x (row lanes). grid (row_chunks, outer). Accumulates sum / sumsq into mean[] / rstd[]
+// (pre-zeroed) through shared-memory then global fp32 atomics; finalised below.
+constexpr int GNV_MAX_THREADS = 512;
+
+SVDX_DEVINL uint4 load_vec8(const GnSrc& s, long long row, int c0) {
+  const bf16* p = (c0 < s.C1) ? (s.x + row * s.ldx + c0) : (s.x2 + row * s.ldx2 + (c0 - s.C1));
+  return *reinterpret_cast<const uint4*>(p);
+}
+
+__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_stats_partial(GnSrc s, int rows, int rows_per_cta, int G, float* sum, float* sumsq) {
   __shared__ float sh_s[32 * 2];
   const int C = s.C1 + s.C2;
+  const int CV = C / 8;
   const int cpg = C / G;
   const int n = blockIdx.y;
-  const int r0 = blockIdx.x * GN_ROWS_PER_CTA;
-  const int r1 = min(r0 + GN_ROWS_PER_CTA, rows);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sh_s[i] = 0.f;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, rows);
+  const int RL = blockDim.x / CV;          // row lanes
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh_s[i] = 0.f;
   __syncthreads();
-  // a lane owns channel pairs c = 2*lane + 64*j; accumulate per pair over the warp's rows, flush per j
-  // blockIdx.z selects a 64-channel slab; a lane owns the channel pair c = slab*64 + 2*lane over the warp's rows
-  const int c = blockIdx.z * 64 + 2 * lane;
-  if (c < C) {
-    float a = 0.f, b = 0.f;
-#pragma unroll 4
-    for (int r = r0 + warp; r < r1; r += GN_WARPS) {
-      const float2 v = load_pair(s, (long long)n * rows + r, c);
-      a += v.x + v.y;
-      b += v.x * v.x + v.y * v.y;
+  if (rl < RL) {
+    const int c0 = cv * 8;
+    float a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = 0.f; b[k] = 0.f; }
+    const long long base = (long long)n * rows;
+    int r = r0 + rl;
+    for (; r + 3 * RL < r1; r += 4 * RL) {
+      uint4 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] = load_vec8(s, base + r + q * RL, c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 v = unpack_bf16x2(w[k]);
+          a[2 * k] += v.x; a[2 * k + 1] += v.y;
+          b[2 * k] += v.x * v.x; b[2 * k + 1] += v.y * v.y;
+        }
+      }
     }
-    const int g = c / cpg;
-    atomicAdd(&sh_s[g], a);
-    atomicAdd(&sh_s[G + g], b);
+    for (; r < r1; r += RL) {
+      const uint4 u = load_vec8(s, base + r, c0);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 v = unpack_bf16x2(w[k]);
+        a[2 * k] += v.x; a[2 * k + 1] += v.y;
+        b[2 * k] += v.x * v.x; b[2 * k + 1] += v.y * v.y;
+      }
+    }
+    // fold the 8 channels into their groups (consecutive channels -> non-decreasing group index)
+    int g = c0 / cpg, left = cpg - (c0 - g * cpg);
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (left == 0) { atomicAdd(&sh_s[g], sa); atomicAdd(&sh_s[G + g], sb); sa = sb = 0.f; ++g; left = cpg; }
+      sa += a[k]; sb += b[k]; --left;
+    }
+    atomicAdd(&sh_s[g], sa); atomicAdd(&sh_s[G + g], sb);
   }
   __syncthreads();
-  const int g_lo = (blockIdx.z * 64) / cpg, g_hi = min(C - 1, blockIdx.z * 64 + 63) / cpg;
-  for (int i = g_lo + threadIdx.x; i <= g_hi; i += GN_THREADS) {
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
     atomicAdd(&sum[n * G + i], sh_s[i]);
     atomicAdd(&sumsq[n * G + i], sh_s[G + i]);
   }
@@ -108,52 +145,80 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, long long total_
 }
 
 // ------------------------------------------------------------------ GroupNorm backward
-// pass 1: per (n, group) s1 = sum(g*gamma), s2 = sum(g*gamma*xhat), g = dy * silu'(z); optional dgamma/dbeta
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_partial(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int G,
-                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             int fuse_silu, float* ws, float* dgamma, float* dbeta) {
+// pass 1: per (n, group) s1 = sum(g*gamma), s2 = sum(g*gamma*xhat), g = dy * silu'(z); optional dgamma/dbeta.
+// Same thread layout as gn_stats_partial (one 8-channel vector per thread, rows in flight).
+__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
+                                                                  int G, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  int fuse_silu, float* ws, float* dgamma, float* dbeta) {
   __shared__ float sh_s[32 * 2];
   const int C = s.C1 + s.C2;
+  const int CV = C / 8;
   const int cpg = C / G;
   const int n = blockIdx.y;
-  const int r0 = blockIdx.x * GN_ROWS_PER_CTA;
-  const int r1 = min(r0 + GN_ROWS_PER_CTA, rows);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 2 * G; i += GN_THREADS) sh_s[i] = 0.f;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, rows);
+  const int RL = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh_s[i] = 0.f;
   __syncthreads();
-  const int c = blockIdx.z * 64 + 2 * lane;
-  if (c < C) {
-    const int g = c / cpg;
-    const float m = mean[n * G + g], rs = rstd[n * G + g];
-    const float g0 = gamma[c], g1 = gamma[c + 1], b0 = beta[c], b1 = beta[c + 1];
-    float a1 = 0.f, a2 = 0.f;          // group sums
-    float dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
-#pragma unroll 4
-    for (int r = r0 + warp; r < r1; r += GN_WARPS) {
-      const long long row = (long long)n * rows + r;
-      const float2 v = load_pair(s, row, c);
-      const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + row * lddy + c));
-      const float xh0 = (v.x - m) * rs, xh1 = (v.y - m) * rs;
-      float e0 = d.x, e1 = d.y;
-      if (fuse_silu) {
-        e0 *= silu_grad_f(xh0 * g0 + b0);
-        e1 *= silu_grad_f(xh1 * g1 + b1);
-      }
-      a1 += e0 * g0 + e1 * g1;
-      a2 += e0 * g0 * xh0 + e1 * g1 * xh1;
-      dg0 += e0 * xh0; dg1 += e1 * xh1; db0 += e0; db1 += e1;
+  if (rl < RL) {
+    const int c0 = cv * 8;
+    float gm[8], bt[8], mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int g = (c0 + k) / cpg;
+      gm[k] = gamma[c0 + k]; bt[k] = beta[c0 + k]; mu[k] = mean[n * G + g]; rs[k] = rstd[n * G + g];
     }
-    atomicAdd(&sh_s[g], a1);
-    atomicAdd(&sh_s[G + g], a2);
+    float a1[8], a2[8], dg[8], db[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a1[k] = a2[k] = dg[k] = db[k] = 0.f; }
+    const long long base = (long long)n * rows;
+    for (int r = r0 + rl; r < r1; r += 2 * RL) {
+      const bool two = (r + RL < r1);
+      const uint4 ux0 = load_vec8(s, base + r, c0);
+      const uint4 ud0 = *reinterpret_cast<const uint4*>(dy + (base + r) * lddy + c0);
+      uint4 ux1 = ux0, ud1 = make_uint4(0, 0, 0, 0);
+      if (two) {
+        ux1 = load_vec8(s, base + r + RL, c0);
+        ud1 = *reinterpret_cast<const uint4*>(dy + (base + r + RL) * lddy + c0);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q == 1 && !two) break;
+        const uint4 ux = q ? ux1 : ux0, ud = q ? ud1 : ud0;
+        const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 v = unpack_bf16x2(wx[k]), d = unpack_bf16x2(wd[k]);
+          const float xh0 = (v.x - mu[2 * k]) * rs[2 * k], xh1 = (v.y - mu[2 * k + 1]) * rs[2 * k + 1];
+          float e0 = d.x, e1 = d.y;
+          if (fuse_silu) {
+            e0 *= silu_grad_f(xh0 * gm[2 * k] + bt[2 * k]);
+            e1 *= silu_grad_f(xh1 * gm[2 * k + 1] + bt[2 * k + 1]);
+          }
+          a1[2 * k] += e0 * gm[2 * k]; a1[2 * k + 1] += e1 * gm[2 * k + 1];
+          a2[2 * k] += e0 * gm[2 * k] * xh0; a2[2 * k + 1] += e1 * gm[2 * k + 1] * xh1;
+          dg[2 * k] += e0 * xh0; dg[2 * k + 1] += e1 * xh1;
+          db[2 * k] += e0; db[2 * k + 1] += e1;
+        }
+      }
+    }
+    int g = c0 / cpg, left = cpg - (c0 - g * cpg);
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (left == 0) { atomicAdd(&sh_s[g], sa); atomicAdd(&sh_s[G + g], sb); sa = sb = 0.f; ++g; left = cpg; }
+      sa += a1[k]; sb += a2[k]; --left;
+    }
+    atomicAdd(&sh_s[g], sa); atomicAdd(&sh_s[G + g], sb);
     if (dgamma) {
-      atomicAdd(&dgamma[c], dg0); atomicAdd(&dgamma[c + 1], dg1);
-      atomicAdd(&dbeta[c], db0); atomicAdd(&dbeta[c + 1], db1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { atomicAdd(&dgamma[c0 + k], dg[k]); atomicAdd(&dbeta[c0 + k], db[k]); }
     }
   }
   __syncthreads();
-  const int g_lo = (blockIdx.z * 64) / cpg, g_hi = min(C - 1, blockIdx.z * 64 + 63) / cpg;
-  for (int i = g_lo + threadIdx.x; i <= g_hi; i += GN_THREADS) {
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
     atomicAdd(&ws[(n * G + i) * 2 + 0], sh_s[i]);
     atomicAdd(&ws[(n * G + i) * 2 + 1], sh_s[G + i]);
   }
@@ -342,9 +407,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
 
 using namespace svdx;
 
+// block = (C/8 channel vectors) x (row lanes) threads; rows per CTA chosen so that ~4 CTAs per SM exist
+static void gn_vec_config(int C, int outer, int rows, int& threads, int& rows_per_cta) {
+  const int CV = C / 8;
+  int RL = 256 / CV;
+  if (RL < 1) RL = 1;
+  threads = CV * RL;
+  const long long want_ctas = 4LL * svdx_num_sms();
+  long long chunks = (want_ctas + outer - 1) / outer;
+  if (chunks < 1) chunks = 1;
+  rows_per_cta = (int)((rows + chunks - 1) / chunks);
+  const int min_rows = 8 * RL;
+  if (rows_per_cta < min_rows) rows_per_cta = min_rows;
+}
+
 static int gn_check(int C1, int C2, int G, int64_t ldx, int64_t ldx2, const void* x, const void* x2) {
   const int C = C1 + C2;
-  if (!x || G <= 0 || G > 32 || C % G || (C / G) % 2 || C % 8 || C1 % 8 || C2 % 8 || C > 2 * MAX_C) return 1;
+  if (!x || G <= 0 || G > 32 || C % G || (C / G) % 2 || C % 8 || C1 % 8 || C2 % 8 || C / 8 > GNV_MAX_THREADS) return 1;
   if (C2 > 0 && !x2) return 1;
   if (ldx % 8 || (C2 > 0 && ldx2 % 8)) return 1;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (x2 && (reinterpret_cast<uintptr_t>(x2) & 15))) return 1;
@@ -360,8 +439,10 @@ extern "C" int svdx_groupnorm_stats(const void* x, int64_t ldx, int32_t C1, cons
   const int total = outer * num_groups;
   cudaMemsetAsync(mean, 0, sizeof(float) * total, st);
   cudaMemsetAsync(rstd, 0, sizeof(float) * total, st);
-  dim3 grid((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, outer, (C1 + C2 + 63) / 64);
-  gn_stats_partial<<<grid, GN_THREADS, 0, st>>>(s, rows, num_groups, mean, rstd);
+  int threads, rpc;
+  gn_vec_config(C1 + C2, outer, rows, threads, rpc);
+  dim3 grid((rows + rpc - 1) / rpc, outer);
+  gn_stats_partial<<<grid, threads, 0, st>>>(s, rows, rpc, num_groups, mean, rstd);
   const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
   gn_stats_finalize<<<(total + 127) / 128, 128, 0, st>>>(mean, rstd, total, inv, eps);
   SVDX_CHECK_LAUNCH("groupnorm_stats");
@@ -394,8 +475,10 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
   const int total = outer * num_groups;
   cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * total, st);
-  dim3 grid((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, outer, (C1 + C2 + 63) / 64);
-  gn_bwd_partial<<<grid, GN_THREADS, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, num_groups, mean, rstd, gamma, beta,
+  int threads, rpc;
+  gn_vec_config(C1 + C2, outer, rows, threads, rpc);
+  dim3 grid((rows + rpc - 1) / rpc, outer);
+  gn_bwd_partial<<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta,
                                               fuse_silu, workspace, dgamma, dbeta);
   const long long total_rows = (long long)outer * rows;
   const long long nvec = total_rows * ((C1 + C2) / 8);

@@ -264,15 +264,17 @@ class Engine:
         return torch.empty(rows, cols, device=like.device, dtype=dtype)
 
     def _bias_grad(self, bias_p, dy: torch.Tensor, scale: Optional[torch.Tensor] = None):
+        """bias gradient = column sums of dy (dy may carry zero-padded extra columns, e.g. conv_out's 4 -> 8)."""
         if bias_p is None or not bias_p.requires_grad:
             return
         g = self.pgrad(bias_p)
-        if scale is None:
+        n = g.numel()
+        if scale is None and dy.shape[1] == n:
             raw.colsum(dy, g, accumulate=True)
         else:
-            tmp = torch.empty_like(g)
+            tmp = torch.empty(dy.shape[1], device=dy.device, dtype=F32)
             raw.colsum(dy, tmp)
-            g.add_(tmp * scale)
+            g.add_(tmp[:n] if scale is None else tmp[:n] * scale)
 
     # ------------------------------------------------------------------ linear family
     def _res_grad(self, r: Optional[Var], dy: torch.Tensor, scale: Optional[torch.Tensor]):
@@ -484,7 +486,7 @@ class Engine:
                 s_acc = None if scales is None else scales[0:1]
                 self._res_grad(res1, dy, None if (scales is None or res1_unit) else scales[1:2])
                 if conv.bias is not None and conv.bias.requires_grad:
-                    self._bias_grad(conv.bias, dy[:, :O], s_acc)
+                    self._bias_grad(conv.bias, dy, s_acc)
                 self._rowbias_grad(rowbias, dy, rowbias_div, s_acc)
                 sc = self._acc_only(s_acc)
                 if w.requires_grad:
