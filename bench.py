@@ -243,47 +243,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also fills the weight-operand cache). With CUDA-graph capture ahead, warm up on a side stream and
-    # keep no reference to the autograd graph: AccumulateGrad nodes remember the stream they were created on, and a
-    # node born on the default stream would make the captured backward depend on uncaptured work.
+    # ---- warm-up (also fills the weight-operand cache); with graphs the warm-up happens inside GraphedStep
     use_graph = (not args.no_graph) and world == 1 and not args.profile_one
     lps = 0
-    side = torch.cuda.Stream() if use_graph else None
-    if side is not None:
-        side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side) if side is not None else torch.cuda.stream(torch.cuda.current_stream()):
-        for _ in range(max(args.warmup, 3)):
-            l_before = raw.LAUNCHES[0]
-            step(devb)
-            lps = raw.LAUNCHES[0] - l_before      # kernels of OUR library launched by one step
-    if side is not None:
-        torch.cuda.current_stream().wait_stream(side)
+    for _ in range(1 if use_graph else max(args.warmup, 3)):
+        l_before = raw.LAUNCHES[0]
+        step(devb)
+        lps = raw.LAUNCHES[0] - l_before      # kernels of OUR library launched by one step
     barrier()
     if args.profile_one:
         step(devb)
         torch.cuda.synchronize()
         return
 
-    # ---- optional CUDA-graph capture of the whole step (kills ~7 k launch overheads per step)
-    graph, static_loss = None, None
+    # ---- CUDA-graph capture of the whole step through the public helper (svd_xtend_b200.train.GraphedStep)
+    graphed = None
     if use_graph:
         try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_loss = step(devb)
-            graph.replay()
-            torch.cuda.synchronize()
+            from svd_xtend_b200.train import GraphedStep
+            l_before = raw.LAUNCHES[0]
+            graphed = GraphedStep(step, devb, warmup=max(args.warmup, 3))
+            lps = (raw.LAUNCHES[0] - l_before) // (max(args.warmup, 3) + 1)
         except Exception as e:  # fall back to eager launches, say so
             import traceback
             traceback.print_exc()
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
-            graph = None
+            graphed = None
             torch.cuda.synchronize()
+    graph = graphed
 
     def run_step():
-        if graph is not None:
-            graph.replay()
-            return static_loss
+        if graphed is not None:
+            return graphed.replay()
         return step(devb)
 
     for _ in range(2):
@@ -313,6 +304,8 @@ def main():
 
     # ---- e2e: public API from pinned host buffers, H2D inside, loss read back every step
     def e2e_step():
+        if graphed is not None:     # pinned host -> static device buffers -> one graph launch -> loss back to the host
+            return float(graphed(host).item())
         b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         return float(step(b).item())
 

@@ -220,10 +220,12 @@ int svdx_colsum(const void* x, int64_t ldx, int64_t rows, int32_t cols, float* o
 /* GEGLU backward: dpre[m][:h] = dout*gelu(gate); dpre[m][h:] = dout*value*gelu'(gate) */
 int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t lddo, void* dpre, int64_t lddpre,
                    int64_t rows, int32_t h, void* stream);
-/* AlphaBlender epilogue scale triples from mix_factor, a = sigmoid(mix_factor); writes float[8]:
- *   out[0..3] = {1-a, a, 1-a, 0}      transformer blend  out = a*x_spatial + (1-a)*(acc + residual)
- *   out[4..7] = {1-a, 1, 0, a*(1-a)}  resnet blend       out = x_spatial + (1-a)*acc */
-int svdx_blend_scales(const float* mix_factor, float* out8, void* stream);
+/* AlphaBlender epilogue scale triples from mix_factor, a = sigmoid(mix_factor); writes float[16]:
+ *   out[0..3]   = {1-a, a, 1-a, 0}      transformer blend  out = a*x_spatial + (1-a)*(acc + residual)
+ *   out[4..7]   = {1-a, 1, 0, a*(1-a)}  resnet blend       out = x_spatial + (1-a)*acc
+ *   out[8..11]  = {1-a, 0, 0, 0}        accumulator-only triple (gradient GEMMs of a blended forward)
+ *   out[12..15] = {a, 0, 1-a, 0}        {s, 0} pairs for svdx_axpby_bf16 (gradients of the residual operands) */
+int svdx_blend_scales(const float* mix_factor, float* out16, void* stream);
 /* fused multi-tensor AdamW on a flat fp32 buffer (torch.optim.AdamW of train_svd.py:767-773) */
 int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int32_t step, float grad_scale, void* stream);

@@ -12,5 +12,5 @@ echo "=== bench graph" >> gpurun_out/bench_dev.log
 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_graph.json 2>> gpurun_out/bench_dev.log
 cat gpurun_out/bench_graph.json >> gpurun_out/bench_dev.log
 echo "=== ncu launch list" >> gpurun_out/bench_dev.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3800 --csv --log-file gpurun_out/launches_r1.csv python bench.py --profile-one --warmup 1 --no-graph >> gpurun_out/bench_dev.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 16000 --csv --log-file gpurun_out/launches_r1.csv python bench.py --profile-one --warmup 1 --no-graph >> gpurun_out/bench_dev.log 2>&1
 tail -c 4000 gpurun_out/bench_dev.log

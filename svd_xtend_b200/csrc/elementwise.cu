@@ -362,6 +362,8 @@ __global__ void blend_scales_kernel(const float* mix, float* out) {
   const float a = 1.f / (1.f + __expf(-mix[0]));
   out[0] = 1.f - a; out[1] = a; out[2] = 1.f - a; out[3] = 0.f;
   out[4] = 1.f - a; out[5] = 1.f; out[6] = 0.f; out[7] = a * (1.f - a);
+  out[8] = 1.f - a; out[9] = 0.f; out[10] = 0.f; out[11] = 0.f;     // accumulator-only triple for the gradient GEMMs
+  out[12] = a; out[13] = 0.f; out[14] = 1.f - a; out[15] = 0.f;      // {s, 0} pairs for svdx_axpby_bf16 (scaled copies)
 }
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,

@@ -324,8 +324,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
   }
 }
 
-// backward: each warp walks rows (grid-stride), keeps per-lane dgamma/dbeta partials in registers,
-// flushes them with atomics at the end. dx = rstd*(gamma*dy - mean(gamma*dy) - xhat*mean(gamma*dy*xhat)) [+ dres]
+// backward: each warp walks rows (grid-stride); a lane owns the 8-channel vectors lane, lane+32, ... (16-byte loads of x,
+// dy and the residual gradient in flight together), keeps its dgamma/dbeta partials in registers, and the block reduces
+// them through shared memory before one atomic per channel.
+// dx = rstd*(gamma*dy - mean(gamma*dy) - xhat*mean(gamma*dy*xhat)) [+ dres]
 template <int NJ>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
                                                      int rows, int C, const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -334,65 +336,82 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  float2 gm[NJ], dg[NJ], db[NJ];
+  const int CV = C / 8;
+  float gm[NJ][8], dg[NJ][8], db[NJ][8];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const int c = 2 * lane + 64 * j;
-    gm[j] = (c < C) ? make_float2(gamma[c], gamma[c + 1]) : make_float2(0.f, 0.f);
-    dg[j] = make_float2(0.f, 0.f);
-    db[j] = make_float2(0.f, 0.f);
+    const int v = lane + 32 * j;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      gm[j][k] = (v < CV) ? gamma[v * 8 + k] : 0.f;
+      dg[j][k] = 0.f;
+      db[j][k] = 0.f;
+    }
   }
+  const float invC = 1.0f / C;
   for (int row = warp0; row < rows; row += nwarps) {
     const bf16* xr = x + (long long)row * ldx;
     const bf16* dr = dy + (long long)row * lddy;
+    uint4 ux[NJ], ud[NJ], ur[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int v = lane + 32 * j;
+      if (v < CV) {
+        ux[j] = *reinterpret_cast<const uint4*>(xr + v * 8);
+        ud[j] = *reinterpret_cast<const uint4*>(dr + v * 8);
+        if (dres) ur[j] = *reinterpret_cast<const uint4*>(dres + (long long)row * lddres + v * 8);
+      }
+    }
     const float m = mean[row], rs = rstd[row];
-    float2 xh[NJ], gd[NJ];
+    float xh[NJ][8], gd[NJ][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int c = 2 * lane + 64 * j;
-      if (c < C) {
-        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
-        const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dr + c));
-        xh[j] = make_float2((v.x - m) * rs, (v.y - m) * rs);
-        gd[j] = make_float2(d.x * gm[j].x, d.y * gm[j].y);
-        s1 += gd[j].x + gd[j].y;
-        s2 += gd[j].x * xh[j].x + gd[j].y * xh[j].y;
-        dg[j].x += d.x * xh[j].x; dg[j].y += d.y * xh[j].y;
-        db[j].x += d.x; db[j].y += d.y;
-      } else {
-        xh[j] = make_float2(0.f, 0.f);
-        gd[j] = make_float2(0.f, 0.f);
+      const int v = lane + 32 * j;
+      if (v < CV) {
+        const uint32_t wx[4] = {ux[j].x, ux[j].y, ux[j].z, ux[j].w}, wd[4] = {ud[j].x, ud[j].y, ud[j].z, ud[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(wx[k]), d = unpack_bf16x2(wd[k]);
+          xh[j][2 * k] = (a.x - m) * rs; xh[j][2 * k + 1] = (a.y - m) * rs;
+          gd[j][2 * k] = d.x * gm[j][2 * k]; gd[j][2 * k + 1] = d.y * gm[j][2 * k + 1];
+          s1 += gd[j][2 * k] + gd[j][2 * k + 1];
+          s2 += gd[j][2 * k] * xh[j][2 * k] + gd[j][2 * k + 1] * xh[j][2 * k + 1];
+          dg[j][2 * k] += d.x * xh[j][2 * k]; dg[j][2 * k + 1] += d.y * xh[j][2 * k + 1];
+          db[j][2 * k] += d.x; db[j][2 * k + 1] += d.y;
+        }
       }
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
     bf16* oxr = dx + (long long)row * lddx;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int c = 2 * lane + 64 * j;
-      if (c < C) {
-        float a = rs * (gd[j].x - s1 - xh[j].x * s2);
-        float b = rs * (gd[j].y - s1 - xh[j].y * s2);
+      const int v = lane + 32 * j;
+      if (v < CV) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = rs * (gd[j][k] - s1 - xh[j][k] * s2);
         if (dres) {
-          const float2 r = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dres + (long long)row * lddres + c));
-          a += r.x; b += r.y;
+          const uint32_t wr[4] = {ur[j].x, ur[j].y, ur[j].z, ur[j].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 r2 = unpack_bf16x2(wr[k]); o[2 * k] += r2.x; o[2 * k + 1] += r2.y; }
         }
-        *reinterpret_cast<uint32_t*>(oxr + c) = pack_bf16x2(a, b);
+        *reinterpret_cast<uint4*>(oxr + v * 8) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
       }
     }
   }
   if (dgamma) {
-    // block-level reduction through shared memory, then one atomic per channel per CTA
-    __shared__ float sh_g[64 * NJ], sh_b[64 * NJ];
-    for (int i = threadIdx.x; i < 64 * NJ; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; }
+    __shared__ float sh_g[256 * NJ], sh_b[256 * NJ];
+    for (int i = threadIdx.x; i < 256 * NJ; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int c = 2 * lane + 64 * j;
-      if (c < C) {
-        atomicAdd(&sh_g[c], dg[j].x); atomicAdd(&sh_g[c + 1], dg[j].y);
-        atomicAdd(&sh_b[c], db[j].x); atomicAdd(&sh_b[c + 1], db[j].y);
+      const int v = lane + 32 * j;
+      if (v < CV) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { atomicAdd(&sh_g[v * 8 + k], dg[j][k]); atomicAdd(&sh_b[v * 8 + k], db[j][k]); }
       }
     }
     __syncthreads();
@@ -530,14 +549,15 @@ extern "C" int svdx_layernorm_bwd(const void* x, int64_t ldx, const void* dy, in
                                   const float* mean, const float* rstd, void* dx, int64_t lddx, const void* dres, int64_t lddres,
                                   float* dgamma, float* dbeta, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
-  if (!x || !dy || !dx || !gamma || !mean || !rstd || rows <= 0 || C <= 0 || C % 2 || C > 64 * LN_MAXJ || ldx % 2 || lddy % 2 || lddx % 2 ||
-      (dgamma && !dbeta) || (dres && lddres % 2))
-    return svdx_fail(SVDX_E_BADARG, "layernorm_bwd: bad arguments");
-  const int nj = (C + 63) / 64;
-  if (nj <= 5) ln_bwd_launch<5>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
-  else if (nj <= 10) ln_bwd_launch<10>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
-  else if (nj <= 20) ln_bwd_launch<20>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
-  else ln_bwd_launch<40>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
+  if (!x || !dy || !dx || !gamma || !mean || !rstd || rows <= 0 || C <= 0 || C % 8 || C > 2560 || ldx % 8 || lddy % 8 || lddx % 8 ||
+      (dgamma && !dbeta) || (dres && lddres % 8))
+    return svdx_fail(SVDX_E_BADARG, "layernorm_bwd: bad arguments (C %% 8, C <= 2560, 16-byte aligned rows)");
+  const int nj = (C / 8 + 31) / 32;
+  if (nj <= 1) ln_bwd_launch<1>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
+  else if (nj <= 2) ln_bwd_launch<2>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
+  else if (nj <= 3) ln_bwd_launch<3>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
+  else if (nj <= 5) ln_bwd_launch<5>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
+  else ln_bwd_launch<10>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
   SVDX_CHECK_LAUNCH("layernorm_bwd");
   return SVDX_OK;
 }

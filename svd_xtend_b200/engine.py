@@ -380,10 +380,21 @@ class Engine:
             self._consts[key] = t
         return t
 
+    @staticmethod
+    def _blend_base(view: torch.Tensor):
+        """(16-float svdx_blend_scales buffer, element offset of `view` in it) when `view` is a slice of one, else (None, 0)"""
+        base = view._base
+        if base is not None and base.numel() == 16 and base.dtype == F32:
+            return base, (view.data_ptr() - base.data_ptr()) // 4
+        return None, 0
+
     def _acc_only(self, s3):
-        """scales triple {s_acc, 0, 0} for gradient GEMMs of a scaled forward."""
+        """scales triple {s_acc, 0, 0} for gradient GEMMs of a scaled forward (precomputed by svdx_blend_scales)."""
         if s3 is None:
             return None
+        base, _ = self._blend_base(s3)
+        if base is not None:
+            return base[8:11]
         t = torch.zeros(3, device=s3.device, dtype=F32)
         t[0:1].copy_(s3[0:1])
         self.keep.append(t)
@@ -392,10 +403,14 @@ class Engine:
     def _scaled(self, t: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
         """fresh tensor s*t (s: device scalar tensor [1])."""
         out = torch.empty_like(t)
-        sc = torch.zeros(2, device=t.device, dtype=F32)
-        sc[0:1].copy_(s)
+        base, off = self._blend_base(s)
+        if base is not None and off in (1, 2):          # alpha / (1 - alpha) of the transformer blend
+            sc = base[12:14] if off == 1 else base[14:16]
+        else:
+            sc = torch.zeros(2, device=t.device, dtype=F32)
+            sc[0:1].copy_(s)
+            self.keep.append(sc)
         raw.axpby(t.reshape(-1), t.reshape(-1), out.reshape(-1), sc)
-        self.keep.append(sc)
         return out
 
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, ws, N, K, M, scales3):

@@ -725,9 +725,9 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         return E.linear(E.silu_cast(h), mlp.linear_2.weight, mlp.linear_2.bias, out_f32=True)
 
     def _blend(self, E: Engine, mixer: AlphaBlender) -> torch.Tensor:
-        """device float[8] epilogue scale triples of an AlphaBlender (image_only_indicator is all zeros, :430)."""
+        """device float[16] epilogue scale triples (svdx_blend_scales layout) of an AlphaBlender (image_only_indicator is all zeros, :430)."""
         mix = mixer.mix_factor
-        return E.wc.get(("blend", id(mix)), [mix], (8,), lambda buf: raw.blend_scales(E.vec_f32(mix), buf), dtype=F32)
+        return E.wc.get(("blend", id(mix)), [mix], (16,), lambda buf: raw.blend_scales(E.vec_f32(mix), buf), dtype=F32)
 
     def _res(self, E: Engine, owner: nn.Module, res: SpatioTemporalResBlock, x: Var, g: Geom) -> Var:
         """a resnet of a down/mid/up block, gradient-checkpointed when the owner's flag is set ([D] unet_3d_blocks.py)."""

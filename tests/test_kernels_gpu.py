@@ -228,12 +228,12 @@ def test_misc_elementwise(raw):
     torch.cuda.synchronize()
     _close(out, x.float().sum(0), tol=1e-3, what="colsum")
     mix = torch.tensor([0.5], device=DEV)
-    s3 = torch.empty(8, device=DEV)
+    s3 = torch.empty(16, device=DEV)
     raw.blend_scales(mix, s3)
     a = torch.sigmoid(mix)
     one, zero = torch.ones_like(a), torch.zeros_like(a)
     torch.cuda.synchronize()
-    assert torch.allclose(s3, torch.stack([1 - a, a, 1 - a, zero, 1 - a, one, zero, a * (1 - a)]).flatten(), atol=1e-6)
+    assert torch.allclose(s3, torch.stack([1 - a, a, 1 - a, zero, 1 - a, one, zero, a * (1 - a), 1 - a, zero, zero, zero, a, zero, 1 - a, zero]).flatten(), atol=1e-6)
     y = torch.empty_like(x)
     raw.axpby(x, x, y, s3)
     torch.cuda.synchronize()
