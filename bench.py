@@ -218,7 +218,7 @@ def main():
     arena = ParamArena(unet)
     unet.attach_arena(arena)
     opt = FusedAdamW(arena, lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)   # train_svd.py:384-418 defaults
-    opt.on_updated = unet.refresh_trainable_operands
+    opt.on_updated = lambda: unet.refresh_trainable_operands(shadow_current=True)   # FusedAdamW rewrites the bf16 shadow itself
     reducer = GradReducer(arena) if world > 1 else None
     if reducer is not None:
         unet.grad_hook = lambda ps: reducer.on_grads_ready(ps) if ps is not None else None

@@ -226,9 +226,14 @@ int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t ldd
  *   out[8..11]  = {1-a, 0, 0, 0}        accumulator-only triple (gradient GEMMs of a blended forward)
  *   out[12..15] = {a, 0, 1-a, 0}        {s, 0} pairs for svdx_axpby_bf16 (gradients of the residual operands) */
 int svdx_blend_scales(const float* mix_factor, float* out16, void* stream);
-/* fused multi-tensor AdamW on a flat fp32 buffer (torch.optim.AdamW of train_svd.py:767-773) */
+/* fused multi-tensor AdamW on a flat fp32 buffer (torch.optim.AdamW of train_svd.py:767-773); when shadow_bf16 is given
+ * the updated parameters are also written as bf16 at the same flat offsets (the forward GEMM operands) */
 int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-               float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+               float eps, float weight_decay, int32_t step, float grad_scale, void* shadow_bf16, void* stream);
+/* many bf16 transposes dst[i][o] = src_base[src_off + o*I + i] in one launch (dgrad operands of all trainable linears).
+ * jobs: device array of {int64 src_off; void* dst; int32 O; int32 I}; tile_prefix[j] = first 32x32 tile of job j. */
+int svdx_multi_transpose(const void* src_base, const void* jobs, const int32_t* tile_prefix, int32_t njobs, int32_t total_tiles,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ for n, p in unet.named_parameters():
         p.requires_grad_(True)
 unet.train()
 arena = ParamArena(unet); unet.attach_arena(arena)
-opt = FusedAdamW(arena, lr=1e-5); opt.on_updated = unet.refresh_trainable_operands
+opt = FusedAdamW(arena, lr=1e-5); opt.on_updated = lambda: unet.refresh_trainable_operands(shadow_current=True)
 b = synthetic_batch(1, 14, 40, 64, seed=1, device=dev) if FULL else synthetic_batch(1, 4, 16, 16, seed=1, device=dev, cross_dim=TINY_CONFIG["cross_attention_dim"])
 
 def fwd():

@@ -91,7 +91,8 @@ _PROTOS = {
     "svdx_geglu_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_void_p],
     "svdx_blend_scales": [c_void_p, c_void_p, c_void_p],
     "svdx_adamw": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
-                   c_int, c_float, c_void_p],
+                   c_int, c_float, c_void_p, c_void_p],
+    "svdx_multi_transpose": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS) + ("svdx_last_error",)

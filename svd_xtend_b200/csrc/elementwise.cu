@@ -367,7 +367,7 @@ __global__ void blend_scales_kernel(const float* mix, float* out) {
 }
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) {
+                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale, bf16* __restrict__ shadow) {
   const long long i = gtid();
   if (i >= n) return;
   const float gi = g[i] * gscale;
@@ -379,6 +379,39 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
   pi -= (lr / bc1) * mi / denom;
   p[i] = pi;
+  if (shadow) shadow[i] = __float2bfloat16(pi);   // bf16 operand copy of the updated weight, same flat offset
+}
+
+struct TransposeJob {
+  long long src_off;   // element offset into the bf16 source arena
+  bf16* dst;           // [I][O] destination
+  int O, I;
+};
+
+// many 2-D transposes dst[i][o] = src[o][i] (bf16) in ONE launch: block -> (job, 32x32 tile) through a tile prefix table
+__global__ void multi_transpose_kernel(const bf16* __restrict__ src_base, const TransposeJob* __restrict__ jobs,
+                                       const int* __restrict__ tile_prefix, int njobs) {
+  __shared__ bf16 tile[32][34];
+  int lo = 0, hi = njobs - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {            // last job whose first tile <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  const TransposeJob j = jobs[lo];
+  const int t = b - tile_prefix[lo];
+  const int tiles_x = (j.I + 31) / 32;
+  const int i0 = (t % tiles_x) * 32, o0 = (t / tiles_x) * 32;
+  const bf16* src = src_base + j.src_off;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int o = o0 + r, i = i0 + threadIdx.x;
+    if (o < j.O && i < j.I) tile[r][threadIdx.x] = src[(long long)o * j.I + i];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, o = o0 + threadIdx.x;
+    if (i < j.I && o < j.O) j.dst[(long long)i * j.O + o] = tile[threadIdx.x][r];
+  }
 }
 
 }  // namespace svdx
@@ -540,11 +573,21 @@ extern "C" int svdx_blend_scales(const float* mix_factor, float* out3, void* str
 }
 
 extern "C" int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                          float weight_decay, int32_t step, float grad_scale, void* stream) {
+                          float weight_decay, int32_t step, float grad_scale, void* shadow_bf16, void* stream) {
   if (!p || !g || !m || !v || n <= 0 || step < 1) return svdx_fail(SVDX_E_BADARG, "adamw: bad arguments");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  adamw_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  adamw_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
+                                                   reinterpret_cast<bf16*>(shadow_bf16));
   SVDX_CHECK_LAUNCH("adamw");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_multi_transpose(const void* src_base, const void* jobs, const int32_t* tile_prefix, int32_t njobs, int32_t total_tiles,
+                                    void* stream) {
+  if (!src_base || !jobs || !tile_prefix || njobs <= 0 || total_tiles <= 0) return svdx_fail(SVDX_E_BADARG, "multi_transpose: bad arguments");
+  multi_transpose_kernel<<<total_tiles, dim3(32, 8), 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src_base),
+                                                                     reinterpret_cast<const TransposeJob*>(jobs), tile_prefix, njobs);
+  SVDX_CHECK_LAUNCH("multi_transpose");
   return SVDX_OK;
 }
 

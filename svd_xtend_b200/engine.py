@@ -126,6 +126,7 @@ class Engine:
         self.pgrads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         self.launches = 0
         self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}   # optional flat gradient arena (train.ParamArena)
+        self.arena = None   # train.ParamArena: bf16 shadow + batched transposes of the trainable linear weights
         self.keep: List[torch.Tensor] = []   # small device scalars referenced by in-flight launches
         self._consts: Dict[Tuple, torch.Tensor] = {}
         self.grad_ready_hook: Optional[Callable[[List[torch.nn.Parameter]], None]] = None
@@ -207,6 +208,10 @@ class Engine:
 
     # ------------------------------------------------------------------ operand preparation
     def w_lin(self, p: torch.Tensor, transposed: bool) -> torch.Tensor:
+        if self.arena is not None and p.dim() == 2:
+            m = self.arena.transposed_matrix([p]) if transposed else self.arena.shadow_matrix([p])
+            if m is not None:
+                return m
         O, I = p.shape[0], p[0].numel()
         src = lambda: p.detach().reshape(O, I)      # re-read at build time: p.data may have been re-homed
         if transposed:
@@ -215,6 +220,10 @@ class Engine:
 
     def w_lin_cat(self, ps: Sequence[torch.Tensor], transposed: bool) -> torch.Tensor:
         """concatenated projection weights [sum O_i, I] (fused q|k|v)."""
+        if self.arena is not None:
+            m = self.arena.transposed_matrix(list(ps)) if transposed else self.arena.shadow_matrix(list(ps))
+            if m is not None:
+                return m
         I = ps[0].shape[1]
         Os = [p.shape[0] for p in ps]
         key = ("catT" if transposed else "cat",) + tuple(id(p) for p in ps)

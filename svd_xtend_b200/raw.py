@@ -406,9 +406,14 @@ def blend_scales(mix_factor, out3):  # out3: float[8]
     return out3
 
 
-def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, shadow=None):
     check(load().svdx_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, weight_decay,
-                            step, grad_scale, _stream()), "adamw")
+                            step, grad_scale, _ptr(shadow), _stream()), "adamw")
+
+
+def multi_transpose(src_base, jobs, tile_prefix, njobs, total_tiles):
+    check(load().svdx_multi_transpose(src_base.data_ptr(), jobs.data_ptr(), tile_prefix.data_ptr(), njobs, total_tiles, _stream()),
+          "svdx_multi_transpose")
 
 
 def unprep_conv_grad(src, dst, O, I, taps, i_pad):

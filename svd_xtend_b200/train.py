@@ -45,12 +45,76 @@ class ParamArena:
         self.data = torch.zeros(off, device=dev, dtype=F32)
         self.grad = torch.zeros(off, device=dev, dtype=F32)
         self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self.offset_of: Dict[torch.nn.Parameter, int] = {}
         with torch.no_grad():
             for p, o in zip(ps, self.offsets):
                 view = self.data[o:o + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
                 self.grad_views[p] = self.grad[o:o + p.numel()].view(p.shape)
+                self.offset_of[p] = o
+        # bf16 shadow of the whole arena at the same offsets: the forward GEMM operands of the trainable linears are
+        # views into it (q|k|v are adjacent, so the fused projection operand is a view too); FusedAdamW rewrites it in
+        # the same pass that updates the fp32 masters.
+        self.shadow = None
+        self._tjobs: List[tuple] = []          # (src_off, dst tensor [I,O], O, I): dgrad (transposed) operands
+        self._tjob_index: Dict[tuple, int] = {}
+        self._tjob_dev = None
+        if self.data.is_cuda:
+            self.shadow = torch.empty(off, device=dev, dtype=torch.bfloat16)
+            raw.cast_f32_bf16(self.data, self.shadow)
+
+    def refresh_shadow(self):
+        """re-derive the bf16 shadow from the fp32 masters (after an out-of-band update such as load_state_dict)"""
+        if self.shadow is not None:
+            raw.cast_f32_bf16(self.data, self.shadow)
+
+    def shadow_matrix(self, params: List[torch.nn.Parameter]) -> Optional[torch.Tensor]:
+        """bf16 [sum O_i, I] view of adjacent 2-D parameters (or of one), None if they are not contiguous in the arena"""
+        if self.shadow is None or any(p not in self.offset_of for p in params):
+            return None
+        I = params[0][0].numel()
+        o0 = self.offset_of[params[0]]
+        o = o0
+        for p in params:
+            if self.offset_of[p] != o or p[0].numel() != I:
+                return None
+            o += p.numel()
+        return self.shadow[o0:o].view(-1, I)
+
+    def transposed_matrix(self, params: List[torch.nn.Parameter]) -> Optional[torch.Tensor]:
+        """bf16 [I, sum O_i] transposed operand, refreshed for ALL registered matrices by one svdx_multi_transpose launch"""
+        src = self.shadow_matrix(params)
+        if src is None:
+            return None
+        key = tuple(id(p) for p in params)
+        j = self._tjob_index.get(key)
+        if j is None:
+            O, I = src.shape
+            dst = torch.empty(I, O, device=src.device, dtype=torch.bfloat16)
+            raw.prep_weight(src, dst, 1, O, I)
+            self._tjob_index[key] = len(self._tjobs)
+            self._tjobs.append((self.offset_of[params[0]], dst, O, I))
+            self._tjob_dev = None
+            return dst
+        return self._tjobs[j][1]
+
+    def refresh_transposes(self):
+        if not self._tjobs:
+            return
+        if self._tjob_dev is None:
+            import struct
+            blob = bytearray()
+            prefix, tiles = [], 0
+            for off, dst, O, I in self._tjobs:
+                blob += struct.pack("<qqii", off, dst.data_ptr(), O, I)
+                prefix.append(tiles)
+                tiles += ((O + 31) // 32) * ((I + 31) // 32)
+            jobs = torch.frombuffer(bytes(blob), dtype=torch.uint8).clone().to(self.data.device)
+            pre = torch.tensor(prefix, dtype=torch.int32, device=self.data.device)
+            self._tjob_dev = (jobs, pre, len(self._tjobs), tiles)
+        jobs, pre, n, tiles = self._tjob_dev
+        raw.multi_transpose(self.shadow, jobs, pre, n, tiles)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -77,7 +141,7 @@ class FusedAdamW:
         self.t += 1
         a = self.arena
         raw.adamw(a.data, a.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                  self.t, grad_scale)
+                  self.t, grad_scale, shadow=a.shadow)
         if self.on_updated is not None:
             self.on_updated()
 

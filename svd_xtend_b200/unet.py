@@ -450,10 +450,17 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         """Accumulate parameter gradients directly into `arena.grad` views (see train.ParamArena)."""
         self._arena = arena
         self._engine.grad_views = arena.grad_views if arena is not None else {}
+        self._engine.arena = arena
         self._engine.wc.clear()
 
-    def refresh_trainable_operands(self):
-        """Re-prepare the bf16 operand layouts of all trainable parameters (after an out-of-band update)."""
+    def refresh_trainable_operands(self, shadow_current: bool = False):
+        """Re-prepare the bf16 operand layouts of all trainable parameters (after an optimizer / out-of-band update).
+        With a ParamArena the plain operands are views of its bf16 shadow (kept current by FusedAdamW) and all
+        transposed (dgrad) operands are refreshed by ONE svdx_multi_transpose launch."""
+        if self._arena is not None:
+            if not shadow_current:          # the updater did not maintain the bf16 shadow (e.g. torch.optim.AdamW)
+                self._arena.refresh_shadow()
+            self._arena.refresh_transposes()
         self._engine.wc.refresh_trainable()
 
     @property

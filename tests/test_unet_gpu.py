@@ -247,3 +247,42 @@ def test_tiny_gradient_checkpointing_equivalence():
             assert g1[n].abs().max() == 0
         else:
             assert _rel(g1[n], g0[n]) < 8e-2, (n, _rel(g1[n], g0[n]))
+
+
+def test_arena_fused_adamw_steps():
+    """train.ParamArena + FusedAdamW: bf16 shadow / batched transposed operands stay consistent with the fp32 masters,
+    and two optimisation steps track the fp32 oracle trained with torch.optim.AdamW."""
+    from oracle.svd_unet_oracle import TINY_CONFIG, synthetic_batch
+    from svd_xtend_b200.train import FusedAdamW, ParamArena
+    oracle, ours = _build(TINY_CONFIG, seed=13)
+    for m in (oracle, ours):
+        _train_filter(m)
+        m.train()
+    arena = ParamArena(ours)
+    ours.attach_arena(arena)
+    opt = FusedAdamW(arena, lr=1e-4, weight_decay=1e-2)
+    opt.on_updated = lambda: ours.refresh_trainable_operands(shadow_current=True)
+    ref_opt = torch.optim.AdamW([p for p in oracle.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-2)
+    batch = synthetic_batch(1, 4, 16, 16, seed=55, device=DEV, cross_dim=TINY_CONFIG["cross_attention_dim"])
+    losses, ref_losses = [], []
+    for _ in range(3):
+        arena.zero_grad()
+        _, loss = _loss(ours, batch)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        ref_opt.zero_grad(set_to_none=True)
+        _, rl = _loss(oracle, batch)
+        rl.backward()
+        ref_opt.step()
+        ref_losses.append(rl.item())
+    torch.cuda.synchronize()
+    assert torch.equal(arena.shadow, arena.data.to(torch.bfloat16))
+    for off, dst, O, I in arena._tjobs:
+        assert torch.equal(dst, arena.shadow[off:off + O * I].view(O, I).t().contiguous())
+    assert len(arena._tjobs) > 0
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 3e-2 * max(1.0, abs(b)), (losses, ref_losses)
+    po = dict(oracle.named_parameters())
+    worst = max(_rel(p, po[n]) for n, p in ours.named_parameters() if p.requires_grad and p.dim() == 2)
+    assert worst < 5e-3, worst
