@@ -578,20 +578,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         tmem_ld32(tDPT + lane_off + c0, vd);
         tc_wait_ld();
         float fp[32], fd[32];
-        const float4* l4 = reinterpret_cast<const float4*>(vec + c0);
-        const float4* d4 = reinterpret_cast<const float4*>(vec + 128 + c0);
+        if (p.G == 1 && ki.valid) {
+          // unmasked fast path (spatial attention): invalid query columns carry lse = +inf -> p = 0
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 ls = l4[k4], dl = d4[k4];   // broadcast 16-byte shared loads: lse / delta of 4 query columns
-          const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int k = 4 * k4 + u;
-            const int c = c0 + k;  // query column
-            const bool ok = ki.valid && (p.G == 1 || (c & p.gmask) == ki.g);
-            const float pr = ok ? fast_exp2(fmaf(__uint_as_float(vs[k]), sc, -lsv[u])) : 0.f;
+          for (int k = 0; k < 32; ++k) {
+            const float pr = fast_exp2(fmaf(__uint_as_float(vs[k]), sc, -vec[c0 + k]));
             fp[k] = pr;
-            fd[k] = pr * p.scale * (__uint_as_float(vd[k]) - dlv[u]);
+            fd[k] = (pr * p.scale) * (__uint_as_float(vd[k]) - vec[128 + c0 + k]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const int c = c0 + k;  // query column
+            const bool ok = ki.valid && ((c & p.gmask) == ki.g);
+            const float pr = ok ? fast_exp2(fmaf(__uint_as_float(vs[k]), sc, -vec[c])) : 0.f;
+            fp[k] = pr;
+            fd[k] = (pr * p.scale) * (__uint_as_float(vd[k]) - vec[128 + c]);
           }
         }
         store_score_chunk(sPT, r, c0, fp);

@@ -439,7 +439,9 @@ class Engine:
             bn = raw.choose_block_n(O, K, mn_major=True)
             tiles = ((O + 127) // 128) * ((K + bn - 1) // bn)
             kb = (M + 63) // 64
-            split = max(1, min(kb, (2 * raw.num_sms()) // max(tiles, 1), 32))
+            # split the token contraction only as far as it still leaves >= 32 k-blocks per CTA and at most one wave:
+            # every split CTA pays a full-tile fp32 atomic epilogue
+            split = max(1, min(kb // 32, raw.num_sms() // max(tiles, 1)))
             raw.tapgemm(dyp, x, g, M=O, N=K, K=M, a_mn=True, b_mn=True, split_k=split, out_dtype=OUT_F32_ATOMIC,
                         block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
 
@@ -454,7 +456,7 @@ class Engine:
         bn = raw.choose_block_n(Opad, ip, mn_major=True)
         tiles = ((Opad + 127) // 128) * ((ip + bn - 1) // bn)
         kb = (K + 63) // 64
-        split = max(1, min(kb, (2 * raw.num_sms()) // max(tiles, 1), 64))
+        split = max(1, min(kb // 32, raw.num_sms() // max(tiles, 1)))
         for t, tap in enumerate(taps):
             raw.tapgemm(dy, x, ws[:, t * ip:(t + 1) * ip], M=Opad, N=ip, K=K, a_mn=True, b_mn=True, b_mode=b_mode, taps=(tap,),
                         conv_whn=conv_whn, rows_per_group=rows_per_group if rows_per_group is not None else K, groups=groups,
