@@ -356,9 +356,18 @@ def main():
         with open(os.environ["SVDX_GEMM_TABLE"], "w") as fh:
             json.dump(table, fh, indent=0)
     sustained, burst, hbm, src = peaks()
+    traffic, traffic_src = None, None
+    for tp in sorted([f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")] if os.path.isdir(os.path.join(ROOT, "profiles")) else [], reverse=True):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", tp)))
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], f"profiles/{tp} (ncu dram__bytes_read+write summed over the {tj['launches_per_step']} tapgemm launches of one step, per launch)"
+            break
+        except Exception:
+            pass
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "svdx::tapgemm_kernel (tcgen05)", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                "frac": achieved / sustained, "traffic": None, "peak_source": src + ", bf16_tflops_sustained (kernel timed inside a long step)",
+                "frac": achieved / sustained, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_note": "tensor-bound kernel: algorithmic work is FLOPs (2*M*N*K*taps per launch, summed); see DESIGN.md §3", "peak_source": src + ", bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": len(recs), "algorithmic_tflop_per_step": gemm_flops / 1e12, "kernel_ms_per_step": gemm_ms,
                 "share_of_step": gemm_ms / ms_per_step}
 

@@ -98,6 +98,43 @@ def source_stalls(rep, out, top=40):
     print("wrote", out)
 
 
+def dram_traffic():
+    """sum of dram bytes / time over every tapgemm launch of one step (cheap 3-metric ncu pass)"""
+    src = os.path.join(G, f"tapgemm_dram_{tag}.csv")
+    if not os.path.exists(src):
+        return
+    with open(src) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    per = collections.defaultdict(dict)
+    order = []
+    for r in csv.DictReader(lines):
+        k = r["ID"]
+        if k not in per:
+            order.append(k)
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        name = r["Metric Name"]
+        if name.startswith("dram__bytes"):
+            v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        else:
+            v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v
+        per[k][name] = v
+        per[k]["kernel"] = re.sub(r"\(.*", "", r["Kernel Name"])
+    ids = order
+    # one steady-state step = the last 1/2 of the captured launches is safest; bench --profile-one runs warm-up(3)+1 steps
+    n_step = len(ids) // 4 if len(ids) >= 8 else len(ids)
+    sel = ids[-n_step:]
+    rd = sum(per[k].get("dram__bytes_read.sum", 0) for k in sel)
+    wr = sum(per[k].get("dram__bytes_write.sum", 0) for k in sel)
+    tm = sum(per[k].get("gpu__time_duration.sum", 0) for k in sel)
+    out = {"kernel": "svdx::tapgemm_kernel + svdx::tapgemm2_kernel", "launches_per_step": n_step, "dram_read_bytes_per_step": rd,
+           "dram_write_bytes_per_step": wr, "traffic_bytes_per_launch": (rd + wr) / max(n_step, 1), "ncu_time_ms_per_step": tm / 1e3,
+           "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:tapgemm; tapgemm_dram_{tag}.csv, "
+                     f"last {n_step} of {len(ids)} captured launches"}
+    json.dump(out, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
+    print("wrote traffic:", out)
+
+
 PICK = [r"^Kernel Name$", r"^Grid Size$", r"^Block Size$", r"gpu__time_duration\.sum$", r"dram__bytes_(read|write)\.sum$",
         r"gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed$", r"sm__pipe_tensor_cycles_active.*pct", r"sm__warps_active\.avg\.pct",
         r"launch__registers_per_thread$", r"l1tex__m_xbar2l1tex_read_bytes\.sum(\.per_second)?$", r"lts__t_bytes\.sum$",
@@ -106,6 +143,7 @@ PICK = [r"^Kernel Name$", r"^Grid Size$", r"^Block Size$", r"gpu__time_duration\
 if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     launch_list()
+    dram_traffic()
     raw_metrics(f"prof_tapgemm_{tag}.ncu-rep", f"{tag}_tapgemm_ncu_full.txt", PICK)
     raw_metrics(f"prof_attn_fwd_{tag}.ncu-rep", f"{tag}_attn_fwd_ncu_full.txt", PICK)
     source_stalls(f"prof_attn_fwd_{tag}.ncu-rep", f"{tag}_attn_fwd_source_stalls.txt")

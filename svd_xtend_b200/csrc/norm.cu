@@ -114,34 +114,50 @@ __global__ void gn_stats_finalize(float* mean, float* rstd, int total, float inv
 }
 
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU)
-// one thread per 8 output channels (16 B store)
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, long long total_rows, int rows, int G, const float* __restrict__ mean,
-                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, int fuse_silu, bf16* __restrict__ y, long long ldy) {
+// same thread layout as the statistics kernel: a thread owns one 8-channel vector, folds mean/rstd/gamma/beta into
+// a per-channel scale and shift once, then streams rows (y = silu(x*scale + shift)), 16 B loads and stores
+__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_kernel(GnSrc s, int rows, int rows_per_cta, int G, const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, int fuse_silu, bf16* __restrict__ y, long long ldy) {
   const int C = s.C1 + s.C2;
-  const int vec_per_row = C / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total_rows * vec_per_row) return;
-  const long long row = idx / vec_per_row;
-  const int c0 = (int)(idx - row * vec_per_row) * 8;
-  const int n = (int)(row / rows);
+  const int CV = C / 8;
   const int cpg = C / G;
-  const bf16* p = (c0 < s.C1) ? (s.x + row * s.ldx + c0) : (s.x2 + row * s.ldx2 + (c0 - s.C1));
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const uint32_t in[4] = {u.x, u.y, u.z, u.w};
-  uint32_t out[4];
+  const int n = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, rows);
+  const int RL = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= RL) return;
+  const int c0 = cv * 8;
+  float sc[8], sh[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c0 + 2 * k;
-    const int g = c / cpg;
-    const float m = mean[n * G + g], rs = rstd[n * G + g];
-    float2 v = unpack_bf16x2(in[k]);
-    float a = (v.x - m) * rs * gamma[c] + beta[c];
-    float b = (v.y - m) * rs * gamma[c + 1] + beta[c + 1];
-    if (fuse_silu) { a = silu_f(a); b = silu_f(b); }
-    out[k] = pack_bf16x2(a, b);
+  for (int k = 0; k < 8; ++k) {
+    const int g = (c0 + k) / cpg;
+    const float rs = rstd[n * G + g];
+    sc[k] = rs * gamma[c0 + k];
+    sh[k] = beta[c0 + k] - mean[n * G + g] * sc[k];
   }
-  *reinterpret_cast<uint4*>(y + row * ldy + c0) = make_uint4(out[0], out[1], out[2], out[3]);
+  const long long base = (long long)n * rows;
+  for (int r = r0 + rl; r < r1; r += 2 * RL) {
+    const bool two = r + RL < r1;
+    const uint4 u0 = load_vec8(s, base + r, c0);
+    const uint4 u1 = two ? load_vec8(s, base + r + RL, c0) : u0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (q == 1 && !two) break;
+      const uint4 u = q ? u1 : u0;
+      const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+      uint32_t out[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 v = unpack_bf16x2(in[k]);
+        float a = fmaf(v.x, sc[2 * k], sh[2 * k]), b = fmaf(v.y, sc[2 * k + 1], sh[2 * k + 1]);
+        if (fuse_silu) { a = silu_f(a); b = silu_f(b); }
+        out[k] = pack_bf16x2(a, b);
+      }
+      *reinterpret_cast<uint4*>(y + (base + r + q * RL) * ldy + c0) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ GroupNorm backward
@@ -224,47 +240,52 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const
   }
 }
 
-// pass 2: dx = rstd * (g*gamma - s1/cnt - xhat * s2/cnt)
-__global__ void __launch_bounds__(256) gn_bwd_apply(GnSrc s, const bf16* __restrict__ dy, long long lddy, long long total_rows, int rows,
-                                                    int G, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                    const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
-                                                    const float* __restrict__ ws, float inv_count, bf16* __restrict__ dx, long long lddx,
-                                                    bf16* __restrict__ dx2, long long lddx2) {
+// pass 2: dx = rstd * (g*gamma - s1/cnt - xhat * s2/cnt); per-thread channel constants, rows streamed
+__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
+                                                                int G, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
+                                                                const float* __restrict__ ws, float inv_count, bf16* __restrict__ dx, long long lddx,
+                                                                bf16* __restrict__ dx2, long long lddx2) {
   const int C = s.C1 + s.C2;
-  const int vec_per_row = C / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total_rows * vec_per_row) return;
-  const long long row = idx / vec_per_row;
-  const int c0 = (int)(idx - row * vec_per_row) * 8;
-  const int n = (int)(row / rows);
+  const int CV = C / 8;
   const int cpg = C / G;
+  const int n = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, rows);
+  const int RL = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= RL) return;
+  const int c0 = cv * 8;
   const bool first = c0 < s.C1;
-  const bf16* p = first ? (s.x + row * s.ldx + c0) : (s.x2 + row * s.ldx2 + (c0 - s.C1));
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const uint4 ud = *reinterpret_cast<const uint4*>(dy + row * lddy + c0);
-  const uint32_t in[4] = {u.x, u.y, u.z, u.w};
-  const uint32_t din[4] = {ud.x, ud.y, ud.z, ud.w};
-  uint32_t out[4];
+  float gm[8], bt[8], mu[8], rs[8], t1[8], t2[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c0 + 2 * k;
-    const int g = c / cpg;
-    const float m = mean[n * G + g], rs = rstd[n * G + g];
-    const float s1 = ws[(n * G + g) * 2] * inv_count, s2 = ws[(n * G + g) * 2 + 1] * inv_count;
-    const float2 v = unpack_bf16x2(in[k]);
-    const float2 d = unpack_bf16x2(din[k]);
-    const float xh0 = (v.x - m) * rs, xh1 = (v.y - m) * rs;
-    float e0 = d.x, e1 = d.y;
-    if (fuse_silu) {
-      e0 *= silu_grad_f(xh0 * gamma[c] + beta[c]);
-      e1 *= silu_grad_f(xh1 * gamma[c + 1] + beta[c + 1]);
-    }
-    const float o0 = rs * (e0 * gamma[c] - s1 - xh0 * s2);
-    const float o1 = rs * (e1 * gamma[c + 1] - s1 - xh1 * s2);
-    out[k] = pack_bf16x2(o0, o1);
+  for (int k = 0; k < 8; ++k) {
+    const int g = (c0 + k) / cpg;
+    gm[k] = gamma[c0 + k]; bt[k] = beta[c0 + k]; mu[k] = mean[n * G + g]; rs[k] = rstd[n * G + g];
+    t1[k] = ws[(n * G + g) * 2] * inv_count; t2[k] = ws[(n * G + g) * 2 + 1] * inv_count;
   }
-  bf16* q = first ? (dx + row * lddx + c0) : (dx2 + row * lddx2 + (c0 - s.C1));
-  *reinterpret_cast<uint4*>(q) = make_uint4(out[0], out[1], out[2], out[3]);
+  const long long base = (long long)n * rows;
+  for (int r = r0 + rl; r < r1; r += RL) {
+    const long long row = base + r;
+    const uint4 u = load_vec8(s, row, c0);
+    const uint4 ud = *reinterpret_cast<const uint4*>(dy + row * lddy + c0);
+    const uint32_t in[4] = {u.x, u.y, u.z, u.w}, din[4] = {ud.x, ud.y, ud.z, ud.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 v = unpack_bf16x2(in[k]), d = unpack_bf16x2(din[k]);
+      const float xh0 = (v.x - mu[2 * k]) * rs[2 * k], xh1 = (v.y - mu[2 * k + 1]) * rs[2 * k + 1];
+      float e0 = d.x, e1 = d.y;
+      if (fuse_silu) {
+        e0 *= silu_grad_f(fmaf(xh0, gm[2 * k], bt[2 * k]));
+        e1 *= silu_grad_f(fmaf(xh1, gm[2 * k + 1], bt[2 * k + 1]));
+      }
+      out[k] = pack_bf16x2(rs[2 * k] * (e0 * gm[2 * k] - t1[2 * k] - xh0 * t2[2 * k]),
+                           rs[2 * k + 1] * (e1 * gm[2 * k + 1] - t1[2 * k + 1] - xh1 * t2[2 * k + 1]));
+    }
+    bf16* q = first ? (dx + row * lddx + c0) : (dx2 + row * lddx2 + (c0 - s.C1));
+    *reinterpret_cast<uint4*>(q) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
 }
 
 // ------------------------------------------------------------------ LayerNorm
@@ -475,10 +496,10 @@ extern "C" int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, cons
   if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !y || ldy % 8 || (reinterpret_cast<uintptr_t>(y) & 15) || !mean || !rstd || !gamma || !beta)
     return svdx_fail(SVDX_E_BADARG, "groupnorm_apply: bad arguments");
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
-  const long long total_rows = (long long)outer * rows;
-  const long long nvec = total_rows * ((C1 + C2) / 8);
-  gn_apply_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>(s, total_rows, rows, num_groups, mean, rstd, gamma, beta, fuse_silu,
-                                                                 reinterpret_cast<bf16*>(y), ldy);
+  int threads, rpc;
+  gn_vec_config(C1 + C2, outer, rows, threads, rpc);
+  gn_apply_kernel<<<dim3((rows + rpc - 1) / rpc, outer), threads, 0, st>>>(s, rows, rpc, num_groups, mean, rstd, gamma, beta, fuse_silu,
+                                                                          reinterpret_cast<bf16*>(y), ldy);
   SVDX_CHECK_LAUNCH("groupnorm_apply");
   return SVDX_OK;
 }
@@ -499,12 +520,9 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
   dim3 grid((rows + rpc - 1) / rpc, outer);
   gn_bwd_partial<<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta,
                                               fuse_silu, workspace, dgamma, dbeta);
-  const long long total_rows = (long long)outer * rows;
-  const long long nvec = total_rows * ((C1 + C2) / 8);
   const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
-  gn_bwd_apply<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, total_rows, rows, num_groups,
-                                                              mean, rstd, gamma, beta, fuse_silu, workspace, inv,
-                                                              reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dx2), lddx2);
+  gn_bwd_apply<<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta, fuse_silu,
+                                         workspace, inv, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dx2), lddx2);
   SVDX_CHECK_LAUNCH("groupnorm_bwd");
   return SVDX_OK;
 }
