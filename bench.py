@@ -83,9 +83,35 @@ def build_oracle_cpu():
     return m
 
 
-def cpu_step(model, frames, seed=1234):
+def usable_cores():
+    """Threads this process can really use: affinity mask and cgroup CPU quota, not the host's core count."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, (q + per // 2) // per))
+        except Exception:
+            pass
+    return n
+
+
+# (frames, latent H, latent W, frame-equivalents) samples of the BASELINE workload, largest first
+CPU_SAMPLES = [(2, LAT_H, LAT_W, 2.0), (1, LAT_H, LAT_W, 1.0), (1, LAT_H, LAT_W // 4, 0.25)]
+
+
+def cpu_step(model, frames, seed=1234, h=LAT_H, w=LAT_W):
     from oracle.svd_unet_oracle import edm_loss, synthetic_batch
-    b = synthetic_batch(1, frames, LAT_H, LAT_W, seed=seed)
+    b = synthetic_batch(1, frames, h, w, seed=seed)
     t0 = time.perf_counter()
     pred = model(b["sample"], b["timestep"], b["encoder_hidden_states"], b["added_time_ids"]).sample
     loss = edm_loss(pred, b["noisy"], b["latents"], b["sigmas"])
@@ -95,17 +121,30 @@ def cpu_step(model, frames, seed=1234):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(steps=1, warmup=1, frames=2):
-    cores = os.cpu_count() or 1
+def pick_cpu_sample(model, n_steps, budget_s):
+    """One quarter-frame probe step, then the largest sample whose n_steps fit the time budget."""
+    f, h, w, eq = CPU_SAMPLES[-1]
+    cpu_step(model, f, h=h, w=w)               # first touch of the weights
+    tq = cpu_step(model, f, h=h, w=w)
+    for s in CPU_SAMPLES:
+        if tq * (s[3] / eq) * n_steps <= budget_s:
+            return s, tq
+    return CPU_SAMPLES[-1], tq
+
+
+def _sample_text(s):
+    return (f"{s[0]} of {T_FRAMES} frames at {s[1]}x{s[2]} latents (= {s[3]} frame-equivalents of the {LAT_H}x{LAT_W} workload)")
+
+
+def cpu_baseline(budget_s=25.0):
+    cores = usable_cores()
     torch.set_num_threads(cores)
     model = build_oracle_cpu()
-    for _ in range(warmup):
-        cpu_step(model, 1)
-    ts = [cpu_step(model, frames) for _ in range(steps)]
-    t = sum(ts)
-    return {"value": frames * steps / t, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} x train step (fwd + EDM loss + bwd, fp32, as-scripted trainable set) on {frames} of {T_FRAMES} frames at "
-                      f"{LAT_H}x{LAT_W} latents, full 1.52 B-param topology, torch CPU fp32, {cores} threads",
+    s, _ = pick_cpu_sample(model, 1, budget_s)
+    t = cpu_step(model, s[0], h=s[1], w=s[2])
+    return {"value": s[3] / t, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"1 x train step (fwd + EDM loss + bwd, fp32, as-scripted trainable set) on {_sample_text(s)}, "
+                      f"full 1.52 B-param topology, torch CPU fp32, {cores} threads",
             "seconds": t}
 
 
@@ -113,20 +152,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # size the per-step sample so that the whole run stays within a few minutes
-    frames = 2 if (args.steps + args.warmup) <= 4 else 1
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     model = build_oracle_cpu()
-    for _ in range(max(args.warmup, 1) if args.warmup > 0 else 0):
-        cpu_step(model, frames)
+    # size the per-step sample so that the whole run stays within a few minutes
+    s, _ = pick_cpu_sample(model, args.steps + args.warmup, 150.0)
+    for _ in range(args.warmup):
+        cpu_step(model, s[0], h=s[1], w=s[2])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(model, frames)
+        cpu_step(model, s[0], h=s[1], w=s[2])
     t = time.perf_counter() - t0
-    val = frames * args.steps / t
-    sample = (f"each step = one train step (fwd + EDM loss + bwd, fp32, as-scripted trainable set) on {frames} of {T_FRAMES} frames, "
-              f"{LAT_H}x{LAT_W} latents, full topology; oracle restatement of the diffusers path (diffusers not installable offline)")
+    val = s[3] * args.steps / t
+    frames = s[3]
+    sample = (f"each step = one train step (fwd + EDM loss + bwd, fp32, as-scripted trainable set) on {_sample_text(s)}, "
+              f"full topology; oracle restatement of the diffusers path (diffusers not installable offline)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -1,0 +1,52 @@
+"""Times individual tapgemm shapes with epilogue variants (GPU dev tool; not part of the product path)."""
+import sys, torch
+sys.path.insert(0, ".")
+from svd_xtend_b200 import raw
+
+dev = torch.device("cuda:0")
+bf = torch.bfloat16
+
+
+def timeit(fn, iters=20):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        tot += s.elapsed_time(e)
+    return tot / iters * 1e3  # us
+
+
+def run(M, N, K, geglu=False, bias=True, pre=False, res=False, block_n=None, f32=False, label=""):
+    a = torch.randn(M, K, device=dev, dtype=bf)
+    w = torch.randn(N, K, device=dev, dtype=bf) * 0.05
+    n_out = N // 2 if geglu else N
+    out = torch.empty(M, n_out, device=dev, dtype=torch.float32 if f32 else bf)
+    b = torch.randn(N, device=dev) if bias else None
+    p = torch.empty(M, N, device=dev, dtype=bf) if pre else None
+    r = torch.randn(M, n_out, device=dev, dtype=bf) if res else None
+    us = timeit(lambda: raw.tapgemm(a, w, out, M=M, N=N, K=K, geglu=geglu, bias=b, pre=p, res1=r, block_n=block_n))
+    tf = 2.0 * M * N * K / us / 1e6
+    print(f"{label:28s} M={M} N={N} K={K} geglu={int(geglu)} pre={int(pre)} res={int(res)} bn={block_n} : {us:8.1f} us  {tf:6.1f} TF", flush=True)
+
+
+if __name__ == "__main__":
+    for bn in (None, 128, 256):
+        run(35840, 2560, 320, geglu=True, pre=True, block_n=bn, label="geglu+pre")
+        run(35840, 2560, 320, geglu=True, pre=False, block_n=bn, label="geglu")
+        run(35840, 2560, 320, geglu=False, block_n=bn, label="plain N=2560")
+    run(35840, 1280, 320, label="plain N=1280")
+    run(8960, 5120, 640, geglu=True, pre=True, label="geglu+pre L1")
+    run(8960, 5120, 640, geglu=True, pre=False, label="geglu L1")
+    run(8960, 5120, 640, label="plain L1")
+    run(35840, 320, 320, label="proj 320")
+    run(35840, 320, 320, res=True, label="proj 320 + res")
+    run(35840, 320, 320, bias=False, label="proj 320 nobias")
+    run(8960, 640, 640, label="proj 640")
+    run(2240, 1280, 1280, label="proj 1280")
+    run(35840, 320, 2560, label="ff2 L0")
+    run(35840, 960, 320, label="qkv L0")

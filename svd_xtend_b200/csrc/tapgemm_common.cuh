@@ -106,11 +106,22 @@ SVDX_DEVINL void epilogue_tile(const TapGemmKParams& p, uint32_t t_base, long lo
 #pragma unroll
           for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(gte[i]);
           if (p.bias) {
+            if (full_chunk && ((p.N / 2) & 3) == 0) {
+              const float4* bv = reinterpret_cast<const float4*>(p.bias + col0);
+              const float4* bg = reinterpret_cast<const float4*>(p.bias + p.N / 2 + col0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (full_chunk || col0 + i < n_out_total) {
-                f[i] += __ldg(p.bias + col0 + i);
-                g[i] += __ldg(p.bias + p.N / 2 + col0 + i);
+              for (int k = 0; k < 8; ++k) {
+                const float4 x4 = __ldg(bv + k), y4 = __ldg(bg + k);
+                f[4 * k] += x4.x; f[4 * k + 1] += x4.y; f[4 * k + 2] += x4.z; f[4 * k + 3] += x4.w;
+                g[4 * k] += y4.x; g[4 * k + 1] += y4.y; g[4 * k + 2] += y4.z; g[4 * k + 3] += y4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (full_chunk || col0 + i < n_out_total) {
+                  f[i] += __ldg(p.bias + col0 + i);
+                  g[i] += __ldg(p.bias + p.N / 2 + col0 + i);
+                }
               }
             }
           }
