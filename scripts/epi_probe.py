@@ -35,6 +35,19 @@ def run(M, N, K, geglu=False, bias=True, pre=False, res=False, block_n=None, f32
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "one":
+        run(35840, 2560, 320, bias=False, label="plain N=2560 nobias")
+        run(35840, 2560, 320, geglu=True, pre=True, label="geglu+pre")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "short":
+        run(35840, 2560, 320, label="plain N=2560")
+        run(35840, 2560, 320, bias=False, label="plain N=2560 nobias")
+        run(35840, 2560, 320, f32=True, label="plain N=2560 f32 out")
+        run(35840, 320, 320, label="proj 320")
+        run(35840, 320, 2560, label="ff2 L0")
+        run(8960, 5120, 640, label="plain L1")
+        run(8960, 640, 5120, label="ff2 L1")
+        sys.exit(0)
     for bn in (None, 128, 256):
         run(35840, 2560, 320, geglu=True, pre=True, block_n=bn, label="geglu+pre")
         run(35840, 2560, 320, geglu=True, pre=False, block_n=bn, label="geglu")

@@ -10,6 +10,9 @@ int svdx_fail_cuda(cudaError_t e, const char* what);
 // bf16 tiled tensor map, 128-byte swizzle, zero OOB fill. strides[] are bytes for dims 1..rank-1.
 int svdx_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                    const uint32_t* box);
+// general form: f32 != 0 -> fp32 elements; swizzle_bytes in {0, 32, 64, 128}
+int svdx_make_tmap_ex(CUtensorMap* out, const void* base, int f32, int swizzle_bytes, int rank, const uint64_t* dims,
+                      const uint64_t* strides, const uint32_t* box);
 extern "C" int svdx_num_sms(void);
 
 #define SVDX_CHECK_LAUNCH(what)                                   \

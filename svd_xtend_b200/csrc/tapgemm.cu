@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
-  const uint32_t sBar = sB + STAGES * B_STAGE_BYTES;
+  const uint32_t sEpi = sB + STAGES * B_STAGE_BYTES;   // epilogue staging (TMA stores), 4 KB per epilogue warp
+  const uint32_t sBar = sEpi + NUM_EPI_WARPS * EPI_STAGE_BYTES;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[ACC], tmem_empty[ACC], then tmem ptr
   const uint32_t bar_full = sBar;
   const uint32_t bar_empty = sBar + 8 * STAGES;
@@ -206,6 +207,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
     if (p.scales) { s_acc = p.scales[0]; s_r1 = p.scales[1]; s_r2 = p.scales[2]; }
     const int n_out_total = p.geglu ? p.N / 2 : p.N;
     const int bn_out = p.geglu ? p.block_n / 2 : p.block_n;
+    EpiStage st;
+    st.base = sEpi + (warp - 2) * EPI_STAGE_BYTES;
+    st.off = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) % p.m_tiles;
@@ -213,16 +217,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
       long long m;
       bool row_ok;
       tile_row(p, mt, q * 32 + lane, m, row_ok);
+      if (p.a_mode == SVDX_A_ROWS && !p.a_mn) {
+        st.grp = mt / p.tiles_per_group;
+        st.row0 = (mt - st.grp * p.tiles_per_group) * BLOCK_M + q * 32;
+      } else {
+        st.grp = 0;
+        st.row0 = mt * BLOCK_M + q * 32;
+      }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      epilogue_tile(p, t_base, m, row_ok, n0, half, bn_out, n_out_total, s_acc, s_r1, s_r2);
+      epilogue_tile(p, t_base, m, row_ok, n0, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait<0>();   // staged stores must have left shared memory (and landed) before the CTA exits
   }
 
   tc_fence_before();
@@ -359,6 +371,37 @@ int svdx_tapgemm_fill(const SvdxTapGemm* d, TapGemmKParams& p, int cg) {
   p.res1 = reinterpret_cast<const bf16*>(d->res1); p.ldr1 = d->ldr1;
   p.res2 = reinterpret_cast<const bf16*>(d->res2); p.ldr2 = d->ldr2;
   p.scales = d->scales; p.pre = reinterpret_cast<bf16*>(d->pre); p.ldpre = d->ldpre;
+  {
+    static int probe = -1;
+    if (probe < 0) { const char* e = getenv("SVDX_EPI_PROBE"); probe = e ? atoi(e) : 0; }
+    p.probe = probe;
+  }
+  // staged TMA stores: the output as a {columns, rows-per-group, groups} tensor so that ragged last tiles are clipped
+  {
+    static int use = -1;
+    if (use < 0) { const char* e = getenv("SVDX_TMA_STORE"); use = e ? atoi(e) : 1; }
+    const bool grouped = (d->a_mode == SVDX_A_ROWS && !d->a_major_mn);
+    const uint64_t R = grouped ? (uint64_t)d->rows_per_group : (uint64_t)d->M;
+    const uint64_t G = grouped ? (uint64_t)d->groups : 1;
+    const bool f32 = d->out_dtype != SVDX_OUT_BF16;
+    const int esz = f32 ? 4 : 2;
+    bool ok = use != 0 && (d->ldo * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0;
+    if (d->geglu && d->pre && ((d->N / 2) % 32 || (d->ldpre % 8) || (reinterpret_cast<uintptr_t>(d->pre) & 15))) ok = false;
+    if (ok) {
+      uint64_t dims[3] = {(uint64_t)n_out, R, G};
+      uint64_t strides[2] = {(uint64_t)d->ldo * esz, (uint64_t)d->ldo * esz * R};
+      uint32_t box[3] = {32, 32, 1};
+      rc = svdx_make_tmap_ex(&p.tmo, d->out, f32, f32 ? 128 : 64, 3, dims, strides, box);
+      if (rc) return rc;
+      if (d->geglu && d->pre) {
+        uint64_t pdims[3] = {(uint64_t)d->N, R, G};
+        uint64_t pstrides[2] = {(uint64_t)d->ldpre * 2, (uint64_t)d->ldpre * 2 * R};
+        rc = svdx_make_tmap_ex(&p.tmpre, d->pre, 0, 64, 3, pdims, pstrides, box);
+        if (rc) return rc;
+      }
+      p.tma_store = 1;
+    }
+  }
   if (p.split_k > 1 && (p.bias || p.rowbias || p.res1 || p.res2 || p.geglu)) return svdx_fail(SVDX_E_BADARG, "tapgemm: split_k with epilogue operands");
   // vector paths need 16 B alignment of every row start
   if (d->out_dtype == SVDX_OUT_BF16 && ((d->ldo % 8) || (reinterpret_cast<uintptr_t>(d->out) & 15))) return svdx_fail(SVDX_E_BADARG, "tapgemm: out alignment");

@@ -21,7 +21,7 @@ namespace svdx {
 
 constexpr int STAGES2 = 6;
 constexpr int B2_STAGE_BYTES = 128 * BLOCK_K * 2;  // half of a <=256-row B tile
-constexpr int SMEM2_BYTES = 1024 + STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) + 256;
+constexpr int SMEM2_BYTES = 1024 + STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) + NUM_EPI_WARPS * EPI_STAGE_BYTES + 256;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
 SVDX_DEVINL uint32_t cluster_ctarank() {
@@ -84,7 +84,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES2 * A_STAGE_BYTES;
-  const uint32_t sBar = sB + STAGES2 * B2_STAGE_BYTES;
+  const uint32_t sEpi = sB + STAGES2 * B2_STAGE_BYTES;
+  const uint32_t sBar = sEpi + NUM_EPI_WARPS * EPI_STAGE_BYTES;
   const uint32_t bar_full = sBar;
   const uint32_t bar_empty = sBar + 8 * STAGES2;
   const uint32_t bar_tfull = sBar + 16 * STAGES2;
@@ -218,23 +219,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
     float s_acc = 1.f, s_r1 = 1.f, s_r2 = 1.f;
     if (p.scales) { s_acc = p.scales[0]; s_r1 = p.scales[1]; s_r2 = p.scales[2]; }
     const int n_out_total = p.geglu ? p.N / 2 : p.N;
+    EpiStage st;
+    st.base = sEpi + (warp - 2) * EPI_STAGE_BYTES;
+    st.off = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int nt = tile % p.n_tiles;
       const int pt = tile / p.n_tiles;
       int g, t;
       my_slice(pt, g, t);
+      st.grp = g;
+      st.row0 = t * BLOCK_M + q * 32;
       const int rin = t * BLOCK_M + q * 32 + lane;
       const bool row_ok = rin < p.rows_per_group;
       const long long m = (long long)g * p.rows_per_group + rin;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      epilogue_tile(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2);
+      epilogue_tile(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);  // the leader's barrier
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait<0>();
   }
 
   tc_fence_before();
