@@ -70,15 +70,18 @@ SVDX_DEVINL void umma2_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+// relaxed: the only hazard this arrive orders is the TMEM read-before-overwrite, which tcgen05.wait::ld + the tcgen05 fence
+// cover; a .release.cluster arrive compiles to MEMBAR.ALL.GPU and stalls every tile on all outstanding global traffic.
 SVDX_DEVINL void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
       ::"r"(bar), "r"(cta)
       : "memory");
 }
 
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapgemm2_kernel(const __grid_constant__ TapGemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -235,7 +238,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      epilogue_tile(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
+      if constexpr (EPI == EPI_FAST) epilogue_fast(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, st.base, st.row0, st.grp, lane);
+      else if constexpr (EPI == EPI_RES) epilogue_res(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.row0, st.grp, lane);
+      else if constexpr (EPI == EPI_GEGLU) epilogue_geglu(p, t_base, nt * bn_out, half, bn_out, st.base, st.row0, st.grp, lane);
+      else epilogue_tile(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);  // the leader's barrier
@@ -280,14 +286,20 @@ bool svdx_tapgemm2_eligible(const SvdxTapGemm* d) {
 int svdx_tapgemm2_launch(const TapGemmKParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm2: set smem attribute");
     attr_set = true;
   }
   const int total_tiles = p.pair_m_tiles * p.n_tiles;
   int clusters = svdx_num_sms() / 2;
   if (clusters > total_tiles) clusters = total_tiles;
-  tapgemm2_kernel<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  if (p.epi_mode == EPI_FAST) tapgemm2_kernel<EPI_FAST><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  else if (p.epi_mode == EPI_GEGLU) tapgemm2_kernel<EPI_GEGLU><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  else if (p.epi_mode == EPI_RES) tapgemm2_kernel<EPI_RES><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  else tapgemm2_kernel<EPI_GENERIC><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm2: launch");
   return SVDX_OK;

@@ -55,6 +55,7 @@ struct __align__(64) TapGemmKParams {
   CUtensorMap tmo;     // output (bf16: 32x32 box, 64B swizzle; fp32: 32x32 box, 128B swizzle), dims {n_out, rows, groups}
   CUtensorMap tmpre;   // GEGLU pre-activation [M, N]
   int tma_store;       // epilogue stores through shared memory + TMA (tmo / tmpre valid)
+  int epi_mode;        // EPI_GENERIC / EPI_FAST / EPI_GEGLU / EPI_RES: which kernel instantiation runs
   int probe;   // dev switch SVDX_EPI_PROBE: 1 = epilogue without global stores, 2 = no epilogue work at all
 };
 
@@ -115,6 +116,178 @@ SVDX_DEVINL void stage_store_f32(const CUtensorMap* tm, EpiStage& st, int lane, 
     if (reduce) tma_reduce_add_3d(tm, st.base, col, st.row0, st.grp);
     else tma_store_3d(tm, st.base, col, st.row0, st.grp);
     bulk_commit();
+  }
+}
+
+// ---- specialised epilogues (kernel template parameter EPI): the hot shapes have short K, so the per-chunk instruction
+// count of the epilogue decides their speed (profiles/r1_epilogue_probe.txt). EPI_FAST / EPI_GEGLU assume a bf16 output
+// written through TMA, whole 32-column chunks (n_out % 32 == 0) and 16-byte aligned bias rows; everything else takes
+// the generic epilogue_tile below.
+constexpr int EPI_GENERIC = 0, EPI_FAST = 1, EPI_GEGLU = 2, EPI_RES = 3;
+
+SVDX_DEVINL void add_vec32(float (&f)[32], const float* __restrict__ src) {
+  const float4* bp = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 b4 = __ldg(bp + k);
+    f[4 * k] += b4.x; f[4 * k + 1] += b4.y; f[4 * k + 2] += b4.z; f[4 * k + 3] += b4.w;
+  }
+}
+SVDX_DEVINL void axpy_bf16x32(float (&f)[32], float s, const uint4 (&r)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 a = unpack_bf16x2(r[k].x), b = unpack_bf16x2(r[k].y), c = unpack_bf16x2(r[k].z), d = unpack_bf16x2(r[k].w);
+    f[8 * k] += s * a.x; f[8 * k + 1] += s * a.y; f[8 * k + 2] += s * b.x; f[8 * k + 3] += s * b.y;
+    f[8 * k + 4] += s * c.x; f[8 * k + 5] += s * c.y; f[8 * k + 6] += s * d.x; f[8 * k + 7] += s * d.y;
+  }
+}
+// one lane's 32 values -> its 64-byte row of a staging half (64B-swizzled)
+SVDX_DEVINL void stage_row_bf16(uint32_t row, int sw, const float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    st_shared_v4(row + ((j ^ sw) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                 pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+}
+
+// plain epilogue (bias / row-bias only): two 32-column chunks per round (both staging halves), one proxy fence and one
+// bulk group per round.
+SVDX_DEVINL void epilogue_fast(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int bn_out,
+                               int n_out_total, uint32_t sbase, int row0, int grp, int lane) {
+  const float* bias = p.bias;
+  const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
+  const uint32_t rowX = sbase + lane * 64, rowY = rowX + 2048;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll 1
+  for (int c = half * 32; c < bn_out; c += 128) {
+    const int colA = n0 + c;
+    if (colA >= n_out_total) break;
+    const int colB = colA + 64;
+    const bool hasB = (c + 64 < bn_out) && (colB < n_out_total);   // warp-uniform
+    uint32_t va[32], vb[32];
+    tmem_ld32(t_base + c, va);
+    if (hasB) tmem_ld32(t_base + c + 64, vb);
+    tc_wait_ld();
+    float fa[32], fb[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { fa[i] = __uint_as_float(va[i]); fb[i] = __uint_as_float(vb[i]); }
+    if (bias) { add_vec32(fa, bias + colA); if (hasB) add_vec32(fb, bias + colB); }
+    if (rb) { add_vec32(fa, rb + colA); if (hasB) add_vec32(fb, rb + colB); }
+    if (lane == 0) bulk_wait_read<0>();   // the previous round's stores have drained both halves
+    __syncwarp();
+    stage_row_bf16(rowX, sw, fa);
+    if (hasB) stage_row_bf16(rowY, sw, fb);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&p.tmo, sbase, colA, row0, grp);
+      if (hasB) tma_store_3d(&p.tmo, sbase + 2048, colB, row0, grp);
+      bulk_commit();
+    }
+  }
+}
+
+// residual / AlphaBlender epilogue: out = s_acc*(acc + bias + rowbias) + s_r1*res1 + s_r2*res2; one chunk per round,
+// alternating staging halves; the residual rows are requested before the TMEM wait.
+SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int bn_out,
+                              int n_out_total, float s_acc, float s_r1, float s_r2, uint32_t sbase, int row0, int grp, int lane) {
+  const float* bias = p.bias;
+  const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
+  const bf16* r1 = (p.res1 && row_ok) ? p.res1 + m * p.ldr1 : nullptr;
+  const bf16* r2 = (p.res2 && row_ok) ? p.res2 + m * p.ldr2 : nullptr;
+  const bool scaled = p.scales != nullptr;
+  const uint32_t row = sbase + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  uint32_t off = 0;
+#pragma unroll 1
+  for (int c = half * 32; c < bn_out; c += 64) {
+    const int col0 = n0 + c;
+    if (col0 >= n_out_total) break;
+    uint4 a1[4], a2[4];
+    if (r1) {
+      const uint4* q = reinterpret_cast<const uint4*>(r1 + col0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a1[k] = q[k];
+    }
+    if (r2) {
+      const uint4* q = reinterpret_cast<const uint4*>(r2 + col0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a2[k] = q[k];
+    }
+    uint32_t v[32];
+    tmem_ld32(t_base + c, v);
+    tc_wait_ld();
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    if (bias) add_vec32(f, bias + col0);
+    if (rb) add_vec32(f, rb + col0);
+    if (scaled) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] *= s_acc;
+    }
+    if (r1) axpy_bf16x32(f, s_r1, a1);
+    if (r2) axpy_bf16x32(f, s_r2, a2);
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+    stage_row_bf16(row + off, sw, f);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_3d(&p.tmo, sbase + off, col0, row0, grp); bulk_commit(); }
+    off ^= 2048;
+  }
+}
+
+// GEGLU epilogue: value | gate column halves of the accumulator; optionally saves the bf16 pre-activation for backward.
+SVDX_DEVINL void epilogue_geglu(const TapGemmKParams& p, uint32_t t_base, int n0, int half, int bn_out, uint32_t sbase, int row0,
+                                int grp, int lane) {
+  const float* bias = p.bias;
+  const bool save_pre = p.pre != nullptr;
+  const int nh = p.N / 2;
+  const uint32_t rowX = sbase + lane * 64, rowY = rowX + 2048;
+  const int sw = (lane >> 1) & 3;
+  uint32_t off = 0;
+#pragma unroll 1
+  for (int c = half * 32; c < bn_out; c += 64) {
+    const int col0 = n0 + c;
+    uint32_t v[32], gte[32];
+    tmem_ld32(t_base + c, v);
+    tmem_ld32(t_base + bn_out + c, gte);
+    tc_wait_ld();
+    float f[32], g[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { f[i] = __uint_as_float(v[i]); g[i] = __uint_as_float(gte[i]); }
+    if (bias) { add_vec32(f, bias + col0); add_vec32(g, bias + nh + col0); }
+    if (save_pre) {
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+      stage_row_bf16(rowX, sw, f);
+      stage_row_bf16(rowY, sw, g);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&p.tmpre, sbase, col0, row0, grp);
+        tma_store_3d(&p.tmpre, sbase + 2048, nh + col0, row0, grp);
+        bulk_commit();
+      }
+    }
+    // the reference applies GEGLU on the bf16-rounded projection (autocast F.linear output)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float fv = __bfloat162float(__float2bfloat16(f[i]));
+      const float gv = __bfloat162float(__float2bfloat16(g[i]));
+      f[i] = fv * gelu_erf_f(gv);
+    }
+    if (save_pre) {
+      if (lane == 0) bulk_wait_read<0>();
+    } else {
+      if (lane == 0) bulk_wait_read<1>();
+    }
+    __syncwarp();
+    stage_row_bf16(save_pre ? rowX : rowX + off, sw, f);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_3d(&p.tmo, save_pre ? sbase : sbase + off, col0, row0, grp); bulk_commit(); }
+    off ^= 2048;
   }
 }
 
