@@ -34,7 +34,37 @@ def run(M, N, K, geglu=False, bias=True, pre=False, res=False, block_n=None, f32
     print(f"{label:28s} M={M} N={N} K={K} geglu={int(geglu)} pre={int(pre)} res={int(res)} bn={block_n} : {us:8.1f} us  {tf:6.1f} TF", flush=True)
 
 
+def runconv(W, H, nimg, C, N, block_n=None, auto=False, label=""):
+    M = W * H * nimg
+    a = torch.randn(M, C, device=dev, dtype=bf)
+    w = torch.randn(N, 9 * C, device=dev, dtype=bf) * 0.02
+    out = torch.empty(M, N, device=dev, dtype=bf)
+    b = torch.randn(N, device=dev)
+    fn = raw.tapgemm_auto if auto else raw.tapgemm
+    us = timeit(lambda: fn(a, w, out, M=M, N=N, K=C, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, nimg), bias=b,
+                           block_n=block_n))
+    tf = 2.0 * M * N * C * 9 / us / 1e6
+    print(f"{label:22s} conv3x3 W={W} H={H} n={nimg} C={C} N={N} bn={block_n} auto={int(auto)} : {us:8.1f} us  {tf:6.1f} TF", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "conv":
+        for bn in (None, 256, 160, 128):
+            runconv(16, 10, 14, 1280, 1280, block_n=bn, label="L2 conv")
+        runconv(16, 10, 14, 1280, 1280, auto=True, label="L2 conv auto")
+        for bn in (None, 256, 160, 128):
+            runconv(8, 5, 14, 1280, 1280, block_n=bn, label="L3 conv")
+        runconv(8, 5, 14, 1280, 1280, auto=True, label="L3 conv auto")
+        for bn in (None, 160, 128):
+            runconv(32, 20, 14, 640, 640, block_n=bn, label="L1 conv")
+        for bn in (None, 160):
+            runconv(64, 40, 14, 320, 320, block_n=bn, label="L0 conv")
+        run(2240, 1280, 11520, label="L2 as plain GEMM")
+        run(2240, 1280, 11520, block_n=160, label="L2 as plain GEMM bn160")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "convone":
+        runconv(16, 10, 14, 1280, 1280, label="L2 conv")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         run(35840, 2560, 320, bias=False, label="plain N=2560 nobias")
         run(35840, 2560, 320, geglu=True, pre=True, label="geglu+pre")

@@ -22,7 +22,8 @@
 
 namespace svdx {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 192;    // forward: producer, MMA issuer, 4 softmax warps
+constexpr int BWD_THREADS = 320;   // backward: producer, MMA issuer, 8 element-wise warps
 constexpr int TILE_BYTES = 128 * 64 * 2;  // one [128 rows][64 cols] bf16 operand tile, 16 KB
 constexpr int PT_BYTES = 2 * TILE_BYTES;  // one [128][128] bf16 score tile (two 64-column halves)
 constexpr float LOG2E = 1.4426950408889634f;
@@ -102,28 +103,35 @@ SVDX_DEVINL void decode_block(const AttnKParams& p, int& tile, int& head, int& o
 
 // =====================================================================================
 // forward
-// smem: Q | KV ring 3 x (K,V) | P x 2 | barriers
-constexpr int FWD_KV_STAGES = 3;
-constexpr int FWD_SMEM = 1024 + TILE_BYTES + FWD_KV_STAGES * 2 * TILE_BYTES + 2 * PT_BYTES + 256;
+// Two CTAs per SM (<= 113 KB shared memory, 256 TMEM columns, <= 168 registers): the softmax of one CTA overlaps
+// the tensor-core work of the other, and every SM sub-partition has two softmax warps to hide MUFU/TMEM latency.
+//   smem : Q | KV ring 2 x (K,V) | P | barriers (in the 1 KB alignment slack)
+//   TMEM : S [128 x 128] | O [128 x 64]. O accumulates in TMEM across key blocks (tcgen05.mma accumulate); the
+//          running maximum is only raised -- and O / l rescaled by the owning warp -- when a row's new maximum
+//          exceeds the one in use by more than 2^8, so the per-block TMEM round trip of O is gone.
+constexpr int FWD_KV_STAGES = 2;
+constexpr int FWD_DATA = TILE_BYTES + FWD_KV_STAGES * 2 * TILE_BYTES + PT_BYTES;   // 112 KB
+constexpr int FWD_SMEM = 1024 + FWD_DATA;                                           // 113 KB: two CTAs per SM
+constexpr float FWD_RESCALE_LOG2 = 8.0f;
 
-__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sQ = base;
   const uint32_t sKV = sQ + TILE_BYTES;
   const uint32_t sP = sKV + FWD_KV_STAGES * 2 * TILE_BYTES;
-  const uint32_t sBar = sP + 2 * PT_BYTES;
+  // 1024 bytes of the allocation are alignment slack: (base - raw) in front, the rest behind the data
+  const uint32_t sBar = (base - raw >= 256u) ? raw : sP + PT_BYTES;
   const uint32_t b_qfull = sBar;
-  const uint32_t b_kvfull = sBar + 8;          // [3]
-  const uint32_t b_kvempty = sBar + 8 * 4;     // [3]
-  const uint32_t b_sfull = sBar + 8 * 7;       // [2]
-  const uint32_t b_sempty = sBar + 8 * 9;      // [2]
-  const uint32_t b_pfull = sBar + 8 * 11;      // [2]
-  const uint32_t b_pempty = sBar + 8 * 13;     // [2]
-  const uint32_t b_ofull = sBar + 8 * 15;      // [2]
-  const uint32_t b_oempty = sBar + 8 * 17;     // [2]
-  const uint32_t tmem_slot = sBar + 8 * 19;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const uint32_t b_kvfull = sBar + 8;          // [2]
+  const uint32_t b_kvempty = sBar + 8 * 3;     // [2]
+  const uint32_t b_sfull = sBar + 8 * 5;
+  const uint32_t b_sempty = sBar + 8 * 6;
+  const uint32_t b_pfull = sBar + 8 * 7;
+  const uint32_t b_odone = sBar + 8 * 8;
+  const uint32_t tmem_slot = sBar + 8 * 9;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tile, head, outer, inner0;
@@ -134,19 +142,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv);
     mbar_init(b_qfull, 1);
     for (int i = 0; i < FWD_KV_STAGES; ++i) { mbar_init(b_kvfull + 8 * i, 1); mbar_init(b_kvempty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(b_sfull + 8 * i, 1); mbar_init(b_sempty + 8 * i, 128);
-      mbar_init(b_pfull + 8 * i, 128); mbar_init(b_pempty + 8 * i, 1);
-      mbar_init(b_ofull + 8 * i, 1); mbar_init(b_oempty + 8 * i, 128);
-    }
+    mbar_init(b_sfull, 1); mbar_init(b_sempty, 128);
+    mbar_init(b_pfull, 128); mbar_init(b_odone, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t tS = tmem, tO = tmem + 256;
+  const uint32_t tS = tmem, tO = tmem + 128;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -169,68 +174,46 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
         if (j < nkv) {
           const int st = j % FWD_KV_STAGES;
           mbar_wait(b_kvfull + 8 * st, (j / FWD_KV_STAGES) & 1);
-          mbar_wait(b_sempty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);
+          mbar_wait(b_sempty, (j & 1) ^ 1);      // the softmax warps hold S_{j-1} in registers
           tc_fence_after();
-          mma_kk64(tS + (j & 1) * 128, sQ, sKV + st * 2 * TILE_BYTES, idesc_s, false);
-          umma_commit(b_sfull + 8 * (j & 1));
+          mma_kk64(tS, sQ, sKV + st * 2 * TILE_BYTES, idesc_s, false);
+          umma_commit(b_sfull);
         }
         if (j >= 1) {
           const int k = j - 1;
           const int st = k % FWD_KV_STAGES;
-          mbar_wait(b_pfull + 8 * (k & 1), (k >> 1) & 1);
-          mbar_wait(b_oempty + 8 * (k & 1), ((k >> 1) & 1) ^ 1);
+          mbar_wait(b_pfull, k & 1);
           tc_fence_after();
-          mma_pv(tO + (k & 1) * 64, sP + (k & 1) * PT_BYTES, sKV + st * 2 * TILE_BYTES + TILE_BYTES, idesc_o, false);
-          umma_commit(b_ofull + 8 * (k & 1));
-          umma_commit(b_pempty + 8 * (k & 1));
+          mma_pv(tO, sP, sKV + st * 2 * TILE_BYTES + TILE_BYTES, idesc_o, k > 0);
+          umma_commit(b_odone);                  // P is free again, O holds blocks 0..k
           umma_commit(b_kvempty + 8 * st);
         }
       }
     }
   } else {
-    // ---------------- softmax / accumulate threads: one thread per tile row
+    // ---------------- softmax threads: one thread per tile row
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const RowInfo ri = row_info(p, r, tile, outer, inner0);
     const float sc = p.scale * LOG2E;
-    float m_run = -INFINITY, l_run = 0.f, alpha_pend = 1.f;
-    float o_acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
-
-    auto absorb = [&](int k, float alpha) {
-      mbar_wait(b_ofull + 8 * (k & 1), (k >> 1) & 1);
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld32(tO + (k & 1) * 64 + lane_off, v0);
-      tmem_ld32(tO + (k & 1) * 64 + 32 + lane_off, v1);
-      tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o_acc[i] = o_acc[i] * alpha + __uint_as_float(v0[i]);
-        o_acc[32 + i] = o_acc[32 + i] * alpha + __uint_as_float(v1[i]);
-      }
-      tc_fence_before();
-      mbar_arrive(b_oempty + 8 * (k & 1));
-    };
+    float m_used = 0.f, l_run = 0.f;   // exponentials are taken relative to m_used
 
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(b_sfull + 8 * (j & 1), (j >> 1) & 1);
+      mbar_wait(b_sfull, j & 1);
       tc_fence_after();
-      const uint32_t ts = tS + (j & 1) * 128 + lane_off;
+      const uint32_t ts = tS + lane_off;
       const int kvalid = p.S - j * p.RT;                 // valid key tokens in this block
       const bool nomask = (p.G == 1) && (kvalid >= 128);  // warp-uniform fast path: nothing to mask
-      // single TMEM pass: the 128 scores of this row stay in registers (TMEM reads are the scarce resource here)
+      // single TMEM pass: the 128 scores of this row stay in registers
       uint32_t sv[4][32];
       tmem_ld32(ts, sv[0]);
       tmem_ld32(ts + 32, sv[1]);
       tmem_ld32(ts + 64, sv[2]);
       tmem_ld32(ts + 96, sv[3]);
       tc_wait_ld();
-      // the S buffer can be overwritten by the next QK^T as soon as the values are in registers
       tc_fence_before();
-      mbar_arrive(b_sempty + 8 * (j & 1));
+      mbar_arrive(b_sempty);   // S can be overwritten by the next QK^T
       float bmax;
       if (nomask) {
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
@@ -257,11 +240,31 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
           }
         }
       }
-      const float m_new = fmaxf(m_run, bmax);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2((m_run - m_use) * sc);
-      const float msc = m_use * sc;
-      mbar_wait(b_pempty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);
+      if (bmax == -INFINITY) bmax = 0.f;   // a row with no visible key in this block (padding rows of a packed tile)
+      if (j == 0) {
+        m_used = bmax;                     // PV_0 overwrites O: nothing to rescale
+      } else {
+        const bool grow = (bmax - m_used) * sc > FWD_RESCALE_LOG2;
+        mbar_wait(b_odone, (j - 1) & 1);   // PV_{j-1} retired: P is free and O is quiescent until we publish P_j
+        if (__any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2((m_used - bmax) * sc) : 1.f;
+          if (grow) m_used = bmax;
+          l_run *= alpha;
+          tc_fence_after();
+#pragma unroll 1
+          for (int h = 0; h < 64; h += 32) {   // 32 columns at a time: the 128 scores stay live in registers
+            uint32_t ov[32];
+            tmem_ld32(tO + h + lane_off, ov);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(tO + h + lane_off, ov);
+          }
+          tc_wait_st();
+          tc_fence_before();
+        }
+      }
+      const float msc = m_used * sc;
       // probabilities: the row sum uses the fp32 values (the bf16 rounding of P averages out, as in flash-attention)
       float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
@@ -285,37 +288,47 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
             r0 += f[i];
           }
         }
-        store_score_chunk(sP + (j & 1) * PT_BYTES, r, q * 32, f);
+        store_score_chunk(sP, r, q * 32, f);
       }
-      const float rsum = (r0 + r1) + (r2 + r3);
-      l_run = l_run * alpha + rsum;
-      m_run = m_new;
+      l_run += (r0 + r1) + (r2 + r3);
       fence_proxy_async_smem();
-      mbar_arrive(b_pfull + 8 * (j & 1));
-      if (j >= 1) absorb(j - 1, alpha_pend);
-      alpha_pend = alpha;
+      mbar_arrive(b_pfull);
     }
-    absorb(nkv - 1, alpha_pend);
-
+    // epilogue: O / l
+    mbar_wait(b_odone, (nkv - 1) & 1);
+    tc_fence_after();
+    uint32_t o0[32], o1[32];
+    tmem_ld32(tO + lane_off, o0);
+    tmem_ld32(tO + 32 + lane_off, o1);
+    tc_wait_ld();
     if (ri.valid) {
       const float inv = 1.f / l_run;
       bf16* orow = p.o + ri.token * p.ldo + head * 64;
 #pragma unroll
-      for (int i = 0; i < 64; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 u;
-        u.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
-        u.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-        u.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-        u.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+        u.x = pack_bf16x2(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv);
         *reinterpret_cast<uint4*>(orow + i) = u;
       }
-      if (p.lse) p.lse[ri.token * p.heads + head] = m_run * p.scale + __logf(l_run);
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + 32 + i) = u;
+      }
+      if (p.lse) p.lse[ri.token * p.heads + head] = m_used * p.scale + __logf(l_run);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // =====================================================================================
@@ -324,7 +337,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
 constexpr int BWD_STAGES = 2;
 constexpr int BDQ_SMEM = 1024 + 2 * TILE_BYTES + BWD_STAGES * 2 * TILE_BYTES + PT_BYTES + 256;
 
-__global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnKParams p) {
+// 8 element-wise warps: warp (w & 3) owns a TMEM lane quarter, ((w - 2) >> 2) picks the 64-column half of the score
+// tile it processes -- two warps per SM sub-partition hide the MUFU / TMEM / shared-memory latencies of each other.
+__global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sDO = sQ + TILE_BYTES;
@@ -351,8 +366,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
     prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv); prefetch_tmap(&p.tdo);
     mbar_init(b_qfull, 1);
     for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(b_kvfull + 8 * i, 1); mbar_init(b_kvempty + 8 * i, 1); }
-    mbar_init(b_sfull, 1); mbar_init(b_sempty, 128);
-    mbar_init(b_dsfull, 128); mbar_init(b_dsempty, 1);
+    mbar_init(b_sfull, 1); mbar_init(b_sempty, 256);
+    mbar_init(b_dsfull, 256); mbar_init(b_dsempty, 1);
     mbar_init(b_done, 1);
     fence_barrier_init();
   }
@@ -400,6 +415,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
     }
   } else {
     const int q4 = warp & 3;
+    const int ch = (warp - 2) >> 2;        // column half of the score tile
     const int r = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const RowInfo ri = row_info(p, r, tile, outer, inner0);
@@ -413,7 +429,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
       const int kvalid = p.S - j * p.RT;
       const bool nomask = (p.G == 1) && (kvalid >= 128);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
         uint32_t vs[32], vd[32];
         tmem_ld32(tS + lane_off + c0, vs);
         tmem_ld32(tDP + lane_off + c0, vd);
@@ -443,12 +459,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
     }
     mbar_wait(b_done, 0);
     tc_fence_after();
-    uint32_t v0[32], v1[32];
-    tmem_ld32(tDQ + lane_off, v0);
-    tmem_ld32(tDQ + lane_off + 32, v1);
+    uint32_t v0[32];
+    tmem_ld32(tDQ + lane_off + ch * 32, v0);   // each warp of the pair writes 32 of the 64 head columns
     tc_wait_ld();
     if (ri.valid) {
-      bf16* orow = p.dq + ri.token * p.lddq + head * 64;
+      bf16* orow = p.dq + ri.token * p.lddq + head * 64 + ch * 32;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 u;
@@ -457,11 +472,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
         u.z = pack_bf16x2(__uint_as_float(v0[i + 4]), __uint_as_float(v0[i + 5]));
         u.w = pack_bf16x2(__uint_as_float(v0[i + 6]), __uint_as_float(v0[i + 7]));
         *reinterpret_cast<uint4*>(orow + i) = u;
-        u.x = pack_bf16x2(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
-        u.y = pack_bf16x2(__uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3]));
-        u.z = pack_bf16x2(__uint_as_float(v1[i + 4]), __uint_as_float(v1[i + 5]));
-        u.w = pack_bf16x2(__uint_as_float(v1[i + 6]), __uint_as_float(v1[i + 7]));
-        *reinterpret_cast<uint4*>(orow + 32 + i) = u;
       }
     }
   }
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dq_kernel(const __grid
 // TMEM: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384)
 constexpr int BKV_SMEM = 1024 + 2 * TILE_BYTES + BWD_STAGES * 2 * TILE_BYTES + 2 * PT_BYTES + 1024 + 256;
 
-__global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnKParams p) {
+__global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base, sV = sK + TILE_BYTES;
@@ -507,8 +517,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv); prefetch_tmap(&p.tdo);
     mbar_init(b_kvfull, 1);
     for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, 1); }
-    mbar_init(b_sfull, 1); mbar_init(b_sempty, 128);
-    mbar_init(b_pfull, 128); mbar_init(b_pempty, 1);
+    mbar_init(b_sfull, 1); mbar_init(b_sempty, 256);
+    mbar_init(b_pfull, 256); mbar_init(b_pempty, 1);
     mbar_init(b_done, 1);
     fence_barrier_init();
   }
@@ -557,6 +567,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     }
   } else {
     const int q4 = warp & 3;
+    const int ch = (warp - 2) >> 2;        // query-column half of the transposed score tile
     const int r = q4 * 32 + lane;          // key row of this thread
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const RowInfo ki = row_info(p, r, tile, outer, inner0);
@@ -564,15 +575,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     for (int i = 0; i < nq; ++i) {
       // stage lse/delta of the 128 queries of tile i (column vectors of the transposed scores)
       const RowInfo qi = row_info(p, r, i, outer, inner0);
-      named_bar_sync(1, 128);  // previous iteration finished reading vec[]
-      vec[r] = qi.valid ? p.lse[qi.token * p.heads + head] * LOG2E : INFINITY;  // +inf -> p = 0
-      vec[128 + r] = qi.valid ? p.delta[qi.token * p.heads + head] : 0.f;
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);  // previous iteration finished reading vec[]
+      if (ch == 0) vec[r] = qi.valid ? p.lse[qi.token * p.heads + head] * LOG2E : INFINITY;  // +inf -> p = 0
+      else vec[128 + r] = qi.valid ? p.delta[qi.token * p.heads + head] : 0.f;
+      named_bar_sync(1, 256);
       mbar_wait(b_sfull, i & 1);
       tc_fence_after();
       mbar_wait(b_pempty, (i & 1) ^ 1);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
         uint32_t vs[32], vd[32];
         tmem_ld32(tST + lane_off + c0, vs);
         tmem_ld32(tDPT + lane_off + c0, vd);
@@ -606,15 +617,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     }
     mbar_wait(b_done, 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    {
+      // warp pair: ch 0 writes dV, ch 1 writes dK
       uint32_t v0[32], v1[32];
-      const uint32_t t = which == 0 ? tDV : tDK;
+      const uint32_t t = ch == 0 ? tDV : tDK;
       tmem_ld32(t + lane_off, v0);
       tmem_ld32(t + lane_off + 32, v1);
       tc_wait_ld();
       if (ki.valid) {
-        bf16* orow = which == 0 ? (p.dv + ki.token * p.lddv + head * 64) : (p.dk + ki.token * p.lddk + head * 64);
+        bf16* orow = ch == 0 ? (p.dv + ki.token * p.lddv + head * 64) : (p.dk + ki.token * p.lddk + head * 64);
 #pragma unroll
         for (int k = 0; k < 32; k += 8) {
           uint4 u;
@@ -742,8 +753,8 @@ extern "C" int svdx_attention_bwd(const SvdxAttn* d, void* stream_v) {
   const long long warps = tokens * d->heads;
   attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(d->o), d->ldo,
                                                                          reinterpret_cast<const bf16*>(d->dout), d->lddo, tokens, d->heads, d->delta);
-  attn_bwd_dq_kernel<<<grid, AT_THREADS, BDQ_SMEM, st>>>(p);
-  attn_bwd_dkv_kernel<<<grid, AT_THREADS, BKV_SMEM, st>>>(p);
+  attn_bwd_dq_kernel<<<grid, BWD_THREADS, BDQ_SMEM, st>>>(p);
+  attn_bwd_dkv_kernel<<<grid, BWD_THREADS, BKV_SMEM, st>>>(p);
   SVDX_CHECK_LAUNCH("attention_bwd");
   return SVDX_OK;
 }

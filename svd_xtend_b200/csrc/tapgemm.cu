@@ -63,7 +63,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    const bool conv_par = (p.a_mode == SVDX_A_CONV2D) && !p.a_mn && !p.b_mn && !p.geglu && (BLOCK_M / p.W) <= 32;
+    if (conv_par) {
+      // warp-wide conv producer: lane 0 owns the barriers and the B tile, every lane with a row box issues it
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = (tile / p.n_tiles) % p.m_tiles;
+        const int ks = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int n0 = nt * p.block_n;
+        ConvBox bx;
+        conv_tile_boxes(p, mt, lane, bx);
+        const CUtensorMap* amap = bx.lg == 0 ? &p.tma : &p.tma_bh[bx.lg - 1];
+        int tap = kb0 / p.kb_per_tap;
+        int kci = kb0 - tap * p.kb_per_tap;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const uint32_t full = bar_full + 8 * stage;
+          if (lane == 0) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(full, A_STAGE_BYTES + b_bytes);
+          }
+          __syncwarp();
+          const int kc = kci * BLOCK_K;
+          if (bx.active)
+            tma_load_4d(amap, full, sA + stage * A_STAGE_BYTES + bx.dst_off, kc, p.tap_d0[tap], bx.hh + p.tap_d1[tap],
+                        bx.nvalid ? bx.n + p.tap_d2[tap] : (1 << 28));
+          if (lane == 0) tma_load_2d(&p.tmb, full, sB + stage * B_STAGE_BYTES, tap * p.K + kc, n0);
+          if (++kci == p.kb_per_tap) { kci = 0; ++tap; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {

@@ -137,7 +137,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ===========================
-    if (lane == 0) {
+    const bool conv_par = (p.a_mode == SVDX_A_CONV2D) && !p.geglu && (BLOCK_M / p.W) <= 32;
+    if (conv_par) {
+      // warp-wide conv producer (see conv_tile_boxes): lane 0 owns the barriers and the B half-tile
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int nt = tile % p.n_tiles;
+        const int pt = tile / p.n_tiles;
+        int g, t;
+        my_slice(pt, g, t);
+        const int n0 = nt * bn_out;
+        ConvBox bx;
+        conv_tile_boxes(p, t, lane, bx);
+        const CUtensorMap* amap = bx.lg == 0 ? &p.tma : &p.tma_bh[bx.lg - 1];
+        int tap = 0, kci = 0;
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          const uint32_t full = bar_full + 8 * stage;
+          if (lane == 0) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            if (leader) mbar_expect_tx(full, 2 * A_STAGE_BYTES + p.block_n * BLOCK_K * 2);
+          }
+          __syncwarp();
+          const int kc = kci * BLOCK_K;
+          if (bx.active)
+            tma2_load_4d(amap, full, sA + stage * A_STAGE_BYTES + bx.dst_off, kc, p.tap_d0[tap], bx.hh + p.tap_d1[tap],
+                         bx.nvalid ? bx.n + p.tap_d2[tap] : (1 << 28));
+          if (lane == 0) tma2_load_2d(&p.tmb, full, sB + stage * B2_STAGE_BYTES, tap * p.K + kc, n0 + (int)rank * b_half_rows);
+          if (++kci == p.kb_per_tap) { kci = 0; ++tap; }
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {

@@ -74,6 +74,36 @@ SVDX_DEVINL void tile_row(const TapGemmKParams& p, int mt, int r, long long& m, 
   }
 }
 
+// ---- conv A tiles: the 128 pixels of a tile are R = 128 / W consecutive image rows, fetched as a few multi-row TMA
+// boxes (image borders and tile/image straddling decide the split). The split depends on the tile only, so it is
+// computed once per tile with lane l of the producer warp keeping box l; per k-block every lane that owns a box
+// issues its TMA. (The per-k-block scalar decomposition cost ~1.5-3 k cycles and made the producer thread the
+// bottleneck of every 3x3 convolution: profiles/r1_conv_probe.txt.)
+struct ConvBox {
+  int lg, hh, n;
+  uint32_t dst_off;
+  bool nvalid, active;
+};
+SVDX_DEVINL void conv_tile_boxes(const TapGemmKParams& p, int t, int lane, ConvBox& mine) {
+  const int R = BLOCK_M / p.W;
+  int rowid = t * R, left = R, idx = 0;
+  uint32_t off = 0;
+  mine.active = false; mine.lg = 0; mine.hh = 0; mine.n = 0; mine.dst_off = 0; mine.nvalid = false;
+  while (left > 0) {
+    const int n = rowid / p.H;
+    const int h = rowid - n * p.H;
+    int run = min(left, p.H - h);
+    int hh = h;
+    while (run > 0) {
+      const int lg = min(p.max_bh_log2, 31 - __clz(run));
+      const int bh = 1 << lg;
+      if (idx == lane) { mine.lg = lg; mine.hh = hh; mine.n = n; mine.nvalid = n < p.nimg; mine.dst_off = off; mine.active = true; }
+      off += bh * p.W * 128;
+      hh += bh; run -= bh; left -= bh; rowid += bh; ++idx;
+    }
+  }
+}
+
 // ---- staged stores: a warp writes its 32-row x 32-column chunk into shared memory (one row per lane, swizzled so
 // that the 16-byte writes are conflict-free) and one lane hands it to the TMA unit. The global writes become full
 // 64/128-byte row segments issued asynchronously, instead of 32 scattered 16-byte sectors per store instruction
