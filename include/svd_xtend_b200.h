@@ -109,8 +109,10 @@ int svdx_tapgemm(const SvdxTapGemm* desc, void* stream);
 
 /* Second half of a split-K svdx_tapgemm (fp32 partial sums accumulated with SVDX_OUT_F32_ATOMIC into ws): applies the
  * same epilogue  out = scales[0]*(ws + bias + rowbias[m / rowbias_div]) + scales[1]*res1 + scales[2]*res2  -> bf16.
- * Used for the 5x8 / 10x16 latent levels where M gives too few output tiles to fill 148 SMs. */
-int svdx_splitk_epilogue(const float* ws, int64_t ldw, void* out, int64_t ldo, int64_t rows, int32_t cols, const float* bias,
+ * Used for the 5x8 / 10x16 latent levels where M gives too few output tiles to fill 148 SMs.
+ * The workspace is CONSUMED: every element read is reset to zero, so a caller can keep one zeroed workspace per shape
+ * and never memset it again. */
+int svdx_splitk_epilogue(float* ws, int64_t ldw, void* out, int64_t ldo, int64_t rows, int32_t cols, const float* bias,
                          const float* rowbias, int32_t rowbias_div, int64_t ldrb, const void* res1, int64_t ldr1,
                          const void* res2, int64_t ldr2, const float* scales, void* stream);
 

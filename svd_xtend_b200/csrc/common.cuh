@@ -210,10 +210,11 @@ SVDX_DEVINL uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major
 }
 
 // ---------------------------------------------------------------- misc math
-SVDX_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// sigmoid through ex2.approx + rcp.approx (2 ulp): the IEEE division would cost ~10 instructions per element
+SVDX_DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 SVDX_DEVINL float silu_grad_f(float x) {
-  float s = 1.0f / (1.0f + __expf(-x));
-  return s * (1.0f + x * (1.0f - s));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-x));
+  return s * fmaf(x, 1.0f - s, 1.0f);
 }
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one rcp, one ex2, 6 FMAs
 SVDX_DEVINL float erf_fast(float z) {

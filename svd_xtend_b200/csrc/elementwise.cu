@@ -316,7 +316,7 @@ __global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __
 }
 
 // epilogue of a split-K contraction: out = s0*(ws + bias + rowbias[m/div]) + s1*res1 + s2*res2  (bf16), 8 columns per thread
-__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __restrict__ ws, long long ldw, bf16* __restrict__ out, long long ldo,
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(float* __restrict__ ws, long long ldw, bf16* __restrict__ out, long long ldo,
                                                               long long rows, int cols, const float* __restrict__ bias,
                                                               const float* __restrict__ rowbias, int rb_div, long long ldrb,
                                                               const bf16* __restrict__ res1, long long ldr1, const bf16* __restrict__ res2,
@@ -330,6 +330,9 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const float* __res
   if (scales) { s0 = scales[0]; s1 = scales[1]; s2 = scales[2]; }
   const float4 a = *reinterpret_cast<const float4*>(ws + r * ldw + c);
   const float4 b = *reinterpret_cast<const float4*>(ws + r * ldw + c + 4);
+  // consume: leave the workspace zeroed for the next split-K accumulation
+  *reinterpret_cast<float4*>(ws + r * ldw + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(ws + r * ldw + c + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   if (bias) {
 #pragma unroll
@@ -388,10 +391,12 @@ struct TransposeJob {
   int O, I;
 };
 
-// many 2-D transposes dst[i][o] = src[o][i] (bf16) in ONE launch: block -> (job, 32x32 tile) through a tile prefix table
+// many 2-D transposes dst[i][o] = src[o][i] (bf16) in ONE launch: block -> (job, 64x64 tile) through a tile prefix
+// table; 4-byte (bf16x2) global accesses so that a warp row covers a full 128-byte line on both sides.
+constexpr int TR_TILE = 64;
 __global__ void multi_transpose_kernel(const bf16* __restrict__ src_base, const TransposeJob* __restrict__ jobs,
                                        const int* __restrict__ tile_prefix, int njobs) {
-  __shared__ bf16 tile[32][34];
+  __shared__ bf16 tile[TR_TILE][TR_TILE + 2];
   int lo = 0, hi = njobs - 1;
   const int b = blockIdx.x;
   while (lo < hi) {            // last job whose first tile <= b
@@ -400,17 +405,37 @@ __global__ void multi_transpose_kernel(const bf16* __restrict__ src_base, const 
   }
   const TransposeJob j = jobs[lo];
   const int t = b - tile_prefix[lo];
-  const int tiles_x = (j.I + 31) / 32;
-  const int i0 = (t % tiles_x) * 32, o0 = (t / tiles_x) * 32;
+  const int tiles_x = (j.I + TR_TILE - 1) / TR_TILE;
+  const int i0 = (t % tiles_x) * TR_TILE, o0 = (t / tiles_x) * TR_TILE;
   const bf16* src = src_base + j.src_off;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int o = o0 + r, i = i0 + threadIdx.x;
-    if (o < j.O && i < j.I) tile[r][threadIdx.x] = src[(long long)o * j.I + i];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool vec_in = (j.I % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+  const bool vec_out = (j.O % 2 == 0) && ((reinterpret_cast<uintptr_t>(j.dst) & 3) == 0);
+  for (int r = ty; r < TR_TILE; r += blockDim.y) {
+    const int o = o0 + r, i = i0 + 2 * tx;
+    if (o < j.O) {
+      if (vec_in && i + 1 < j.I) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + (long long)o * j.I + i);
+        tile[r][2 * tx] = v.x; tile[r][2 * tx + 1] = v.y;
+      } else {
+        if (i < j.I) tile[r][2 * tx] = src[(long long)o * j.I + i];
+        if (i + 1 < j.I) tile[r][2 * tx + 1] = src[(long long)o * j.I + i + 1];
+      }
+    }
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int i = i0 + r, o = o0 + threadIdx.x;
-    if (i < j.I && o < j.O) j.dst[(long long)i * j.O + o] = tile[threadIdx.x][r];
+  for (int r = ty; r < TR_TILE; r += blockDim.y) {
+    const int i = i0 + r, o = o0 + 2 * tx;
+    if (i < j.I) {
+      if (vec_out && o + 1 < j.O) {
+        __nv_bfloat162 v;
+        v.x = tile[2 * tx][r]; v.y = tile[2 * tx + 1][r];
+        *reinterpret_cast<__nv_bfloat162*>(j.dst + (long long)i * j.O + o) = v;
+      } else {
+        if (o < j.O) j.dst[(long long)i * j.O + o] = tile[2 * tx][r];
+        if (o + 1 < j.O) j.dst[(long long)i * j.O + o + 1] = tile[2 * tx + 1][r];
+      }
+    }
   }
 }
 
@@ -617,7 +642,7 @@ extern "C" int svdx_silu_bwd_f32(const float* x, const float* dy, float* dx, int
   return SVDX_OK;
 }
 
-extern "C" int svdx_splitk_epilogue(const float* ws, int64_t ldw, void* out, int64_t ldo, int64_t rows, int32_t cols, const float* bias,
+extern "C" int svdx_splitk_epilogue(float* ws, int64_t ldw, void* out, int64_t ldo, int64_t rows, int32_t cols, const float* bias,
                                     const float* rowbias, int32_t rowbias_div, int64_t ldrb, const void* res1, int64_t ldr1,
                                     const void* res2, int64_t ldr2, const float* scales, void* stream) {
   if (!ws || !out || rows <= 0 || cols <= 0 || cols % 8 || ldw % 4 || ldo % 8 || (res1 && ldr1 % 8) || (res2 && ldr2 % 8) ||

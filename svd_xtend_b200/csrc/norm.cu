@@ -138,15 +138,16 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_kernel(GnSrc s, int 
     sh[k] = beta[c0 + k] - mean[n * G + g] * sc[k];
   }
   const long long base = (long long)n * rows;
-  for (int r = r0 + rl; r < r1; r += 2 * RL) {
-    const bool two = r + RL < r1;
-    const uint4 u0 = load_vec8(s, base + r, c0);
-    const uint4 u1 = two ? load_vec8(s, base + r + RL, c0) : u0;
+  for (int r = r0 + rl; r < r1; r += 4 * RL) {
+    // four independent row loads in flight per thread before any math (the kernel is latency x bytes-in-flight bound)
+    uint4 u[4];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      if (q == 1 && !two) break;
-      const uint4 u = q ? u1 : u0;
-      const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+    for (int q = 0; q < 4; ++q)
+      if (r + q * RL < r1) u[q] = load_vec8(s, base + r + q * RL, c0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (r + q * RL >= r1) break;
+      const uint32_t in[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
       uint32_t out[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_kernel(GnSrc s, int 
 // ------------------------------------------------------------------ GroupNorm backward
 // pass 1: per (n, group) s1 = sum(g*gamma), s2 = sum(g*gamma*xhat), g = dy * silu'(z); optional dgamma/dbeta.
 // Same thread layout as gn_stats_partial (one 8-channel vector per thread, rows in flight).
+template <bool DG>
 __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
                                                                   int G, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -190,20 +192,19 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a1[k] = a2[k] = dg[k] = db[k] = 0.f; }
     const long long base = (long long)n * rows;
-    for (int r = r0 + rl; r < r1; r += 2 * RL) {
-      const bool two = (r + RL < r1);
-      const uint4 ux0 = load_vec8(s, base + r, c0);
-      const uint4 ud0 = *reinterpret_cast<const uint4*>(dy + (base + r) * lddy + c0);
-      uint4 ux1 = ux0, ud1 = make_uint4(0, 0, 0, 0);
-      if (two) {
-        ux1 = load_vec8(s, base + r + RL, c0);
-        ud1 = *reinterpret_cast<const uint4*>(dy + (base + r + RL) * lddy + c0);
+    for (int r = r0 + rl; r < r1; r += 4 * RL) {
+      uint4 ux[4], ud[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (r + q * RL < r1) {
+          ux[q] = load_vec8(s, base + r + q * RL, c0);
+          ud[q] = *reinterpret_cast<const uint4*>(dy + (base + r + q * RL) * lddy + c0);
+        }
       }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q == 1 && !two) break;
-        const uint4 ux = q ? ux1 : ux0, ud = q ? ud1 : ud0;
-        const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+      for (int q = 0; q < 4; ++q) {
+        if (r + q * RL >= r1) break;
+        const uint32_t wx[4] = {ux[q].x, ux[q].y, ux[q].z, ux[q].w}, wd[4] = {ud[q].x, ud[q].y, ud[q].z, ud[q].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 v = unpack_bf16x2(wx[k]), d = unpack_bf16x2(wd[k]);
@@ -215,8 +216,10 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const
           }
           a1[2 * k] += e0 * gm[2 * k]; a1[2 * k + 1] += e1 * gm[2 * k + 1];
           a2[2 * k] += e0 * gm[2 * k] * xh0; a2[2 * k + 1] += e1 * gm[2 * k + 1] * xh1;
-          dg[2 * k] += e0 * xh0; dg[2 * k + 1] += e1 * xh1;
-          db[2 * k] += e0; db[2 * k + 1] += e1;
+          if (DG) {
+            dg[2 * k] += e0 * xh0; dg[2 * k + 1] += e1 * xh1;
+            db[2 * k] += e0; db[2 * k + 1] += e1;
+          }
         }
       }
     }
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const
       sa += a1[k]; sb += a2[k]; --left;
     }
     atomicAdd(&sh_s[g], sa); atomicAdd(&sh_s[G + g], sb);
-    if (dgamma) {
+    if (DG) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) { atomicAdd(&dgamma[c0 + k], dg[k]); atomicAdd(&dbeta[c0 + k], db[k]); }
     }
@@ -265,26 +268,36 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
     t1[k] = ws[(n * G + g) * 2] * inv_count; t2[k] = ws[(n * G + g) * 2 + 1] * inv_count;
   }
   const long long base = (long long)n * rows;
-  for (int r = r0 + rl; r < r1; r += RL) {
-    const long long row = base + r;
-    const uint4 u = load_vec8(s, row, c0);
-    const uint4 ud = *reinterpret_cast<const uint4*>(dy + row * lddy + c0);
-    const uint32_t in[4] = {u.x, u.y, u.z, u.w}, din[4] = {ud.x, ud.y, ud.z, ud.w};
-    uint32_t out[4];
+  for (int r = r0 + rl; r < r1; r += 4 * RL) {
+    uint4 ux[4], ug[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 v = unpack_bf16x2(in[k]), d = unpack_bf16x2(din[k]);
-      const float xh0 = (v.x - mu[2 * k]) * rs[2 * k], xh1 = (v.y - mu[2 * k + 1]) * rs[2 * k + 1];
-      float e0 = d.x, e1 = d.y;
-      if (fuse_silu) {
-        e0 *= silu_grad_f(fmaf(xh0, gm[2 * k], bt[2 * k]));
-        e1 *= silu_grad_f(fmaf(xh1, gm[2 * k + 1], bt[2 * k + 1]));
+    for (int q = 0; q < 4; ++q) {
+      if (r + q * RL < r1) {
+        ux[q] = load_vec8(s, base + r + q * RL, c0);
+        ug[q] = *reinterpret_cast<const uint4*>(dy + (base + r + q * RL) * lddy + c0);
       }
-      out[k] = pack_bf16x2(rs[2 * k] * (e0 * gm[2 * k] - t1[2 * k] - xh0 * t2[2 * k]),
-                           rs[2 * k + 1] * (e1 * gm[2 * k + 1] - t1[2 * k + 1] - xh1 * t2[2 * k + 1]));
     }
-    bf16* q = first ? (dx + row * lddx + c0) : (dx2 + row * lddx2 + (c0 - s.C1));
-    *reinterpret_cast<uint4*>(q) = make_uint4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (r + q * RL >= r1) break;
+      const long long row = base + r + q * RL;
+      const uint32_t in[4] = {ux[q].x, ux[q].y, ux[q].z, ux[q].w}, din[4] = {ug[q].x, ug[q].y, ug[q].z, ug[q].w};
+      uint32_t out[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 v = unpack_bf16x2(in[k]), d = unpack_bf16x2(din[k]);
+        const float xh0 = (v.x - mu[2 * k]) * rs[2 * k], xh1 = (v.y - mu[2 * k + 1]) * rs[2 * k + 1];
+        float e0 = d.x, e1 = d.y;
+        if (fuse_silu) {
+          e0 *= silu_grad_f(fmaf(xh0, gm[2 * k], bt[2 * k]));
+          e1 *= silu_grad_f(fmaf(xh1, gm[2 * k + 1], bt[2 * k + 1]));
+        }
+        out[k] = pack_bf16x2(rs[2 * k] * (e0 * gm[2 * k] - t1[2 * k] - xh0 * t2[2 * k]),
+                             rs[2 * k + 1] * (e1 * gm[2 * k + 1] - t1[2 * k + 1] - xh1 * t2[2 * k + 1]));
+      }
+      bf16* qd = first ? (dx + row * lddx + c0) : (dx2 + row * lddx2 + (c0 - s.C1));
+      *reinterpret_cast<uint4*>(qd) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
   }
 }
 
@@ -349,7 +362,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 // dy and the residual gradient in flight together), keeps its dgamma/dbeta partials in registers, and the block reduces
 // them through shared memory before one atomic per channel.
 // dx = rstd*(gamma*dy - mean(gamma*dy) - xhat*mean(gamma*dy*xhat)) [+ dres]
-template <int NJ>
+template <int NJ, bool DG>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
                                                      int rows, int C, const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, bf16* __restrict__ dx, long long lddx,
@@ -384,7 +397,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
       }
     }
     const float m = mean[row], rs = rstd[row];
-    float xh[NJ][8], gd[NJ][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
@@ -394,25 +406,34 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 a = unpack_bf16x2(wx[k]), d = unpack_bf16x2(wd[k]);
-          xh[j][2 * k] = (a.x - m) * rs; xh[j][2 * k + 1] = (a.y - m) * rs;
-          gd[j][2 * k] = d.x * gm[j][2 * k]; gd[j][2 * k + 1] = d.y * gm[j][2 * k + 1];
-          s1 += gd[j][2 * k] + gd[j][2 * k + 1];
-          s2 += gd[j][2 * k] * xh[j][2 * k] + gd[j][2 * k + 1] * xh[j][2 * k + 1];
-          dg[j][2 * k] += d.x * xh[j][2 * k]; dg[j][2 * k + 1] += d.y * xh[j][2 * k + 1];
-          db[j][2 * k] += d.x; db[j][2 * k + 1] += d.y;
+          const float x0 = (a.x - m) * rs, x1 = (a.y - m) * rs;
+          const float g0 = d.x * gm[j][2 * k], g1 = d.y * gm[j][2 * k + 1];
+          s1 += g0 + g1;
+          s2 += g0 * x0 + g1 * x1;
+          if (DG) {
+            dg[j][2 * k] += d.x * x0; dg[j][2 * k + 1] += d.y * x1;
+            db[j][2 * k] += d.x; db[j][2 * k + 1] += d.y;
+          }
         }
       }
     }
     s1 = warp_sum(s1) * invC;
     s2 = warp_sum(s2) * invC;
     bf16* oxr = dx + (long long)row * lddx;
+    // second pass recomputes xhat / g*gamma from the raw vectors still in registers (cheaper than keeping them live)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int v = lane + 32 * j;
       if (v < CV) {
+        const uint32_t wx[4] = {ux[j].x, ux[j].y, ux[j].z, ux[j].w}, wd[4] = {ud[j].x, ud[j].y, ud[j].z, ud[j].w};
         float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = rs * (gd[j][k] - s1 - xh[j][k] * s2);
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(wx[k]), d = unpack_bf16x2(wd[k]);
+          const float x0 = (a.x - m) * rs, x1 = (a.y - m) * rs;
+          o[2 * k] = rs * (d.x * gm[j][2 * k] - s1 - x0 * s2);
+          o[2 * k + 1] = rs * (d.y * gm[j][2 * k + 1] - s1 - x1 * s2);
+        }
         if (dres) {
           const uint32_t wr[4] = {ur[j].x, ur[j].y, ur[j].z, ur[j].w};
 #pragma unroll
@@ -423,7 +444,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
       }
     }
   }
-  if (dgamma) {
+  if (DG) {
     __shared__ float sh_g[256 * NJ], sh_b[256 * NJ];
     for (int i = threadIdx.x; i < 256 * NJ; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; }
     __syncthreads();
@@ -453,12 +474,13 @@ static void gn_vec_config(int C, int outer, int rows, int& threads, int& rows_pe
   int RL = 256 / CV;
   if (RL < 1) RL = 1;
   threads = CV * RL;
-  const long long want_ctas = 4LL * svdx_num_sms();
+  // ~8 CTAs per SM, each thread streams a multiple of 4 rows (4 independent 16-byte loads per tensor in flight)
+  const long long want_ctas = 8LL * svdx_num_sms();
   long long chunks = (want_ctas + outer - 1) / outer;
   if (chunks < 1) chunks = 1;
   rows_per_cta = (int)((rows + chunks - 1) / chunks);
-  const int min_rows = 8 * RL;
-  if (rows_per_cta < min_rows) rows_per_cta = min_rows;
+  const int quantum = 4 * RL;
+  rows_per_cta = ((rows_per_cta + quantum - 1) / quantum) * quantum;
 }
 
 static int gn_check(int C1, int C2, int G, int64_t ldx, int64_t ldx2, const void* x, const void* x2) {
@@ -518,8 +540,12 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
   int threads, rpc;
   gn_vec_config(C1 + C2, outer, rows, threads, rpc);
   dim3 grid((rows + rpc - 1) / rpc, outer);
-  gn_bwd_partial<<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta,
-                                              fuse_silu, workspace, dgamma, dbeta);
+  if (dgamma)
+    gn_bwd_partial<true><<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta,
+                                                   fuse_silu, workspace, dgamma, dbeta);
+  else
+    gn_bwd_partial<false><<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta,
+                                                    fuse_silu, workspace, dgamma, dbeta);
   const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
   gn_bwd_apply<<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta, fuse_silu,
                                          workspace, inv, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dx2), lddx2);
@@ -557,10 +583,16 @@ static void ln_bwd_launch(const void* x, int64_t ldx, const void* dy, int64_t ld
                           const float* rstd, void* dx, int64_t lddx, const void* dres, int64_t lddres, float* dgamma, float* dbeta,
                           cudaStream_t st) {
   int ctas = (rows + 7) / 8;
-  const int cap = svdx_num_sms() * 2;   // few CTAs: the dgamma/dbeta atomics contend per address
+  // with parameter gradients: few CTAs (the dgamma/dbeta atomics contend per address); without: fill the SMs with
+  // resident warps, one row in flight per warp
+  const int cap = svdx_num_sms() * (dgamma ? 2 : 8);
   if (ctas > cap) ctas = cap;
-  ln_bwd_kernel<NJ><<<ctas, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(dy), lddy, rows, C, g, mean,
-                                          rstd, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<const bf16*>(dres), lddres, dgamma, dbeta);
+  if (dgamma)
+    ln_bwd_kernel<NJ, true><<<ctas, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(dy), lddy, rows, C, g, mean,
+                                                  rstd, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<const bf16*>(dres), lddres, dgamma, dbeta);
+  else
+    ln_bwd_kernel<NJ, false><<<ctas, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(dy), lddy, rows, C, g, mean,
+                                                   rstd, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<const bf16*>(dres), lddres, dgamma, dbeta);
 }
 
 extern "C" int svdx_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int32_t rows, int32_t C, const float* gamma,

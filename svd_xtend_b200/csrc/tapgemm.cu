@@ -96,6 +96,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+    } else if (p.a_mn && p.b_mn && p.b_mode != 1) {
+      // weight-gradient forms (MN-major A and B): 2 A boxes + block_n/64 B boxes per k-block, one lane per box
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nb = p.block_n / 64;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = (tile / p.n_tiles) % p.m_tiles;
+        const int ks = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int n0 = nt * p.block_n;
+        int g = 0, kbi = kb0;
+        if (p.b_mode == 2) { g = kb0 / p.kb_per_group; kbi = kb0 - g * p.kb_per_group; }
+        const int shift = p.b_mode == 2 ? p.tap_d0[0] : 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const uint32_t full = bar_full + 8 * stage;
+          if (lane == 0) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(full, A_STAGE_BYTES + b_bytes);
+          }
+          __syncwarp();
+          const uint32_t dA = sA + stage * A_STAGE_BYTES;
+          const uint32_t dB = sB + stage * B_STAGE_BYTES;
+          if (p.b_mode == 2) {
+            // group-bounded k rows (3-D maps): rows past the end of the group read as zero
+            const int k0 = kbi * BLOCK_K;
+            if (lane < 2) tma_load_3d(&p.tma, full, dA + lane * 8192, mt * BLOCK_M + 64 * lane, k0, g);
+            else if (lane < 2 + nb) tma_load_3d(&p.tmb, full, dB + (lane - 2) * 8192, n0 + 64 * (lane - 2), k0 + shift, g);
+            if (++kbi == p.kb_per_group) { kbi = 0; ++g; }
+          } else {
+            if (lane < 2) tma_load_2d(&p.tma, full, dA + lane * 8192, mt * BLOCK_M + 64 * lane, kb * BLOCK_K);
+            else if (lane < 2 + nb) tma_load_2d(&p.tmb, full, dB + (lane - 2) * 8192, n0 + 64 * (lane - 2), kb * BLOCK_K);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
     } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -106,14 +143,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         const int n0 = nt * (p.geglu ? p.block_n / 2 : p.block_n);
+        int tap = kb0 / p.kb_per_tap;
+        int kci = kb0 - tap * p.kb_per_tap - 1;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (++kci == p.kb_per_tap) { kci = 0; ++tap; }   // no per-k-block division on the issue path
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
           mbar_expect_tx(full, A_STAGE_BYTES + b_bytes);
           const uint32_t dA = sA + stage * A_STAGE_BYTES;
           const uint32_t dB = sB + stage * B_STAGE_BYTES;
-          const int tap = kb / p.kb_per_tap;
-          const int kc = (kb - tap * p.kb_per_tap) * BLOCK_K;
+          const int kc = kci * BLOCK_K;
           // ---- A
           if (p.a_mn) {
             // memory [k rows][m cols]: two 64x64 boxes. b_mode 2 walks the k rows group by group.

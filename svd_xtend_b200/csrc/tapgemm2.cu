@@ -177,14 +177,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
         int g, t;
         my_slice(pt, g, t);
         const int n0 = nt * bn_out;
+        int tap = 0, kci = -1;
         for (int kb = 0; kb < p.kb_total; ++kb) {
+          if (++kci == p.kb_per_tap) { kci = 0; ++tap; }   // no per-k-block division on the issue path
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
           if (leader) mbar_expect_tx(full, 2 * A_STAGE_BYTES + p.block_n * BLOCK_K * 2);
           const uint32_t dA = sA + stage * A_STAGE_BYTES;
           const uint32_t dB = sB + stage * B2_STAGE_BYTES;
-          const int tap = kb / p.kb_per_tap;
-          const int kc = (kb - tap * p.kb_per_tap) * BLOCK_K;
+          const int kc = kci * BLOCK_K;
           if (p.a_mode == SVDX_A_ROWS) {
             // rows past the end of the group (t >= tiles_per_group) are out of bounds -> zero
             tma2_load_3d(&p.tma, full, dA, kc, t * BLOCK_M + p.tap_d0[tap], g);

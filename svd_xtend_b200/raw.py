@@ -202,6 +202,20 @@ def tapgemm(
     return out
 
 
+_SPLITK_WS: dict = {}
+
+
+def _splitk_workspace(M: int, N: int, device) -> torch.Tensor:
+    """one zeroed fp32 [M, N] workspace per shape and device: svdx_splitk_epilogue re-zeroes what it reads, so the
+    accumulate -> epilogue pairs of a stream can share it without a memset per launch"""
+    key = (M, N, str(device))
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(M, N, device=device, dtype=torch.float32)
+        _SPLITK_WS[key] = ws
+    return ws
+
+
 def tapgemm_auto(a, b, out, *, M, N, K, taps=((0, 0, 0),), bias=None, rowbias=None, rowbias_div=1, res1=None, res2=None,
                  scales=None, **kw):
     """svdx_tapgemm with automatic split-K for small-M / long-K problems (bf16 output, K-major operands, no GEGLU):
@@ -219,7 +233,7 @@ def tapgemm_auto(a, b, out, *, M, N, K, taps=((0, 0, 0),), bias=None, rowbias=No
             tiles = m_tiles * (N // bn)
             split = min(num_sms() // max(tiles, 1), kb // 8)
             if tiles <= num_sms() // 3 and split >= 2:
-                ws = torch.zeros(M, N, device=out.device, dtype=torch.float32)
+                ws = _splitk_workspace(M, N, out.device)
                 tapgemm(a, b, ws, M=M, N=N, K=K, taps=taps, block_n=bn, split_k=split, out_dtype=OUT_F32_ATOMIC, **kw)
                 check(load().svdx_splitk_epilogue(ws.data_ptr(), N, out.data_ptr(), _rowmajor(out, "out"), M, N, _ptr(bias), _ptr(rowbias),
                                                   rowbias_div, _rowmajor(rowbias, "rowbias") if rowbias is not None else 0,

@@ -109,7 +109,7 @@ class ParamArena:
             for off, dst, O, I in self._tjobs:
                 blob += struct.pack("<qqii", off, dst.data_ptr(), O, I)
                 prefix.append(tiles)
-                tiles += ((O + 31) // 32) * ((I + 31) // 32)
+                tiles += ((O + 63) // 64) * ((I + 63) // 64)   # TR_TILE of multi_transpose_kernel
             jobs = torch.frombuffer(bytes(blob), dtype=torch.uint8).clone().to(self.data.device)
             pre = torch.tensor(prefix, dtype=torch.int32, device=self.data.device)
             self._tjob_dev = (jobs, pre, len(self._tjobs), tiles)

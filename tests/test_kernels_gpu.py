@@ -251,3 +251,27 @@ def test_misc_elementwise(raw):
         raw.adamw(p, g, m, v, 1e-2, 0.9, 0.999, 1e-8, 1e-2, step)
     torch.cuda.synchronize()
     assert torch.allclose(p, pt.detach(), atol=1e-5, rtol=1e-5)
+
+
+def test_multi_transpose_bit_exact(raw):
+    """All dgrad operand transposes in one launch (train.ParamArena.refresh_transposes): ragged and odd shapes."""
+    import struct
+    shapes = [(320, 320), (1280, 320), (96, 200), (33, 65), (64, 1), (5, 7), (640, 2560)]
+    offs, total = [], 0
+    for O, I in shapes:
+        offs.append(total)
+        total += ((O * I + 63) // 64) * 64
+    src = torch.randn(total, device=DEV).to(bf16)
+    dsts = [torch.zeros(I, O, device=DEV, dtype=bf16) for O, I in shapes]
+    blob, prefix, tiles = bytearray(), [], 0
+    for (O, I), off, d in zip(shapes, offs, dsts):
+        blob += struct.pack("<qqii", off, d.data_ptr(), O, I)
+        prefix.append(tiles)
+        tiles += ((O + 63) // 64) * ((I + 63) // 64)
+    jobs = torch.frombuffer(bytes(blob), dtype=torch.uint8).clone().to(DEV)
+    pre = torch.tensor(prefix, dtype=torch.int32, device=DEV)
+    raw.multi_transpose(src, jobs, pre, len(shapes), tiles)
+    torch.cuda.synchronize()
+    for (O, I), off, d in zip(shapes, offs, dsts):
+        ref = src[off:off + O * I].view(O, I).t().contiguous()
+        assert torch.equal(d, ref), f"transpose {O}x{I}"

@@ -271,3 +271,9 @@ def test_conv3x3_auto_split_k(raw, N, H, W, Cin, Cout):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
     ref = 0.4 * (ref + rb.repeat_interleave(M // 2, 0)) + res.float()
     _close(out, ref, what="conv split-k")
+    # the fp32 workspace is cached per shape and re-zeroed by the epilogue: a second launch must give the same result
+    out2 = torch.empty_like(out)
+    raw.tapgemm_auto(x.view(-1, Cin), wk, out2, M=M, N=Cout, K=Cin, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, N),
+                     bias=bias, rowbias=rb, rowbias_div=M // 2, res1=res, scales=scales)
+    torch.cuda.synchronize()
+    _close(out2, ref, what="conv split-k (workspace reuse)")
