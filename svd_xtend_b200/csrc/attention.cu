@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
     prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv);
     mbar_init(b_qfull, 1);
     for (int i = 0; i < FWD_KV_STAGES; ++i) { mbar_init(b_kvfull + 8 * i, 1); mbar_init(b_kvempty + 8 * i, 1); }
-    mbar_init(b_sfull, 1); mbar_init(b_sempty, 128);
-    mbar_init(b_pfull, 128); mbar_init(b_odone, 1);
+    mbar_init(b_sfull, 1); mbar_init(b_sempty, 4);     // one arrive per softmax warp (not per thread:
+    mbar_init(b_pfull, 4); mbar_init(b_odone, 1);      // 128 same-address arrives serialise in the SYNCS unit)
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
       tmem_ld32(ts + 96, sv[3]);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(b_sempty);   // S can be overwritten by the next QK^T
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_sempty);   // S can be overwritten by the next QK^T
       float bmax;
       if (nomask) {
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // 4 independent chains
@@ -292,7 +293,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
       }
       l_run += (r0 + r1) + (r2 + r3);
       fence_proxy_async_smem();
-      mbar_arrive(b_pfull);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_pfull);
     }
     // epilogue: O / l
     mbar_wait(b_odone, (nkv - 1) & 1);
@@ -334,6 +336,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
 // =====================================================================================
 // backward, dQ:  CTA owns a query tile, loops key tiles.
 // smem: Q | dO | KV ring 2 x (K,V) | dS | barriers.  TMEM: S [0,128) dP [128,256) dQ [256,320)
+// Each 128-key block is processed as two 64-key halves with their own barriers: while the element-wise warps drain
+// S/dP of one half from TMEM (the scarce resource: 128 KB per block at ~64 B/clk), the tensor core already computes
+// the other half, and dQ += dS_h K_h trails by one half.
 constexpr int BWD_STAGES = 2;
 constexpr int BDQ_SMEM = 1024 + 2 * TILE_BYTES + BWD_STAGES * 2 * TILE_BYTES + PT_BYTES + 256;
 
@@ -349,12 +354,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
   const uint32_t b_qfull = sBar;
   const uint32_t b_kvfull = sBar + 8;        // [2]
   const uint32_t b_kvempty = sBar + 8 * 3;   // [2]
-  const uint32_t b_sfull = sBar + 8 * 5;
-  const uint32_t b_sempty = sBar + 8 * 6;
-  const uint32_t b_dsfull = sBar + 8 * 7;
-  const uint32_t b_dsempty = sBar + 8 * 8;
-  const uint32_t b_done = sBar + 8 * 9;
-  const uint32_t tmem_slot = sBar + 8 * 10;
+  const uint32_t b_sfull = sBar + 8 * 5;     // [2] one per 64-key half
+  const uint32_t b_sempty = sBar + 8 * 7;    // [2]
+  const uint32_t b_dsfull = sBar + 8 * 9;    // [2]
+  const uint32_t b_dsempty = sBar + 8 * 11;  // [2]
+  const uint32_t b_done = sBar + 8 * 13;
+  const uint32_t tmem_slot = sBar + 8 * 14;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -366,8 +371,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
     prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv); prefetch_tmap(&p.tdo);
     mbar_init(b_qfull, 1);
     for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(b_kvfull + 8 * i, 1); mbar_init(b_kvempty + 8 * i, 1); }
-    mbar_init(b_sfull, 1); mbar_init(b_sempty, 256);
-    mbar_init(b_dsfull, 256); mbar_init(b_dsempty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_sfull + 8 * i, 1); mbar_init(b_sempty + 8 * i, 8);     // one arrive per element-wise warp
+      mbar_init(b_dsfull + 8 * i, 8); mbar_init(b_dsempty + 8 * i, 1);
+    }
     mbar_init(b_done, 1);
     fence_barrier_init();
   }
@@ -393,24 +400,37 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // one 64-key half of S / dP
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      // dQ += dS_h K_h for sub-block t = 2 * block + half (trails the score MMAs by one sub-block)
+      auto dq_step = [&](int t) {
+        const int jj = t >> 1, hh = t & 1;
+        const uint32_t sKj = sKV + (jj % BWD_STAGES) * 2 * TILE_BYTES;
+        mbar_wait(b_dsfull + 8 * hh, jj & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tDQ, make_smem_desc_sw128(sDS + hh * TILE_BYTES + ks * 32, 16, 1024),
+                    make_smem_desc_sw128(sKj + (4 * hh + ks) * 2048, 8192, 1024), idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(b_dsempty + 8 * hh);
+        if (hh == 1) umma_commit(b_kvempty + 8 * (jj % BWD_STAGES));
+      };
       mbar_wait(b_qfull, 0);
+      int t = 0;
       for (int j = 0; j < nkv; ++j) {
         const int st = j % BWD_STAGES;
         const uint32_t sK = sKV + st * 2 * TILE_BYTES, sV = sK + TILE_BYTES;
         mbar_wait(b_kvfull + 8 * st, (j / BWD_STAGES) & 1);
-        mbar_wait(b_sempty, (j & 1) ^ 1);
-        tc_fence_after();
-        mma_kk64(tS, sQ, sK, idesc_s, false);     // S  = Q K^T
-        mma_kk64(tDP, sDO, sV, idesc_s, false);   // dP = dO V^T
-        umma_commit(b_sfull);
-        mbar_wait(b_dsfull, j & 1);
-        tc_fence_after();
-        mma_pv(tDQ, sDS, sK, idesc_o, j > 0);     // dQ += dS K   (K tile as MN-major B)
-        umma_commit(b_dsempty);
-        umma_commit(b_kvempty + 8 * st);
+        for (int h = 0; h < 2; ++h, ++t) {
+          mbar_wait(b_sempty + 8 * h, (j & 1) ^ 1);
+          tc_fence_after();
+          mma_kk64(tS + h * 64, sQ, sK + h * 8192, idesc_s, false);     // S_h  = Q K_h^T
+          mma_kk64(tDP + h * 64, sDO, sV + h * 8192, idesc_s, false);   // dP_h = dO V_h^T
+          umma_commit(b_sfull + 8 * h);
+          if (t >= 1) dq_step(t - 1);
+        }
       }
+      dq_step(t - 1);
       umma_commit(b_done);
     }
   } else {
@@ -423,17 +443,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
     const float lse2 = ri.valid ? p.lse[ri.token * p.heads + head] * LOG2E : 0.f;
     const float dlt = ri.valid ? p.delta[ri.token * p.heads + head] : 0.f;
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(b_sfull, j & 1);
-      tc_fence_after();
-      mbar_wait(b_dsempty, (j & 1) ^ 1);
       const int kvalid = p.S - j * p.RT;
       const bool nomask = (p.G == 1) && (kvalid >= 128);
 #pragma unroll 1
-      for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(b_sfull + 8 * h, j & 1);
+        tc_fence_after();
+        mbar_wait(b_dsempty + 8 * h, (j & 1) ^ 1);
+        const int c0 = h * 64 + ch * 32;
         uint32_t vs[32], vd[32];
         tmem_ld32(tS + lane_off + c0, vs);
         tmem_ld32(tDP + lane_off + c0, vd);
         tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_sempty + 8 * h);     // this half of S / dP may be overwritten by the next block
         float f[32];
         if (nomask && ri.valid) {
 #pragma unroll
@@ -451,11 +475,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
           }
         }
         store_score_chunk(sDS, r, c0, f);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_dsfull + 8 * h);
       }
-      tc_fence_before();
-      mbar_arrive(b_sempty);
-      fence_proxy_async_smem();
-      mbar_arrive(b_dsfull);
     }
     mbar_wait(b_done, 0);
     tc_fence_after();
@@ -485,6 +508,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
 // (S^T = K Q^T, dP^T = V dO^T) so that P^T / dS^T land row-major-in-keys = K-major A operands.
 // smem: K | V | Q/dO ring 2 | P^T | dS^T | lse/delta | barriers
 // TMEM: S^T [0,128) dP^T [128,256) dV [256,320) dK [320,384)
+// Like the dQ kernel, every 128-query tile is processed as two 64-query halves with their own barriers, so that the
+// TMEM drain of one half overlaps the tensor-core work of the other; dV/dK accumulation trails by one half.
 constexpr int BKV_SMEM = 1024 + 2 * TILE_BYTES + BWD_STAGES * 2 * TILE_BYTES + 2 * PT_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnKParams p) {
@@ -499,12 +524,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __gr
   const uint32_t b_kvfull = sBar;
   const uint32_t b_qfull = sBar + 8;        // [2]
   const uint32_t b_qempty = sBar + 8 * 3;   // [2]
-  const uint32_t b_sfull = sBar + 8 * 5;
-  const uint32_t b_sempty = sBar + 8 * 6;
-  const uint32_t b_pfull = sBar + 8 * 7;
-  const uint32_t b_pempty = sBar + 8 * 8;
-  const uint32_t b_done = sBar + 8 * 9;
-  const uint32_t tmem_slot = sBar + 8 * 10;
+  const uint32_t b_sfull = sBar + 8 * 5;     // [2] one per 64-query half
+  const uint32_t b_sempty = sBar + 8 * 7;    // [2]
+  const uint32_t b_pfull = sBar + 8 * 9;     // [2]
+  const uint32_t b_pempty = sBar + 8 * 11;   // [2]
+  const uint32_t b_done = sBar + 8 * 13;
+  const uint32_t tmem_slot = sBar + 8 * 14;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* vec = reinterpret_cast<float*>(smem_raw + (sVec - smem_u32(smem_raw)));
 
@@ -517,8 +542,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __gr
     prefetch_tmap(&p.tq); prefetch_tmap(&p.tk); prefetch_tmap(&p.tv); prefetch_tmap(&p.tdo);
     mbar_init(b_kvfull, 1);
     for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, 1); }
-    mbar_init(b_sfull, 1); mbar_init(b_sempty, 256);
-    mbar_init(b_pfull, 256); mbar_init(b_pempty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_sfull + 8 * i, 1); mbar_init(b_sempty + 8 * i, 8);     // one arrive per element-wise warp
+      mbar_init(b_pfull + 8 * i, 8); mbar_init(b_pempty + 8 * i, 1);
+    }
     mbar_init(b_done, 1);
     fence_barrier_init();
   }
@@ -544,25 +571,41 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __gr
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // one 64-query half of S^T / dP^T
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      // dV += P^T_h dO_h, dK += dS^T_h Q_h for sub-block t = 2 * tile + half (trails the score MMAs by one sub-block)
+      auto acc_step = [&](int t) {
+        const int ii = t >> 1, hh = t & 1;
+        const uint32_t sQi = sQD + (ii % BWD_STAGES) * 2 * TILE_BYTES, sDOi = sQi + TILE_BYTES;
+        mbar_wait(b_pfull + 8 * hh, ii & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tDV, make_smem_desc_sw128(sPT + hh * TILE_BYTES + ks * 32, 16, 1024),
+                    make_smem_desc_sw128(sDOi + (4 * hh + ks) * 2048, 8192, 1024), idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tDK, make_smem_desc_sw128(sDST + hh * TILE_BYTES + ks * 32, 16, 1024),
+                    make_smem_desc_sw128(sQi + (4 * hh + ks) * 2048, 8192, 1024), idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(b_pempty + 8 * hh);
+        if (hh == 1) umma_commit(b_qempty + 8 * (ii % BWD_STAGES));
+      };
       mbar_wait(b_kvfull, 0);
+      int t = 0;
       for (int i = 0; i < nq; ++i) {
         const int st = i % BWD_STAGES;
         const uint32_t sQ = sQD + st * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES;
         mbar_wait(b_qfull + 8 * st, (i / BWD_STAGES) & 1);
-        mbar_wait(b_sempty, (i & 1) ^ 1);
-        tc_fence_after();
-        mma_kk64(tST, sK, sQ, idesc_s, false);     // S^T  = K Q^T
-        mma_kk64(tDPT, sV, sDO, idesc_s, false);   // dP^T = V dO^T
-        umma_commit(b_sfull);
-        mbar_wait(b_pfull, i & 1);
-        tc_fence_after();
-        mma_pv(tDV, sPT, sDO, idesc_o, i > 0);     // dV += P^T dO
-        mma_pv(tDK, sDST, sQ, idesc_o, i > 0);     // dK += dS^T Q
-        umma_commit(b_pempty);
-        umma_commit(b_qempty + 8 * st);
+        for (int h = 0; h < 2; ++h, ++t) {
+          mbar_wait(b_sempty + 8 * h, (i & 1) ^ 1);
+          tc_fence_after();
+          mma_kk64(tST + h * 64, sK, sQ + h * 8192, idesc_s, false);     // S^T_h  = K Q_h^T
+          mma_kk64(tDPT + h * 64, sV, sDO + h * 8192, idesc_s, false);   // dP^T_h = V dO_h^T
+          umma_commit(b_sfull + 8 * h);
+          if (t >= 1) acc_step(t - 1);
+        }
       }
+      acc_step(t - 1);
       umma_commit(b_done);
     }
   } else {
@@ -572,22 +615,33 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __gr
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const RowInfo ki = row_info(p, r, tile, outer, inner0);
     const float sc = p.scale * LOG2E;
-    for (int i = 0; i < nq; ++i) {
-      // stage lse/delta of the 128 queries of tile i (column vectors of the transposed scores)
+    // lse (warps with ch == 0) / delta (ch == 1) of query row r of a tile; +inf lse -> p = 0 for padding queries
+    auto load_stat = [&](int i) -> float {
       const RowInfo qi = row_info(p, r, i, outer, inner0);
+      if (ch == 0) return qi.valid ? p.lse[qi.token * p.heads + head] * LOG2E : INFINITY;
+      return qi.valid ? p.delta[qi.token * p.heads + head] : 0.f;
+    };
+    float stat = load_stat(0);
+    for (int i = 0; i < nq; ++i) {
+      // stage lse/delta of the 128 queries of tile i (column vectors of the transposed scores); the values of the
+      // next tile are requested right away so that their latency hides behind this tile's work
       named_bar_sync(1, 256);  // previous iteration finished reading vec[]
-      if (ch == 0) vec[r] = qi.valid ? p.lse[qi.token * p.heads + head] * LOG2E : INFINITY;  // +inf -> p = 0
-      else vec[128 + r] = qi.valid ? p.delta[qi.token * p.heads + head] : 0.f;
+      vec[ch * 128 + r] = stat;
       named_bar_sync(1, 256);
-      mbar_wait(b_sfull, i & 1);
-      tc_fence_after();
-      mbar_wait(b_pempty, (i & 1) ^ 1);
+      if (i + 1 < nq) stat = load_stat(i + 1);
 #pragma unroll 1
-      for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(b_sfull + 8 * h, i & 1);
+        tc_fence_after();
+        mbar_wait(b_pempty + 8 * h, (i & 1) ^ 1);
+        const int c0 = h * 64 + ch * 32;
         uint32_t vs[32], vd[32];
         tmem_ld32(tST + lane_off + c0, vs);
         tmem_ld32(tDPT + lane_off + c0, vd);
         tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_sempty + 8 * h);
         float fp[32], fd[32];
         if (p.G == 1 && ki.valid) {
           // unmasked fast path (spatial attention): invalid query columns carry lse = +inf -> p = 0
@@ -609,11 +663,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __gr
         }
         store_score_chunk(sPT, r, c0, fp);
         store_score_chunk(sDST, r, c0, fd);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pfull + 8 * h);
       }
-      tc_fence_before();
-      mbar_arrive(b_sempty);
-      fence_proxy_async_smem();
-      mbar_arrive(b_pfull);
     }
     mbar_wait(b_done, 0);
     tc_fence_after();
