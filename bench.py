@@ -284,7 +284,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up (also fills the weight-operand cache); with graphs the warm-up happens inside GraphedStep
-    use_graph = (not args.no_graph) and world == 1 and not args.profile_one
+    # world > 1: the bucketed NCCL all-reduces of GradReducer are captured into the same graph (side-stream fork/join)
+    use_graph = (not args.no_graph) and not args.profile_one and (world == 1 or os.environ.get("SVDX_DDP_GRAPH", "1") != "0")
     lps = 0
     for _ in range(1 if use_graph else max(args.warmup, 3)):
         l_before = raw.LAUNCHES[0]
@@ -404,11 +405,38 @@ def main():
             break
         except Exception:
             pass
+    # In eager mode the CPU (descriptor build + cuLaunchKernel, ~10 us) trails the GPU, so an event pair around one launch
+    # also times host work whenever the stream is idle. With the whole step in a CUDA graph the in-step cost of the
+    # kernel is measured by ablation instead: capture the same step with every svdx_tapgemm launch skipped and take the
+    # difference of the two replay times (CUDA events, same K steps). Done last: the ablated steps compute garbage.
+    method = "sum of CUDA-event pairs around every svdx_tapgemm launch of one eager step"
+    if graphed is not None and world == 1:
+        try:
+            raw.tapgemm = lambda a, b, out, **kw: out
+            ablated = GraphedStep(step, devb, warmup=2)
+            for _ in range(2):
+                ablated.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                ablated.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_wo = e0.elapsed_time(e1) / args.steps
+            if 0.0 < ms_wo < ms_per_step:
+                gemm_ms = ms_per_step - ms_wo
+                method = ("graph-replay ablation: ms_per_step minus the replay time of the same captured step with every svdx_tapgemm "
+                          f"launch skipped ({ms_wo:.3f} ms), CUDA events over {args.steps} replays each")
+        except Exception as e:
+            print(f"[bench] ablation graph failed ({type(e).__name__}: {e}); keeping the per-launch event sum", file=sys.stderr)
+        finally:
+            raw.tapgemm = orig
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "svdx::tapgemm_kernel (tcgen05)", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                 "frac": achieved / sustained, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_note": "tensor-bound kernel: algorithmic work is FLOPs (2*M*N*K*taps per launch, summed); see DESIGN.md §3", "peak_source": src + ", bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": len(recs), "algorithmic_tflop_per_step": gemm_flops / 1e12, "kernel_ms_per_step": gemm_ms,
+                "avg_launch_us": 1e3 * gemm_ms / max(len(recs), 1), "timing_method": method,
                 "share_of_step": gemm_ms / ms_per_step}
 
     if rank != 0:

@@ -94,6 +94,21 @@ SVDX_DEVINL void mma_pv(uint32_t d_tmem, uint32_t pbase, uint32_t v, uint32_t id
               make_smem_desc_sw128(v + ks * 2048, 8192, 1024), idesc, (acc_first || ks > 0) ? 1u : 0u);
 }
 
+// The MMA issuer is ONE thread: rebuilding two 64-bit shared-memory descriptors per tcgen05.mma (a dozen dependent
+// integer ops each) made it the critical path of the backward kernels (ncu: 8 element-wise warps waiting 25 % of the
+// time for S). Descriptors are therefore built once per tile; a k-step / half-tile advance is an add on the
+// 14-bit start-address field (units of 16 bytes, no carry: shared memory is < 256 KB).
+SVDX_DEVINL void mma_kk64_d(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, bool acc_first) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) umma_bf16(d_tmem, a + 2 * ks, b + 2 * ks, idesc, (acc_first || ks > 0) ? 1u : 0u);
+}
+// acc[128 x 64] (+)= P[128 x 64 keys] (K-major half score tile) * V[64 keys x 64] (MN-major rows, 2 KB per 16 keys)
+SVDX_DEVINL void mma_pv64_d(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, bool acc_first) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) umma_bf16(d_tmem, a + 2 * ks, b + 128 * ks, idesc, (acc_first || ks > 0) ? 1u : 0u);
+}
+constexpr uint64_t HALF_ROWS_DESC = 8192 >> 4;   // 64 rows of 128 bytes further down an operand tile
+
 SVDX_DEVINL void decode_block(const AttnKParams& p, int& tile, int& head, int& outer, int& inner0) {
   tile = blockIdx.x;
   head = blockIdx.y;
@@ -109,7 +124,7 @@ SVDX_DEVINL void decode_block(const AttnKParams& p, int& tile, int& head, int& o
 //   TMEM : S [128 x 128] | O [128 x 64]. O accumulates in TMEM across key blocks (tcgen05.mma accumulate); the
 //          running maximum is only raised -- and O / l rescaled by the owning warp -- when a row's new maximum
 //          exceeds the one in use by more than 2^8, so the per-block TMEM round trip of O is gone.
-constexpr int FWD_KV_STAGES = 2;
+constexpr int FWD_KV_STAGES = 2;   // the MMA issuer keeps one descriptor per stage
 constexpr int FWD_DATA = TILE_BYTES + FWD_KV_STAGES * 2 * TILE_BYTES + PT_BYTES;   // 112 KB
 constexpr int FWD_SMEM = 1024 + FWD_DATA;                                           // 113 KB: two CTAs per SM
 constexpr float FWD_RESCALE_LOG2 = 8.0f;
@@ -169,6 +184,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      const uint64_t dQ = make_smem_desc_sw128(sQ, 16, 1024);
+      const uint64_t dK0 = make_smem_desc_sw128(sKV, 16, 1024), dK1 = make_smem_desc_sw128(sKV + 2 * TILE_BYTES, 16, 1024);
+      const uint64_t dV0 = make_smem_desc_sw128(sKV + TILE_BYTES, 8192, 1024), dV1 = make_smem_desc_sw128(sKV + 3 * TILE_BYTES, 8192, 1024);
+      const uint64_t dP0 = make_smem_desc_sw128(sP, 16, 1024), dP1 = make_smem_desc_sw128(sP + TILE_BYTES, 16, 1024);
       mbar_wait(b_qfull, 0);
       for (int j = 0; j <= nkv; ++j) {
         if (j < nkv) {
@@ -176,7 +195,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
           mbar_wait(b_kvfull + 8 * st, (j / FWD_KV_STAGES) & 1);
           mbar_wait(b_sempty, (j & 1) ^ 1);      // the softmax warps hold S_{j-1} in registers
           tc_fence_after();
-          mma_kk64(tS, sQ, sKV + st * 2 * TILE_BYTES, idesc_s, false);
+          mma_kk64_d(tS, dQ, st ? dK1 : dK0, idesc_s, false);
           umma_commit(b_sfull);
         }
         if (j >= 1) {
@@ -184,7 +203,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_kernel(const __grid_co
           const int st = k % FWD_KV_STAGES;
           mbar_wait(b_pfull, k & 1);
           tc_fence_after();
-          mma_pv(tO, sP, sKV + st * 2 * TILE_BYTES + TILE_BYTES, idesc_o, k > 0);
+          const uint64_t dV = st ? dV1 : dV0;
+          mma_pv64_d(tO, dP0, dV, idesc_o, k > 0);
+          mma_pv64_d(tO, dP1, dV + HALF_ROWS_DESC, idesc_o, true);
           umma_commit(b_odone);                  // P is free again, O holds blocks 0..k
           umma_commit(b_kvempty + 8 * st);
         }
@@ -403,15 +424,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // one 64-key half of S / dP
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
       // dQ += dS_h K_h for sub-block t = 2 * block + half (trails the score MMAs by one sub-block)
+      const uint64_t dQa = make_smem_desc_sw128(sQ, 16, 1024), dDOa = make_smem_desc_sw128(sDO, 16, 1024);
+      const uint64_t dKk0 = make_smem_desc_sw128(sKV, 16, 1024), dKk1 = make_smem_desc_sw128(sKV + 2 * TILE_BYTES, 16, 1024);
+      const uint64_t dVk0 = make_smem_desc_sw128(sKV + TILE_BYTES, 16, 1024), dVk1 = make_smem_desc_sw128(sKV + 3 * TILE_BYTES, 16, 1024);
+      const uint64_t dKm0 = make_smem_desc_sw128(sKV, 8192, 1024), dKm1 = make_smem_desc_sw128(sKV + 2 * TILE_BYTES, 8192, 1024);
+      const uint64_t dDS0 = make_smem_desc_sw128(sDS, 16, 1024), dDS1 = make_smem_desc_sw128(sDS + TILE_BYTES, 16, 1024);
       auto dq_step = [&](int t) {
         const int jj = t >> 1, hh = t & 1;
-        const uint32_t sKj = sKV + (jj % BWD_STAGES) * 2 * TILE_BYTES;
         mbar_wait(b_dsfull + 8 * hh, jj & 1);
         tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tDQ, make_smem_desc_sw128(sDS + hh * TILE_BYTES + ks * 32, 16, 1024),
-                    make_smem_desc_sw128(sKj + (4 * hh + ks) * 2048, 8192, 1024), idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
+        mma_pv64_d(tDQ, hh ? dDS1 : dDS0, ((jj % BWD_STAGES) ? dKm1 : dKm0) + hh * HALF_ROWS_DESC, idesc_o, t > 0);
         umma_commit(b_dsempty + 8 * hh);
         if (hh == 1) umma_commit(b_kvempty + 8 * (jj % BWD_STAGES));
       };
@@ -419,13 +441,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dq_kernel(const __gri
       int t = 0;
       for (int j = 0; j < nkv; ++j) {
         const int st = j % BWD_STAGES;
-        const uint32_t sK = sKV + st * 2 * TILE_BYTES, sV = sK + TILE_BYTES;
         mbar_wait(b_kvfull + 8 * st, (j / BWD_STAGES) & 1);
         for (int h = 0; h < 2; ++h, ++t) {
           mbar_wait(b_sempty + 8 * h, (j & 1) ^ 1);
           tc_fence_after();
-          mma_kk64(tS + h * 64, sQ, sK + h * 8192, idesc_s, false);     // S_h  = Q K_h^T
-          mma_kk64(tDP + h * 64, sDO, sV + h * 8192, idesc_s, false);   // dP_h = dO V_h^T
+          mma_kk64_d(tS + h * 64, dQa, (st ? dKk1 : dKk0) + h * HALF_ROWS_DESC, idesc_s, false);     // S_h  = Q K_h^T
+          mma_kk64_d(tDP + h * 64, dDOa, (st ? dVk1 : dVk0) + h * HALF_ROWS_DESC, idesc_s, false);   // dP_h = dO V_h^T
           umma_commit(b_sfull + 8 * h);
           if (t >= 1) dq_step(t - 1);
         }
@@ -574,19 +595,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __gr
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // one 64-query half of S^T / dP^T
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
       // dV += P^T_h dO_h, dK += dS^T_h Q_h for sub-block t = 2 * tile + half (trails the score MMAs by one sub-block)
+      const uint64_t dKa = make_smem_desc_sw128(sK, 16, 1024), dVa = make_smem_desc_sw128(sV, 16, 1024);
+      const uint64_t dQk0 = make_smem_desc_sw128(sQD, 16, 1024), dQk1 = make_smem_desc_sw128(sQD + 2 * TILE_BYTES, 16, 1024);
+      const uint64_t dOk0 = make_smem_desc_sw128(sQD + TILE_BYTES, 16, 1024), dOk1 = make_smem_desc_sw128(sQD + 3 * TILE_BYTES, 16, 1024);
+      const uint64_t dQm0 = make_smem_desc_sw128(sQD, 8192, 1024), dQm1 = make_smem_desc_sw128(sQD + 2 * TILE_BYTES, 8192, 1024);
+      const uint64_t dOm0 = make_smem_desc_sw128(sQD + TILE_BYTES, 8192, 1024), dOm1 = make_smem_desc_sw128(sQD + 3 * TILE_BYTES, 8192, 1024);
+      const uint64_t dPT0 = make_smem_desc_sw128(sPT, 16, 1024), dPT1 = make_smem_desc_sw128(sPT + TILE_BYTES, 16, 1024);
+      const uint64_t dST0 = make_smem_desc_sw128(sDST, 16, 1024), dST1 = make_smem_desc_sw128(sDST + TILE_BYTES, 16, 1024);
       auto acc_step = [&](int t) {
         const int ii = t >> 1, hh = t & 1;
-        const uint32_t sQi = sQD + (ii % BWD_STAGES) * 2 * TILE_BYTES, sDOi = sQi + TILE_BYTES;
+        const bool s1 = (ii % BWD_STAGES) != 0;
         mbar_wait(b_pfull + 8 * hh, ii & 1);
         tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tDV, make_smem_desc_sw128(sPT + hh * TILE_BYTES + ks * 32, 16, 1024),
-                    make_smem_desc_sw128(sDOi + (4 * hh + ks) * 2048, 8192, 1024), idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tDK, make_smem_desc_sw128(sDST + hh * TILE_BYTES + ks * 32, 16, 1024),
-                    make_smem_desc_sw128(sQi + (4 * hh + ks) * 2048, 8192, 1024), idesc_o, (t > 0 || ks > 0) ? 1u : 0u);
+        mma_pv64_d(tDV, hh ? dPT1 : dPT0, (s1 ? dOm1 : dOm0) + hh * HALF_ROWS_DESC, idesc_o, t > 0);   // dV += P^T_h dO_h
+        mma_pv64_d(tDK, hh ? dST1 : dST0, (s1 ? dQm1 : dQm0) + hh * HALF_ROWS_DESC, idesc_o, t > 0);   // dK += dS^T_h Q_h
         umma_commit(b_pempty + 8 * hh);
         if (hh == 1) umma_commit(b_qempty + 8 * (ii % BWD_STAGES));
       };
@@ -594,13 +616,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const __gr
       int t = 0;
       for (int i = 0; i < nq; ++i) {
         const int st = i % BWD_STAGES;
-        const uint32_t sQ = sQD + st * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES;
         mbar_wait(b_qfull + 8 * st, (i / BWD_STAGES) & 1);
         for (int h = 0; h < 2; ++h, ++t) {
           mbar_wait(b_sempty + 8 * h, (i & 1) ^ 1);
           tc_fence_after();
-          mma_kk64(tST + h * 64, sK, sQ + h * 8192, idesc_s, false);     // S^T_h  = K Q_h^T
-          mma_kk64(tDPT + h * 64, sV, sDO + h * 8192, idesc_s, false);   // dP^T_h = V dO_h^T
+          mma_kk64_d(tST + h * 64, dKa, (st ? dQk1 : dQk0) + h * HALF_ROWS_DESC, idesc_s, false);     // S^T_h  = K Q_h^T
+          mma_kk64_d(tDPT + h * 64, dVa, (st ? dOk1 : dOk0) + h * HALF_ROWS_DESC, idesc_s, false);   // dP^T_h = V dO_h^T
           umma_commit(b_sfull + 8 * h);
           if (t >= 1) acc_step(t - 1);
         }

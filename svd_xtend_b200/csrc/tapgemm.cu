@@ -255,12 +255,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
           tc_fence_after();
           const uint32_t aaddr = sA + stage * A_STAGE_BYTES;
           const uint32_t baddr = sB + stage * B_STAGE_BYTES;
+          // one descriptor per operand and stage; a 16-deep k-step advances the 16-byte start-address field
+          const uint64_t ad0 = p.a_mn ? make_smem_desc_sw128(aaddr, 8192, 1024) : make_smem_desc_sw128(aaddr, 16, 1024);
+          const uint64_t bd0 = p.b_mn ? make_smem_desc_sw128(baddr, 8192, 1024) : make_smem_desc_sw128(baddr, 16, 1024);
+          const uint64_t astep = p.a_mn ? (2048 >> 4) : (32 >> 4), bstep = p.b_mn ? (2048 >> 4) : (32 >> 4);
 #pragma unroll
           for (int j = 0; j < BLOCK_K / 16; ++j) {
-            const uint64_t ad = p.a_mn ? make_smem_desc_sw128(aaddr + j * 2048, 8192, 1024)
-                                       : make_smem_desc_sw128(aaddr + j * 32, 16, 1024);
-            const uint64_t bd = p.b_mn ? make_smem_desc_sw128(baddr + j * 2048, 8192, 1024)
-                                       : make_smem_desc_sw128(baddr + j * 32, 16, 1024);
+            const uint64_t ad = ad0 + j * astep;
+            const uint64_t bd = bd0 + j * bstep;
             umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
           }
           umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire

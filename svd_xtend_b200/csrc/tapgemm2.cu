@@ -234,10 +234,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
           tc_fence_after();
           const uint32_t aaddr = sA + stage * A_STAGE_BYTES;
           const uint32_t baddr = sB + stage * B2_STAGE_BYTES;
+          const uint64_t ad0 = make_smem_desc_sw128(aaddr, 16, 1024), bd0 = make_smem_desc_sw128(baddr, 16, 1024);
 #pragma unroll
-          for (int j = 0; j < BLOCK_K / 16; ++j)
-            umma2_bf16(d_tmem, make_smem_desc_sw128(aaddr + j * 32, 16, 1024), make_smem_desc_sw128(baddr + j * 32, 16, 1024), idesc,
-                       (kb > 0 || j > 0) ? 1u : 0u);
+          for (int j = 0; j < BLOCK_K / 16; ++j)   // a 16-deep k-step = +32 bytes = +2 in the start-address field
+            umma2_bf16(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
           umma2_commit_mc(bar_empty + 8 * stage, 3);  // frees this smem stage in both CTAs
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
