@@ -191,7 +191,14 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def count(self):
+        """samples written so far (used to bracket the timed region)"""
+        try:
+            return sum(1 for r in open(self.f.name) if r.strip())
+        except Exception:
+            return 0
+
+    def stop(self, first=0, last=None):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -203,6 +210,13 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
+        if last is not None:
+            # samples taken inside the timed region; a region shorter than the 100 ms period keeps its two neighbours
+            # (the GPU runs the same replays right before and after the region)
+            sel = rows[first:last]
+            if not sel:
+                sel = rows[max(first - 1, 0):last + 1]
+            rows = sel
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -323,18 +337,25 @@ def main():
     barrier()
 
     # ---- timed region: K steps, device events, max over ranks
-    l0 = raw.LAUNCHES[0]
     clocks = ClockSampler(local) if rank == 0 else None
+    for _ in range(8):          # nvidia-smi needs a few hundred ms to emit its first sample: keep the GPU under the same load
+        run_step()
+    l0 = raw.LAUNCHES[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    c0 = clocks.count() if clocks is not None else 0
     e0.record()
     for _ in range(args.steps):
         loss = run_step()
     e1.record()
     barrier()
+    c1 = clocks.count() if clocks is not None else 0
     ms = e0.elapsed_time(e1)
     launches = raw.LAUNCHES[0] - l0
-    clk = clocks.stop() if clocks is not None else None
+    for _ in range(2):          # one more sampling period under load before the sampler stops
+        run_step()
+    torch.cuda.synchronize()
+    clk = clocks.stop(c0, c1) if clocks is not None else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -439,9 +460,20 @@ def main():
                 "avg_launch_us": 1e3 * gemm_ms / max(len(recs), 1), "timing_method": method,
                 "share_of_step": gemm_ms / ms_per_step}
 
-    if rank != 0:
+    def finish():
+        """leave without tearing NCCL down: communicators referenced by live CUDA graphs block destroy_process_group()"""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            try:
+                dist.barrier()
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     cpu = None
@@ -467,8 +499,7 @@ def main():
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ def timeit(fn, iters=20):
     return tot / iters * 1e3  # us
 
 
-def run(M, N, K, geglu=False, bias=True, pre=False, res=False, block_n=None, f32=False, label=""):
+def run(M, N, K, geglu=False, bias=True, pre=False, res=False, block_n=None, f32=False, label="", res2=False):
     a = torch.randn(M, K, device=dev, dtype=bf)
     w = torch.randn(N, K, device=dev, dtype=bf) * 0.05
     n_out = N // 2 if geglu else N
@@ -29,7 +29,9 @@ def run(M, N, K, geglu=False, bias=True, pre=False, res=False, block_n=None, f32
     b = torch.randn(N, device=dev) if bias else None
     p = torch.empty(M, N, device=dev, dtype=bf) if pre else None
     r = torch.randn(M, n_out, device=dev, dtype=bf) if res else None
-    us = timeit(lambda: raw.tapgemm(a, w, out, M=M, N=N, K=K, geglu=geglu, bias=b, pre=p, res1=r, block_n=block_n))
+    r2 = torch.randn(M, n_out, device=dev, dtype=bf) if res2 else None
+    sc = torch.tensor([0.5, 1.0, 0.5, 0.0], device=dev) if res2 else None
+    us = timeit(lambda: raw.tapgemm(a, w, out, M=M, N=N, K=K, geglu=geglu, bias=b, pre=p, res1=r, res2=r2, scales=sc, block_n=block_n))
     tf = 2.0 * M * N * K / us / 1e6
     print(f"{label:28s} M={M} N={N} K={K} geglu={int(geglu)} pre={int(pre)} res={int(res)} bn={block_n} : {us:8.1f} us  {tf:6.1f} TF", flush=True)
 
@@ -64,6 +66,16 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "convone":
         runconv(16, 10, 14, 1280, 1280, label="L2 conv")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "res":
+        for K in (320, 1280, 2560):
+            run(35840, 320, K, label="L0 plain")
+            run(35840, 320, K, res=True, label="L0 +res")
+            run(35840, 320, K, res=True, res2=True, label="L0 +res+blend")
+        run(8960, 640, 2560, label="L1 plain")
+        run(8960, 640, 2560, res=True, label="L1 +res")
+        run(2240, 1280, 5120, label="L2 plain")
+        run(2240, 1280, 5120, res=True, label="L2 +res")
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         run(35840, 2560, 320, bias=False, label="plain N=2560 nobias")

@@ -499,8 +499,12 @@ extern "C" int svdx_groupnorm_stats(const void* x, int64_t ldx, int32_t C1, cons
     return svdx_fail(SVDX_E_BADARG, "groupnorm_stats: bad arguments");
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
   const int total = outer * num_groups;
-  cudaMemsetAsync(mean, 0, sizeof(float) * total, st);
-  cudaMemsetAsync(rstd, 0, sizeof(float) * total, st);
+  if (rstd == mean + total) {
+    cudaMemsetAsync(mean, 0, sizeof(float) * 2 * total, st);   // adjacent accumulators: one memset node in a captured graph
+  } else {
+    cudaMemsetAsync(mean, 0, sizeof(float) * total, st);
+    cudaMemsetAsync(rstd, 0, sizeof(float) * total, st);
+  }
   int threads, rpc;
   gn_vec_config(C1 + C2, outer, rows, threads, rpc);
   dim3 grid((rows + rpc - 1) / rpc, outer);

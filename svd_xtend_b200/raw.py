@@ -286,8 +286,8 @@ def attention_bwd(q, k, v, o, dout, dq, dk, dv, lse, delta, *, heads, S, nseq, i
 def groupnorm_stats(x, x2, outer, rows, eps, groups=32):
     C1 = x.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
-    mean = torch.empty(outer * groups, device=x.device, dtype=torch.float32)
-    rstd = torch.empty_like(mean)
+    stats = torch.empty(2, outer * groups, device=x.device, dtype=torch.float32)   # adjacent: zeroed by ONE memset node
+    mean, rstd = stats[0], stats[1]
     check(load().svdx_groupnorm_stats(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0,
                                       C2, outer, rows, groups, eps, mean.data_ptr(), rstd.data_ptr(), _stream()), "svdx_groupnorm_stats")
     return mean, rstd
