@@ -79,21 +79,6 @@ SVDX_DEVINL float fast_exp2(float x) {
 
 SVDX_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// acc[128 x N] (+)= A[128 x 64] (K-major tile) * B[N x 64]^T (K-major tile)
-SVDX_DEVINL void mma_kk64(uint32_t d_tmem, uint32_t a, uint32_t b, uint32_t idesc, bool acc_first) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    umma_bf16(d_tmem, make_smem_desc_sw128(a + ks * 32, 16, 1024), make_smem_desc_sw128(b + ks * 32, 16, 1024), idesc,
-              (acc_first || ks > 0) ? 1u : 0u);
-}
-// acc[128 x 64] (+)= P[128 x 128] (K-major score tile, 2 halves) * V[128 keys x 64] (MN-major B tile)
-SVDX_DEVINL void mma_pv(uint32_t d_tmem, uint32_t pbase, uint32_t v, uint32_t idesc, bool acc_first) {
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks)
-    umma_bf16(d_tmem, make_smem_desc_sw128(pbase + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024),
-              make_smem_desc_sw128(v + ks * 2048, 8192, 1024), idesc, (acc_first || ks > 0) ? 1u : 0u);
-}
-
 // The MMA issuer is ONE thread: rebuilding two 64-bit shared-memory descriptors per tcgen05.mma (a dozen dependent
 // integer ops each) made it the critical path of the backward kernels (ncu: 8 element-wise warps waiting 25 % of the
 // time for S). Descriptors are therefore built once per tile; a k-step / half-tile advance is an add on the
