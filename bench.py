@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — SVD UNet train-step frames/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|4|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -15,6 +15,12 @@ HBM; e2e = the same step driven from pinned HOST buffers through the public
 --impl reference times the reference's CPU path: the oracle restatement of the diffusers blocks under the
 reference's own wiring (diffusers itself is not installable offline), fp32, all host threads, on a bounded
 sample of the same workload (fewer frames of the same 40x64 latents per step).
+
+--config selects the BASELINE.json configuration (default 2, the one the metric is quoted on; 4 = 25 frames 576x1024 with
+gradient checkpointing, 5 = rank-64 LoRA): same step, same JSON line, `config.workload` names it.
+
+Only the baseline legs (`cpu_baseline`, `--impl reference`, `gpu_eager_baseline`) import `oracle/`; the product arm takes
+its synthetic batches and the EDM loss from svd_xtend_b200.workload.
 """
 import argparse
 import json
@@ -35,6 +41,9 @@ T_FRAMES, LAT_H, LAT_W = 14, 40, 64
 METRIC = "SVD UNet train-step frames/sec @ 14x320x512 bf16"
 WORKLOAD = ("train_svd.py full-finetune step as scripted (trainable = *temporal_transformer_block* params, "
             "train_svd.py:761-766), bs=1/GPU, 14 frames 320x512 (latents 14x8x40x64), bf16 compute, fp32 master weights, AdamW")
+CPU_ARM_NOTE = ("CPU arm = oracle port (diffusers not installable offline), fp32, on a BOUNDED SAMPLE of the workload: fewer frames per "
+                "step than the 14 of the GPU arm (same_config: false; a short clip shortens the temporal convolution / attention axis), "
+                "scaled to frames/s by frame-equivalents")
 
 
 def parse():
@@ -43,7 +52,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager bf16-autocast oracle timing on the GPU")
+    ap.add_argument("--no-families", action="store_true", help="skip the per-family ablation rooflines")
+    ap.add_argument("--no-script-path", action="store_true", help="skip the unchanged-script (eager, torch.optim.AdamW) timing")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--profile-one", action="store_true", help="run warm-up + one eager step only (for ncu)")
     return ap.parse_args()
@@ -233,7 +246,58 @@ class ClockSampler:
         return out
 
 
+# ----------------------------------------------------------------------------- GPU torch-eager baseline (the "bar to beat")
+def gpu_eager_baseline(dev, cfg, steps=3, warmup=2):
+    """What the reference's script really executes on a GPU: the diffusers-style module graph
+    (here: the oracle restatement of it) under torch bf16 autocast — cuDNN convolutions, cuBLASLt linears, SDPA flash
+    attention, eager elementwise kernels — with fp32 master weights, torch.optim.AdamW over the as-scripted trainable set.
+    Baseline leg only (imports oracle/); informational: it is NOT the reference arm the driver computes its ratio with."""
+    from oracle.svd_unet_oracle import SVD_CONFIG, UNetSpatioTemporalConditionModel as Oracle, edm_loss, synthetic_batch
+    torch.manual_seed(1234)
+    with torch.device(dev):
+        m = Oracle(**SVD_CONFIG)
+    m.requires_grad_(False)
+    for n, p in m.named_parameters():
+        if "temporal_transformer_block" in n:
+            p.requires_grad_(True)
+    m.train()
+    if cfg["grad_ckpt"]:
+        m.enable_gradient_checkpointing()
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-5, weight_decay=1e-2)
+    b = synthetic_batch(1, cfg["frames"], cfg["h"], cfg["w"], seed=1234, device=dev)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = m(b["sample"], b["timestep"], b["encoder_hidden_states"], b["added_time_ids"]).sample
+        loss = edm_loss(pred.float(), b["noisy"], b["latents"], b["sigmas"])
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": cfg["frames"] / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms, "steps": steps,
+           "what": "oracle restatement of the diffusers modules under torch.autocast(bf16) on this GPU (cuDNN / cuBLASLt / SDPA / ATen eager), "
+                   "fp32 masters, torch.optim.AdamW, as-scripted trainable set; informational"}
+    del m, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm
+FAMILY_BOUND = {"linear": "tensor", "conv": "tensor", "attention": "tensor", "groupnorm": "hbm", "layernorm": "hbm", "adamw": "hbm",
+                "elementwise": "hbm"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -241,11 +305,13 @@ def main():
         return
 
     import torch.distributed as dist
-    from oracle.svd_unet_oracle import SVD_CONFIG, edm_loss, synthetic_batch   # synthetic inputs + loss of train_svd.py:951-1036
     from svd_xtend_b200 import raw
-    from svd_xtend_b200.train import FusedAdamW, GradReducer, ParamArena
+    from svd_xtend_b200.train import FusedAdamW, GradReducer, GraphedStep, ParamArena
     from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel
+    from svd_xtend_b200.workload import BENCH_CONFIGS, SVD_CONFIG, edm_loss, synthetic_batch   # train_svd.py:951-1036
 
+    cfg = BENCH_CONFIGS[args.config]
+    frames, lat_h, lat_w = cfg["frames"], cfg["h"], cfg["w"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -256,19 +322,31 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- model: SVD topology, seeded default init (no checkpoints offline), fp32 master weights
+    # ---- model: SVD topology, seeded default init (no checkpoints offline)
     torch.manual_seed(1234)
     with torch.device(dev):
         unet = UNetSpatioTemporalConditionModel(**SVD_CONFIG)
     unet.to(dev)
     unet.requires_grad_(False)
-    n_train = 0
-    for n, p in unet.named_parameters():
-        if "temporal_transformer_block" in n:   # train_svd.py:761-766
-            p.requires_grad_(True)
-            n_train += p.numel()
+    if cfg["lora_rank"]:
+        # train_svd_lora.py:645-675: frozen base in the mixed-precision dtype, LoRA on q/k/v/out of every Attention; the LoRA
+        # parameters are kept in fp32 here (>= the reference's precision: its bf16 run keeps them in bf16)
+        from types import SimpleNamespace
+        unet.to(torch.bfloat16)
+        r = cfg["lora_rank"]
+        unet.add_adapter(SimpleNamespace(r=r, lora_alpha=r, init_lora_weights="gaussian", target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+        for p in unet.parameters():
+            if p.requires_grad:
+                p.data = p.data.float()
+    else:
+        for n, p in unet.named_parameters():
+            if "temporal_transformer_block" in n:   # train_svd.py:761-766
+                p.requires_grad_(True)
+    n_train = sum(p.numel() for p in unet.parameters() if p.requires_grad)
     n_total = sum(p.numel() for p in unet.parameters())
     unet.train()
+    if cfg["grad_ckpt"]:
+        unet.enable_gradient_checkpointing()     # train_svd.py:731-732
     arena = ParamArena(unet)
     unet.attach_arena(arena)
     opt = FusedAdamW(arena, lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)   # train_svd.py:384-418 defaults
@@ -277,7 +355,7 @@ def main():
     if reducer is not None:
         unet.grad_hook = lambda ps: reducer.on_grads_ready(ps) if ps is not None else None
 
-    host = synthetic_batch(1, T_FRAMES, LAT_H, LAT_W, seed=1234 + rank)
+    host = synthetic_batch(1, frames, lat_h, lat_w, seed=1234 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
     devb = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
@@ -301,9 +379,20 @@ def main():
     # world > 1: the bucketed NCCL all-reduces of GradReducer are captured into the same graph (side-stream fork/join)
     use_graph = (not args.no_graph) and not args.profile_one and (world == 1 or os.environ.get("SVDX_DDP_GRAPH", "1") != "0")
     lps = 0
-    for _ in range(1 if use_graph else max(args.warmup, 3)):
+    account = {}
+
+    def acc(fam, flops, nbytes):
+        a = account.setdefault(fam, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += flops
+        a[2] += nbytes
+
+    for i in range(1 if use_graph else max(args.warmup, 3)):
         l_before = raw.LAUNCHES[0]
+        if i == 0:
+            raw.ACCOUNT = acc           # algorithmic FLOPs / bytes of every launch of ONE step, by kernel family
         step(devb)
+        raw.ACCOUNT = None
         lps = raw.LAUNCHES[0] - l_before      # kernels of OUR library launched by one step
     barrier()
     if args.profile_one:
@@ -315,7 +404,6 @@ def main():
     graphed = None
     if use_graph:
         try:
-            from svd_xtend_b200.train import GraphedStep
             l_before = raw.LAUNCHES[0]
             graphed = GraphedStep(step, devb, warmup=max(args.warmup, 3))
             lps = (raw.LAUNCHES[0] - l_before) // (max(args.warmup, 3) + 1)
@@ -325,7 +413,7 @@ def main():
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
             graphed = None
             torch.cuda.synchronize()
-    graph = graphed
+    graph_captured = graphed is not None
 
     def run_step():
         if graphed is not None:
@@ -361,7 +449,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = T_FRAMES * world * args.steps / (ms / 1e3)
+    value = frames * world * args.steps / (ms / 1e3)
     final_loss = float(loss.item())
 
     # ---- e2e: public API from pinned host buffers, H2D inside, loss read back every step
@@ -381,84 +469,139 @@ def main():
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = T_FRAMES * world * args.steps / (float(t.item()) / 1e3)
+    e2e_value = frames * world * args.steps / (float(t.item()) / 1e3)
 
-    # ---- roofline of the dominant kernel (tapgemm, tensor-bound): events around every launch of one eager step
-    recs = []
-    orig = raw.tapgemm
-
-    def timed_tapgemm(a, b, out, *, M, N, K, **kw):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig(a, b, out, M=M, N=N, K=K, **kw)
-        e.record()
-        ntaps = len(kw.get("taps", ((0, 0, 0),)))
-        recs.append((s, e, 2.0 * M * N * K * ntaps, (M, N, K, ntaps, int(kw.get("mode", 0)), bool(kw.get("geglu", False)),
-                                                      bool(kw.get("a_mn", False)), int(kw.get("split_k", 1)))))
-        return r
-
-    raw.tapgemm = timed_tapgemm
-    try:
-        step(devb)
-        torch.cuda.synchronize()
-    finally:
-        raw.tapgemm = orig
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
-    gemm_flops = sum(f for _, _, f, _ in recs)
-    if rank == 0 and os.environ.get("SVDX_GEMM_TABLE"):
-        agg = {}
-        for s_, e_, f_, key in recs:
-            a = agg.setdefault(key, [0, 0.0, 0.0])
-            a[0] += 1
-            a[1] += s_.elapsed_time(e_)
-            a[2] += f_
-        table = [{"M": k[0], "N": k[1], "K": k[2], "taps": k[3], "mode": k[4], "geglu": k[5], "wgrad": k[6], "split_k": k[7], "n": v[0],
-                  "ms": v[1], "tflops": v[2] / v[1] / 1e9 if v[1] > 0 else 0.0} for k, v in agg.items()]
-        table.sort(key=lambda r_: -r_["ms"])
-        with open(os.environ["SVDX_GEMM_TABLE"], "w") as fh:
-            json.dump(table, fh, indent=0)
+    # ---- rooflines. In eager mode the CPU (descriptor build + cuLaunchKernel, ~10 us) trails the GPU, so an event pair around one
+    # launch also times host work whenever the stream is idle. With the whole step in a CUDA graph the in-step cost of a kernel
+    # FAMILY is measured by ablation instead: capture the same step with every launch of that family skipped (raw.ABLATE) and
+    # take the difference of the two replay times (CUDA events, the same K replays, max over ranks). Same method at every N.
+    # Algorithmic work per family comes from raw.ACCOUNT over one step. Done last: the ablated steps compute garbage.
     sustained, burst, hbm, src = peaks()
-    traffic, traffic_src = None, None
-    for tp in sorted([f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")] if os.path.isdir(os.path.join(ROOT, "profiles")) else [], reverse=True):
+
+    def ablated_ms(fams):
+        raw.ABLATE = set(fams)
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", tp)))
+            g = GraphedStep(step, devb, warmup=2)
+            for _ in range(2):
+                g.replay()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                g.replay()
+            e1.record()
+            barrier()
+            tt = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            del g
+            return float(tt.item())
+        finally:
+            raw.ABLATE = set()
+
+    fam_ms = {}
+    method = None
+    if graph_captured and args.config == 4:
+        graphed = None              # one captured step of config 4 holds > 60 GB of activations: release it before re-capturing
+        torch.cuda.empty_cache()
+    if graph_captured:
+        todo = [("tapgemm", ["linear", "conv"])]
+        if not args.no_families and world == 1:
+            todo += [(f, [f]) for f in ("linear", "conv", "attention", "groupnorm", "layernorm", "adamw", "elementwise") if f in account]
+        for name, fams in todo:
+            try:
+                wo = ablated_ms(fams)
+                if 0.0 < wo < ms_per_step:
+                    fam_ms[name] = ms_per_step - wo
+            except Exception as e:
+                print(f"[bench] ablation of {name} failed ({type(e).__name__}: {e})", file=sys.stderr)
+        method = ("graph-replay ablation: ms_per_step minus the replay time of the same captured step with every launch of the kernel "
+                  f"family skipped, CUDA events over {args.steps} replays each")
+    gemm_flops = sum(account.get(f, [0, 0.0, 0.0])[1] for f in ("linear", "conv"))
+    gemm_launches = sum(account.get(f, [0, 0.0, 0.0])[0] for f in ("linear", "conv"))
+    gemm_ms = fam_ms.get("tapgemm")
+    if gemm_ms is None:       # no graph: events around every tapgemm launch of one eager step (includes host launch gaps)
+        recs = []
+        orig = raw.tapgemm
+
+        def timed_tapgemm(a, b, out, **kw):
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            r_ = orig(a, b, out, **kw)
+            e_.record()
+            recs.append((s_, e_))
+            return r_
+
+        raw.tapgemm = timed_tapgemm
+        try:
+            step(devb)
+            torch.cuda.synchronize()
+        finally:
+            raw.tapgemm = orig
+        gemm_ms = sum(s_.elapsed_time(e_) for s_, e_ in recs)
+        method = "sum of CUDA-event pairs around every svdx_tapgemm launch of one eager step (host launch gaps included)"
+    traffic, traffic_src = None, None
+    pdir = os.path.join(ROOT, "profiles")
+    for tp in sorted([f for f in os.listdir(pdir) if f.endswith("_traffic.json")] if os.path.isdir(pdir) else [], reverse=True):
+        try:
+            tj = json.load(open(os.path.join(pdir, tp)))
             traffic, traffic_src = tj["traffic_bytes_per_launch"], f"profiles/{tp} (ncu dram__bytes_read+write summed over the {tj['launches_per_step']} tapgemm launches of one step, per launch)"
             break
         except Exception:
             pass
-    # In eager mode the CPU (descriptor build + cuLaunchKernel, ~10 us) trails the GPU, so an event pair around one launch
-    # also times host work whenever the stream is idle. With the whole step in a CUDA graph the in-step cost of the
-    # kernel is measured by ablation instead: capture the same step with every svdx_tapgemm launch skipped and take the
-    # difference of the two replay times (CUDA events, same K steps). Done last: the ablated steps compute garbage.
-    method = "sum of CUDA-event pairs around every svdx_tapgemm launch of one eager step"
-    if graphed is not None and world == 1:
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms and gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "svdx::tapgemm2_kernel / tapgemm_kernel (tcgen05)", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                "frac": achieved / sustained, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_note": "tensor-bound kernel: algorithmic work is FLOPs (2*M*N*K*taps per launch, summed); see DESIGN.md §3",
+                "peak_source": src + ", bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_per_step": gemm_launches, "algorithmic_tflop_per_step": gemm_flops / 1e12, "kernel_ms_per_step": gemm_ms,
+                "avg_launch_us": 1e3 * gemm_ms / max(gemm_launches, 1), "timing_method": method,
+                "share_of_step": gemm_ms / ms_per_step}
+    by_family = {}
+    for fam, (n_l, fl, by) in account.items():
+        if fam not in fam_ms:
+            continue
+        t_ms = fam_ms[fam]
+        if FAMILY_BOUND[fam] == "tensor":
+            ach = fl / (t_ms / 1e3) / 1e12
+            by_family[fam] = {"bound": "tensor", "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
+                              "ms_per_step": t_ms, "launches_per_step": n_l, "algorithmic_tflop_per_step": fl / 1e12}
+        else:
+            ach = by / (t_ms / 1e3) / 1e9
+            by_family[fam] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                              "ms_per_step": t_ms, "launches_per_step": n_l, "algorithmic_gb_per_step": by / 1e9}
+
+    # ---- the unchanged-script calling pattern (train_svd.py:1021-1049): eager launches from Python, forward inside an autocast
+    # region, torch.optim.AdamW over p.grad, zero_grad(set_to_none=True); no GraphedStep, no FusedAdamW.
+    script_path = None
+    if world == 1 and not args.no_script_path:
         try:
-            raw.tapgemm = lambda a, b, out, **kw: out
-            ablated = GraphedStep(step, devb, warmup=2)
+            topt = torch.optim.AdamW([p for p in unet.parameters() if p.requires_grad], lr=1e-5, weight_decay=1e-2)
+
+            def script_step():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    pred = unet(devb["sample"], devb["timestep"], devb["encoder_hidden_states"], added_time_ids=devb["added_time_ids"]).sample
+                loss_ = edm_loss(pred.float(), devb["noisy"], devb["latents"], devb["sigmas"])
+                loss_.backward()
+                topt.step()
+                topt.zero_grad(set_to_none=True)
+                return loss_
+
             for _ in range(2):
-                ablated.replay()
+                script_step()
             torch.cuda.synchronize()
+            n_s = max(3, min(args.steps, 10))
             e0.record()
-            for _ in range(args.steps):
-                ablated.replay()
+            for _ in range(n_s):
+                script_step()
             e1.record()
             torch.cuda.synchronize()
-            ms_wo = e0.elapsed_time(e1) / args.steps
-            if 0.0 < ms_wo < ms_per_step:
-                gemm_ms = ms_per_step - ms_wo
-                method = ("graph-replay ablation: ms_per_step minus the replay time of the same captured step with every svdx_tapgemm "
-                          f"launch skipped ({ms_wo:.3f} ms), CUDA events over {args.steps} replays each")
+            sp_ms = e0.elapsed_time(e1) / n_s
+            script_path = {"ms_per_step": sp_ms, "value": frames / (sp_ms / 1e3), "unit": "frames/s", "steps": n_s,
+                           "what": "unet(...) inside torch.autocast + loss.backward() + torch.optim.AdamW.step() + zero_grad(set_to_none=True), "
+                                   "every kernel launched eagerly from Python through the C ABI (train_svd.py:1021-1049 pattern)"}
+            del topt
         except Exception as e:
-            print(f"[bench] ablation graph failed ({type(e).__name__}: {e}); keeping the per-launch event sum", file=sys.stderr)
-        finally:
-            raw.tapgemm = orig
-    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "svdx::tapgemm_kernel (tcgen05)", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                "frac": achieved / sustained, "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_note": "tensor-bound kernel: algorithmic work is FLOPs (2*M*N*K*taps per launch, summed); see DESIGN.md §3", "peak_source": src + ", bf16_tflops_sustained (kernel timed inside a long step)",
-                "launches_per_step": len(recs), "algorithmic_tflop_per_step": gemm_flops / 1e12, "kernel_ms_per_step": gemm_ms,
-                "avg_launch_us": 1e3 * gemm_ms / max(len(recs), 1), "timing_method": method,
-                "share_of_step": gemm_ms / ms_per_step}
+            script_path = {"failed": f"{type(e).__name__}: {e}"}
 
     def finish():
         """leave without tearing NCCL down: communicators referenced by live CUDA graphs block destroy_process_group()"""
@@ -478,6 +621,15 @@ def main():
         finish()
         return
 
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        try:
+            graphed = None
+            torch.cuda.empty_cache()
+            gpu_base = gpu_eager_baseline(dev, cfg)
+        except Exception as e:
+            gpu_base = {"failed": f"{type(e).__name__}: {e}"}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -489,15 +641,18 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (seeded default-init weights, randn latents per train_svd.py:951-1017)",
-        "config": {"workload": WORKLOAD, "frames": T_FRAMES, "latent_hw": [LAT_H, LAT_W], "per_gpu_batch": 1, "global_batch": world,
-                   "trainable_params": n_train, "total_params": n_total, "parallelism": f"dp{world}",
-                   "cuda_graph": graph is not None,
+        "config": {"workload": cfg["name"], "baseline_config": args.config, "frames": frames, "latent_hw": [lat_h, lat_w], "per_gpu_batch": 1,
+                   "global_batch": world, "trainable_params": n_train, "total_params": n_total, "parallelism": f"dp{world}",
+                   "cuda_graph": graph_captured, "gradient_checkpointing": bool(cfg["grad_ckpt"]), "lora_rank": cfg["lora_rank"],
                    "l2": "no explicit flush: the per-step working set (3 GB bf16 operand weights + >10 GB activations) is >> 126 MB L2",
-                   "final_loss": final_loss},
+                   "final_loss": final_loss, "cpu_arm": CPU_ARM_NOTE},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-        "gpu_launches": launches if graph is None else lps * args.steps,   # graph replay re-launches the captured kernels
+        "gpu_launches": launches if not graph_captured else lps * args.steps,   # graph replay re-launches the captured kernels
         "roofline": roofline,
+        "roofline_by_family": by_family,
+        "script_path": script_path,
+        "gpu_eager_baseline": gpu_base,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

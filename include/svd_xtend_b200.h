@@ -183,7 +183,8 @@ int svdx_attention_fwd(const SvdxAttn* d, void* stream);
 int svdx_attention_bwd(const SvdxAttn* d, void* stream);
 
 /* ------------------------------------------------------------------ elementwise / layout */
-/* fp32 (or bf16 when src_bf16) weights -> bf16, optionally re-laid-out:
+/* weights -> bf16, optionally re-laid-out. src_bf16 is the SOURCE DTYPE CODE used by every entry of this section:
+ * 0 = fp32, 1 = bf16, 2 = fp16 (train_svd_lora.py:669 moves the frozen UNet to fp16 / bf16 `weight_dtype`).
  *   mode 0: plain copy           dst[n][k]           = src[n][k]
  *   mode 1: transpose            dst[k][n]           = src[n][k]            (dgrad operand of a linear)
  *   mode 2: conv OIHW -> O(HW)I  dst[o][t][i(pad)]   = src[o][i][t]         (fwd operand; taps = kh*kw or kt)
@@ -199,7 +200,8 @@ int svdx_dot_diff(const void* dy, const void* a, const void* b, int64_t n, float
 int svdx_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, void* stream);
 int svdx_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int svdx_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
-/* NCHW (fp32 or bf16) -> [N][H][W][c_pad] bf16 (zero padded channels) and back (to fp32 / bf16 NCHW) */
+int svdx_cast_f16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* NCHW (dtype code 0/1/2) -> [N][H][W][c_pad] bf16 (zero padded channels) and back (to an NCHW tensor of dtype code dst_bf16) */
 int svdx_nchw_to_nhwc(const void* src, int32_t src_bf16, void* dst, int32_t N, int32_t C, int32_t H, int32_t W,
                       int32_t c_pad, void* stream);
 int svdx_nhwc_to_nchw(const void* src, int64_t lds, void* dst, int32_t dst_bf16, int32_t N, int32_t C, int32_t H,
@@ -232,6 +234,12 @@ int svdx_blend_scales(const float* mix_factor, float* out16, void* stream);
  * the updated parameters are also written as bf16 at the same flat offsets (the forward GEMM operands) */
 int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int32_t step, float grad_scale, void* shadow_bf16, void* stream);
+/* the same update with every step-varying scalar in DEVICE memory, so that it can be captured in a CUDA graph and replayed:
+ * state = float[8] {lr, beta1, beta2, eps, weight_decay, step, 1-beta1^step, 1-beta2^step}. The call first advances
+ * step and the bias corrections on the device (a 1-thread kernel), then updates; the host changes the learning rate by
+ * writing state[0] (lr scheduler of train_svd.py:790-796). Two launches. */
+int svdx_adamw_graph(float* p, const float* g, float* m, float* v, int64_t n, float* state, float grad_scale,
+                     void* shadow_bf16, void* stream);
 /* many bf16 transposes dst[i][o] = src_base[src_off + o*I + i] in one launch (dgrad operands of all trainable linears).
  * jobs: device array of {int64 src_off; void* dst; int32 O; int32 I}; tile_prefix[j] = first 32x32 tile of job j. */
 int svdx_multi_transpose(const void* src_base, const void* jobs, const int32_t* tile_prefix, int32_t njobs, int32_t total_tiles,

@@ -76,6 +76,7 @@ _PROTOS = {
     "svdx_silu_bwd_f32": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
     "svdx_cast_f32_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "svdx_cast_bf16_f32": [c_void_p, c_void_p, c_i64, c_void_p],
+    "svdx_cast_f16_f32": [c_void_p, c_void_p, c_i64, c_void_p],
     "svdx_nchw_to_nhwc": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "svdx_nhwc_to_nchw": [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "svdx_upsample2x": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -92,6 +93,7 @@ _PROTOS = {
     "svdx_blend_scales": [c_void_p, c_void_p, c_void_p],
     "svdx_adamw": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
                    c_int, c_float, c_void_p, c_void_p],
+    "svdx_adamw_graph": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_float, c_void_p, c_void_p],
     "svdx_multi_transpose": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
 }
 

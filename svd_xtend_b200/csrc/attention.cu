@@ -783,11 +783,12 @@ extern "C" int svdx_attention_fwd(const SvdxAttn* d, void* stream_v) {
   dim3 grid;
   int rc = attn_setup(d, p, false, grid);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[SVDX_MAX_DEVICES] = {false};
+  const int slot = svdx_device_slot();
+  if (!attr[slot]) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
     if (e != cudaSuccess) return svdx_fail_cuda(e, "attention_fwd: smem attribute");
-    attr = true;
+    attr[slot] = true;
   }
   attn_fwd_kernel<<<grid, AT_THREADS, FWD_SMEM, st>>>(p);
   SVDX_CHECK_LAUNCH("attention_fwd");
@@ -800,12 +801,13 @@ extern "C" int svdx_attention_bwd(const SvdxAttn* d, void* stream_v) {
   dim3 grid;
   int rc = attn_setup(d, p, true, grid);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[SVDX_MAX_DEVICES] = {false};
+  const int slot = svdx_device_slot();
+  if (!attr[slot]) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BDQ_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BKV_SMEM);
     if (e != cudaSuccess) return svdx_fail_cuda(e, "attention_bwd: smem attribute");
-    attr = true;
+    attr[slot] = true;
   }
   // tokens covered = nseq * S (dense token-major matrices)
   const long long tokens = (long long)d->nseq * d->S;

@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "../../include/svd_xtend_b200.h"
 #include "host_util.h"
+#include <cuda_fp16.h>
+#include <type_traits>
 
 namespace svdx {
 
@@ -19,6 +21,8 @@ template <>
 SVDX_DEVINL float ldf<float>(const float* p, long long i) { return p[i]; }
 template <>
 SVDX_DEVINL float ldf<bf16>(const bf16* p, long long i) { return __bfloat162float(p[i]); }
+template <>
+SVDX_DEVINL float ldf<__half>(const __half* p, long long i) { return __half2float(p[i]); }
 
 // mode 0: dst[o][i]            = src[o][i]          (taps == 1)
 // mode 2: dst[o][t][i_pad]     = src[o][i][t]
@@ -78,6 +82,10 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
   const long long i = gtid();
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
+__global__ void cast_f16_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = gtid();
+  if (i < n) dst[i] = __half2float(src[i]);
+}
 
 // ------------------------------------------------------------------ layout boundary
 template <typename T>
@@ -102,7 +110,9 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, long long lds,
   const int c = (int)((idx / ((long long)W * H)) % C);
   const int n = (int)(idx / ((long long)W * H * C));
   const float v = __bfloat162float(src[(((long long)n * H + h) * W + w) * lds + c]);
-  if constexpr (sizeof(T) == 4) dst[idx] = v; else dst[idx] = __float2bfloat16(v);
+  if constexpr (sizeof(T) == 4) dst[idx] = v;
+  else if constexpr (std::is_same<T, __half>::value) dst[idx] = __float2half(v);
+  else dst[idx] = __float2bfloat16(v);
 }
 
 // nearest 2x: dst[n][2h+a][2w+b][:] = src[n][h][w][:]   (16 B vectors)
@@ -385,6 +395,54 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   if (shadow) shadow[i] = __float2bfloat16(pi);   // bf16 operand copy of the updated weight, same flat offset
 }
 
+// CUDA-graph-safe form: every scalar that changes between steps lives in a small device buffer
+//   state[0] lr  [1] beta1  [2] beta2  [3] eps  [4] weight_decay  [5] step (float, exact up to 2^24)  [6] 1-beta1^step  [7] 1-beta2^step
+// adamw_tick advances the step count and the bias corrections on the device, so a captured graph that contains
+// tick + update replays torch.optim.AdamW's step sequence; the learning rate is whatever the host last wrote to state[0].
+__global__ void adamw_tick_kernel(float* state) {
+  const float step = state[5] + 1.f;
+  state[5] = step;
+  state[6] = 1.f - powf(state[1], step);
+  state[7] = 1.f - powf(state[2], step);
+}
+__global__ void adamw_state_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n4,
+                                   long long n, const float* __restrict__ state, float gscale, bf16* __restrict__ shadow) {
+  const long long i4 = gtid();
+  if (i4 >= n4) return;
+  const float lr = state[0], b1 = state[1], b2 = state[2], eps = state[3], wd = state[4], bc1 = state[6], bc2 = state[7];
+  const float decay = 1.f - lr * wd, step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const long long i = i4 * 4;
+  if (i + 3 < n) {
+    const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+    float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float gg[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] = b1 * mm[k] + (1.f - b1) * gg[k];
+      vv[k] = b2 * vv[k] + (1.f - b2) * gg[k] * gg[k];
+      pp[k] = pp[k] * decay - step_size * mm[k] / (sqrtf(vv[k]) * inv_sqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (shadow) {
+      uint2 o;
+      o.x = pack_bf16x2(pp[0], pp[1]);
+      o.y = pack_bf16x2(pp[2], pp[3]);
+      *reinterpret_cast<uint2*>(shadow + i) = o;
+    }
+  } else {
+    for (long long k = i; k < n; ++k) {
+      const float gi = g[k] * gscale;
+      const float mi = b1 * m[k] + (1.f - b1) * gi, vi = b2 * v[k] + (1.f - b2) * gi * gi;
+      const float pi = p[k] * decay - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+      m[k] = mi; v[k] = vi; p[k] = pi;
+      if (shadow) shadow[k] = __float2bfloat16(pi);
+    }
+  }
+}
+
 struct TransposeJob {
   long long src_off;   // element offset into the bf16 source arena
   bf16* dst;           // [I][O] destination
@@ -446,17 +504,20 @@ using namespace svdx;
 
 extern "C" int svdx_prep_weight(const void* src, int32_t src_bf16, void* dst, int32_t mode, int32_t O, int32_t I, int32_t taps,
                                 int32_t i_pad, void* stream) {
-  if (!src || !dst || O <= 0 || I <= 0 || taps <= 0 || mode < 0 || mode > 3) return svdx_fail(SVDX_E_BADARG, "prep_weight: bad arguments");
+  if (!src || !dst || O <= 0 || I <= 0 || taps <= 0 || mode < 0 || mode > 3 || src_bf16 < 0 || src_bf16 > 2)
+    return svdx_fail(SVDX_E_BADARG, "prep_weight: bad arguments (source dtype code: 0 fp32, 1 bf16, 2 fp16)");
   if ((mode == 0 || mode == 1) && taps != 1) return svdx_fail(SVDX_E_BADARG, "prep_weight: modes 0/1 need taps == 1");
   if (mode == 2 && i_pad < I) return svdx_fail(SVDX_E_BADARG, "prep_weight: i_pad < I");
   bf16* d = reinterpret_cast<bf16*>(dst);
   if (mode == 1) {
     dim3 grid((I + 31) / 32, (O + 31) / 32), block(32, 8);
-    if (src_bf16) prep_transpose_kernel<bf16><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), d, O, I);
+    if (src_bf16 == 1) prep_transpose_kernel<bf16><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), d, O, I);
+    else if (src_bf16 == 2) prep_transpose_kernel<__half><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const __half*>(src), d, O, I);
     else prep_transpose_kernel<float><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), d, O, I);
   } else {
     const long long total = mode == 0 ? (long long)O * I : mode == 2 ? (long long)O * taps * i_pad : (long long)I * taps * O;
-    if (src_bf16) prep_gather_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), d, mode, O, I, taps, i_pad);
+    if (src_bf16 == 1) prep_gather_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), d, mode, O, I, taps, i_pad);
+    else if (src_bf16 == 2) prep_gather_kernel<__half><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(src), d, mode, O, I, taps, i_pad);
     else prep_gather_kernel<float><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), d, mode, O, I, taps, i_pad);
   }
   SVDX_CHECK_LAUNCH("prep_weight");
@@ -477,11 +538,19 @@ extern "C" int svdx_cast_bf16_f32(const void* src, float* dst, int64_t n, void* 
   return SVDX_OK;
 }
 
+extern "C" int svdx_cast_f16_f32(const void* src, float* dst, int64_t n, void* stream) {
+  if (!src || !dst || n <= 0) return svdx_fail(SVDX_E_BADARG, "cast_f16_f32: bad arguments");
+  cast_f16_f32_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(src), dst, n);
+  SVDX_CHECK_LAUNCH("cast_f16_f32");
+  return SVDX_OK;
+}
+
 extern "C" int svdx_nchw_to_nhwc(const void* src, int32_t src_bf16, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, int32_t c_pad,
                                  void* stream) {
   if (!src || !dst || N <= 0 || C <= 0 || H <= 0 || W <= 0 || c_pad < C) return svdx_fail(SVDX_E_BADARG, "nchw_to_nhwc: bad arguments");
   const long long total = (long long)N * H * W * c_pad;
-  if (src_bf16) nchw_to_nhwc_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(dst), N, C, H, W, c_pad);
+  if (src_bf16 == 1) nchw_to_nhwc_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(dst), N, C, H, W, c_pad);
+  else if (src_bf16 == 2) nchw_to_nhwc_kernel<__half><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(src), reinterpret_cast<bf16*>(dst), N, C, H, W, c_pad);
   else nchw_to_nhwc_kernel<float><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(src), reinterpret_cast<bf16*>(dst), N, C, H, W, c_pad);
   SVDX_CHECK_LAUNCH("nchw_to_nhwc");
   return SVDX_OK;
@@ -490,7 +559,8 @@ extern "C" int svdx_nhwc_to_nchw(const void* src, int64_t lds, void* dst, int32_
                                  void* stream) {
   if (!src || !dst || N <= 0 || C <= 0 || H <= 0 || W <= 0 || lds < C) return svdx_fail(SVDX_E_BADARG, "nhwc_to_nchw: bad arguments");
   const long long total = (long long)N * C * H * W;
-  if (dst_bf16) nhwc_to_nchw_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<bf16*>(dst), N, C, H, W);
+  if (dst_bf16 == 1) nhwc_to_nchw_kernel<bf16><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<bf16*>(dst), N, C, H, W);
+  else if (dst_bf16 == 2) nhwc_to_nchw_kernel<__half><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<__half*>(dst), N, C, H, W);
   else nhwc_to_nchw_kernel<float><<<nblocks(total), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<float*>(dst), N, C, H, W);
   SVDX_CHECK_LAUNCH("nhwc_to_nchw");
   return SVDX_OK;
@@ -604,6 +674,18 @@ extern "C" int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t 
   adamw_kernel<<<nblocks(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
                                                    reinterpret_cast<bf16*>(shadow_bf16));
   SVDX_CHECK_LAUNCH("adamw");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_adamw_graph(float* p, const float* g, float* m, float* v, int64_t n, float* state, float grad_scale,
+                                void* shadow_bf16, void* stream) {
+  if (!p || !g || !m || !v || !state || n <= 0 || (reinterpret_cast<uintptr_t>(p) & 15) || (reinterpret_cast<uintptr_t>(g) & 15) ||
+      (reinterpret_cast<uintptr_t>(m) & 15) || (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(shadow_bf16) & 7))
+    return svdx_fail(SVDX_E_BADARG, "adamw_graph: bad arguments (16-byte aligned flat buffers, device state[8])");
+  adamw_tick_kernel<<<1, 1, 0, ST(stream)>>>(state);
+  const long long n4 = (n + 3) / 4;
+  adamw_state_kernel<<<nblocks(n4), 256, 0, ST(stream)>>>(p, g, m, v, n4, n, state, grad_scale, reinterpret_cast<bf16*>(shadow_bf16));
+  SVDX_CHECK_LAUNCH("adamw_graph");
   return SVDX_OK;
 }
 

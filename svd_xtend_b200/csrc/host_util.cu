@@ -14,16 +14,23 @@ int svdx_fail_cuda(cudaError_t e, const char* what) {
 }
 extern "C" const char* svdx_last_error(void) { return g_err; }
 
+int svdx_device_slot(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev < SVDX_MAX_DEVICES ? dev : SVDX_MAX_DEVICES - 1;
+}
+
 extern "C" int svdx_num_sms(void) {
-  static int n = 0;
-  if (n == 0) {
+  static int n[SVDX_MAX_DEVICES] = {0};
+  const int slot = svdx_device_slot();
+  if (n[slot] == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    n = v;
+    n[slot] = v;
   }
-  return n;
+  return n[slot];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -14,6 +14,10 @@ int svdx_make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int svdx_make_tmap_ex(CUtensorMap* out, const void* base, int f32, int swizzle_bytes, int rank, const uint64_t* dims,
                       const uint64_t* strides, const uint32_t* box);
 extern "C" int svdx_num_sms(void);
+// index of the calling thread's current CUDA device (0 when the runtime cannot tell), clamped to [0, 64):
+// function attributes such as the dynamic shared-memory limit are per device, so "set once" flags are arrays of this size
+int svdx_device_slot(void);
+#define SVDX_MAX_DEVICES 64
 
 #define SVDX_CHECK_LAUNCH(what)                                   \
   do {                                                            \

@@ -507,14 +507,15 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
   int rc = svdx_tapgemm_fill(d, p, pair ? 2 : 1);
   if (rc) return rc;
   if (pair) return svdx_tapgemm2_launch(p, stream);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[SVDX_MAX_DEVICES] = {false};
+  const int slot = svdx_device_slot();
+  if (!attr_done[slot]) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm: set smem attribute");
-    attr_set = true;
+    attr_done[slot] = true;
   }
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
   int grid = svdx_num_sms();

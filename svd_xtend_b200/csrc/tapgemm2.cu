@@ -316,14 +316,15 @@ bool svdx_tapgemm2_eligible(const SvdxTapGemm* d) {
 }
 
 int svdx_tapgemm2_launch(const TapGemmKParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[SVDX_MAX_DEVICES] = {false};
+  const int slot = svdx_device_slot();
+  if (!attr_done[slot]) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm2: set smem attribute");
-    attr_set = true;
+    attr_done[slot] = true;
   }
   const int total_tiles = p.pair_m_tiles * p.n_tiles;
   int clusters = svdx_num_sms() / 2;

@@ -133,18 +133,33 @@ class Engine:
 
     # ------------------------------------------------------------------ tape
     def begin(self, recording: bool):
+        """start a forward: a fresh tape (the previous forward's tape, if any, stays with ITS autograd node — see
+        `detach_tape`), so two forwards before a backward, or a no_grad forward in between, cannot clobber each other"""
         self.tape = []
         self.recording = recording
-        self.pgrads = {}
+
+    def detach_tape(self) -> List[Callable[[], None]]:
+        """hand the recorded tape to the caller (the autograd node of this forward) and stop recording"""
+        tape, self.tape = self.tape, []
+        self.recording = False
+        return tape
 
     def record(self, fn: Callable[[], None]):
         if self.recording:
             self.tape.append(fn)
 
-    def run_backward(self):
-        tape, self.tape = self.tape, []
-        while tape:
-            tape.pop()()
+    def run_backward(self, tape: Optional[List[Callable[[], None]]] = None):
+        """replay a tape in reverse. Closures may record onto self.tape (gradient checkpointing re-runs forward pieces),
+        so recording is on while the tape runs; parameter gradients of THIS backward collect in self.pgrads."""
+        if tape is None:
+            tape, self.tape = self.tape, []
+        self.pgrads = {}
+        was, self.recording = self.recording, True
+        try:
+            while tape:
+                tape.pop()()
+        finally:
+            self.recording = was
         self.keep.clear()
 
     def checkpoint(self, fn: Callable[..., Var], *inputs: Var) -> Var:
@@ -265,7 +280,7 @@ class Engine:
             return None
         if p.dtype == F32:
             return p.detach()
-        return self.wc.get(("f32", id(p)), [p], tuple(p.shape), lambda buf: raw.cast_bf16_f32(p.detach(), buf), dtype=F32)
+        return self.wc.get(("f32", id(p)), [p], tuple(p.shape), lambda buf: raw.cast_to_f32(p.detach().contiguous(), buf), dtype=F32)
 
     # ------------------------------------------------------------------ small helpers
     @staticmethod
@@ -328,11 +343,14 @@ class Engine:
         lora = [l for l in (lora or []) if l is not None]
         lora_t = []
         for (off, n, A, Bm, sc) in lora:
-            # LoRA side path (train_svd_lora.py:659-671): out[:, off:off+n] += scale * (x A^T) B^T, accumulated in place
-            t = self.empty(M, A.shape[0], x.data)
-            raw.tapgemm(x.data, self.w_lin(A, False), t, M=M, N=A.shape[0], K=K)
+            # LoRA side path (train_svd_lora.py:659-671): out[:, off:off+n] += scale * (x A^T) B^T, accumulated in place.
+            # The rank axis is padded to a multiple of 8 in the OPERAND copies (16-byte rows for TMA); parameter and
+            # gradient shapes stay [r, in] / [out, r] (the reference default is --rank 4, train_svd_lora.py:551-553).
+            rp = (A.shape[0] + 7) // 8 * 8
+            t = self.empty(M, rp, x.data)
+            raw.tapgemm(x.data, self.w_lora(A, "A", False), t, M=M, N=rp, K=K)
             ov = out[:, off:off + n]
-            raw.tapgemm(t, self.w_lin(Bm, False), ov, M=M, N=n, K=A.shape[0], res1=ov, scales=self._lora_scales(sc, out.device))
+            raw.tapgemm(t, self.w_lora(Bm, "B", False), ov, M=M, N=n, K=rp, res1=ov, scales=self._lora_scales(sc, out.device))
             lora_t.append(t)
         w_train = any(p.requires_grad for p in ws) or (bias is not None and bias.requires_grad) \
             or (blend is not None and blend[0].requires_grad) or any(l[2].requires_grad or l[3].requires_grad for l in lora)
@@ -366,17 +384,18 @@ class Engine:
                     self._bias_grad(bias, dyl, s_acc)
                 for (off, n, A, Bm, sc), t in zip(lora, lora_t):
                     r = A.shape[0]
+                    rp = (r + 7) // 8 * 8
                     dys = dyl[:, off:off + n]
                     s3 = self._lora_scales(sc, dyl.device, acc_only=True)
-                    dt = self.empty(M, r, x.data)
-                    raw.tapgemm(dys, self.w_lin(Bm, True), dt, M=M, N=r, K=n, scales=s3)      # dt = scale * dy B
+                    dt = self.empty(M, rp, x.data)
+                    raw.tapgemm(dys, self.w_lora(Bm, "B", True), dt, M=M, N=rp, K=n, scales=s3)   # dt = scale * dy B
                     if Bm.requires_grad:
-                        self._wgrad(dys, t, [Bm], n, r, M, s3)                                  # dB += scale * dy^T t
+                        self._wgrad(dys, t, [Bm], n, rp, M, s3, pad_to=(n, rp))                  # dB += scale * dy^T t
                     if A.requires_grad:
-                        self._wgrad(dt, x.data, [A], r, K, M, None)                             # dA += dt^T x
+                        self._wgrad(dt, x.data, [A], rp, K, M, None, pad_to=(rp, K))             # dA += dt^T x
                     if x.needs_grad:
                         dxl = self.empty(M, K, x.data)
-                        raw.tapgemm(dt, self.w_lin(A, True), dxl, M=M, N=K, K=r)
+                        raw.tapgemm(dt, self.w_lora(A, "A", True), dxl, M=M, N=K, K=rp)
                         self.add_grad(x, dxl)
             self.record(bwd)
         return y
@@ -422,8 +441,37 @@ class Engine:
         raw.axpby(t.reshape(-1), t.reshape(-1), out.reshape(-1), sc)
         return out
 
-    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, ws, N, K, M, scales3):
-        """dW[N,K] += dy[M,N]^T @ x[M,K] — both operands MN-major, split-K over tokens, fp32 atomics."""
+    def w_lora(self, p: torch.Tensor, which: str, transposed: bool) -> torch.Tensor:
+        """bf16 operand of a LoRA factor with the rank axis zero-padded to a multiple of 8: A [r,in] -> [rp,in] (or its
+        transpose [in,rp]); B [out,r] -> [out,rp] (or [rp,out]). rp == r: the plain (cached / arena) operand."""
+        r = p.shape[0] if which == "A" else p.shape[1]
+        rp = (r + 7) // 8 * 8
+        if rp == r:
+            return self.w_lin(p, transposed)
+        O, I = p.shape
+        Op, Ip = (rp, I) if which == "A" else (O, rp)
+        shape = (Ip, Op) if transposed else (Op, Ip)
+
+        def build(buf):
+            buf.zero_()
+            src = p.detach().t() if transposed else p.detach()
+            buf[:src.shape[0], :src.shape[1]].copy_(src)
+        return self.wc.get(("lora", id(p), transposed), [p], shape, build)
+
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, ws, N, K, M, scales3, pad_to=None):
+        """dW[N,K] += dy[M,N]^T @ x[M,K] — both operands MN-major, split-K over tokens, fp32 atomics.
+        pad_to=(N, K): the operands carry zero-padded rank columns (LoRA, r % 8 != 0); the product is formed in a padded
+        fp32 scratch and its valid block is added to the parameter gradient."""
+        if pad_to is not None and tuple(pad_to) != tuple(ws[0].shape):
+            p = ws[0]
+            if not p.requires_grad:
+                return
+            tmp = torch.zeros(pad_to, device=dy.device, dtype=F32)
+            bn = raw.choose_block_n(pad_to[0], pad_to[1], mn_major=True)
+            raw.tapgemm(dy, x, tmp, M=pad_to[0], N=pad_to[1], K=M, a_mn=True, b_mn=True, split_k=1, out_dtype=OUT_F32_ATOMIC,
+                        block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
+            self.pgrad(p).add_(tmp[:p.shape[0], :p.shape[1]])
+            return
         if len(ws) == 1:
             targets = [(ws[0], 0, N)]
         else:

@@ -12,14 +12,40 @@ from ._lib import A_CONV2D, A_ROWS, OUT_BF16, OUT_F32, OUT_F32_ATOMIC, SvdxAttn,
 
 bf16 = torch.bfloat16
 
+# source-dtype codes of the C ABI (include/svd_xtend_b200.h, "elementwise / layout")
+_DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def dtype_code(t: torch.Tensor, what: str) -> int:
+    """dtype code of a parameter / boundary tensor; anything but fp32 / bf16 / fp16 is rejected loudly (a silently
+    misread buffer would be an out-of-bounds read)."""
+    try:
+        return _DTYPE_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f"svd_xtend_b200: {what} has dtype {t.dtype}; supported: float32, bfloat16, float16") from None
+
 # number of kernels launched through the C ABI since import (each wrapper adds what its entry point launches)
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"svdx_groupnorm_stats": 2, "svdx_groupnorm_bwd": 2, "svdx_attention_bwd": 3}
+_KERNELS_PER_CALL = {"svdx_groupnorm_stats": 2, "svdx_groupnorm_bwd": 2, "svdx_attention_bwd": 3, "svdx_adamw_graph": 2}
 
 
 def check(rc: int, what: str = "") -> None:
     LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 1)
     _lib.check(rc, what)
+
+
+# ---- measurement hooks (bench.py): per-family accounting of algorithmic work and in-graph ablation -------------------
+# Families: "linear" / "conv" (svdx_tapgemm), "attention", "groupnorm", "layernorm", "adamw", "elementwise".
+# ACCOUNT(family, flops, bytes) is called for every launch while set; a family named in ABLATE is NOT launched (its
+# outputs stay uninitialised: only for timing a captured step with that family removed, never for results).
+ABLATE: set = set()
+ACCOUNT = None
+
+
+def _fam(family: str, flops: float = 0.0, nbytes: float = 0.0) -> bool:
+    if ACCOUNT is not None:
+        ACCOUNT(family, flops, nbytes)
+    return family in ABLATE
 
 
 def _stream() -> int:
@@ -146,6 +172,9 @@ def tapgemm(
     pre: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """Launch svdx_tapgemm on the current stream. All tensors are CUDA; a/b/res/pre are bf16."""
+    family = "conv" if (mode == A_CONV2D or len(taps) > 1 or b_mode != 0) else "linear"
+    if _fam(family, 2.0 * M * N * K * len(taps)):
+        return out
     d = SvdxTapGemm()
     assert a.dtype == bf16 and b.dtype == bf16
     d.a = a.data_ptr()
@@ -208,7 +237,8 @@ _SPLITK_WS: dict = {}
 def _splitk_workspace(M: int, N: int, device) -> torch.Tensor:
     """one zeroed fp32 [M, N] workspace per shape and device: svdx_splitk_epilogue re-zeroes what it reads, so the
     accumulate -> epilogue pairs of a stream can share it without a memset per launch"""
-    key = (M, N, str(device))
+    # per stream: two streams must never interleave accumulate -> epilogue pairs on one workspace
+    key = (M, N, str(device), _stream() if torch.device(device).type == "cuda" else 0)
     ws = _SPLITK_WS.get(key)
     if ws is None:
         ws = torch.zeros(M, N, device=device, dtype=torch.float32)
@@ -235,6 +265,8 @@ def tapgemm_auto(a, b, out, *, M, N, K, taps=((0, 0, 0),), bias=None, rowbias=No
             if tiles <= num_sms() // 3 and split >= 2:
                 ws = _splitk_workspace(M, N, out.device)
                 tapgemm(a, b, ws, M=M, N=N, K=K, taps=taps, block_n=bn, split_k=split, out_dtype=OUT_F32_ATOMIC, **kw)
+                if _fam("conv" if (kw.get("mode", A_ROWS) == A_CONV2D or len(taps) > 1) else "linear"):
+                    return out
                 check(load().svdx_splitk_epilogue(ws.data_ptr(), N, out.data_ptr(), _rowmajor(out, "out"), M, N, _ptr(bias), _ptr(rowbias),
                                                   rowbias_div, _rowmajor(rowbias, "rowbias") if rowbias is not None else 0,
                                                   _ptr(res1), _rowmajor(res1, "res1") if res1 is not None else 0,
@@ -265,6 +297,8 @@ def attention_fwd(q, k, v, o, *, heads, S, nseq, inner=1, outer_stride=None, inn
     """q/k/v/o: [tokens, >=heads*64] bf16 (column slices allowed). Spatial: inner=1, outer_stride=S."""
     if outer_stride is None:
         outer_stride = S
+    if _fam("attention", 4.0 * nseq * heads * S * S * 64):
+        return o
     d = _attn_desc(q, k, v, o, heads, S, nseq, inner, outer_stride, inner_stride, tok_stride, scale, lse)
     check(load().svdx_attention_fwd(C.byref(d), _stream()), "svdx_attention_fwd")
     return o
@@ -274,6 +308,8 @@ def attention_bwd(q, k, v, o, dout, dq, dk, dv, lse, delta, *, heads, S, nseq, i
                   inner_stride=0, tok_stride=1, scale=0.125):
     if outer_stride is None:
         outer_stride = S
+    if _fam("attention", 10.0 * nseq * heads * S * S * 64):     # flash backward = 2.5 x forward (5 GEMMs of S^2 x 64)
+        return
     d = _attn_desc(q, k, v, o, heads, S, nseq, inner, outer_stride, inner_stride, tok_stride, scale, lse)
     d.dout, d.lddo = dout.data_ptr(), _rowmajor(dout, "dout")
     d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
@@ -288,6 +324,8 @@ def groupnorm_stats(x, x2, outer, rows, eps, groups=32):
     C2 = x2.shape[-1] if x2 is not None else 0
     stats = torch.empty(2, outer * groups, device=x.device, dtype=torch.float32)   # adjacent: zeroed by ONE memset node
     mean, rstd = stats[0], stats[1]
+    if _fam("groupnorm", 0.0, 2.0 * x.shape[0] * (C1 + C2)):
+        return mean, rstd
     check(load().svdx_groupnorm_stats(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0,
                                       C2, outer, rows, groups, eps, mean.data_ptr(), rstd.data_ptr(), _stream()), "svdx_groupnorm_stats")
     return mean, rstd
@@ -296,6 +334,8 @@ def groupnorm_stats(x, x2, outer, rows, eps, groups=32):
 def groupnorm_apply(x, x2, outer, rows, mean, rstd, gamma, beta, silu, y, groups=32):
     C1 = x.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
+    if _fam("groupnorm", 0.0, 4.0 * x.shape[0] * (C1 + C2)):
+        return y
     check(load().svdx_groupnorm_apply(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0,
                                       C2, outer, rows, groups, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                       int(silu), y.data_ptr(), _rowmajor(y, "y"), _stream()), "groupnorm_apply")
@@ -306,6 +346,8 @@ def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2
     C1 = x.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     ws = torch.empty(outer * groups * 2, device=x.device, dtype=torch.float32)
+    if _fam("groupnorm", 0.0, 6.0 * x.shape[0] * (C1 + C2)):       # minimal traffic: read x, dy once, write dx
+        return
     check(load().svdx_groupnorm_bwd(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0, C2,
                                     dy.data_ptr(), _rowmajor(dy, "dy"), outer, rows, groups, mean.data_ptr(), rstd.data_ptr(),
                                     gamma.data_ptr(), beta.data_ptr(), int(silu), dx.data_ptr(), _rowmajor(dx, "dx"),
@@ -317,6 +359,8 @@ def layernorm_fwd(x, gamma, beta, eps, y, addvec=None, add_div=1, xsum=None):
     rows, Cc = x.shape
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty_like(mean)
+    if _fam("layernorm", 0.0, (6.0 if xsum is not None else 4.0) * rows * Cc):
+        return mean, rstd
     check(load().svdx_layernorm_fwd(x.data_ptr(), _rowmajor(x, "x"), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps,
                                     y.data_ptr(), _rowmajor(y, "y"), mean.data_ptr(), rstd.data_ptr(), _ptr(addvec), add_div,
                                     _ptr(xsum), _rowmajor(xsum, "xsum") if xsum is not None else 0, _stream()), "layernorm_fwd")
@@ -325,6 +369,8 @@ def layernorm_fwd(x, gamma, beta, eps, y, addvec=None, add_div=1, xsum=None):
 
 def layernorm_bwd(x, dy, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=None):
     rows, Cc = x.shape
+    if _fam("layernorm", 0.0, (8.0 if dres is not None else 6.0) * rows * Cc):
+        return
     check(load().svdx_layernorm_bwd(x.data_ptr(), _rowmajor(x, "x"), dy.data_ptr(), _rowmajor(dy, "dy"), rows, Cc, gamma.data_ptr(),
                                     mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), _rowmajor(dx, "dx"), _ptr(dres),
                                     _rowmajor(dres, "dres") if dres is not None else 0, _ptr(dgamma), _ptr(dbeta), _stream()),
@@ -333,12 +379,14 @@ def layernorm_bwd(x, dy, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=No
 
 # ----------------------------------------------------------------------------- elementwise / layout
 def prep_weight(src, dst, mode, O, I, taps=1, i_pad=None):
-    check(load().svdx_prep_weight(src.data_ptr(), int(src.dtype == bf16), dst.data_ptr(), mode, O, I, taps,
+    check(load().svdx_prep_weight(src.data_ptr(), dtype_code(src, "weight"), dst.data_ptr(), mode, O, I, taps,
                                   i_pad if i_pad is not None else I, _stream()), "prep_weight")
     return dst
 
 
 def cast_f32_bf16(src, dst):
+    if _fam("elementwise", 0.0, 6.0 * src.numel()):
+        return dst
     check(load().svdx_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast_f32_bf16")
     return dst
 
@@ -348,13 +396,24 @@ def cast_bf16_f32(src, dst):
     return dst
 
 
+def cast_to_f32(src, dst):
+    """fp32 copy of a bf16 / fp16 vector (biases and norm affine vectors of a half-precision model)"""
+    code = dtype_code(src, "vector")
+    if code == 1:
+        return cast_bf16_f32(src, dst)
+    if code == 2:
+        check(load().svdx_cast_f16_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast_f16_f32")
+        return dst
+    raise TypeError("cast_to_f32: source is already fp32")
+
+
 def nchw_to_nhwc(src, dst, N, Cc, H, W, c_pad):
-    check(load().svdx_nchw_to_nhwc(src.data_ptr(), int(src.dtype == bf16), dst.data_ptr(), N, Cc, H, W, c_pad, _stream()), "nchw_to_nhwc")
+    check(load().svdx_nchw_to_nhwc(src.data_ptr(), dtype_code(src, "NCHW input"), dst.data_ptr(), N, Cc, H, W, c_pad, _stream()), "nchw_to_nhwc")
     return dst
 
 
 def nhwc_to_nchw(src, dst, N, Cc, H, W):
-    check(load().svdx_nhwc_to_nchw(src.data_ptr(), _rowmajor(src, "src"), dst.data_ptr(), int(dst.dtype == bf16), N, Cc, H, W, _stream()),
+    check(load().svdx_nhwc_to_nchw(src.data_ptr(), _rowmajor(src, "src"), dst.data_ptr(), dtype_code(dst, "NCHW output"), N, Cc, H, W, _stream()),
           "nhwc_to_nchw")
     return dst
 
@@ -380,6 +439,8 @@ def planes_to_space(src, dst, N, H, W, Cc):
 
 
 def concat_channels(a, b, dst):
+    if _fam("elementwise", 0.0, 4.0 * dst.numel()):
+        return dst
     check(load().svdx_concat_channels(a.data_ptr(), a.shape[-1], b.data_ptr(), b.shape[-1], dst.data_ptr(), a.numel() // a.shape[-1],
                                       _stream()), "concat_channels")
     return dst
@@ -388,11 +449,15 @@ def concat_channels(a, b, dst):
 def split_channels(src, a, b, accumulate_a=False):
     Ca = a.shape[-1]
     Cb = src.shape[-1] - Ca
+    if _fam("elementwise", 0.0, 4.0 * src.numel()):
+        return
     check(load().svdx_split_channels(src.data_ptr(), a.data_ptr(), Ca, _ptr(b), Cb, src.numel() // src.shape[-1], int(accumulate_a),
                                      _stream()), "split_channels")
 
 
 def axpby(a, b, y, scales=None):
+    if _fam("elementwise", 0.0, 6.0 * a.numel()):
+        return y
     check(load().svdx_axpby_bf16(a.data_ptr(), b.data_ptr(), _ptr(scales), y.data_ptr(), a.numel(), _stream()), "axpby_bf16")
     return y
 
@@ -404,12 +469,16 @@ def silu_f32(x, y):
 
 def colsum(x, out, accumulate=False):
     rows, cols = x.shape
+    if _fam("elementwise", 0.0, 2.0 * rows * cols):
+        return out
     check(load().svdx_colsum(x.data_ptr(), _rowmajor(x, "x"), rows, cols, out.data_ptr(), int(accumulate), _stream()), "colsum")
     return out
 
 
 def geglu_bwd(pre, dout, dpre):
     rows, h2 = pre.shape
+    if _fam("elementwise", 0.0, 10.0 * rows * (h2 // 2)):
+        return dpre
     check(load().svdx_geglu_bwd(pre.data_ptr(), _rowmajor(pre, "pre"), dout.data_ptr(), _rowmajor(dout, "dout"), dpre.data_ptr(),
                                 _rowmajor(dpre, "dpre"), rows, h2 // 2, _stream()), "geglu_bwd")
     return dpre
@@ -421,11 +490,23 @@ def blend_scales(mix_factor, out3):  # out3: float[8]
 
 
 def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, shadow=None):
+    if _fam("adamw", 0.0, (30.0 if shadow is not None else 28.0) * p.numel()):
+        return
     check(load().svdx_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, weight_decay,
                             step, grad_scale, _ptr(shadow), _stream()), "adamw")
 
 
+def adamw_graph(p, g, m, v, state, grad_scale=1.0, shadow=None):
+    """CUDA-graph-safe AdamW: lr / betas / eps / weight decay / step / bias corrections live in the device float[8] `state`"""
+    if _fam("adamw", 0.0, (30.0 if shadow is not None else 28.0) * p.numel()):
+        return
+    check(load().svdx_adamw_graph(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), state.data_ptr(), grad_scale,
+                                  _ptr(shadow), _stream()), "svdx_adamw_graph")
+
+
 def multi_transpose(src_base, jobs, tile_prefix, njobs, total_tiles):
+    if _fam("elementwise", 0.0, 4.0 * 64 * 64 * total_tiles):
+        return
     check(load().svdx_multi_transpose(src_base.data_ptr(), jobs.data_ptr(), tile_prefix.data_ptr(), njobs, total_tiles, _stream()),
           "svdx_multi_transpose")
 

@@ -63,6 +63,21 @@ class ParamArena:
         if self.data.is_cuda:
             self.shadow = torch.empty(off, device=dev, dtype=torch.bfloat16)
             raw.cast_f32_bf16(self.data, self.shadow)
+        self.mark_synced()
+
+    # ---- staleness of the derived bf16 operands -------------------------------------------------------------
+    # FusedAdamW updates masters, shadow and transposes together. Anything ELSE that writes the parameters
+    # (torch.optim.AdamW.step, load_state_dict, an EMA copy_to, p.data.copy_) goes through torch and bumps the
+    # parameters' version counters: the model compares the stamp below at the start of every forward and re-derives
+    # the operands when it moved (UNetSpatioTemporalConditionModel._validate).
+    def _stamp(self) -> int:
+        return sum(p._version for p in self.params)
+
+    def stale(self) -> bool:
+        return self._stamp() != getattr(self, "_synced_stamp", None)
+
+    def mark_synced(self):
+        self._synced_stamp = self._stamp()
 
     def refresh_shadow(self):
         """re-derive the bf16 shadow from the fp32 masters (after an out-of-band update such as load_state_dict)"""
@@ -125,28 +140,62 @@ class ParamArena:
 
 
 class FusedAdamW:
-    """torch.optim.AdamW semantics (train_svd.py:767-773) as ONE elementwise kernel over the arena."""
+    """torch.optim.AdamW semantics (train_svd.py:767-773) as ONE elementwise kernel over the arena (+ a 1-thread kernel
+    that advances the step count). Every quantity that changes from step to step — learning rate, step, bias
+    corrections — lives in the device buffer `state` (float[8]: lr, beta1, beta2, eps, weight_decay, step, 1-b1^t,
+    1-b2^t), so a CUDA graph that captured `step()` replays the CORRECT sequence of updates; an lr scheduler writes
+    `opt.lr = value` (a 4-byte H2D copy outside the graph) between replays."""
 
     def __init__(self, arena: ParamArena, lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8):
         self.arena = arena
-        self.lr, self.betas, self.weight_decay, self.eps = lr, betas, weight_decay, eps
+        self.betas, self.weight_decay, self.eps = betas, weight_decay, eps
         self.m = torch.zeros_like(arena.data)
         self.v = torch.zeros_like(arena.data)
-        self.t = 0
+        self._lr = float(lr)
+        self.state = torch.tensor([float(lr), betas[0], betas[1], eps, weight_decay, 0.0, 1.0, 1.0], device=arena.data.device, dtype=F32)
+        self._lr_host = torch.empty(1, dtype=F32).pin_memory() if arena.data.is_cuda else torch.empty(1, dtype=F32)
         # called after every update; wire it to `unet.refresh_trainable_operands` so the bf16 operand copies of
         # the trainable weights are re-prepared (the flat in-place update does not bump tensor version counters)
         self.on_updated = None
+        # torch.optim-style view for lr schedulers: `for g in opt.param_groups: g["lr"] = ...` then `opt.sync_lr()`
+        self.param_groups = [{"lr": float(lr), "params": arena.params}]
+
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float):
+        self._lr = float(value)
+        self.param_groups[0]["lr"] = self._lr
+        self._lr_host[0] = self._lr
+        self.state[0:1].copy_(self._lr_host, non_blocking=True)
+
+    def sync_lr(self):
+        """push param_groups[0]['lr'] (written by a torch lr scheduler) to the device state"""
+        if self.param_groups[0]["lr"] != self._lr:
+            self.lr = self.param_groups[0]["lr"]
+
+    @property
+    def t(self) -> int:
+        """number of updates applied so far (reads the device counter: synchronises)"""
+        return int(self.state[5].item())
 
     def step(self, grad_scale: float = 1.0):
-        self.t += 1
         a = self.arena
-        raw.adamw(a.data, a.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                  self.t, grad_scale, shadow=a.shadow)
+        raw.adamw_graph(a.data, a.grad, self.m, self.v, self.state, grad_scale, shadow=a.shadow)
         if self.on_updated is not None:
             self.on_updated()
 
     def zero_grad(self, set_to_none: bool = False):
         self.arena.zero_grad()
+
+    def snapshot_tensors(self) -> List[torch.Tensor]:
+        """everything a warm-up step mutates (for GraphedStep(restore=...))"""
+        ts = [self.arena.data, self.m, self.v, self.state]
+        if self.arena.shadow is not None:
+            ts.append(self.arena.shadow)
+        return ts
 
 
 class GradReducer:
@@ -228,9 +277,16 @@ class GraphedStep:
     AccumulateGrad nodes remember the stream they were created on, hence the warm-up runs on the capture side stream
     and no reference to a warm-up autograd graph is kept."""
 
-    def __init__(self, fn, static_inputs: Dict[str, torch.Tensor], warmup: int = 3):
+    def __init__(self, fn, static_inputs: Dict[str, torch.Tensor], warmup: int = 3, restore: Optional[List[torch.Tensor]] = None,
+                 on_restored=None):
+        """restore: tensors whose contents the warm-up / capture runs must not change (pass
+        `opt.snapshot_tensors()`): they are cloned first and copied back after the capture, so that training starts from
+        the caller's weights, optimizer moments and step count, not from `warmup + 2` stray updates on the static batch.
+        on_restored: called after the copy-back (e.g. `lambda: unet.refresh_trainable_operands(shadow_current=True)` to
+        re-derive the transposed weight operands from the restored bf16 shadow)."""
         self.fn = fn
         self.static = static_inputs
+        saved = [t.clone() for t in restore] if restore else []
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -241,7 +297,13 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = fn(self.static)
-        self.graph.replay()
+        if restore:
+            for t, c in zip(restore, saved):
+                t.copy_(c)
+            if on_restored is not None:
+                on_restored()
+        else:
+            self.graph.replay()
         torch.cuda.synchronize()
 
     def replay(self):

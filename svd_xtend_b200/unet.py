@@ -44,6 +44,26 @@ class SvdxAttnProcessor:
         return "SvdxAttnProcessor(sm_100a)"
 
 
+# Processors whose arithmetic IS plain scaled-dot-product attention (softmax(q k^T / sqrt(d)) v followed by to_out): the
+# diffusers classes the reference can install — `AttnProcessor()` by set_default_attn_processor
+# (src/unet_spatio_temporal_condition.py:310-321), `AttnProcessor2_0` (the constructor default [D]) and
+# `XFormersAttnProcessor` (enable_xformers_memory_efficient_attention, train_svd.py:681-693). Setting one of them keeps the
+# object (the dict API round-trips) and the sm_100a kernel computes the same function. Any OTHER processor would change
+# the arithmetic (the reference calls it, :276-308); it cannot run on this path, so it is rejected instead of being
+# silently ignored.
+_SDPA_EQUIVALENT_PROCESSORS = ("SvdxAttnProcessor", "AttnProcessor", "AttnProcessor2_0", "XFormersAttnProcessor")
+
+
+def _check_processor(processor):
+    name = type(processor).__name__
+    if name not in _SDPA_EQUIVALENT_PROCESSORS:
+        raise ValueError(
+            f"svd_xtend_b200: attention processor {name!r} is not supported — the B200 path computes plain scaled-dot-product "
+            f"attention in one fused kernel and cannot call a custom processor; accepted (arithmetically identical): "
+            f"{', '.join(_SDPA_EQUIVALENT_PROCESSORS)}")
+    return processor
+
+
 class Attention(nn.Module):
     def __init__(self, query_dim: int, cross_attention_dim: Optional[int] = None, heads: int = 8, dim_head: int = 64):
         super().__init__()
@@ -63,7 +83,7 @@ class Attention(nn.Module):
         return self.processor
 
     def set_processor(self, processor):
-        self.processor = processor
+        self.processor = _check_processor(processor)
 
 
 class GEGLU(nn.Module):
@@ -461,6 +481,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
             if not shadow_current:          # the updater did not maintain the bf16 shadow (e.g. torch.optim.AdamW)
                 self._arena.refresh_shadow()
             self._arena.refresh_transposes()
+            self._arena.mark_synced()
         self._engine.wc.refresh_trainable()
 
     @property
@@ -621,8 +642,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         """Same contract as src/unet_spatio_temporal_condition.py:357-490."""
         if not sample.is_cuda:
             raise RuntimeError("svd_xtend_b200: the UNet hot path only runs on a CUDA (sm_100a) device; there is no CPU fallback")
-        if any(p.device != sample.device for p in self.parameters()):
-            raise RuntimeError("svd_xtend_b200: all parameters must live on the device of `sample`")
+        self._validate(sample)
         timesteps = timestep
         if not torch.is_tensor(timesteps):
             dtype = torch.float64 if isinstance(timestep, float) else torch.int64
@@ -638,6 +658,21 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         if not return_dict:
             return (out,)
         return UNetSpatioTemporalConditionOutput(sample=out)
+
+    def _validate(self, sample: torch.Tensor):
+        """boundary checks, cached on (parameter count, dtype/device signature): every parameter on the sample's device
+        and of a dtype the weight-preparation kernels can read (fp32 / bf16 / fp16; anything else would be misread)."""
+        sig = (sample.device, tuple((p.dtype, p.device) for p in self.parameters()))
+        if getattr(self, "_validated_sig", None) != sig:
+            for n, p in self.named_parameters():
+                if p.device != sample.device:
+                    raise RuntimeError("svd_xtend_b200: all parameters must live on the device of `sample`")
+                raw.dtype_code(p, f"parameter {n}")
+            self._validated_sig = sig
+        if self._arena is not None and self._arena.stale():
+            # an optimizer other than FusedAdamW, load_state_dict or an EMA copy-back touched the fp32 masters:
+            # the bf16 shadow / transposed operands are re-derived before they are used
+            self.refresh_trainable_operands(shadow_current=False)
 
     # the tape-driven network -------------------------------------------------
     def _run(self, sample, timesteps, encoder_hidden_states, added_time_ids) -> Tuple[torch.Tensor, Var, Geom]:
@@ -671,7 +706,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
             for p in projs:
                 temb_slices[p] = Var(temb_all[:, o0:o0 + p.out_features])
                 o0 += p.out_features
-        self._temb = temb_slices
+        temb = temb_slices     # per forward (closures of checkpointed blocks keep THIS forward's projections)
 
         # image embedding per clip (encoder_hidden_states is [B,1,1024]; :425 repeats it per frame)
         enc = Var(encoder_hidden_states.reshape(B, -1).to(bf16).contiguous())
@@ -680,14 +715,14 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         x_nchw = sample.reshape(N, Cin, H, W).contiguous()
         cpad = 64
         x0 = torch.empty(N * H * W, cpad, device=dev, dtype=bf16)
-        raw.nchw_to_nhwc(x_nchw if x_nchw.dtype in (F32, bf16) else x_nchw.float(), x0, N, Cin, H, W, cpad)
+        raw.nchw_to_nhwc(x_nchw if x_nchw.dtype in (F32, bf16, torch.float16) else x_nchw.float(), x0, N, Cin, H, W, cpad)
         x = E.conv2d_3x3(Var(x0), g, self.conv_in, i_pad=cpad)
 
         # ---- 3. down (:432-448)
         skips = [(x, g)]
         for blk in self.down_blocks:
             for j, res in enumerate(blk.resnets):
-                x = self._res(E, blk, res, x, g)
+                x = self._res(E, blk, res, x, g, temb)
                 if blk.has_cross_attention:
                     x = self._transformer(E, blk.attentions[j], x, g, enc)
                 skips.append((x, g))
@@ -698,17 +733,17 @@ class UNetSpatioTemporalConditionModel(nn.Module):
                 skips.append((x, g))
 
         # ---- 4. mid (:451-456)
-        x = self._resblock(E, self.mid_block.resnets[0], x, g)     # [D]: the first mid resnet is never checkpointed
+        x = self._resblock(E, self.mid_block.resnets[0], x, g, temb)     # [D]: the first mid resnet is never checkpointed
         for attn, res in zip(self.mid_block.attentions, self.mid_block.resnets[1:]):
             x = self._transformer(E, attn, x, g, enc)
-            x = self._res(E, self.mid_block, res, x, g)
+            x = self._res(E, self.mid_block, res, x, g, temb)
 
         # ---- 5. up (:459-477)
         for blk in self.up_blocks:
             for j, res in enumerate(blk.resnets):
                 skip, _ = skips.pop()
                 x = E.concat(x, skip)
-                x = self._res(E, blk, res, x, g)
+                x = self._res(E, blk, res, x, g, temb)
                 if blk.has_cross_attention:
                     x = self._transformer(E, blk.attentions[j], x, g, enc)
             if blk.upsamplers is not None:
@@ -720,7 +755,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         h = E.groupnorm(x, self.conv_norm_out, outer=N, rows=g.HW, silu=True)
         y = E.conv2d_3x3(h, g, self.conv_out, n_pad=8)
         Cout = cfg.out_channels
-        out = torch.empty(B, T, Cout, H, W, device=dev, dtype=sample.dtype if sample.dtype in (F32, bf16) else F32)
+        out = torch.empty(B, T, Cout, H, W, device=dev, dtype=sample.dtype if sample.dtype in (F32, bf16, torch.float16) else F32)
         raw.nhwc_to_nchw(y.data, out, N, Cout, H, W)
         return out, y, g
 
@@ -736,24 +771,24 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         mix = mixer.mix_factor
         return E.wc.get(("blend", id(mix)), [mix], (16,), lambda buf: raw.blend_scales(E.vec_f32(mix), buf), dtype=F32)
 
-    def _res(self, E: Engine, owner: nn.Module, res: SpatioTemporalResBlock, x: Var, g: Geom) -> Var:
+    def _res(self, E: Engine, owner: nn.Module, res: SpatioTemporalResBlock, x: Var, g: Geom, temb) -> Var:
         """a resnet of a down/mid/up block, gradient-checkpointed when the owner's flag is set ([D] unet_3d_blocks.py)."""
         if self.training and getattr(owner, "gradient_checkpointing", False):
-            return E.checkpoint(lambda v: self._resblock(E, res, v, g), x)
-        return self._resblock(E, res, x, g)
+            return E.checkpoint(lambda v: self._resblock(E, res, v, g, temb), x)
+        return self._resblock(E, res, x, g, temb)
 
-    def _resblock(self, E: Engine, blk: SpatioTemporalResBlock, x: Var, g: Geom) -> Var:
+    def _resblock(self, E: Engine, blk: SpatioTemporalResBlock, x: Var, g: Geom, temb) -> Var:
         """SpatioTemporalResBlock [D: resnet.py]: spatial ResnetBlock2D -> TemporalResnetBlock -> AlphaBlender."""
         sp, tp = blk.spatial_res_block, blk.temporal_res_block
         N = g.B * g.T
         per_clip = g.T * g.HW
         h = E.groupnorm(x, sp.norm1, outer=N, rows=g.HW, silu=True)
-        h = E.conv2d_3x3(h, g, sp.conv1, rowbias=self._temb[sp.time_emb_proj], rowbias_div=per_clip)
+        h = E.conv2d_3x3(h, g, sp.conv1, rowbias=temb[sp.time_emb_proj], rowbias_div=per_clip)
         h = E.groupnorm(h, sp.norm2, outer=N, rows=g.HW, silu=True)
         xs = x if sp.conv_shortcut is None else E.linear(x, sp.conv_shortcut.weight, sp.conv_shortcut.bias)
         hs = E.conv2d_3x3(h, g, sp.conv2, res1=xs)
         t = E.groupnorm(hs, tp.norm1, outer=g.B, rows=per_clip, silu=True)
-        t = E.conv_temporal(t, g, tp.conv1, rowbias=self._temb[tp.time_emb_proj], rowbias_div=per_clip)
+        t = E.conv_temporal(t, g, tp.conv1, rowbias=temb[tp.time_emb_proj], rowbias_div=per_clip)
         t = E.groupnorm(t, tp.norm2, outer=g.B, rows=per_clip, silu=True)
         s8 = self._blend(E, blk.time_mixer)
         # alpha*hs + (1-alpha)*(hs + conv) = hs + (1-alpha)*conv
@@ -844,8 +879,7 @@ class _UNetFn(torch.autograd.Function):
         out, y, g = model._run(sample, timesteps, enc, added_time_ids)
         ctx.model, ctx.y, ctx.g, ctx.params = model, y, g, params
         ctx.n_out = model.config.out_channels
-        if not record:
-            E.begin(recording=False)
+        ctx.tape = E.detach_tape()      # this forward's tape lives on ITS autograd node (no cross-forward clobbering)
         return out
 
     @staticmethod
@@ -858,9 +892,16 @@ class _UNetFn(torch.autograd.Function):
             d = d.float()
         dy = torch.empty(N * g.H * g.W, y.data.shape[1], device=d.device, dtype=bf16)
         raw.nchw_to_nhwc(d, dy, N, ctx.n_out, g.H, g.W, y.data.shape[1])
-        E.add_grad(y, dy)
-        E.run_backward()
         views = E.grad_views
+        if views and all(p.grad is None for p in params if p in views):
+            # optimizer.zero_grad(set_to_none=True) (train_svd.py:1049) dropped the .grad views: the flat gradient arena the
+            # kernels accumulate into must start this backward at zero, or gradients would pile up across steps
+            model._arena.zero_grad()
+        E.add_grad(y, dy)
+        tape, ctx.tape = ctx.tape, None
+        if tape is None:
+            raise RuntimeError("svd_xtend_b200: backward called twice on the same forward (retain_graph is not supported)")
+        E.run_backward(tape)
         for p in params:
             if p in views:
                 p.grad = views[p]        # the kernels accumulated straight into the arena

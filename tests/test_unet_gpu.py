@@ -110,6 +110,36 @@ def test_tiny_inference_no_grad_and_api():
         ours.set_attn_processor({})
 
 
+def test_tiny_two_clips_match_reference_file_golden():
+    """B = 2 against tests/golden/ref_wiring_tiny.pt — the fp64 output of the REFERENCE'S OWN
+    src/unet_spatio_temporal_condition.py (run over the oracle's blocks, tests/golden/make_ref_wiring_golden.py): per-clip
+    time embeddings, per-clip image embedding (`time_context`), frame-index embedding tiled over the batch."""
+    import importlib.util
+    import os
+    from oracle.svd_unet_oracle import TINY_CONFIG, UNetSpatioTemporalConditionModel as Oracle
+    from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel as Ours
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_ref_wiring_golden", os.path.join(root, "tests", "golden", "make_ref_wiring_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = torch.load(os.path.join(root, "tests", "golden", "ref_wiring_tiny.pt"), weights_only=False)
+    ora = gen.build(Oracle)
+    chk = float(sum(p.detach().double().abs().sum() for p in ora.parameters()))
+    assert abs(chk - gold["tiny_param_checksum"]) < 1e-9 * gold["tiny_param_checksum"]
+    ours = Ours(**TINY_CONFIG)
+    ours.load_state_dict({k: v.float() for k, v in ora.state_dict().items()})
+    ours.to(DEV).eval()
+    b = {k: v.to(DEV, torch.float32) for k, v in gen.batch().items()}
+    with torch.no_grad():
+        out = ours(b["sample"], b["timestep"], b["encoder_hidden_states"], b["added_time_ids"]).sample
+    torch.cuda.synchronize()
+    e = _rel(out.cpu(), gold["tiny_out"])
+    print("two clips vs reference-file golden: rel-l2", e)
+    assert e < 2e-2, e      # bf16 compute vs the fp64 reference run
+    # the clips must not be mixed up: swapping them must change the error by orders of magnitude
+    assert _rel(out.cpu().flip(0), gold["tiny_out"]) > 10 * e
+
+
 def test_svd_config_forward_matches_oracle():
     """config 1 of BASELINE.json on the GPU: 1x14x8x40x64, full 1.52 B-parameter topology."""
     from oracle.svd_unet_oracle import SVD_CONFIG, synthetic_batch
@@ -167,14 +197,15 @@ def test_tiny_full_finetune_all_gradients():
     assert not bad, bad[:10]
 
 
-def test_tiny_lora_matches_merged_weight_oracle():
+@pytest.mark.parametrize("r", [4, 16])
+def test_tiny_lora_matches_merged_weight_oracle(r):
     """config 5 (train_svd_lora.py:659-671): y = W x + (alpha/r) B A x on to_q/to_k/to_v/to_out.0.
-    Reference = the oracle with merged weights W' = W + s*B@A; dA = s*B^T dW', dB = s*dW' A^T."""
+    Reference = the oracle with merged weights W' = W + s*B@A; dA = s*B^T dW', dB = s*dW' A^T.
+    r = 4 is the reference's default rank (train_svd_lora.py:551-553): not a multiple of 8, the operands are padded."""
     from types import SimpleNamespace
     from oracle.svd_unet_oracle import TINY_CONFIG, synthetic_batch
     torch.backends.cuda.matmul.allow_tf32 = False
     oracle, ours = _build(TINY_CONFIG, seed=21)
-    r = 16
     n = ours.add_adapter(SimpleNamespace(r=r, lora_alpha=r, init_lora_weights="gaussian",
                                          target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
     assert n == 64
@@ -221,32 +252,99 @@ def test_tiny_lora_matches_merged_weight_oracle():
     assert not bad, bad[:8]
 
 
-def test_tiny_gradient_checkpointing_equivalence():
-    """--gradient_checkpointing (train_svd.py:731-732): same loss and gradients with the flag on and off."""
+def test_tiny_gradient_checkpointing_matches_oracle():
+    """--gradient_checkpointing (train_svd.py:731-732): with the flag on, loss and every trainable gradient still match the
+    fp32 ORACLE (which runs torch.utils.checkpoint in the same places, oracle `_maybe_ckpt`), and the checkpointed run
+    agrees with our own un-checkpointed run."""
     from oracle.svd_unet_oracle import TINY_CONFIG, synthetic_batch
-    _, ours = _build(TINY_CONFIG, seed=8)
-    _train_filter(ours)
-    ours.train()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, ours = _build(TINY_CONFIG, seed=8)
+    for m in (oracle, ours):
+        _train_filter(m)
+        m.train()
     batch = synthetic_batch(1, 4, 16, 16, seed=77, device=DEV, cross_dim=TINY_CONFIG["cross_attention_dim"])
 
-    def run():
-        ours.zero_grad(set_to_none=True)
-        pred, loss = _loss(ours, batch)
+    def run(model, autocast=False):
+        model.zero_grad(set_to_none=True)
+        pred, loss = _loss(model, batch, autocast)
         loss.backward()
         torch.cuda.synchronize()
-        return pred.detach().clone(), {n: p.grad.clone() for n, p in ours.named_parameters() if p.requires_grad}
+        return pred.detach().clone(), loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
 
-    p0, g0 = run()
+    oracle.enable_gradient_checkpointing()
+    p_ref, l_ref, g_ref = run(oracle)
+    _, _, g_ac = run(oracle, autocast=True)
+    p0, l0, g0 = run(ours)
     ours.enable_gradient_checkpointing()
     assert ours.is_gradient_checkpointing
-    p1, g1 = run()
-    # fp32 atomics (GroupNorm statistics, split-K) make runs differ at bf16-rounding level; same tolerance as parity
+    launches0 = ours.kernel_launches
+    p1, l1, g1 = run(ours)
+    assert ours.kernel_launches - launches0 > 0
+    assert _rel(p1, p_ref) < 2e-2 and abs(l1 - l_ref) < 3e-2 * max(1.0, abs(l_ref))
+    for n in g_ref:
+        if g_ref[n].abs().max() == 0:
+            assert g1[n].abs().max() == 0, n
+            continue
+        e, ea = _rel(g1[n], g_ref[n]), _rel(g_ac[n], g_ref[n])
+        assert e <= max(3 * ea, 5e-2), f"ckpt grad {n}: rel-l2 {e:.4g} vs autocast {ea:.4g}"
+        # fp32 atomics (GroupNorm statistics, split-K) make runs differ at bf16-rounding level
+        assert _rel(g1[n], g0[n]) < 8e-2, (n, _rel(g1[n], g0[n]))
     assert _rel(p1, p0) < 3e-2
-    for n in g0:
-        if g0[n].abs().max() == 0:
-            assert g1[n].abs().max() == 0
-        else:
-            assert _rel(g1[n], g0[n]) < 8e-2, (n, _rel(g1[n], g0[n]))
+
+
+def test_svd_config_train_step_matches_oracle():
+    """config 2 of BASELINE.json END TO END: full 1.52 B-parameter topology, 1x14x8x40x64, the as-scripted trainable
+    set (train_svd.py:761-766): EDM loss and EVERY trainable gradient against the fp32 oracle on the same GPU
+    (CTA-pair dgrad at M = 35 840, split-K weight gradients with K = 35 840, S = 2560 x 5-head attention backward inside the
+    tape). Tolerance: rel-L2 <= max(3 x err(oracle under torch bf16 autocast), 5e-2)."""
+    from oracle.svd_unet_oracle import SVD_CONFIG, synthetic_batch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, ours = _build(SVD_CONFIG, seed=11)
+    for m in (oracle, ours):
+        _train_filter(m)
+        m.train()
+    batch = synthetic_batch(1, 14, 40, 64, seed=1234, device=DEV)
+    pred_ref, loss_ref = _loss(oracle, batch)
+    loss_ref.backward()
+    g_ref = {n: p.grad for n, p in oracle.named_parameters() if p.requires_grad}
+    for p in oracle.parameters():
+        p.grad = None
+    pred_ac, loss_ac = _loss(oracle, batch, autocast=True)
+    loss_ac.backward()
+    g_ac = {n: p.grad for n, p in oracle.named_parameters() if p.requires_grad}
+    for p in oracle.parameters():
+        p.grad = None
+    e_ac = _rel(pred_ac, pred_ref)
+    del pred_ac, loss_ac
+    torch.cuda.empty_cache()
+
+    pred, loss = _loss(ours, batch)
+    loss.backward()
+    torch.cuda.synchronize()
+    e_out = _rel(pred, pred_ref)
+    assert torch.isfinite(pred).all()
+    assert e_out <= max(2 * e_ac, 2e-2), f"output rel-l2 {e_out:.4g} vs autocast {e_ac:.4g}"
+    assert abs(loss.item() - loss_ref.item()) <= 3e-2 * max(1.0, abs(loss_ref.item())), (loss.item(), loss_ref.item())
+    rows, n_zero = [], 0
+    for n, p in ours.named_parameters():
+        if not p.requires_grad:
+            continue
+        assert p.grad is not None, n
+        ref = g_ref[n]
+        if ref.abs().max() == 0:   # attn2.to_q / to_k / norm2 of the 1-token cross attention: exactly zero in the reference
+            assert p.grad.abs().max() == 0, n
+            n_zero += 1
+            continue
+        e, ea = _rel(p.grad, ref), _rel(g_ac[n], ref)
+        rows.append((e / max(ea, 1e-3), e, ea, n))
+    assert len(rows) + n_zero == len(g_ref) and len(rows) > 300
+    rows.sort(reverse=True)
+    print(f"svd train step: loss {loss.item():.5f} (oracle {loss_ref.item():.5f}) output rel-l2 {e_out:.4g} (autocast {e_ac:.4g}); "
+          f"{len(rows)} gradients, median rel-l2 {sorted(r[1] for r in rows)[len(rows) // 2]:.4g}, worst vs autocast {rows[:3]}")
+    bad = [(n, round(e, 4), round(ea, 4)) for _, e, ea, n in rows if e > max(3 * ea, 5e-2)]
+    assert not bad, bad[:10]
 
 
 def test_arena_fused_adamw_steps():
