@@ -256,6 +256,7 @@ def gpu_eager_baseline(dev, cfg, steps=3, warmup=2):
     torch.manual_seed(1234)
     with torch.device(dev):
         m = Oracle(**SVD_CONFIG)
+    m.to(dev)      # AlphaBlender.mix_factor is built with the legacy torch.Tensor([..]) constructor, which ignores the device context
     m.requires_grad_(False)
     for n, p in m.named_parameters():
         if "temporal_transformer_block" in n:
@@ -396,8 +397,13 @@ def main():
         lps = raw.LAUNCHES[0] - l_before      # kernels of OUR library launched by one step
     barrier()
     if args.profile_one:
+        if os.environ.get("SVDX_SHAPE_LOG"):
+            raw.SHAPE_LOG = []
         step(devb)
         torch.cuda.synchronize()
+        if raw.SHAPE_LOG is not None:     # the tapgemm launches of the LAST step, in launch order (scripts/join_shapes.py)
+            with open(os.environ["SVDX_SHAPE_LOG"], "w") as fh:
+                json.dump(raw.SHAPE_LOG, fh)
         return
 
     # ---- CUDA-graph capture of the whole step through the public helper (svd_xtend_b200.train.GraphedStep)

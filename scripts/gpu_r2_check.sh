@@ -13,6 +13,6 @@ timeout 1500 python bench.py > gpurun_out/bench_$R.json 2>> $L
 cat gpurun_out/bench_$R.json >> $L
 if [ "$2" != "nolist" ]; then
 echo "=== ncu launch list" >> $L
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 16000 --csv --log-file gpurun_out/launches_$R.csv python bench.py --profile-one --warmup 1 --no-graph >> $L 2>&1
+SVDX_SHAPE_LOG=gpurun_out/shapes_$R.json timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 16000 --csv --log-file gpurun_out/launches_$R.csv python bench.py --profile-one --warmup 1 --no-graph >> $L 2>&1
 fi
 tail -c 6000 $L

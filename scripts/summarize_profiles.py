@@ -29,7 +29,7 @@ def launch_list():
     with open(src) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
-    idx = [i for i, r in enumerate(rows) if "adamw" in r["Kernel Name"]]
+    idx = [i for i, r in enumerate(rows) if "adamw_state_kernel" in r["Kernel Name"] or "adamw_kernel" in r["Kernel Name"]]
     seg = rows[idx[-2] + 1: idx[-1] + 1] if len(idx) >= 2 else rows
     tot, cnt = collections.defaultdict(float), collections.Counter()
     for r in seg:

@@ -472,7 +472,14 @@ class Engine:
                         block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
             self.pgrad(p).add_(tmp[:p.shape[0], :p.shape[1]])
             return
-        if len(ws) == 1:
+        fused_g = None
+        if len(ws) > 1 and self.arena is not None and all(p.requires_grad for p in ws):
+            fused_g = self.arena.grad_matrix(list(ws))     # q|k|v are adjacent in the arena: ONE [3C, C] weight-gradient GEMM
+        if fused_g is not None:
+            for p in ws:
+                self.pgrads.setdefault(p, self.grad_views[p])
+            targets = [(None, 0, N)]
+        elif len(ws) == 1:
             targets = [(ws[0], 0, N)]
         else:
             targets, o0 = [], 0
@@ -480,9 +487,9 @@ class Engine:
                 targets.append((p, o0, p.shape[0]))
                 o0 += p.shape[0]
         for p, o0, O in targets:
-            if not p.requires_grad:
+            if p is not None and not p.requires_grad:
                 continue
-            g = self.pgrad(p).view(O, -1)
+            g = fused_g if p is None else self.pgrad(p).view(O, -1)
             dyp = dy[:, o0:o0 + O]
             bn = raw.choose_block_n(O, K, mn_major=True)
             tiles = ((O + 127) // 128) * ((K + bn - 1) // bn)

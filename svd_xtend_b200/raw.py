@@ -40,6 +40,7 @@ def check(rc: int, what: str = "") -> None:
 # outputs stay uninitialised: only for timing a captured step with that family removed, never for results).
 ABLATE: set = set()
 ACCOUNT = None
+SHAPE_LOG = None     # list: one record per svdx_tapgemm launch, in launch order (joined with the ncu launch list by scripts/)
 
 
 def _fam(family: str, flops: float = 0.0, nbytes: float = 0.0) -> bool:
@@ -175,6 +176,11 @@ def tapgemm(
     family = "conv" if (mode == A_CONV2D or len(taps) > 1 or b_mode != 0) else "linear"
     if _fam(family, 2.0 * M * N * K * len(taps)):
         return out
+    if SHAPE_LOG is not None:
+        SHAPE_LOG.append(dict(M=M, N=N, K=K, taps=len(taps), conv2d=int(mode == A_CONV2D), geglu=int(geglu), a_mn=int(a_mn), b_mode=b_mode,
+                              split_k=split_k, block_n=block_n, f32out=int(out.dtype != bf16), bias=int(bias is not None),
+                              rowbias=int(rowbias is not None), res=int(res1 is not None) + int(res2 is not None),
+                              scales=int(scales is not None), pre=int(pre is not None)))
     d = SvdxTapGemm()
     assert a.dtype == bf16 and b.dtype == bf16
     d.a = a.data_ptr()

@@ -97,6 +97,19 @@ class ParamArena:
             o += p.numel()
         return self.shadow[o0:o].view(-1, I)
 
+    def grad_matrix(self, params: List[torch.nn.Parameter]) -> Optional[torch.Tensor]:
+        """fp32 [sum O_i, I] view of the gradient arena over adjacent 2-D parameters, None if they are not contiguous"""
+        if any(p not in self.offset_of for p in params):
+            return None
+        I = params[0][0].numel()
+        o0 = self.offset_of[params[0]]
+        o = o0
+        for p in params:
+            if self.offset_of[p] != o or p[0].numel() != I:
+                return None
+            o += p.numel()
+        return self.grad[o0:o].view(-1, I)
+
     def transposed_matrix(self, params: List[torch.nn.Parameter]) -> Optional[torch.Tensor]:
         """bf16 [I, sum O_i] transposed operand, refreshed for ALL registered matrices by one svdx_multi_transpose launch"""
         src = self.shadow_matrix(params)

@@ -82,3 +82,40 @@ def test_tile_selection_and_geometry():
     assert pick_block_n(4) == 32
     g = Geom(2, 14, 40, 64)
     assert g.M == 2 * 14 * 2560 and g.down().HW == 640 and g.down().up().W == 64
+
+
+def test_shim_installs_the_replacement_under_both_reference_import_paths(monkeypatch):
+    """svd_xtend_b200.shim.install(): `from diffusers import UNetSpatioTemporalConditionModel` (train_svd.py:49) and
+    `from src.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel` (train_svd_lora.py:60) must both
+    resolve to the B200 class. diffusers is absent here, so a stand-in package plays its role."""
+    import importlib
+    import sys
+    import types
+    from svd_xtend_b200 import shim
+    from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel as Ours
+    fake = types.ModuleType("diffusers")
+    fake.__path__ = []
+    fake.UNetSpatioTemporalConditionModel = object
+    sub = types.ModuleType("diffusers.models")
+    sub.__path__ = []
+    sub.UNetSpatioTemporalConditionModel = object
+    monkeypatch.setitem(sys.modules, "diffusers", fake)
+    monkeypatch.setitem(sys.modules, "diffusers.models", sub)
+    monkeypatch.delitem(sys.modules, "src", raising=False)
+    monkeypatch.delitem(sys.modules, "src.unet_spatio_temporal_condition", raising=False)
+    shim.install()
+    assert importlib.import_module("diffusers").UNetSpatioTemporalConditionModel is Ours
+    assert importlib.import_module("diffusers.models").UNetSpatioTemporalConditionModel is Ours
+    from src.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel as viaSrc   # noqa: the shim's module
+    assert viaSrc is Ours
+    monkeypatch.delitem(sys.modules, "src", raising=False)
+    monkeypatch.delitem(sys.modules, "src.unet_spatio_temporal_condition", raising=False)
+
+
+def test_shim_fails_loudly_without_diffusers(monkeypatch):
+    import sys
+    import pytest
+    from svd_xtend_b200 import shim
+    monkeypatch.setitem(sys.modules, "diffusers", None)      # import diffusers -> ModuleNotFoundError
+    with pytest.raises(RuntimeError, match="diffusers"):
+        shim.install()
