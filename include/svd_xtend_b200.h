@@ -103,6 +103,16 @@ typedef struct SvdxTapGemm {
   const float* scales;  /* device float[3] {acc, res1, res2} or NULL (= 1,1,1) */
   void* pre;            /* geglu: bf16 [M][ldpre] pre-activation (value | gate) saved for backward, or NULL */
   int64_t ldpre;
+  /* GroupNorm statistics of the OUTPUT, fused into the epilogue ("GroupNorm fused into the conv epilogue"): when gn_sum is
+   * not NULL the epilogue also accumulates, per statistics slab s = m / gn_rows and output channel n, the sum and the sum
+   * of squares of the bf16 values it stores:  gn_sum[(2*s + 0) * gn_ld + n] += out[m][n],  gn_sum[(2*s + 1) * gn_ld + n] +=
+   * out[m][n]^2  (fp32 red.add; column sums of each staged 32x32 chunk, warp-reduced). gn_rows = rows per slab (H*W per
+   * frame for the spatial GroupNorms, T*H*W per clip for the temporal ones); the buffer must be zero on entry. The consumer
+   * (svdx_groupnorm_apply_fused) folds channels into groups, so a later channel concatenation needs no extra pass.
+   * Requires a bf16 output written through the TMA-store epilogues (N % 32 == 0, 16-byte aligned rows), no split-K, no GEGLU. */
+  float* gn_sum;
+  int64_t gn_ld;        /* floats per (slab, moment) row, >= N */
+  int32_t gn_rows;
 } SvdxTapGemm;
 
 int svdx_tapgemm(const SvdxTapGemm* desc, void* stream);
@@ -137,13 +147,23 @@ int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, const void* x2,
                          int32_t outer, int32_t rows, int32_t num_groups,
                          const float* mean, const float* rstd, const float* gamma, const float* beta,
                          int32_t fuse_silu, void* y, int64_t ldy, void* stream);
-/* backward: dx (and optional dgamma/dbeta accumulation, fp32 atomic) */
+/* GroupNorm(+SiLU) apply from per-CHANNEL sums produced by the svdx_tapgemm epilogues (gn_sum above): csum1 / csum2 are the
+ * [outer][2][ld] fp32 sum / sum-of-squares arrays of the two channel-concatenated sources (csum2 NULL when C2 == 0). Every
+ * CTA first folds the channels of its slab into the 32 group statistics (shared memory), the CTA with blockIdx.x == 0 of
+ * each slab also writes mean / rstd [outer][groups] for the backward. Replaces stats + finalize + apply by ONE launch. */
+int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                               int32_t outer, int32_t rows, int32_t num_groups, float eps,
+                               const float* csum1, int64_t ldc1, const float* csum2, int64_t ldc2,
+                               float* mean, float* rstd, const float* gamma, const float* beta,
+                               int32_t fuse_silu, void* y, int64_t ldy, void* stream);
+/* backward: dx (and optional dgamma/dbeta accumulation, fp32 atomic). workspace: float[2 * outer * groups]; it must be
+ * ZERO on entry when workspace_is_zero != 0 (a slice of a pre-zeroed arena: no memset node), else it is cleared here. */
 int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
                        const void* dy, int64_t lddy,
                        int32_t outer, int32_t rows, int32_t num_groups,
                        const float* mean, const float* rstd, const float* gamma, const float* beta,
                        int32_t fuse_silu, void* dx, int64_t lddx, void* dx2, int64_t lddx2,
-                       float* dgamma, float* dbeta, float* workspace, void* stream);
+                       float* dgamma, float* dbeta, float* workspace, int32_t workspace_is_zero, void* stream);
 
 /* LayerNorm over the last dim (C <= 2560, C % 8 == 0), replaces F.layer_norm of
  * BasicTransformerBlock.norm1-3 / TemporalBasicTransformerBlock.norm_in,norm1-3 [D].

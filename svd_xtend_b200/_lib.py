@@ -34,6 +34,7 @@ class SvdxTapGemm(C.Structure):
         ("bias", c_void_p), ("rowbias", c_void_p), ("rowbias_div", c_int), ("ldrb", c_i64),
         ("res1", c_void_p), ("ldr1", c_i64), ("res2", c_void_p), ("ldr2", c_i64),
         ("scales", c_void_p), ("pre", c_void_p), ("ldpre", c_i64),
+        ("gn_sum", c_void_p), ("gn_ld", c_i64), ("gn_rows", c_int),
     ]
 
 
@@ -61,9 +62,11 @@ _PROTOS = {
                              c_void_p, c_void_p, c_void_p],
     "svdx_groupnorm_apply": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p],
+    "svdx_groupnorm_apply_fused": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_float,
+                                   c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p],
     "svdx_groupnorm_bwd": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p, c_i64,
-                           c_void_p, c_void_p, c_void_p, c_void_p],
+                           c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "svdx_layernorm_fwd": [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_i64,
                            c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p],
     "svdx_layernorm_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "../../include/svd_xtend_b200.h"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace svdx {
 
@@ -140,6 +141,93 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_kernel(GnSrc s, int 
   const long long base = (long long)n * rows;
   for (int r = r0 + rl; r < r1; r += 4 * RL) {
     // four independent row loads in flight per thread before any math (the kernel is latency x bytes-in-flight bound)
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (r + q * RL < r1) u[q] = load_vec8(s, base + r + q * RL, c0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (r + q * RL >= r1) break;
+      const uint32_t in[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+      uint32_t out[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 v = unpack_bf16x2(in[k]);
+        float a = fmaf(v.x, sc[2 * k], sh[2 * k]), b = fmaf(v.y, sc[2 * k + 1], sh[2 * k + 1]);
+        if (fuse_silu) { a = silu_f(a); b = silu_f(b); }
+        out[k] = pack_bf16x2(a, b);
+      }
+      *reinterpret_cast<uint4*>(y + (base + r + q * RL) * ldy + c0) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+  }
+}
+
+// GroupNorm apply straight from the per-channel sums the producing svdx_tapgemm epilogue accumulated (gn_sum): every CTA
+// folds the C channel sums of its slab into the G group statistics in shared memory (C <= 2560 values from L2, a few hundred
+// ns), CTA x == 0 of the slab publishes mean / rstd for the backward, then rows are streamed exactly as in gn_apply_kernel.
+// One launch instead of memset + partial statistics + finalize + apply, and no extra pass over x for the statistics.
+__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_fused_kernel(GnSrc s, int rows, int rows_per_cta, int RL, int G, float eps, float inv_count,
+                                                                         const float* __restrict__ csum1, long long ldc1,
+                                                                         const float* __restrict__ csum2, long long ldc2,
+                                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                         int fuse_silu, bf16* __restrict__ y, long long ldy) {
+  __shared__ float sh_sum[32], sh_sq[32], sh_mean[32], sh_rstd[32];
+  const int C = s.C1 + s.C2;
+  const int CV = C / 8;
+  const int cpg = C / G;
+  const int n = blockIdx.y;
+  if (threadIdx.x < 32) { sh_sum[threadIdx.x] = 0.f; sh_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  {
+    // a warp's 32 consecutive channels fall into at most 1 + 31 / cpg groups: reduce runs of equal group with shuffles,
+    // one shared-memory atomic per run
+    const int lane = threadIdx.x & 31;
+    for (int c0 = (threadIdx.x & ~31); c0 < C; c0 += blockDim.x) {
+      const int c = c0 + lane;
+      float a = 0.f, b = 0.f;
+      int g = -1;
+      if (c < C) {
+        const float* base = (c < s.C1) ? (csum1 + (2LL * n) * ldc1 + c) : (csum2 + (2LL * n) * ldc2 + (c - s.C1));
+        a = base[0];
+        b = base[(c < s.C1) ? ldc1 : ldc2];
+        g = c / cpg;
+      }
+      // segmented inclusive suffix sum over equal-g runs (g is non-decreasing across lanes)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float a2 = __shfl_down_sync(0xffffffffu, a, o), b2 = __shfl_down_sync(0xffffffffu, b, o);
+        const int g2 = __shfl_down_sync(0xffffffffu, g, o);
+        if (lane + o < 32 && g2 == g) { a += a2; b += b2; }
+      }
+      const int gprev = __shfl_up_sync(0xffffffffu, g, 1);
+      if (g >= 0 && (lane == 0 || gprev != g)) { atomicAdd(&sh_sum[g], a); atomicAdd(&sh_sq[g], b); }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const float m = sh_sum[threadIdx.x] * inv_count;
+    const float var = fmaxf(sh_sq[threadIdx.x] * inv_count - m * m, 0.f);
+    const float rs = rsqrtf(var + eps);
+    sh_mean[threadIdx.x] = m;
+    sh_rstd[threadIdx.x] = rs;
+    if (blockIdx.x == 0) { mean_out[n * G + threadIdx.x] = m; rstd_out[n * G + threadIdx.x] = rs; }
+  }
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, rows);
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;      // the block is padded to whole warps: lanes past CV * RL only folded
+  if (rl >= RL) return;
+  const int c0 = cv * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int g = (c0 + k) / cpg;
+    sc[k] = sh_rstd[g] * gamma[c0 + k];
+    sh[k] = beta[c0 + k] - sh_mean[g] * sc[k];
+  }
+  const long long base = (long long)n * rows;
+  for (int r = r0 + rl; r < r1; r += 4 * RL) {
     uint4 u[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -474,8 +562,11 @@ static void gn_vec_config(int C, int outer, int rows, int& threads, int& rows_pe
   int RL = 256 / CV;
   if (RL < 1) RL = 1;
   threads = CV * RL;
-  // ~8 CTAs per SM, each thread streams a multiple of 4 rows (4 independent 16-byte loads per tensor in flight)
-  const long long want_ctas = 8LL * svdx_num_sms();
+  // ~8 CTAs per SM (tunable for experiments: SVDX_GN_CTAS_PER_SM), each thread streams a multiple of 4 rows (4 independent
+  // 16-byte loads per tensor in flight)
+  static int cps = 0;
+  if (cps == 0) { const char* e = getenv("SVDX_GN_CTAS_PER_SM"); cps = (e && atoi(e) > 0) ? atoi(e) : 8; }
+  const long long want_ctas = (long long)cps * svdx_num_sms();
   long long chunks = (want_ctas + outer - 1) / outer;
   if (chunks < 1) chunks = 1;
   rows_per_cta = (int)((rows + chunks - 1) / chunks);
@@ -530,17 +621,37 @@ extern "C" int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, cons
   return SVDX_OK;
 }
 
+extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, int32_t outer,
+                                          int32_t rows, int32_t num_groups, float eps, const float* csum1, int64_t ldc1,
+                                          const float* csum2, int64_t ldc2, float* mean, float* rstd, const float* gamma,
+                                          const float* beta, int32_t fuse_silu, void* y, int64_t ldy, void* stream_v) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !y || ldy % 8 || (reinterpret_cast<uintptr_t>(y) & 15) || !mean || !rstd || !gamma || !beta ||
+      !csum1 || ldc1 < C1 || (C2 > 0 && (!csum2 || ldc2 < C2)) || outer <= 0 || rows <= 0)
+    return svdx_fail(SVDX_E_BADARG, "groupnorm_apply_fused: bad arguments");
+  GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
+  int threads, rpc;
+  gn_vec_config(C1 + C2, outer, rows, threads, rpc);
+  const int RL = threads / ((C1 + C2) / 8);
+  const int padded = (threads + 31) & ~31;      // whole warps: the channel fold uses full-mask shuffles
+  const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
+  gn_apply_fused_kernel<<<dim3((rows + rpc - 1) / rpc, outer), padded, 0, st>>>(s, rows, rpc, RL, num_groups, eps, inv, csum1, ldc1, csum2, ldc2, mean, rstd,
+                                                                               gamma, beta, fuse_silu, reinterpret_cast<bf16*>(y), ldy);
+  SVDX_CHECK_LAUNCH("groupnorm_apply_fused");
+  return SVDX_OK;
+}
+
 extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, const void* dy,
                                   int64_t lddy, int32_t outer, int32_t rows, int32_t num_groups, const float* mean, const float* rstd,
                                   const float* gamma, const float* beta, int32_t fuse_silu, void* dx, int64_t lddx, void* dx2,
-                                  int64_t lddx2, float* dgamma, float* dbeta, float* workspace, void* stream_v) {
+                                  int64_t lddx2, float* dgamma, float* dbeta, float* workspace, int32_t workspace_is_zero, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !dy || lddy % 8 || !dx || lddx % 8 || (C2 > 0 && (!dx2 || lddx2 % 8)) || !workspace ||
       (dgamma && !dbeta))
     return svdx_fail(SVDX_E_BADARG, "groupnorm_bwd: bad arguments");
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
   const int total = outer * num_groups;
-  cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * total, st);
+  if (!workspace_is_zero) cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * total, st);
   int threads, rpc;
   gn_vec_config(C1 + C2, outer, rows, threads, rpc);
   dim3 grid((rows + rpc - 1) / rpc, outer);

@@ -270,8 +270,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      if constexpr (EPI == EPI_FAST) epilogue_fast(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, st.base, st.row0, st.grp, lane);
-      else if constexpr (EPI == EPI_RES) epilogue_res(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.row0, st.grp, lane);
+      const long long m0 = (long long)g * p.rows_per_group + st.row0;        // fused GroupNorm statistics: first row / rows that exist
+      const int valid_rows = max(0, min(32, p.rows_per_group - st.row0));
+      if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
+      else if constexpr (EPI == EPI_RES || EPI == EPI_RES_GN) epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.row0, st.grp, lane, m0, valid_rows);
       else if constexpr (EPI == EPI_GEGLU) epilogue_geglu(p, t_base, nt * bn_out, half, bn_out, st.base, st.row0, st.grp, lane);
       else epilogue_tile(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
       tc_fence_before();
@@ -323,13 +325,17 @@ int svdx_tapgemm2_launch(const TapGemmKParams& p, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm2: set smem attribute");
     attr_done[slot] = true;
   }
   const int total_tiles = p.pair_m_tiles * p.n_tiles;
   int clusters = svdx_num_sms() / 2;
   if (clusters > total_tiles) clusters = total_tiles;
-  if (p.epi_mode == EPI_FAST) tapgemm2_kernel<EPI_FAST><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm2_kernel<EPI_FAST_GN><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  else if (p.epi_mode == EPI_RES && p.gn_sum) tapgemm2_kernel<EPI_RES_GN><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  else if (p.epi_mode == EPI_FAST) tapgemm2_kernel<EPI_FAST><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_GEGLU) tapgemm2_kernel<EPI_GEGLU><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_RES) tapgemm2_kernel<EPI_RES><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   else tapgemm2_kernel<EPI_GENERIC><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);

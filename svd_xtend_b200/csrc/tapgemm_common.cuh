@@ -54,6 +54,9 @@ struct __align__(64) TapGemmKParams {
   long long ldpre;
   CUtensorMap tmo;     // output (bf16: 32x32 box, 64B swizzle; fp32: 32x32 box, 128B swizzle), dims {n_out, rows, groups}
   CUtensorMap tmpre;   // GEGLU pre-activation [M, N]
+  float* gn_sum;       // fused GroupNorm statistics of the output (per slab m / gn_rows, per channel): [slab][2][gn_ld]
+  long long gn_ld;
+  int gn_rows;
   int tma_store;       // epilogue stores through shared memory + TMA (tmo / tmpre valid)
   int epi_mode;        // EPI_GENERIC / EPI_FAST / EPI_GEGLU / EPI_RES: which kernel instantiation runs
   int probe;   // dev switch SVDX_EPI_PROBE: 1 = epilogue without global stores, 2 = no epilogue work at all
@@ -149,11 +152,48 @@ SVDX_DEVINL void stage_store_f32(const CUtensorMap* tm, EpiStage& st, int lane, 
   }
 }
 
+// ---- GroupNorm statistics of the output, fused into the epilogue: column sums (and sums of squares) of one staged
+// 32-row x 32-column bf16 chunk, i.e. of exactly the values the TMA store writes. Lane l takes the column pair l % 16 and
+// the rows of parity l / 16 (two 64-byte rows per wavefront: conflict-free with the 64B swizzle), the two halves are
+// combined with one shuffle and lanes 0..15 issue two red.global.add.v2.f32. Rows are walked slab by slab (a slab = gn_rows
+// consecutive rows = one frame or one clip), so tiles that straddle frames (5x8 latents) stay correct.
+// m0 = global row index of the chunk's row 0, valid_rows = how many of its 32 rows exist.
+SVDX_DEVINL void gn_chunk_sums(const TapGemmKParams& p, uint32_t buf, int lane, int col0, int n_out_total, long long m0, int valid_rows) {
+  const int pr = lane & 15, h = lane >> 4;
+  const uint32_t in_chunk = (uint32_t)(pr & 3) * 4u;
+  const int jch = pr >> 2;
+  long long slab = m0 / p.gn_rows;
+  int left = p.gn_rows - (int)(m0 - slab * p.gn_rows);
+  int r = 0;
+  while (r < valid_rows) {                                     // warp-uniform trip count
+    const int seg_end = min(valid_rows, r + left);
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    for (int rr = r + ((h ^ r) & 1); rr < seg_end; rr += 2) {
+      uint32_t w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(buf + rr * 64 + ((uint32_t)(jch ^ ((rr >> 1) & 3)) << 4) + in_chunk));
+      const float2 v = unpack_bf16x2(w);
+      s0 += v.x; s1 += v.y;
+      q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+    const int col = col0 + 2 * pr;
+    if (h == 0 && col < n_out_total) {
+      float* d = p.gn_sum + (2 * slab) * p.gn_ld + col;
+      asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d), "f"(s0), "f"(s1) : "memory");
+      asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d + p.gn_ld), "f"(q0), "f"(q1) : "memory");
+    }
+    r = seg_end; ++slab; left = p.gn_rows;
+  }
+}
+
 // ---- specialised epilogues (kernel template parameter EPI): the hot shapes have short K, so the per-chunk instruction
 // count of the epilogue decides their speed (profiles/r1_epilogue_probe.txt). EPI_FAST / EPI_GEGLU assume a bf16 output
 // written through TMA, whole 32-column chunks (n_out % 32 == 0) and 16-byte aligned bias rows; everything else takes
 // the generic epilogue_tile below.
 constexpr int EPI_GENERIC = 0, EPI_FAST = 1, EPI_GEGLU = 2, EPI_RES = 3;
+// + fused GroupNorm statistics of the output (separate instantiations: the plain ones keep their register budget)
+constexpr int EPI_FAST_GN = 4, EPI_RES_GN = 5;
 
 SVDX_DEVINL void add_vec32(float (&f)[32], const float* __restrict__ src) {
   const float4* bp = reinterpret_cast<const float4*>(src);
@@ -181,8 +221,9 @@ SVDX_DEVINL void stage_row_bf16(uint32_t row, int sw, const float (&f)[32]) {
 
 // plain epilogue (bias / row-bias only): two 32-column chunks per round (both staging halves), one proxy fence and one
 // bulk group per round.
+template <bool GN>
 SVDX_DEVINL void epilogue_fast(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int bn_out,
-                               int n_out_total, uint32_t sbase, int row0, int grp, int lane) {
+                               int n_out_total, uint32_t sbase, int row0, int grp, int lane, long long m0, int valid_rows) {
   const float* bias = p.bias;
   const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
   const uint32_t rowX = sbase + lane * 64, rowY = rowX + 2048;
@@ -213,13 +254,19 @@ SVDX_DEVINL void epilogue_fast(const TapGemmKParams& p, uint32_t t_base, long lo
       if (hasB) tma_store_3d(&p.tmo, sbase + 2048, colB, row0, grp);
       bulk_commit();
     }
+    if constexpr (GN) {
+      gn_chunk_sums(p, sbase, lane, colA, n_out_total, m0, valid_rows);
+      if (hasB) gn_chunk_sums(p, sbase + 2048, lane, colB, n_out_total, m0, valid_rows);
+    }
   }
 }
 
 // residual / AlphaBlender epilogue: out = s_acc*(acc + bias + rowbias) + s_r1*res1 + s_r2*res2; one chunk per round,
 // alternating staging halves; the residual rows are requested before the TMEM wait.
+template <bool GN>
 SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int bn_out,
-                              int n_out_total, float s_acc, float s_r1, float s_r2, uint32_t sbase, int row0, int grp, int lane) {
+                              int n_out_total, float s_acc, float s_r1, float s_r2, uint32_t sbase, int row0, int grp, int lane,
+                              long long m0, int valid_rows) {
   const float* bias = p.bias;
   const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
   const bf16* r1 = (p.res1 && row_ok) ? p.res1 + m * p.ldr1 : nullptr;
@@ -263,6 +310,7 @@ SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long lon
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) { tma_store_3d(&p.tmo, sbase + off, col0, row0, grp); bulk_commit(); }
+    if constexpr (GN) gn_chunk_sums(p, sbase + off, lane, col0, n_out_total, m0, valid_rows);
     off ^= 2048;
   }
 }

@@ -26,13 +26,16 @@ F32 = torch.float32
 class Var:
     """An activation on the tape: bf16 ``[rows, C]`` data plus (lazily) its gradient."""
 
-    __slots__ = ("data", "grad", "needs_grad", "owned")
+    __slots__ = ("data", "grad", "needs_grad", "owned", "csum")
 
     def __init__(self, data: torch.Tensor, needs_grad: bool = False):
         self.data = data
         self.grad: Optional[torch.Tensor] = None
         self.needs_grad = needs_grad
         self.owned = False  # True when .grad is a tensor no other Var can see (safe to accumulate in place)
+        # fused GroupNorm statistics of this tensor, produced by the GEMM / conv epilogue that wrote it:
+        # (rows per statistics slab, [(fp32 [slabs, 2, C_i] channel sums, C_i), ...]) — several parts after a channel concat
+        self.csum = None
 
     def take_grad(self) -> Optional[torch.Tensor]:
         g, self.grad, self.owned = self.grad, None, False
@@ -130,6 +133,11 @@ class Engine:
         self.keep: List[torch.Tensor] = []   # small device scalars referenced by in-flight launches
         self._consts: Dict[Tuple, torch.Tensor] = {}
         self.grad_ready_hook: Optional[Callable[[List[torch.nn.Parameter]], None]] = None
+        # zeroed fp32 scratch for every fused-statistics / GroupNorm-backward accumulator of a step: ONE memset per
+        # forward instead of one per GroupNorm (the buffers are consumed before the next forward zeroes them again)
+        self._stat_arena: Optional[torch.Tensor] = None
+        self._stat_ptr = 0
+        self.fuse_gn_stats = True
 
     # ------------------------------------------------------------------ tape
     def begin(self, recording: bool):
@@ -137,6 +145,32 @@ class Engine:
         `detach_tape`), so two forwards before a backward, or a no_grad forward in between, cannot clobber each other"""
         self.tape = []
         self.recording = recording
+        if self._stat_arena is not None:
+            self._stat_arena.zero_()
+        self._stat_ptr = 0
+
+    STAT_ARENA_FLOATS = 8 << 20      # 32 MB
+
+    def stat_zeros(self, n: int, device) -> torch.Tensor:
+        """n zeroed floats: a slice of the per-step arena (zeroed once at `begin`), or a fresh tensor when it is exhausted"""
+        n_al = (n + 63) // 64 * 64
+        if self._stat_arena is None or self._stat_arena.device != torch.device(device):
+            self._stat_arena = torch.zeros(self.STAT_ARENA_FLOATS, device=device, dtype=F32)
+            self._stat_ptr = 0
+        if self._stat_ptr + n_al > self._stat_arena.numel():
+            return torch.zeros(n, device=device, dtype=F32)
+        t = self._stat_arena[self._stat_ptr:self._stat_ptr + n]
+        self._stat_ptr += n_al
+        return t
+
+    def _gn_sink(self, gn_rows: Optional[int], M: int, N: int, K: int, ntaps: int, device, n_out: Optional[int] = None):
+        """channel-sum buffer for the fused GroupNorm statistics of a GEMM / conv output, or None when the launch cannot
+        carry them (split-K path, ragged widths) — the consumer then runs the stand-alone statistics kernel"""
+        if gn_rows is None or not self.fuse_gn_stats or N % 32 or M % gn_rows:
+            return None
+        if raw.split_plan(True, M, N, K, ntaps) is not None:
+            return None
+        return self.stat_zeros((M // gn_rows) * 2 * N, device).view(M // gn_rows, 2, N)
 
     def detach_tape(self) -> List[Callable[[], None]]:
         """hand the recorded tape to the caller (the autograd node of this forward) and stop recording"""
@@ -325,7 +359,7 @@ class Engine:
     def linear(self, x: Var, weight, bias=None, *, res1: Optional[Var] = None, res2: Optional[Var] = None,
                scales: Optional[torch.Tensor] = None, res1_unit: bool = False, geglu: bool = False,
                rowbias: Optional[Var] = None, rowbias_div: int = 1, out_f32: bool = False,
-               fused: Optional[Sequence] = None, blend=None, lora: Optional[Sequence] = None) -> Var:
+               fused: Optional[Sequence] = None, blend=None, lora: Optional[Sequence] = None, gn_rows: Optional[int] = None) -> Var:
         """y = epilogue(x @ W^T). `weight` is a parameter [N,K] (or conv 1x1 [N,K,1,1]); `fused` = list of
         parameters whose rows are concatenated (q|k|v). scales (device float[>=3]) = {acc, res1, res2};
         res1_unit: scales[1] is known to be exactly 1. rowbias: Var with fp32 data [ceil(M/div), N]."""
@@ -337,10 +371,11 @@ class Engine:
         out = self.empty(M, n_out, x.data, F32 if out_f32 else bf16)
         pre = self.empty(M, N, x.data) if (geglu and self.recording) else None
         b32 = self.vec_f32(bias)
+        lora = [l for l in (lora or []) if l is not None]
+        sink = None if (geglu or out_f32 or lora) else self._gn_sink(gn_rows, M, N, K, 1, out.device)
         raw.tapgemm_auto(x.data, wf, out, M=M, N=N, K=K, bias=b32, res1=None if res1 is None else res1.data,
                          res2=None if res2 is None else res2.data, scales=scales, geglu=geglu, pre=pre,
-                         rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div)
-        lora = [l for l in (lora or []) if l is not None]
+                         rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div, gn_sum=sink, gn_rows=gn_rows or 0)
         lora_t = []
         for (off, n, A, Bm, sc) in lora:
             # LoRA side path (train_svd_lora.py:659-671): out[:, off:off+n] += scale * (x A^T) B^T, accumulated in place.
@@ -356,6 +391,8 @@ class Engine:
             or (blend is not None and blend[0].requires_grad) or any(l[2].requires_grad or l[3].requires_grad for l in lora)
         need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, res2, rowbias))
         y = Var(out, need)
+        if sink is not None:
+            y.csum = (gn_rows, [(sink, N)])
         if need and self.recording:
             def bwd():
                 dy = y.take_grad()
@@ -529,7 +566,7 @@ class Engine:
         self.pgrad(mix).add_((acc * alpha).to(F32).view(mix.shape))
 
     def conv2d_3x3(self, x: Var, g: Geom, conv, *, rowbias: Optional[Var] = None, rowbias_div=1, res1: Optional[Var] = None,
-                   scales=None, res1_unit: bool = False, i_pad=None, n_pad=None, planes: bool = False) -> Var:
+                   scales=None, res1_unit: bool = False, i_pad=None, n_pad=None, planes: bool = False, gn_rows: Optional[int] = None) -> Var:
         """3x3 conv, padding 1, on channels-last [N*H*W, Cin]. planes=True: x holds the 4 stride-2 parity planes
         of a [N,2H,2W] image and the result is the stride-2 conv at geometry g (= output geometry)."""
         w = conv.weight
@@ -552,13 +589,16 @@ class Engine:
         else:
             taps = CONV3x3_TAPS
             whn = (g.W, g.H, nimg)
+        sink = None if (n_alloc != O or O < 32) else self._gn_sink(gn_rows, M, O, ip, len(taps), out.device)
         raw.tapgemm_auto(x.data, wf, out, M=M, N=O, K=ip, mode=A_CONV2D, taps=taps, conv_whn=whn, bias=self.vec_f32(conv.bias),
                          rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
                          res1=None if res1 is None else res1.data, scales=scales,
-                         block_n=None if O >= 32 else 32)
+                         block_n=None if O >= 32 else 32, gn_sum=sink, gn_rows=gn_rows or 0)
         w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad)
         need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, rowbias))
         y = Var(out, need)
+        if sink is not None:
+            y.csum = (gn_rows, [(sink, O)])
         if need and self.recording:
             def bwd():
                 dy = y.take_grad()
@@ -595,7 +635,7 @@ class Engine:
         return y
 
     def conv_temporal(self, x: Var, g: Geom, conv, *, rowbias: Optional[Var] = None, rowbias_div=1, res1: Optional[Var] = None,
-                      scales=None, res1_unit: bool = False, blend=None) -> Var:
+                      scales=None, res1_unit: bool = False, blend=None, gn_rows: Optional[int] = None) -> Var:
         """Conv3d kernel (3,1,1), padding (1,0,0): frames are HW rows apart in the token matrix.
         blend = (mix_factor parameter, device alpha[1]) when this conv carries the AlphaBlender epilogue."""
         w = conv.weight
@@ -605,12 +645,15 @@ class Engine:
         HW = g.HW
         taps = ((-HW, 0, 0), (0, 0, 0), (HW, 0, 0))
         out = self.empty(M, O, x.data)
+        sink = self._gn_sink(gn_rows, M, O, I, 3, out.device)
         raw.tapgemm_auto(x.data, wf, out, M=M, N=O, K=I, taps=taps, rows_per_group=g.T * HW, groups=g.B, bias=self.vec_f32(conv.bias),
                          rowbias=None if rowbias is None else rowbias.data, rowbias_div=rowbias_div,
-                         res1=None if res1 is None else res1.data, scales=scales)
+                         res1=None if res1 is None else res1.data, scales=scales, gn_sum=sink, gn_rows=gn_rows or 0)
         w_train = w.requires_grad or (conv.bias is not None and conv.bias.requires_grad) or (blend is not None and blend[0].requires_grad)
         need = x.needs_grad or w_train or any(v is not None and v.needs_grad for v in (res1, rowbias))
         y = Var(out, need)
+        if sink is not None:
+            y.csum = (gn_rows, [(sink, O)])
         if need and self.recording:
             def bwd():
                 dy = y.take_grad()
@@ -673,12 +716,23 @@ class Engine:
 
     # ------------------------------------------------------------------ normalisation
     def groupnorm(self, x: Var, gn, outer: int, rows: int, silu: bool) -> Var:
-        """GroupNorm(32) (+SiLU); one statistics group spans `rows` rows (H*W per frame, or T*H*W per clip)."""
+        """GroupNorm(32) (+SiLU); one statistics group spans `rows` rows (H*W per frame, or T*H*W per clip).
+        When the producer(s) of x accumulated per-channel sums in their epilogues (x.csum, slab = `rows` rows), the group
+        statistics are folded from them inside the apply kernel: ONE launch, no pass over x for the statistics."""
         C = x.cols
         gamma, beta = self.vec_f32(gn.weight), self.vec_f32(gn.bias)
-        mean, rstd = raw.groupnorm_stats(x.data, None, outer, rows, gn.eps, gn.num_groups)
         out = self.empty(x.rows, C, x.data)
-        raw.groupnorm_apply(x.data, None, outer, rows, mean, rstd, gamma, beta, silu, out, gn.num_groups)
+        cs = x.csum
+        if cs is not None and cs[0] == rows and len(cs[1]) <= 2 and sum(c for _, c in cs[1]) == C and all(t.shape[0] == outer for t, _ in cs[1]):
+            parts = cs[1]
+            C1 = parts[0][1]
+            x1 = x.data if len(parts) == 1 else x.data[:, :C1]
+            x2 = None if len(parts) == 1 else x.data[:, C1:]
+            mean, rstd = raw.groupnorm_apply_fused(x1, x2, outer, rows, gn.eps, parts[0][0], None if len(parts) == 1 else parts[1][0],
+                                                   gamma, beta, silu, out, gn.num_groups)
+        else:
+            mean, rstd = raw.groupnorm_stats(x.data, None, outer, rows, gn.eps, gn.num_groups)
+            raw.groupnorm_apply(x.data, None, outer, rows, mean, rstd, gamma, beta, silu, out, gn.num_groups)
         p_train = gn.weight.requires_grad
         need = x.needs_grad or p_train
         y = Var(out, need)
@@ -690,7 +744,8 @@ class Engine:
                 dx = self.empty(x.rows, C, x.data)
                 dg = self.pgrad(gn.weight) if p_train else None
                 db = self.pgrad(gn.bias) if p_train else None
-                raw.groupnorm_bwd(x.data, None, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, None, dg, db, gn.num_groups)
+                ws = self.stat_zeros(2 * outer * gn.num_groups, dy.device)
+                raw.groupnorm_bwd(x.data, None, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, None, dg, db, gn.num_groups, ws=ws)
                 self.add_grad(x, dx)
             self.record(bwd)
         return y
@@ -770,6 +825,8 @@ class Engine:
         raw.concat_channels(a.data, b.data, out)
         need = a.needs_grad or b.needs_grad
         y = Var(out, need)
+        if a.csum is not None and b.csum is not None and a.csum[0] == b.csum[0] and len(a.csum[1]) == 1 and len(b.csum[1]) == 1:
+            y.csum = (a.csum[0], [a.csum[1][0], b.csum[1][0]])      # GroupNorm over the concatenation folds both producers' sums
         if need and self.recording:
             def bwd():
                 dy = y.take_grad()

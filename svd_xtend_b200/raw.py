@@ -26,7 +26,7 @@ def dtype_code(t: torch.Tensor, what: str) -> int:
 
 # number of kernels launched through the C ABI since import (each wrapper adds what its entry point launches)
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"svdx_groupnorm_stats": 2, "svdx_groupnorm_bwd": 2, "svdx_attention_bwd": 3, "svdx_adamw_graph": 2}
+_KERNELS_PER_CALL = {"svdx_groupnorm_stats": 2, "svdx_groupnorm_bwd": 2, "svdx_groupnorm_apply_fused": 1, "svdx_attention_bwd": 3, "svdx_adamw_graph": 2}
 
 
 def check(rc: int, what: str = "") -> None:
@@ -171,8 +171,12 @@ def tapgemm(
     res2: Optional[torch.Tensor] = None,
     scales: Optional[torch.Tensor] = None,
     pre: Optional[torch.Tensor] = None,
+    gn_sum: Optional[torch.Tensor] = None,
+    gn_rows: int = 0,
 ) -> torch.Tensor:
-    """Launch svdx_tapgemm on the current stream. All tensors are CUDA; a/b/res/pre are bf16."""
+    """Launch svdx_tapgemm on the current stream. All tensors are CUDA; a/b/res/pre are bf16.
+    gn_sum: zeroed fp32 [slabs, 2, C] buffer that receives the per-channel sum / sum of squares of the output (fused
+    GroupNorm statistics), one slab per gn_rows output rows."""
     family = "conv" if (mode == A_CONV2D or len(taps) > 1 or b_mode != 0) else "linear"
     if _fam(family, 2.0 * M * N * K * len(taps)):
         return out
@@ -233,6 +237,11 @@ def tapgemm(
         assert pre.dtype == bf16
         d.pre = pre.data_ptr()
         d.ldpre = _rowmajor(pre, "pre")
+    if gn_sum is not None:
+        assert gn_sum.dtype == torch.float32 and gn_sum.dim() == 3 and gn_sum.shape[1] == 2 and gn_sum.is_contiguous() and gn_rows > 0
+        d.gn_sum = gn_sum.data_ptr()
+        d.gn_ld = gn_sum.shape[2]
+        d.gn_rows = gn_rows
     check(load().svdx_tapgemm(C.byref(d), _stream()), "svdx_tapgemm")
     return out
 
@@ -252,35 +261,47 @@ def _splitk_workspace(M: int, N: int, device) -> torch.Tensor:
     return ws
 
 
+def split_plan(out_is_bf16: bool, M: int, N: int, K: int, ntaps: int = 1, geglu=False, a_mn=False, b_mn=False, block_n=None):
+    """(tile width, split factor) of the automatic split-K path of tapgemm_auto, or None when the problem is launched whole.
+    Small-M / long-K problems whose 128x256 tiles cannot fill the SMs split the contraction over CTAs."""
+    if not (out_is_bf16 and not geglu and not a_mn and not b_mn and block_n is None and N % 8 == 0 and N >= 256):
+        return None
+    bn = 256 if N % 256 == 0 else (160 if N % 160 == 0 else 0)
+    if not bn:
+        return None
+    kb = ((K + 63) // 64) * ntaps
+    tiles = ((M + 127) // 128) * (N // bn)
+    split = min(num_sms() // max(tiles, 1), kb // 8)
+    if tiles <= num_sms() // 3 and split >= 2:
+        return bn, split
+    return None
+
+
 def tapgemm_auto(a, b, out, *, M, N, K, taps=((0, 0, 0),), bias=None, rowbias=None, rowbias_div=1, res1=None, res2=None,
-                 scales=None, **kw):
+                 scales=None, gn_sum=None, gn_rows=0, **kw):
     """svdx_tapgemm with automatic split-K for small-M / long-K problems (bf16 output, K-major operands, no GEGLU):
     when 128x256 tiles cannot fill the SMs, the contraction is split over CTAs (fp32 atomics into a workspace) and
-    svdx_splitk_epilogue applies bias / row-bias / residuals / scales."""
-    kb = ((K + 63) // 64) * len(taps)
-    m_tiles = (M + 127) // 128
+    svdx_splitk_epilogue applies bias / row-bias / residuals / scales. Fused GroupNorm statistics (gn_sum) exist on the
+    whole-problem path only: callers ask `split_plan` first and keep the stand-alone statistics kernel for split outputs."""
     kw = dict(kw)
     if kw.get("block_n") is None:
         kw.pop("block_n", None)
-    if (out.dtype == bf16 and not kw.get("geglu") and not kw.get("a_mn") and not kw.get("b_mn") and kw.get("block_n") is None
-            and N % 8 == 0 and N >= 256):
-        bn = 256 if N % 256 == 0 else (160 if N % 160 == 0 else 0)
-        if bn:
-            tiles = m_tiles * (N // bn)
-            split = min(num_sms() // max(tiles, 1), kb // 8)
-            if tiles <= num_sms() // 3 and split >= 2:
-                ws = _splitk_workspace(M, N, out.device)
-                tapgemm(a, b, ws, M=M, N=N, K=K, taps=taps, block_n=bn, split_k=split, out_dtype=OUT_F32_ATOMIC, **kw)
-                if _fam("conv" if (kw.get("mode", A_ROWS) == A_CONV2D or len(taps) > 1) else "linear"):
-                    return out
-                check(load().svdx_splitk_epilogue(ws.data_ptr(), N, out.data_ptr(), _rowmajor(out, "out"), M, N, _ptr(bias), _ptr(rowbias),
-                                                  rowbias_div, _rowmajor(rowbias, "rowbias") if rowbias is not None else 0,
-                                                  _ptr(res1), _rowmajor(res1, "res1") if res1 is not None else 0,
-                                                  _ptr(res2), _rowmajor(res2, "res2") if res2 is not None else 0,
-                                                  _ptr(scales), _stream()), "svdx_splitk_epilogue")
-                return out
+    plan = split_plan(out.dtype == bf16, M, N, K, len(taps), kw.get("geglu"), kw.get("a_mn"), kw.get("b_mn"), kw.get("block_n"))
+    if plan is not None:
+        assert gn_sum is None, "fused GroupNorm statistics are not available on the split-K path"
+        bn, split = plan
+        ws = _splitk_workspace(M, N, out.device)
+        tapgemm(a, b, ws, M=M, N=N, K=K, taps=taps, block_n=bn, split_k=split, out_dtype=OUT_F32_ATOMIC, **kw)
+        if _fam("conv" if (kw.get("mode", A_ROWS) == A_CONV2D or len(taps) > 1) else "linear"):
+            return out
+        check(load().svdx_splitk_epilogue(ws.data_ptr(), N, out.data_ptr(), _rowmajor(out, "out"), M, N, _ptr(bias), _ptr(rowbias),
+                                          rowbias_div, _rowmajor(rowbias, "rowbias") if rowbias is not None else 0,
+                                          _ptr(res1), _rowmajor(res1, "res1") if res1 is not None else 0,
+                                          _ptr(res2), _rowmajor(res2, "res2") if res2 is not None else 0,
+                                          _ptr(scales), _stream()), "svdx_splitk_epilogue")
+        return out
     return tapgemm(a, b, out, M=M, N=N, K=K, taps=taps, bias=bias, rowbias=rowbias, rowbias_div=rowbias_div, res1=res1, res2=res2,
-                   scales=scales, **kw)
+                   scales=scales, gn_sum=gn_sum, gn_rows=gn_rows, **kw)
 
 
 CONV3x3_TAPS = tuple((kw - 1, kh - 1, 0) for kh in range(3) for kw in range(3))
@@ -348,17 +369,36 @@ def groupnorm_apply(x, x2, outer, rows, mean, rstd, gamma, beta, silu, y, groups
     return y
 
 
-def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2, dgamma=None, dbeta=None, groups=32):
+def groupnorm_apply_fused(x, x2, outer, rows, eps, csum1, csum2, gamma, beta, silu, y, groups=32):
+    """GroupNorm(+SiLU) from the per-channel sums of the producing epilogues; returns (mean, rstd) [outer*groups] for backward"""
     C1 = x.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
-    ws = torch.empty(outer * groups * 2, device=x.device, dtype=torch.float32)
+    stats = torch.empty(2, outer * groups, device=x.device, dtype=torch.float32)
+    mean, rstd = stats[0], stats[1]
+    if _fam("groupnorm", 0.0, 4.0 * x.shape[0] * (C1 + C2)):
+        return mean, rstd
+    check(load().svdx_groupnorm_apply_fused(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0, C2,
+                                            outer, rows, groups, eps, csum1.data_ptr(), csum1.shape[2],
+                                            _ptr(csum2), csum2.shape[2] if csum2 is not None else 0, mean.data_ptr(), rstd.data_ptr(),
+                                            gamma.data_ptr(), beta.data_ptr(), int(silu), y.data_ptr(), _rowmajor(y, "y"), _stream()),
+          "svdx_groupnorm_apply_fused")
+    return mean, rstd
+
+
+def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2, dgamma=None, dbeta=None, groups=32, ws=None):
+    """ws: optional pre-ZEROED float[2 * outer * groups] workspace (a slice of a zeroed arena: no memset node)"""
+    C1 = x.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    ws_zero = ws is not None
+    if ws is None:
+        ws = torch.empty(outer * groups * 2, device=x.device, dtype=torch.float32)
     if _fam("groupnorm", 0.0, 6.0 * x.shape[0] * (C1 + C2)):       # minimal traffic: read x, dy once, write dx
         return
     check(load().svdx_groupnorm_bwd(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0, C2,
                                     dy.data_ptr(), _rowmajor(dy, "dy"), outer, rows, groups, mean.data_ptr(), rstd.data_ptr(),
                                     gamma.data_ptr(), beta.data_ptr(), int(silu), dx.data_ptr(), _rowmajor(dx, "dx"),
                                     _ptr(dx2), _rowmajor(dx2, "dx2") if dx2 is not None else 0, _ptr(dgamma), _ptr(dbeta),
-                                    ws.data_ptr(), _stream()), "svdx_groupnorm_bwd")
+                                    ws.data_ptr(), int(ws_zero), _stream()), "svdx_groupnorm_bwd")
 
 
 def layernorm_fwd(x, gamma, beta, eps, y, addvec=None, add_div=1, xsum=None):

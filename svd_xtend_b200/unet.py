@@ -716,7 +716,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         cpad = 64
         x0 = torch.empty(N * H * W, cpad, device=dev, dtype=bf16)
         raw.nchw_to_nhwc(x_nchw if x_nchw.dtype in (F32, bf16, torch.float16) else x_nchw.float(), x0, N, Cin, H, W, cpad)
-        x = E.conv2d_3x3(Var(x0), g, self.conv_in, i_pad=cpad)
+        x = E.conv2d_3x3(Var(x0), g, self.conv_in, i_pad=cpad, gn_rows=g.HW)
 
         # ---- 3. down (:432-448)
         skips = [(x, g)]
@@ -729,7 +729,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
             if blk.downsamplers is not None:
                 p = E.space_to_planes(x, g)
                 g = g.down()
-                x = E.conv2d_3x3(p, g, blk.downsamplers[0].conv, planes=True)
+                x = E.conv2d_3x3(p, g, blk.downsamplers[0].conv, planes=True, gn_rows=g.HW)
                 skips.append((x, g))
 
         # ---- 4. mid (:451-456)
@@ -749,7 +749,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
             if blk.upsamplers is not None:
                 u = E.upsample2x(x, g)
                 g = g.up()
-                x = E.conv2d_3x3(u, g, blk.upsamplers[0].conv)
+                x = E.conv2d_3x3(u, g, blk.upsamplers[0].conv, gn_rows=g.HW)
 
         # ---- 6. post-process (:480-485)
         h = E.groupnorm(x, self.conv_norm_out, outer=N, rows=g.HW, silu=True)
@@ -783,16 +783,17 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         N = g.B * g.T
         per_clip = g.T * g.HW
         h = E.groupnorm(x, sp.norm1, outer=N, rows=g.HW, silu=True)
-        h = E.conv2d_3x3(h, g, sp.conv1, rowbias=temb[sp.time_emb_proj], rowbias_div=per_clip)
+        h = E.conv2d_3x3(h, g, sp.conv1, rowbias=temb[sp.time_emb_proj], rowbias_div=per_clip, gn_rows=g.HW)
         h = E.groupnorm(h, sp.norm2, outer=N, rows=g.HW, silu=True)
         xs = x if sp.conv_shortcut is None else E.linear(x, sp.conv_shortcut.weight, sp.conv_shortcut.bias)
-        hs = E.conv2d_3x3(h, g, sp.conv2, res1=xs)
+        hs = E.conv2d_3x3(h, g, sp.conv2, res1=xs, gn_rows=per_clip)     # -> temporal norm1: statistics per clip
         t = E.groupnorm(hs, tp.norm1, outer=g.B, rows=per_clip, silu=True)
-        t = E.conv_temporal(t, g, tp.conv1, rowbias=temb[tp.time_emb_proj], rowbias_div=per_clip)
+        t = E.conv_temporal(t, g, tp.conv1, rowbias=temb[tp.time_emb_proj], rowbias_div=per_clip, gn_rows=per_clip)
         t = E.groupnorm(t, tp.norm2, outer=g.B, rows=per_clip, silu=True)
         s8 = self._blend(E, blk.time_mixer)
         # alpha*hs + (1-alpha)*(hs + conv) = hs + (1-alpha)*conv
-        return E.conv_temporal(t, g, tp.conv2, res1=hs, scales=s8[4:7], res1_unit=True, blend=(blk.time_mixer.mix_factor, s8[1:2]))
+        return E.conv_temporal(t, g, tp.conv2, res1=hs, scales=s8[4:7], res1_unit=True, blend=(blk.time_mixer.mix_factor, s8[1:2]),
+                               gn_rows=g.HW)     # block output: the next GroupNorm (resnet norm1 / transformer norm / concat) is per frame
 
     @staticmethod
     def _qkv_lora(attn: Attention):
@@ -865,7 +866,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         # alpha*x_spatial + (1-alpha)*(ff + y2)
         xb = E.linear(ff, tb.ff.net[2].weight, tb.ff.net[2].bias, res1=x2, res2=y2, scales=s8[0:3],
                       blend=(tr.time_mixer.mix_factor, s8[1:2]))
-        return E.linear(xb, tr.proj_out.weight, tr.proj_out.bias, res1=x_in)
+        return E.linear(xb, tr.proj_out.weight, tr.proj_out.bias, res1=x_in, gn_rows=g.HW)
 
 
 class _UNetFn(torch.autograd.Function):

@@ -275,3 +275,48 @@ def test_multi_transpose_bit_exact(raw):
     for (O, I), off, d in zip(shapes, offs, dsts):
         ref = src[off:off + O * I].view(O, I).t().contiguous()
         assert torch.equal(d, ref), f"transpose {O}x{I}"
+
+
+@pytest.mark.parametrize("outer,rows,C1,C2,silu", [(14, 2560, 320, 0, True), (14, 160, 1280, 640, True), (2, 560, 640, 320, False),
+                                                    (3, 40, 1280, 1280, True), (1, 1000, 64, 0, True)])
+def test_groupnorm_apply_fused_from_channel_sums(raw, outer, rows, C1, C2, silu):
+    """svdx_groupnorm_apply_fused: group statistics folded from per-channel sums (as the GEMM epilogues produce them), one or
+    two channel-concatenated sources, against F.group_norm; mean / rstd published for the backward."""
+    C = C1 + C2
+    x1 = _rand(outer * rows, C1, seed=5).to(bf16) + 0.5
+    x2 = _rand(outer * rows, C2, seed=6).to(bf16) if C2 else None
+    gamma = _rand(C, seed=7) * 0.2 + 1.0
+    beta = _rand(C, seed=8) * 0.1
+
+    def sums(t):
+        v = t.float().view(outer, rows, -1)
+        return torch.stack([v.sum(1), (v * v).sum(1)], dim=1).contiguous()      # [outer, 2, Ci]
+
+    y = torch.empty(outer * rows, C, device=DEV, dtype=bf16)
+    mean, rstd = raw.groupnorm_apply_fused(x1, x2, outer, rows, 1e-5, sums(x1), sums(x2) if C2 else None, gamma, beta, silu, y)
+    torch.cuda.synchronize()
+    xcat = torch.cat([x1, x2], 1) if C2 else x1
+    xr = xcat.float().reshape(outer, rows, C).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    _close(y.view(outer, rows, C), ref.permute(0, 2, 1), what="groupnorm fused fwd")
+    v = xr.reshape(outer, 32, -1)
+    assert torch.allclose(mean.view(outer, 32), v.mean(-1), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(rstd.view(outer, 32), torch.rsqrt(v.var(-1, unbiased=False) + 1e-5), atol=1e-3, rtol=1e-3)
+    # the published statistics drive the (unchanged) backward kernels; zeroed-workspace form
+    dy = _rand(outer * rows, C, seed=9).to(bf16)
+    dx1 = torch.zeros_like(x1)
+    dx2 = torch.zeros_like(x2) if C2 else None
+    ws = torch.zeros(2 * outer * 32, device=DEV)
+    raw.groupnorm_bwd(x1, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx1, dx2, ws=ws)
+    torch.cuda.synchronize()
+    xg = xcat.float().reshape(outer, rows, C).permute(0, 2, 1).requires_grad_(True)
+    r2 = F.group_norm(xg, 32, gamma, beta, 1e-5)
+    if silu:
+        r2 = F.silu(r2)
+    r2.backward(dy.float().view(outer, rows, C).permute(0, 2, 1))
+    dxr = xg.grad.permute(0, 2, 1).reshape(outer * rows, C)
+    _close(dx1, dxr[:, :C1], what="groupnorm dx (fused stats)")
+    if C2:
+        _close(dx2, dxr[:, C1:], what="groupnorm dx2 (fused stats)")

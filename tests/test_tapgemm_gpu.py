@@ -277,3 +277,65 @@ def test_conv3x3_auto_split_k(raw, N, H, W, Cin, Cout):
                      bias=bias, rowbias=rb, rowbias_div=M // 2, res1=res, scales=scales)
     torch.cuda.synchronize()
     _close(out2, ref, what="conv split-k (workspace reuse)")
+
+
+def _check_gn_sums(sums, out, rows_per_slab, what):
+    """sums [slabs, 2, C] against fp64 column sums of the STORED bf16 output"""
+    slabs, _, C = sums.shape
+    o = out.double().view(slabs, rows_per_slab, C)
+    ref1, ref2 = o.sum(1), (o * o).sum(1)
+    e1 = (sums[:, 0].double() - ref1).abs().max().item() / (ref1.abs().max().item() + 1e-9)
+    e2 = (sums[:, 1].double() - ref2).abs().max().item() / (ref2.abs().max().item() + 1e-9)
+    assert e1 < 2e-5 and e2 < 2e-5, f"{what}: channel-sum error {e1:.3g} / {e2:.3g}"
+
+
+@pytest.mark.parametrize("M,N,K,rows", [(35840, 320, 320, 2560), (2240, 640, 1280, 160), (560, 1280, 640, 40), (280, 320, 128, 40),
+                                        (1024, 64, 64, 256), (4480, 1280, 320, 2240)])
+@pytest.mark.parametrize("res", [False, True])
+def test_fused_groupnorm_sums_linear(raw, M, N, K, rows, res):
+    """gn_sum of svdx_tapgemm: per (slab, channel) sum / sum of squares of the stored output, plain and residual epilogues,
+    CTA-pair and 1-CTA kernels (M < 512), slabs aligned (2560, 160) and NOT aligned (40) to the 32-row warp slices."""
+    a = _rand(M, K, seed=1).to(bf16)
+    w = _rand(N, K, scale=K ** -0.5, seed=2).to(bf16)
+    bias = _rand(N, seed=3)
+    r1 = _rand(M, N, seed=4).to(bf16) if res else None
+    out = torch.empty(M, N, device=_dev(), dtype=bf16)
+    sums = torch.zeros(M // rows, 2, N, device=_dev())
+    raw.tapgemm(a, w, out, M=M, N=N, K=K, bias=bias, res1=r1, gn_sum=sums, gn_rows=rows)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias + (r1.float() if res else 0)
+    _close(out, ref, what="linear + gn_sum")
+    _check_gn_sums(sums, out, rows, f"linear {M}x{N}x{K} rows {rows} res {res}")
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,per_clip", [(14, 40, 64, 64, 320, False), (14, 5, 8, 128, 160, False), (14, 10, 16, 320, 640, True),
+                                                       (4, 20, 32, 192, 320, True)])
+def test_fused_groupnorm_sums_conv3x3(raw, N, H, W, Cin, Cout, per_clip):
+    x = _rand(N, H, W, Cin, seed=20).to(bf16)
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=21).to(bf16)
+    bias = _rand(Cout, seed=22)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9 * Cin)
+    out = torch.empty(N * H * W, Cout, device=_dev(), dtype=bf16)
+    rows = N * H * W if per_clip else H * W
+    sums = torch.zeros(N * H * W // rows, 2, Cout, device=_dev())
+    raw.tapgemm(x.view(-1, Cin), wk, out, M=N * H * W, N=Cout, K=Cin, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS,
+                conv_whn=(W, H, N), bias=bias, gn_sum=sums, gn_rows=rows)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    _close(out, ref, what="conv3x3 + gn_sum")
+    _check_gn_sums(sums, out, rows, f"conv {N}x{H}x{W} {Cin}->{Cout}")
+
+
+def test_fused_groupnorm_sums_temporal_conv_grouped(raw):
+    """grouped ROWS mode (B = 2 clips): slab index must follow the GLOBAL row (group * rows_per_group + row)"""
+    B, T, HW, C = 2, 5, 40, 320
+    x = _rand(B, T, HW, C, seed=17).to(bf16)
+    w = _rand(C, C, 3, scale=(3 * C) ** -0.5, seed=18).to(bf16)
+    wk = w.permute(0, 2, 1).contiguous().view(C, 3 * C)
+    out = torch.empty(B * T * HW, C, device=_dev(), dtype=bf16)
+    taps = [(-HW, 0, 0), (0, 0, 0), (HW, 0, 0)]
+    for rows in (HW, T * HW):
+        sums = torch.zeros(B * T * HW // rows, 2, C, device=_dev())
+        raw.tapgemm(x.view(-1, C), wk, out, M=B * T * HW, N=C, K=C, taps=taps, rows_per_group=T * HW, groups=B, gn_sum=sums, gn_rows=rows)
+        torch.cuda.synchronize()
+        _check_gn_sums(sums, out, rows, f"temporal conv slab {rows}")
