@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configuration")
+    ap.add_argument("--ddp", default="sharded", choices=["sharded", "allreduce"],
+                    help="N > 1: reduce-scatter + sharded AdamW + bf16 all-gather (default) or bucketed all-reduce + replicated AdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager bf16-autocast oracle timing on the GPU")
     ap.add_argument("--no-families", action="store_true", help="skip the per-family ablation rooflines")
@@ -307,7 +309,7 @@ def main():
 
     import torch.distributed as dist
     from svd_xtend_b200 import raw
-    from svd_xtend_b200.train import FusedAdamW, GradReducer, GraphedStep, ParamArena
+    from svd_xtend_b200.train import FusedAdamW, GradReducer, GraphedStep, ParamArena, ShardedAdamW
     from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel
     from svd_xtend_b200.workload import BENCH_CONFIGS, SVD_CONFIG, edm_loss, synthetic_batch   # train_svd.py:951-1036
 
@@ -348,11 +350,15 @@ def main():
     unet.train()
     if cfg["grad_ckpt"]:
         unet.enable_gradient_checkpointing()     # train_svd.py:731-732
-    arena = ParamArena(unet)
+    sharded = world > 1 and args.ddp == "sharded"
+    arena = ParamArena(unet, pad_to=world * 64)
     unet.attach_arena(arena)
-    opt = FusedAdamW(arena, lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)   # train_svd.py:384-418 defaults
-    opt.on_updated = lambda: unet.refresh_trainable_operands(shadow_current=True)   # FusedAdamW rewrites the bf16 shadow itself
-    reducer = GradReducer(arena) if world > 1 else None
+    hyper = dict(lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)             # train_svd.py:384-418 defaults
+    # N > 1 (default): reduce-scatter of the gradient arena + AdamW on this rank's 1/N slice + all-gather of the bf16 operand
+    # weights (0.75x the NVLink bytes of an all-reduce, 1/N of the optimizer traffic); --ddp allreduce keeps replicated AdamW
+    opt = ShardedAdamW(arena, **hyper) if sharded else FusedAdamW(arena, **hyper)
+    opt.on_updated = lambda: unet.refresh_trainable_operands(shadow_current=True)   # the optimizer rewrites the bf16 shadow itself
+    reducer = GradReducer(arena) if (world > 1 and not sharded) else None
     if reducer is not None:
         unet.grad_hook = lambda ps: reducer.on_grads_ready(ps) if ps is not None else None
 
@@ -648,7 +654,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (seeded default-init weights, randn latents per train_svd.py:951-1017)",
         "config": {"workload": cfg["name"], "baseline_config": args.config, "frames": frames, "latent_hw": [lat_h, lat_w], "per_gpu_batch": 1,
-                   "global_batch": world, "trainable_params": n_train, "total_params": n_total, "parallelism": f"dp{world}",
+                   "global_batch": world, "trainable_params": n_train, "total_params": n_total, "parallelism": f"dp{world}" + ("" if world == 1 else "-zero1" if sharded else "-allreduce"),
                    "cuda_graph": graph_captured, "gradient_checkpointing": bool(cfg["grad_ckpt"]), "lora_rank": cfg["lora_rank"],
                    "l2": "no explicit flush: the per-step working set (3 GB bf16 operand weights + >10 GB activations) is >> 126 MB L2",
                    "final_loss": final_loss, "cpu_arm": CPU_ARM_NOTE},

@@ -241,9 +241,10 @@ int svdx_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream
 int svdx_axpby_bf16(const void* a, const void* b, const float* scales, void* y, int64_t n, void* stream);
 int svdx_silu_f32(const float* x, float* y, int64_t n, void* stream);
 int svdx_colsum(const void* x, int64_t ldx, int64_t rows, int32_t cols, float* out, int32_t accumulate, void* stream);
-/* GEGLU backward: dpre[m][:h] = dout*gelu(gate); dpre[m][h:] = dout*value*gelu'(gate) */
+/* GEGLU backward: dpre[m][:h] = dout*gelu(gate); dpre[m][h:] = dout*value*gelu'(gate). bias_grad (optional, fp32 [2h], accumulated):
+ * += column sums of the dpre values written — the bias gradient of the GEGLU projection, fused into the same pass */
 int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t lddo, void* dpre, int64_t lddpre,
-                   int64_t rows, int32_t h, void* stream);
+                   int64_t rows, int32_t h, float* bias_grad, void* stream);
 /* AlphaBlender epilogue scale triples from mix_factor, a = sigmoid(mix_factor); writes float[16]:
  *   out[0..3]   = {1-a, a, 1-a, 0}      transformer blend  out = a*x_spatial + (1-a)*(acc + residual)
  *   out[4..7]   = {1-a, 1, 0, a*(1-a)}  resnet blend       out = x_spatial + (1-a)*acc

@@ -1,45 +1,102 @@
-"""N-rank equivalence check (run under torchrun): the all-reduced gradient on every rank equals the mean of the
-single-rank gradients computed with the same weights on each rank's clip."""
-import os, sys
+"""N-rank equivalence checks (run under torchrun, one rank per GPU):
+ (1) all-reduce path: the reduced gradient on every rank equals the mean of the single-rank gradients computed with the same
+     weights on each rank's clip, bit-identical across ranks;
+ (2) sharded path (ShardedAdamW: reduce-scatter + AdamW on 1/N + bf16 all-gather): after one step every rank holds the same
+     bf16 operand weights, equal to those of the all-reduce + replicated FusedAdamW step, and gather_masters() restores the
+     fp32 masters everywhere."""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch, torch.distributed as dist
-from oracle.svd_unet_oracle import TINY_CONFIG, edm_loss, synthetic_batch
+import torch
+import torch.distributed as dist
+
+from svd_xtend_b200.train import FusedAdamW, GradReducer, ParamArena, ShardedAdamW
 from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel
-from svd_xtend_b200.train import ParamArena, GradReducer
+from svd_xtend_b200.workload import edm_loss, synthetic_batch
+
+TINY = dict(sample_size=None, in_channels=8, out_channels=4,
+            down_block_types=("CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal"),
+            up_block_types=("UpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal"),
+            block_out_channels=(64, 128), addition_time_embed_dim=32, projection_class_embeddings_input_dim=96, layers_per_block=1,
+            cross_attention_dim=64, transformer_layers_per_block=1, num_attention_heads=(1, 2), num_frames=4)
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-torch.manual_seed(0)
-unet = UNetSpatioTemporalConditionModel(**TINY_CONFIG).to(dev)
-unet.requires_grad_(False)
-for n, p in unet.named_parameters():
-    if "temporal_transformer_block" in n:
-        p.requires_grad_(True)
-unet.train()
-arena = ParamArena(unet); unet.attach_arena(arena)
-red = GradReducer(arena, bucket_mb=0.5)
-unet.grad_hook = lambda ps: red.on_grads_ready(ps) if ps is not None else None
 
-def grads_for(seed, reduce):
-    b = synthetic_batch(1, 4, 16, 16, seed=seed, device=dev, cross_dim=TINY_CONFIG["cross_attention_dim"])
+
+def build():
+    torch.manual_seed(0)
+    unet = UNetSpatioTemporalConditionModel(**TINY).to(dev)
+    unet.requires_grad_(False)
+    for n, p in unet.named_parameters():
+        if "temporal_transformer_block" in n:
+            p.requires_grad_(True)
+    unet.train()
+    arena = ParamArena(unet, pad_to=world * 64)
+    unet.attach_arena(arena)
+    return unet, arena
+
+
+def backward(unet, arena, seed):
+    b = synthetic_batch(1, 4, 16, 16, seed=seed, device=dev, cross_dim=TINY["cross_attention_dim"])
     arena.zero_grad()
-    unet.grad_hook = (lambda ps: red.on_grads_ready(ps) if ps is not None else None) if reduce else None
     pred = unet(b["sample"], b["timestep"], b["encoder_hidden_states"], b["added_time_ids"]).sample
     edm_loss(pred.float(), b["noisy"], b["latents"], b["sigmas"]).backward()
-    if reduce:
-        red.finish()
-    torch.cuda.synchronize()
-    return arena.grad.clone()
 
-g_red = grads_for(100 + rank, True)
-singles = [grads_for(100 + r, False) for r in range(world)]
+
+# ---- (1) all-reduce path
+unet, arena = build()
+red = GradReducer(arena, bucket_mb=0.5)
+unet.grad_hook = lambda ps: red.on_grads_ready(ps) if ps is not None else None
+backward(unet, arena, 100 + rank)
+red.finish()
+torch.cuda.synchronize()
+g_red = arena.grad.clone()
+unet.grad_hook = None
+singles = []
+for r in range(world):
+    backward(unet, arena, 100 + r)
+    torch.cuda.synchronize()
+    singles.append(arena.grad.clone())
 ref = sum(singles) / world
 rel = ((g_red - ref).norm() / ref.norm()).item()
 others = [torch.empty_like(g_red) for _ in range(world)]
 dist.all_gather(others, g_red)
 same = all(torch.equal(o, g_red) for o in others)
-print(f"[ddp_check] rank {rank}: reduced-vs-mean rel-l2 {rel:.3e}, identical across ranks: {same}, buckets {len(red.buckets)}")
+print(f"[ddp_check] rank {rank}: all-reduce path: reduced-vs-mean rel-l2 {rel:.3e}, identical across ranks: {same}, buckets {len(red.buckets)}", flush=True)
 assert rel < 2e-2 and same
+
+# ---- (2) sharded path vs all-reduce + replicated AdamW, same gradients
+w0 = arena.data.clone()
+arena.grad.copy_(singles[rank])
+opt_ref = FusedAdamW(arena, lr=1e-3, weight_decay=1e-2)
+dist.all_reduce(arena.grad)
+arena.grad.mul_(1.0 / world)
+opt_ref.step()
+torch.cuda.synchronize()
+shadow_ref, data_ref = arena.shadow.clone(), arena.data.clone()
+
+arena.data.copy_(w0)
+arena.refresh_shadow()
+arena.grad.copy_(singles[rank])
+opt = ShardedAdamW(arena, lr=1e-3, weight_decay=1e-2)
+opt.step()
+torch.cuda.synchronize()
+upd_ref = (shadow_ref.float() - w0)
+upd = (arena.shadow.float() - w0)
+e_shadow = ((upd - upd_ref).norm() / upd_ref.norm()).item()
+others = [torch.empty_like(arena.shadow) for _ in range(world)]
+dist.all_gather(others, arena.shadow)
+same_shadow = all(torch.equal(o, arena.shadow) for o in others)
+own = ((arena.data[opt.lo:opt.hi] - data_ref[opt.lo:opt.hi]).abs().max() / (data_ref[opt.lo:opt.hi] - w0[opt.lo:opt.hi]).abs().max()).item()
+opt.gather_masters()
+torch.cuda.synchronize()
+e_masters = ((arena.data - data_ref).norm() / (data_ref - w0).norm()).item()
+print(f"[ddp_check] rank {rank}: sharded path: bf16 operand update vs all-reduce+AdamW rel-l2 {e_shadow:.3e}, identical across ranks: {same_shadow}, "
+      f"own-slice master max err / max update {own:.3e}, masters after gather rel-l2 of update {e_masters:.3e}, t = {opt.t}", flush=True)
+assert e_shadow < 2e-2 and same_shadow and own < 1e-3 and e_masters < 1e-3 and opt.t == 1
+dist.barrier()
 dist.destroy_process_group()

@@ -265,27 +265,69 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   }
 }
 
-// GEGLU backward. pre = [value | gate] (bf16, the saved projection), dout [rows][h]
-__global__ void geglu_bwd_kernel(const bf16* __restrict__ pre, long long ldpre, const bf16* __restrict__ dout, long long lddo,
-                                 bf16* __restrict__ dpre, long long lddpre, long long rows, int h) {
-  const long long idx = gtid();  // one thread per 8 columns
-  const int hv = h / 8;
-  if (idx >= rows * hv) return;
-  const long long r = idx / hv;
-  const int c = (int)(idx - r * hv) * 8;
-  const uint4 uv = *reinterpret_cast<const uint4*>(pre + r * ldpre + c);
-  const uint4 ug = *reinterpret_cast<const uint4*>(pre + r * ldpre + h + c);
-  const uint4 ud = *reinterpret_cast<const uint4*>(dout + r * lddo + c);
-  const uint32_t v[4] = {uv.x, uv.y, uv.z, uv.w}, g[4] = {ug.x, ug.y, ug.z, ug.w}, d[4] = {ud.x, ud.y, ud.z, ud.w};
-  uint32_t ov[4], og[4];
+// GEGLU backward. pre = [value | gate] (bf16, the saved projection), dout [rows][h]:
+//   dpre[:, :h] = dout * gelu(gate),  dpre[:, h:] = dout * value * gelu'(gate)
+// and, fused, the bias gradient of the projection = column sums of the (bf16-rounded) dpre it writes — saving the separate
+// column-sum pass over the [rows][2h] tensor (the largest activation gradient of a transformer block).
+// Block = 32 column vectors (8 columns each) x 8 row lanes, rows streamed in chunks of rows_per_cta like colsum_kernel.
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__ pre, long long ldpre, const bf16* __restrict__ dout, long long lddo,
+                                                        bf16* __restrict__ dpre, long long lddpre, long long rows, int h, long long rows_per_cta,
+                                                        float* __restrict__ bias_grad) {
+  __shared__ float sh[8][2][256 + 8];
+  const int cvl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cvl) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, rows);
+  float av[8], ag[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 fv = unpack_bf16x2(v[k]), fg = unpack_bf16x2(g[k]), fd = unpack_bf16x2(d[k]);
-    ov[k] = pack_bf16x2(fd.x * gelu_erf_f(fg.x), fd.y * gelu_erf_f(fg.y));
-    og[k] = pack_bf16x2(fd.x * fv.x * gelu_erf_grad_f(fg.x), fd.y * fv.y * gelu_erf_grad_f(fg.y));
+  for (int k = 0; k < 8; ++k) { av[k] = 0.f; ag[k] = 0.f; }
+  if (c < h) {
+    for (long long r = r0 + rl; r < r1; r += 16) {
+      // two rows in flight per thread
+      const bool two = (r + 8 < r1);
+      uint4 uv[2], ug[2], ud[2];
+      uv[0] = *reinterpret_cast<const uint4*>(pre + r * ldpre + c);
+      ug[0] = *reinterpret_cast<const uint4*>(pre + r * ldpre + h + c);
+      ud[0] = *reinterpret_cast<const uint4*>(dout + r * lddo + c);
+      if (two) {
+        uv[1] = *reinterpret_cast<const uint4*>(pre + (r + 8) * ldpre + c);
+        ug[1] = *reinterpret_cast<const uint4*>(pre + (r + 8) * ldpre + h + c);
+        ud[1] = *reinterpret_cast<const uint4*>(dout + (r + 8) * lddo + c);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q == 1 && !two) break;
+        const uint32_t v[4] = {uv[q].x, uv[q].y, uv[q].z, uv[q].w}, g[4] = {ug[q].x, ug[q].y, ug[q].z, ug[q].w}, d[4] = {ud[q].x, ud[q].y, ud[q].z, ud[q].w};
+        uint32_t ov[4], og[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 fv = unpack_bf16x2(v[k]), fg = unpack_bf16x2(g[k]), fd = unpack_bf16x2(d[k]);
+          ov[k] = pack_bf16x2(fd.x * gelu_erf_f(fg.x), fd.y * gelu_erf_f(fg.y));
+          og[k] = pack_bf16x2(fd.x * fv.x * gelu_erf_grad_f(fg.x), fd.y * fv.y * gelu_erf_grad_f(fg.y));
+          if (bias_grad) {
+            const float2 rv = unpack_bf16x2(ov[k]), rg = unpack_bf16x2(og[k]);
+            av[2 * k] += rv.x; av[2 * k + 1] += rv.y;
+            ag[2 * k] += rg.x; ag[2 * k + 1] += rg.y;
+          }
+        }
+        const long long rr = r + 8 * q;
+        *reinterpret_cast<uint4*>(dpre + rr * lddpre + c) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        *reinterpret_cast<uint4*>(dpre + rr * lddpre + h + c) = make_uint4(og[0], og[1], og[2], og[3]);
+      }
+    }
   }
-  *reinterpret_cast<uint4*>(dpre + r * lddpre + c) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-  *reinterpret_cast<uint4*>(dpre + r * lddpre + h + c) = make_uint4(og[0], og[1], og[2], og[3]);
+  if (!bias_grad) return;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sh[rl][0][cvl * 8 + k] = av[k]; sh[rl][1][cvl * 8 + k] = ag[k]; }
+  __syncthreads();
+  {
+    const int cc = threadIdx.x;   // 256 columns of this block, both halves
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s0 += sh[k][0][cc]; s1 += sh[k][1][cc]; }
+    const int col = blockIdx.x * 256 + cc;
+    if (col < h) { atomicAdd(bias_grad + col, s0); atomicAdd(bias_grad + h + col, s1); }
+  }
 }
 
 __global__ void unprep_conv_grad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int taps, int i_pad) {
@@ -651,11 +693,18 @@ extern "C" int svdx_colsum(const void* x, int64_t ldx, int64_t rows, int32_t col
 }
 
 extern "C" int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t lddo, void* dpre, int64_t lddpre, int64_t rows,
-                              int32_t h, void* stream) {
+                              int32_t h, float* bias_grad, void* stream) {
   if (!pre || !dout || !dpre || rows <= 0 || h <= 0 || h % 8 || ldpre % 8 || lddo % 8 || lddpre % 8)
     return svdx_fail(SVDX_E_BADARG, "geglu_bwd: bad arguments");
-  geglu_bwd_kernel<<<nblocks(rows * (h / 8)), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), ldpre, reinterpret_cast<const bf16*>(dout),
-                                                                    lddo, reinterpret_cast<bf16*>(dpre), lddpre, rows, h);
+  const int col_blocks = (h + 255) / 256;
+  long long chunks = (8LL * svdx_num_sms() + col_blocks - 1) / col_blocks;
+  if (chunks < 1) chunks = 1;
+  long long rows_per_cta = (rows + chunks - 1) / chunks;
+  rows_per_cta = (rows_per_cta + 15) / 16 * 16;
+  if (rows_per_cta < 16) rows_per_cta = 16;
+  chunks = (rows + rows_per_cta - 1) / rows_per_cta;
+  geglu_bwd_kernel<<<dim3(col_blocks, (unsigned)chunks), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), ldpre, reinterpret_cast<const bf16*>(dout),
+                                                                             lddo, reinterpret_cast<bf16*>(dpre), lddpre, rows, h, rows_per_cta, bias_grad);
   SVDX_CHECK_LAUNCH("geglu_bwd");
   return SVDX_OK;
 }

@@ -390,58 +390,93 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
 }
 
 // ------------------------------------------------------------------ LayerNorm
-constexpr int LN_MAXJ = 40;  // C <= 2560
 
-template <int NJ>
+// forward: a warp takes RPW rows at a time (grid-stride), lane l owns the 8-channel vectors l, l + 32, ... of each (16-byte loads
+// and stores; all RPW rows' loads are issued before any arithmetic so that a warp keeps RPW * C * 2 bytes in flight); the
+// rows stay in registers between the two statistics passes and the normalisation
+template <int NJ, int RPW>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int rows, int C,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                      bf16* __restrict__ y, long long ldy, float* __restrict__ mean, float* __restrict__ rstd,
                                                      const float* __restrict__ addvec, int add_div, bf16* __restrict__ xsum, long long ldxs) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const bf16* xr = x + (long long)warp * ldx;
-  const float* av = addvec ? addvec + (long long)(warp / add_div) * C : nullptr;
-  float2 v[NJ];
-  float sum = 0.f;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int CV = C / 8;
+  const float invC = 1.0f / C;
+  for (int row0 = warp0 * RPW; row0 < rows; row0 += nwarps * RPW) {
+    uint4 u[RPW][NJ];
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int c = 2 * lane + 64 * j;
-    if (c < C) {
-      v[j] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
-      if (av) {
-        // x + addvec is rounded to bf16 (it is the residual stream value the reference materialises)
-        const uint32_t pk = pack_bf16x2(v[j].x + av[c], v[j].y + av[c + 1]);
-        *reinterpret_cast<uint32_t*>(xsum + (long long)warp * ldxs + c) = pk;
-        v[j] = unpack_bf16x2(pk);
+    for (int r = 0; r < RPW; ++r) {
+      if (row0 + r < rows) {
+        const bf16* xr = x + (long long)(row0 + r) * ldx;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int v = lane + 32 * j;
+          if (v < CV) u[r][j] = *reinterpret_cast<const uint4*>(xr + v * 8);
+        }
       }
-      sum += v[j].x + v[j].y;
-    } else {
-      v[j] = make_float2(0.f, 0.f);
     }
-  }
-  sum = warp_sum(sum);
-  const float m = sum / C;
-  float sq = 0.f;
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int c = 2 * lane + 64 * j;
-    if (c < C) {
-      const float a = v[j].x - m, b = v[j].y - m;
-      sq += a * a + b * b;
-    }
-  }
-  sq = warp_sum(sq);
-  const float rs = rsqrtf(sq / C + eps);
-  if (lane == 0) { mean[warp] = m; rstd[warp] = rs; }
-  bf16* yr = y + (long long)warp * ldy;
+    for (int r = 0; r < RPW; ++r) {
+      const int row = row0 + r;
+      if (row >= rows) break;                     // warp-uniform
+      const float* av = addvec ? addvec + (long long)(row / add_div) * C : nullptr;
+      float f[NJ][8];
+      float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int c = 2 * lane + 64 * j;
-    if (c < C) {
-      const float a = (v[j].x - m) * rs * gamma[c] + beta[c];
-      const float b = (v[j].y - m) * rs * gamma[c + 1] + beta[c + 1];
-      *reinterpret_cast<uint32_t*>(yr + c) = pack_bf16x2(a, b);
+      for (int j = 0; j < NJ; ++j) {
+        const int v = lane + 32 * j;
+        if (v < CV) {
+          const uint32_t w[4] = {u[r][j].x, u[r][j].y, u[r][j].z, u[r][j].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 a = unpack_bf16x2(w[k]); f[j][2 * k] = a.x; f[j][2 * k + 1] = a.y; }
+          if (av) {
+            // x + addvec is rounded to bf16 (it is the residual stream value the reference materialises)
+            const float4 a0 = *reinterpret_cast<const float4*>(av + v * 8), a1 = *reinterpret_cast<const float4*>(av + v * 8 + 4);
+            const float ad[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              pk[k] = pack_bf16x2(f[j][2 * k] + ad[2 * k], f[j][2 * k + 1] + ad[2 * k + 1]);
+              const float2 r2 = unpack_bf16x2(pk[k]);
+              f[j][2 * k] = r2.x; f[j][2 * k + 1] = r2.y;
+            }
+            *reinterpret_cast<uint4*>(xsum + (long long)row * ldxs + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) sum += f[j][k];
+        }
+      }
+      sum = warp_sum(sum);
+      const float m = sum * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int v = lane + 32 * j;
+        if (v < CV) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const float d = f[j][k] - m; sq = fmaf(d, d, sq); }
+        }
+      }
+      sq = warp_sum(sq);
+      const float rs = rsqrtf(sq * invC + eps);
+      if (lane == 0) { mean[row] = m; rstd[row] = rs; }
+      bf16* yr = y + (long long)row * ldy;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int v = lane + 32 * j;
+        if (v < CV) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            pk[k] = pack_bf16x2(fmaf((f[j][2 * k] - m) * rs, gm[2 * k], bt[2 * k]), fmaf((f[j][2 * k + 1] - m) * rs, gm[2 * k + 1], bt[2 * k + 1]));
+          *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
     }
   }
 }
@@ -668,27 +703,31 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
   return SVDX_OK;
 }
 
-template <int NJ>
+template <int NJ, int RPW>
 static void ln_fwd_launch(const void* x, int64_t ldx, int rows, int C, const float* g, const float* b, float eps, void* y, int64_t ldy,
                           float* mean, float* rstd, const float* addvec, int add_div, void* xsum, int64_t ldxs, cudaStream_t st) {
-  const int warps_per_cta = 8;
-  ln_fwd_kernel<NJ><<<(rows + warps_per_cta - 1) / warps_per_cta, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, rows, C, g, b, eps,
-                                                                              reinterpret_cast<bf16*>(y), ldy, mean, rstd, addvec, add_div,
-                                                                              reinterpret_cast<bf16*>(xsum), ldxs);
+  int ctas = (rows + 8 * RPW - 1) / (8 * RPW);     // 8 warps per CTA, RPW rows in flight per warp, grid-stride over rows
+  const int cap = svdx_num_sms() * 8;
+  if (ctas > cap) ctas = cap;
+  ln_fwd_kernel<NJ, RPW><<<ctas, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, rows, C, g, b, eps, reinterpret_cast<bf16*>(y), ldy, mean, rstd,
+                                          addvec, add_div, reinterpret_cast<bf16*>(xsum), ldxs);
 }
 
 extern "C" int svdx_layernorm_fwd(const void* x, int64_t ldx, int32_t rows, int32_t C, const float* gamma, const float* beta, float eps,
                                   void* y, int64_t ldy, float* mean, float* rstd, const float* addvec, int32_t add_div, void* xsum,
                                   int64_t ldxs, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
-  if (!x || !y || !gamma || !beta || !mean || !rstd || rows <= 0 || C <= 0 || C % 2 || C > 64 * LN_MAXJ || ldx % 2 || ldy % 2 ||
-      (addvec && (!xsum || add_div <= 0 || ldxs % 2)))
-    return svdx_fail(SVDX_E_BADARG, "layernorm_fwd: bad arguments");
-  const int nj = (C + 63) / 64;
-  if (nj <= 5) ln_fwd_launch<5>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
-  else if (nj <= 10) ln_fwd_launch<10>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
-  else if (nj <= 20) ln_fwd_launch<20>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
-  else ln_fwd_launch<40>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  if (!x || !y || !gamma || !beta || !mean || !rstd || rows <= 0 || C <= 0 || C % 8 || C > 2560 || ldx % 8 || ldy % 8 ||
+      (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(gamma) & 15) ||
+      (reinterpret_cast<uintptr_t>(beta) & 15) ||
+      (addvec && (!xsum || add_div <= 0 || ldxs % 8 || (reinterpret_cast<uintptr_t>(addvec) & 15) || (reinterpret_cast<uintptr_t>(xsum) & 15))))
+    return svdx_fail(SVDX_E_BADARG, "layernorm_fwd: bad arguments (C %% 8, C <= 2560, 16-byte aligned rows and vectors)");
+  const int nj = (C / 8 + 31) / 32;
+  if (nj <= 1) ln_fwd_launch<1, 4>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  else if (nj <= 2) ln_fwd_launch<2, 2>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  else if (nj <= 3) ln_fwd_launch<3, 2>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  else if (nj <= 5) ln_fwd_launch<5, 1>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  else ln_fwd_launch<10, 1>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
   SVDX_CHECK_LAUNCH("layernorm_fwd");
   return SVDX_OK;
 }

@@ -404,8 +404,12 @@ class Engine:
                 self._mix_grad(blend, dy, res1, out)
                 self._res_grad(res1, dy, None if (scales is None or res1_unit) else scales[1:2])
                 self._res_grad(res2, dy, None if scales is None else scales[2:3])
+                bias_done = False
                 if geglu:
-                    dyl = raw.geglu_bwd(pre, dy, torch.empty_like(pre))
+                    # the projection's bias gradient (column sums of dpre) rides in the same pass
+                    fuse_b = bias is not None and bias.requires_grad and scales is None and self.pgrad(bias).numel() == pre.shape[1]
+                    dyl = raw.geglu_bwd(pre, dy, torch.empty_like(pre), bias_grad=self.pgrad(bias) if fuse_b else None)
+                    bias_done = fuse_b
                 else:
                     dyl = dy
                 self._rowbias_grad(rowbias, dyl, rowbias_div, s_acc)
@@ -417,7 +421,7 @@ class Engine:
                     self.add_grad(x, dx)
                 if any(p.requires_grad for p in ws):
                     self._wgrad(dyl, x.data, ws, N, K, M, sc3)
-                if bias is not None and bias.requires_grad:
+                if bias is not None and bias.requires_grad and not bias_done:
                     self._bias_grad(bias, dyl, s_acc)
                 for (off, n, A, Bm, sc), t in zip(lora, lora_t):
                     r = A.shape[0]

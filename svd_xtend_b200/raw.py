@@ -521,12 +521,13 @@ def colsum(x, out, accumulate=False):
     return out
 
 
-def geglu_bwd(pre, dout, dpre):
+def geglu_bwd(pre, dout, dpre, bias_grad=None):
+    """bias_grad: fp32 [2h] accumulator of the GEGLU projection's bias gradient (column sums of dpre, fused in the same pass)"""
     rows, h2 = pre.shape
     if _fam("elementwise", 0.0, 10.0 * rows * (h2 // 2)):
         return dpre
     check(load().svdx_geglu_bwd(pre.data_ptr(), _rowmajor(pre, "pre"), dout.data_ptr(), _rowmajor(dout, "dout"), dpre.data_ptr(),
-                                _rowmajor(dpre, "dpre"), rows, h2 // 2, _stream()), "geglu_bwd")
+                                _rowmajor(dpre, "dpre"), rows, h2 // 2, _ptr(bias_grad), _stream()), "geglu_bwd")
     return dpre
 
 

@@ -464,6 +464,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         self._resblocks: List[SpatioTemporalResBlock] = [m for m in self.modules() if isinstance(m, SpatioTemporalResBlock)]
         self.grad_hook = None   # callable(list_of_params) invoked as soon as parameter gradients are final (DDP overlap)
         self._arena = None
+        self._graphs = None     # autograph.GraphRunner: shape-keyed CUDA graphs of this module's forward / backward
 
     # ------------------------------------------------------------------ training plumbing (svd_xtend_b200.train)
     def attach_arena(self, arena):
@@ -472,6 +473,16 @@ class UNetSpatioTemporalConditionModel(nn.Module):
         self._engine.grad_views = arena.grad_views if arena is not None else {}
         self._engine.arena = arena
         self._engine.wc.clear()
+
+    def enable_cuda_graphs(self, warmup: int = 2):
+        """Serve `forward` / `backward` of the unchanged training script from shape-keyed CUDA graphs (svd_xtend_b200.autograph):
+        after `warmup` eager calls per input signature the ~2 200 launches of a step become two graph launches. Needs fp32
+        trainable parameters (they are re-homed into a flat arena). Call after `requires_grad_` / `add_adapter` set-up."""
+        from . import autograph
+        return autograph.enable(self, warmup)
+
+    def disable_cuda_graphs(self):
+        self._graphs = None
 
     def refresh_trainable_operands(self, shadow_current: bool = False):
         """Re-prepare the bf16 operand layouts of all trainable parameters (after an optimizer / out-of-band update).
@@ -669,10 +680,6 @@ class UNetSpatioTemporalConditionModel(nn.Module):
                     raise RuntimeError("svd_xtend_b200: all parameters must live on the device of `sample`")
                 raw.dtype_code(p, f"parameter {n}")
             self._validated_sig = sig
-        if self._arena is not None and self._arena.stale():
-            # an optimizer other than FusedAdamW, load_state_dict or an EMA copy-back touched the fp32 masters:
-            # the bf16 shadow / transposed operands are re-derived before they are used
-            self.refresh_trainable_operands(shadow_current=False)
 
     # the tape-driven network -------------------------------------------------
     def _run(self, sample, timesteps, encoder_hidden_states, added_time_ids) -> Tuple[torch.Tensor, Var, Geom]:
@@ -876,10 +883,22 @@ class _UNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model: UNetSpatioTemporalConditionModel, record: bool, sample, timesteps, enc, added_time_ids, *params):
         E = model._engine
+        ctx.model, ctx.params = model, params
+        ctx.n_out = model.config.out_channels
+        ctx.entry = None
+        if model._graphs is not None:
+            served = model._graphs.forward(record, sample, timesteps, enc, added_time_ids)
+            if served is not None:
+                out, ctx.entry = served
+                ctx.y, ctx.g, ctx.tape = ctx.entry.y, ctx.entry.geom, None
+                return out
+        if model._arena is not None and model._arena.stale():
+            # an optimizer other than FusedAdamW, load_state_dict or an EMA copy-back touched the fp32 masters: the bf16
+            # shadow / transposed operands are re-derived before they are used (a captured forward does this in-graph)
+            model.refresh_trainable_operands(shadow_current=False)
         E.begin(recording=record)
         out, y, g = model._run(sample, timesteps, enc, added_time_ids)
-        ctx.model, ctx.y, ctx.g, ctx.params = model, y, g, params
-        ctx.n_out = model.config.out_channels
+        ctx.y, ctx.g = y, g
         ctx.tape = E.detach_tape()      # this forward's tape lives on ITS autograd node (no cross-forward clobbering)
         return out
 
@@ -888,21 +907,27 @@ class _UNetFn(torch.autograd.Function):
         model, y, g, params = ctx.model, ctx.y, ctx.g, ctx.params
         E = model._engine
         N = g.B * g.T
-        d = dout.reshape(N, ctx.n_out, g.H, g.W).contiguous()
-        if d.dtype not in (F32, bf16):
-            d = d.float()
-        dy = torch.empty(N * g.H * g.W, y.data.shape[1], device=d.device, dtype=bf16)
-        raw.nchw_to_nhwc(d, dy, N, ctx.n_out, g.H, g.W, y.data.shape[1])
         views = E.grad_views
         if views and all(p.grad is None for p in params if p in views):
             # optimizer.zero_grad(set_to_none=True) (train_svd.py:1049) dropped the .grad views: the flat gradient arena the
             # kernels accumulate into must start this backward at zero, or gradients would pile up across steps
             model._arena.zero_grad()
-        E.add_grad(y, dy)
-        tape, ctx.tape = ctx.tape, None
-        if tape is None:
-            raise RuntimeError("svd_xtend_b200: backward called twice on the same forward (retain_graph is not supported)")
-        E.run_backward(tape)
+        if ctx.entry is not None:
+            entry, ctx.entry = ctx.entry, None
+            if not entry.pending_backward:
+                raise RuntimeError("svd_xtend_b200: backward called twice on the same forward (retain_graph is not supported)")
+            E.pgrads = dict(model._graphs.backward(entry, dout, ctx.n_out))      # static buffers of the captured backward
+        else:
+            d = dout.reshape(N, ctx.n_out, g.H, g.W).contiguous()
+            if d.dtype not in (F32, bf16):
+                d = d.float()
+            dy = torch.empty(N * g.H * g.W, y.data.shape[1], device=d.device, dtype=bf16)
+            raw.nchw_to_nhwc(d, dy, N, ctx.n_out, g.H, g.W, y.data.shape[1])
+            E.add_grad(y, dy)
+            tape, ctx.tape = ctx.tape, None
+            if tape is None:
+                raise RuntimeError("svd_xtend_b200: backward called twice on the same forward (retain_graph is not supported)")
+            E.run_backward(tape)
         for p in params:
             if p in views:
                 p.grad = views[p]        # the kernels accumulated straight into the arena
@@ -911,7 +936,7 @@ class _UNetFn(torch.autograd.Function):
             if gp is None:
                 gp = torch.zeros(p.shape, device=p.device, dtype=F32)   # e.g. attn2.to_q/to_k/norm2: exactly zero
             gp = gp if p.dtype == F32 else gp.to(p.dtype)
-            if p.grad is None:
+            if p.grad is None or p.grad is gp:      # (a captured backward re-fills the same static buffer every step)
                 p.grad = gp
             else:
                 p.grad.add_(gp)

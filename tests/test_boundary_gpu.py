@@ -258,3 +258,55 @@ def test_graph_replays_track_torch_adamw_with_lr_schedule():
             moved = (po[n] - pi[n]).norm()
             # the UPDATE (not just the weight) must match: frozen bias corrections would shrink it ~6x
             assert ((p.detach() - pi[n]) - (po[n] - pi[n])).norm() < 0.5 * moved, n
+
+
+def test_internal_cuda_graphs_serve_the_unchanged_script_loop():
+    """unet.enable_cuda_graphs(): the script's own loop (forward under autocast, loss.backward(), torch.optim.AdamW.step(),
+    zero_grad(set_to_none=True), train_svd.py:1021-1049) replays captured forward / backward graphs after the warm-up calls and
+    follows the fp32 oracle trained the same way; a no_grad forward in between and a changed input are served correctly."""
+    from oracle.svd_unet_oracle import TINY_CONFIG
+    oracle, ours = _build(TINY_CONFIG, seed=19)
+    for m in (oracle, ours):
+        _train_filter(m)
+        m.train()
+    runner = ours.enable_cuda_graphs(warmup=2)
+    assert ours._arena is not None
+    opts = [torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=2e-4, weight_decay=1e-2) for m in (oracle, ours)]
+    batches = [_tiny_batch(100 + i) for i in range(6)]
+    losses = [[], []]
+    for i, b in enumerate(batches):
+        for k, (m, o) in enumerate(zip((oracle, ours), opts)):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(k == 1)):
+                pred = _call(m, b)
+            from oracle.svd_unet_oracle import edm_loss
+            loss = edm_loss(pred.float(), b["noisy"], b["latents"], b["sigmas"])
+            loss.backward()
+            o.step()
+            o.zero_grad(set_to_none=True)
+            losses[k].append(loss.item())
+        if i == 3:
+            with torch.no_grad():          # validation-style forward between training steps
+                a, r = _call(ours, batches[0]), _call(oracle, batches[0])
+            assert _rel(a, r) < 3e-2
+    torch.cuda.synchronize()
+    ent = [e for e in runner.entries.values() if e.g_bwd is not None]
+    assert len(ent) == 1 and ent[0].calls == len(batches), "the training signature must have been captured and replayed"
+    for a, b in zip(*losses):
+        assert abs(a - b) < 4e-2 * max(1.0, abs(a)), losses
+    po = dict(oracle.named_parameters())
+    worst = max(_rel(p, po[n]) for n, p in ours.named_parameters() if p.requires_grad and p.dim() == 2)
+    assert worst < 1.5e-2, worst
+    # gradients of a replayed step equal the eager gradients of the same step
+    b = batches[1]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred = _call(ours, b)
+    (pred.float() ** 2).mean().backward()
+    g_graph = {n: p.grad.clone() for n, p in ours.named_parameters() if p.requires_grad}
+    ours.zero_grad(set_to_none=True)
+    ours.disable_cuda_graphs()
+    pred = _call(ours, b)
+    (pred.float() ** 2).mean().backward()
+    torch.cuda.synchronize()
+    for n, p in ours.named_parameters():
+        if p.requires_grad and g_graph[n].abs().max() > 0:
+            assert _rel(g_graph[n], p.grad) < 5e-2, n

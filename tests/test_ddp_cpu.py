@@ -42,6 +42,28 @@ def _worker(rank, world, port, q):
                 assert torch.allclose(arena.grad_views[p], torch.full_like(p, expect)), (rank, i, step)
         arena.attach_grads()
         assert all(p.grad is arena.grad_views[p] for p in arena.params)
+        # ---- sharded optimizer plumbing (ZeRO-1): equal aligned shards, reduce-scatter leaves the SUM of this rank's slice,
+        # the in-place all-gather assembles every rank's slice (the AdamW kernel itself is covered on the GPU)
+        from svd_xtend_b200.train import ShardedAdamW
+        net2 = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Linear(53, 200))
+        arena2 = ParamArena(net2, pad_to=world * 64)
+        assert arena2.numel % (world * 64) == 0
+        opt = ShardedAdamW(arena2, lr=1e-3)
+        assert (opt.hi - opt.lo) * world == arena2.numel and opt.lo == rank * (arena2.numel // world) and opt.m.numel() == opt.hi - opt.lo
+        arena2.grad.copy_(torch.arange(arena2.numel, dtype=torch.float32) * (rank + 1))
+        shard = opt.reduce_scatter_grads()
+        expect = torch.arange(arena2.numel, dtype=torch.float32)[opt.lo:opt.hi] * sum(r + 1 for r in range(world))
+        assert torch.equal(shard, expect)
+        flat = torch.full((arena2.numel,), -1.0)
+        flat[opt.lo:opt.hi] = float(rank + 10)
+        opt.all_gather_(flat)
+        n = arena2.numel // world
+        assert all(torch.all(flat[r * n:(r + 1) * n] == float(r + 10)) for r in range(world))
+        try:
+            ShardedAdamW(ParamArena(torch.nn.Linear(3, 5, bias=False)), lr=1e-3)      # a 64-float arena: not divisible by world * 64
+            raise AssertionError("unpadded arena accepted")
+        except ValueError:
+            pass
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -35,7 +35,7 @@ def _sdpa_ref(q, k, v, scale):
     return (att @ vh).permute(0, 2, 1, 3)
 
 
-@pytest.mark.parametrize("nseq,S,heads", [(2, 256, 2), (3, 640, 5), (2, 160, 3), (4, 40, 2), (1, 2560, 1)])
+@pytest.mark.parametrize("nseq,S,heads", [(2, 256, 2), (3, 640, 5), (2, 160, 3), (4, 40, 2), (1, 2560, 1), (1, 9216, 1), (2, 2304, 2), (3, 144, 2)])
 def test_attention_spatial_fwd_bwd(raw, nseq, S, heads):
     C = heads * 64
     qkv = _rand(nseq * S, 3 * C, seed=1).to(bf16)          # fused projection buffer: q|k|v column slices
@@ -222,6 +222,19 @@ def test_misc_elementwise(raw):
     (pr[:, :h] * F.gelu(pr[:, h:])).backward(dout.float())
     torch.cuda.synchronize()
     _close(dpre, pr.grad, what="geglu bwd")
+    # fused bias gradient of the projection: column sums of the dpre that was written (accumulating), ragged row count
+    for rows2, h2 in ((333, 256), (35840, 1280), (17, 64)):
+        pre2 = _rand(rows2, 2 * h2, seed=31).to(bf16)
+        dout2 = _rand(rows2, h2, seed=32).to(bf16)
+        dpre2 = torch.empty_like(pre2)
+        bg = torch.full((2 * h2,), 0.5, device=DEV)
+        raw.geglu_bwd(pre2, dout2, dpre2, bias_grad=bg)
+        torch.cuda.synchronize()
+        ref2 = torch.empty_like(pre2)
+        raw.geglu_bwd(pre2, dout2, ref2)
+        torch.cuda.synchronize()
+        assert torch.equal(dpre2, ref2)
+        _close(bg, 0.5 + dpre2.float().sum(0), tol=2e-3, what=f"geglu bwd fused bias gradient {rows2}x{h2}")
     x = _rand(5000, 320, seed=23).to(bf16)
     out = torch.empty(320, device=DEV)
     raw.colsum(x, out)

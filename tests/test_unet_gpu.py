@@ -384,3 +384,114 @@ def test_arena_fused_adamw_steps():
     po = dict(oracle.named_parameters())
     worst = max(_rel(p, po[n]) for n, p in ours.named_parameters() if p.requires_grad and p.dim() == 2)
     assert worst < 5e-3, worst
+
+
+def test_svd_topology_config4_features_match_oracle():
+    """BASELINE config 4's distinguishing features on the full 1.52 B topology: 25 frames (temporal attention packs 4 pixel
+    sequences of T = 25 per tile, frame-index embedding of 25 frames), latent width 128 (one conv tile = one full image row),
+    gradient checkpointing on every resnet and spatial transformer block (train_svd.py:731-732) — loss and every trainable
+    gradient against the fp32 oracle (checkpointed too). Latents are 8 x 128 instead of 72 x 128 so that the fp32 oracle's
+    activations fit next to ours; S = 9216 spatial attention is covered at kernel level (test_attention_spatial_fwd_bwd)."""
+    from oracle.svd_unet_oracle import SVD_CONFIG, synthetic_batch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, ours = _build(SVD_CONFIG, seed=12)
+    for m in (oracle, ours):
+        _train_filter(m)
+        m.train()
+        m.enable_gradient_checkpointing()
+    batch = synthetic_batch(1, 25, 8, 128, seed=77, device=DEV)
+    pred_ref, loss_ref = _loss(oracle, batch)
+    loss_ref.backward()
+    g_ref = {n: p.grad for n, p in oracle.named_parameters() if p.requires_grad}
+    for p in oracle.parameters():
+        p.grad = None
+    pred_ac, loss_ac = _loss(oracle, batch, autocast=True)
+    loss_ac.backward()
+    g_ac = {n: p.grad for n, p in oracle.named_parameters() if p.requires_grad}
+    for p in oracle.parameters():
+        p.grad = None
+    e_ac = _rel(pred_ac, pred_ref)
+    del pred_ac, loss_ac
+    torch.cuda.empty_cache()
+    pred, loss = _loss(ours, batch)
+    loss.backward()
+    torch.cuda.synchronize()
+    e_out = _rel(pred, pred_ref)
+    assert e_out <= max(2 * e_ac, 2e-2), f"output rel-l2 {e_out:.4g} vs autocast {e_ac:.4g}"
+    assert abs(loss.item() - loss_ref.item()) <= 3e-2 * max(1.0, abs(loss_ref.item()))
+    bad, n_cmp = [], 0
+    for n, p in ours.named_parameters():
+        if not p.requires_grad:
+            continue
+        ref = g_ref[n]
+        if ref.abs().max() == 0:
+            assert p.grad.abs().max() == 0, n
+            continue
+        e, ea = _rel(p.grad, ref), _rel(g_ac[n], ref)
+        n_cmp += 1
+        if e > max(3 * ea, 5e-2):
+            bad.append((n, round(e, 4), round(ea, 4)))
+    print(f"config-4 features: output rel-l2 {e_out:.4g} (autocast {e_ac:.4g}), {n_cmp} gradients compared")
+    assert n_cmp > 300 and not bad, bad[:10]
+
+
+def test_svd_topology_lora_rank64_matches_merged_weight_oracle():
+    """BASELINE config 5 on the full topology: rank-64 LoRA on to_q / to_k / to_v / to_out.0 of all 64 Attention modules
+    (256 adapted linears, 26 558 464 LoRA parameters, train_svd_lora.py:659-671) over a bf16 base (`weight_dtype`, :669).
+    Reference = the fp32 oracle with bf16-rounded base weights and W' = W + B A merged; dA = B^T dW', dB = dW' A^T."""
+    from types import SimpleNamespace
+    from oracle.svd_unet_oracle import SVD_CONFIG, synthetic_batch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oracle, ours = _build(SVD_CONFIG, seed=23)
+    ours.requires_grad_(False)
+    ours.to(torch.bfloat16)
+    n = ours.add_adapter(SimpleNamespace(r=64, lora_alpha=64, init_lora_weights="gaussian", target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+    assert n == 256
+    for p in ours.parameters():
+        if p.requires_grad:
+            p.data = p.data.float()
+    assert sum(p.numel() for p in ours.parameters() if p.requires_grad) == 26_558_464
+    torch.manual_seed(5)
+    sd = oracle.state_dict()
+    merged = []
+    with torch.no_grad():
+        for k in sd:
+            sd[k].copy_(sd[k].to(torch.bfloat16).float())
+        for name, mod in ours.named_modules():
+            if hasattr(mod, "lora_B"):
+                mod.lora_B["default"].weight.normal_(0, 0.02)
+                sd[name + ".weight"].add_(mod.lora_B["default"].weight @ mod.lora_A["default"].weight)
+                merged.append(name + ".weight")
+    oracle.requires_grad_(False)
+    po = dict(oracle.named_parameters())
+    for k in merged:
+        po[k].requires_grad_(True)
+    oracle.train()
+    ours.train()
+    batch = synthetic_batch(1, 14, 16, 32, seed=99, device=DEV)
+    pred_ref, loss_ref = _loss(oracle, batch)
+    loss_ref.backward()
+    hb = dict(batch)
+    hb["sample"] = batch["sample"].to(torch.bfloat16)
+    pred, loss = _loss(ours, hb)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _rel(pred, pred_ref) < 2.5e-2, _rel(pred, pred_ref)
+    bad, n_cmp = [], 0
+    for name, mod in ours.named_modules():
+        if not hasattr(mod, "lora_B"):
+            continue
+        dW = po[name + ".weight"].grad
+        A, B = mod.lora_A["default"].weight, mod.lora_B["default"].weight
+        for g, ref, tag in ((A.grad, B.detach().t() @ dW, "A"), (B.grad, dW @ A.detach().t(), "B")):
+            if ref.abs().max() == 0:
+                assert g.abs().max() == 0, (name, tag)
+                continue
+            n_cmp += 1
+            e = _rel(g, ref)
+            if e > 8e-2:
+                bad.append((name, tag, round(e, 4)))
+    print(f"config-5: output rel-l2 {_rel(pred, pred_ref):.4g}, {n_cmp} LoRA gradients compared")
+    assert n_cmp > 350 and not bad, bad[:8]
