@@ -68,7 +68,7 @@ typedef struct SvdxTapGemm {
   int32_t a_mode;       /* SVDX_A_ROWS / SVDX_A_CONV2D */
   int32_t a_major_mn;   /* 0: A[m][k] k contiguous. 1 (ROWS, groups==1 only): memory is [k][m], m contiguous */
   int32_t rows_per_group, groups;      /* ROWS   */
-  int32_t W, H, nimg;                  /* CONV2D: 128 % W == 0 */
+  int32_t W, H, nimg;                  /* CONV2D: 128 % W == 0, or W % 128 == 0 (wide images: a tile is 128 pixels of one row) */
   int32_t num_taps;
   int32_t tap_d0[SVDX_MAX_TAPS];
   int32_t tap_d1[SVDX_MAX_TAPS];
@@ -245,6 +245,10 @@ int svdx_colsum(const void* x, int64_t ldx, int64_t rows, int32_t cols, float* o
  * += column sums of the dpre values written — the bias gradient of the GEGLU projection, fused into the same pass */
 int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t lddo, void* dpre, int64_t lddpre,
                    int64_t rows, int32_t h, float* bias_grad, void* stream);
+/* y[r][:] = softmax(scale * x[r][:]) over bf16 rows (fp32 arithmetic, in place allowed). Used by the VAE encoder's mid-block
+ * attention (1 head of dim 512, [D] AutoencoderKLTemporalDecoder.encoder.mid_block.attentions.0): scores = Q K^T and P V go through
+ * svdx_tapgemm, the row softmax through this kernel. */
+int svdx_softmax_rows(const void* x, int64_t ldx, int64_t rows, int32_t cols, float scale, void* y, int64_t ldy, void* stream);
 /* AlphaBlender epilogue scale triples from mix_factor, a = sigmoid(mix_factor); writes float[16]:
  *   out[0..3]   = {1-a, a, 1-a, 0}      transformer blend  out = a*x_spatial + (1-a)*(acc + residual)
  *   out[4..7]   = {1-a, 1, 0, a*(1-a)}  resnet blend       out = x_spatial + (1-a)*acc

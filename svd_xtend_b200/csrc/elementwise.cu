@@ -485,6 +485,58 @@ __global__ void adamw_state_kernel(float* __restrict__ p, const float* __restric
   }
 }
 
+// row softmax of a bf16 score matrix, y[r][:] = softmax(scale * x[r][:]) (fp32 arithmetic, in place allowed): the single-head,
+// head_dim 512 attention of the VAE encoder's mid block goes through two GEMMs and this kernel (its S x S scores are small).
+// One CTA per row; a row of <= 16 K columns stays L1/L2 resident over the three passes.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const bf16* __restrict__ x, long long ldx, int cols, float scale, bf16* __restrict__ y,
+                                                           long long ldy) {
+  __shared__ float sh[8];
+  const bf16* xr = x + (long long)blockIdx.x * ldx;
+  bf16* yr = y + (long long)blockIdx.x * ldy;
+  const int nv = cols / 8;
+  const float sc = scale * 1.4426950408889634f;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + v * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 a = unpack_bf16x2(w[k]); m = fmaxf(m, fmaxf(a.x, a.y)); }
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = sh[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) m = fmaxf(m, sh[k]);
+  __syncthreads();
+  const float msc = m * sc;
+  float l = 0.f;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + v * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 a = unpack_bf16x2(w[k]); l += exp2_fast(fmaf(a.x, sc, -msc)) + exp2_fast(fmaf(a.y, sc, -msc)); }
+  }
+  l = warp_sum(l);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = l;
+  __syncthreads();
+  l = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) l += sh[k];
+  const float inv = 1.0f / l;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + v * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = unpack_bf16x2(w[k]);
+      o[k] = pack_bf16x2(exp2_fast(fmaf(a.x, sc, -msc)) * inv, exp2_fast(fmaf(a.y, sc, -msc)) * inv);
+    }
+    *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 struct TransposeJob {
   long long src_off;   // element offset into the bf16 source arena
   bf16* dst;           // [I][O] destination
@@ -706,6 +758,15 @@ extern "C" int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, 
   geglu_bwd_kernel<<<dim3(col_blocks, (unsigned)chunks), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), ldpre, reinterpret_cast<const bf16*>(dout),
                                                                              lddo, reinterpret_cast<bf16*>(dpre), lddpre, rows, h, rows_per_cta, bias_grad);
   SVDX_CHECK_LAUNCH("geglu_bwd");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_softmax_rows(const void* x, int64_t ldx, int64_t rows, int32_t cols, float scale, void* y, int64_t ldy, void* stream) {
+  if (!x || !y || rows <= 0 || cols <= 0 || cols % 8 || ldx % 8 || ldy % 8 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+      rows > 0x7fffffffLL)
+    return svdx_fail(SVDX_E_BADARG, "softmax_rows: bad arguments (cols, ldx, ldy multiples of 8; 16 B aligned)");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, cols, scale, reinterpret_cast<bf16*>(y), ldy);
+  SVDX_CHECK_LAUNCH("softmax_rows");
   return SVDX_OK;
 }
 

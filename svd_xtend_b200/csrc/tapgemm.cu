@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    const bool conv_par = (p.a_mode == SVDX_A_CONV2D) && !p.a_mn && !p.b_mn && !p.geglu && (BLOCK_M / p.W) <= 32;
+    const bool conv_par = (p.a_mode == SVDX_A_CONV2D) && !p.a_mn && !p.b_mn && !p.geglu && !p.wtiles && (BLOCK_M / p.W) <= 32;
     if (conv_par) {
       // warp-wide conv producer: lane 0 owns the barriers and the B tile, every lane with a row box issues it
       int stage = 0;
@@ -170,6 +170,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
             const int g = mt / p.tiles_per_group;
             const int t = mt - g * p.tiles_per_group;
             tma_load_3d(&p.tma, full, dA, kc, t * BLOCK_M + p.tap_d0[tap], g);
+          } else if (p.wtiles) {
+            // wide images (VAE encoder, W = 256 / 512): the tile is 128 consecutive pixels of one image row; the shifted
+            // box (w0 + dw, h + dh) is zero-filled where it leaves the image, which IS the convolution's padding
+            const int row = mt / p.wtiles;
+            const int w0 = (mt - row * p.wtiles) * BLOCK_M;
+            const int n = row / p.H;
+            const int h = row - n * p.H;
+            tma_load_4d(&p.tma, full, dA, kc, w0 + p.tap_d0[tap], h + p.tap_d1[tap], (n < p.nimg) ? n + p.tap_d2[tap] : (1 << 28));
           } else {
             // the tile's 128 pixels = R consecutive image rows; walk them image by image and cover each run with
             // the largest power-of-two row boxes available (few big TMA requests instead of R one-row requests)
@@ -388,14 +396,17 @@ int svdx_tapgemm_fill(const SvdxTapGemm* d, TapGemmKParams& p, int cg) {
     p.tiles_per_group = (d->rows_per_group + BLOCK_M - 1) / BLOCK_M;
     p.m_tiles = p.tiles_per_group * d->groups;
   } else if (d->a_mode == SVDX_A_CONV2D) {
-    if (d->W <= 0 || d->W > 128 || (128 % d->W) || d->H <= 0 || d->nimg <= 0) return svdx_fail(SVDX_E_BADARG, "tapgemm: conv2d needs W | 128");
+    const bool wide = d->W > 128;
+    if (d->W <= 0 || (wide ? (d->W % 128 != 0) : (128 % d->W != 0)) || d->H <= 0 || d->nimg <= 0)
+      return svdx_fail(SVDX_E_BADARG, "tapgemm: conv2d needs W | 128 or 128 | W");
     // M counts output pixels of the first `M / (H*W)` images; the tensor may hold more images (parity planes)
     uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->nimg};
     uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->lda * 2 * d->W, (uint64_t)d->lda * 2 * d->W * d->H};
-    uint32_t box[4] = {64, (uint32_t)d->W, 1, 1};
+    uint32_t box[4] = {64, (uint32_t)(wide ? 128 : d->W), 1, 1};
     rc = svdx_make_tmap(&p.tma, d->a, 4, dims, strides, box);
     p.max_bh_log2 = 0;
-    for (int lg = 1; lg <= 4 && !rc; ++lg) {
+    p.wtiles = wide ? d->W / 128 : 0;
+    for (int lg = 1; lg <= 4 && !rc && !wide; ++lg) {
       const int bh = 1 << lg;
       if (bh * d->W > BLOCK_M || bh > d->H) break;
       uint32_t boxh[4] = {64, (uint32_t)d->W, (uint32_t)bh, 1};

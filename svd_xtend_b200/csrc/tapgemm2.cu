@@ -137,7 +137,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ===========================
-    const bool conv_par = (p.a_mode == SVDX_A_CONV2D) && !p.geglu && (BLOCK_M / p.W) <= 32;
+    const bool conv_par = (p.a_mode == SVDX_A_CONV2D) && !p.geglu && !p.wtiles && (BLOCK_M / p.W) <= 32;
     if (conv_par) {
       // warp-wide conv producer (see conv_tile_boxes): lane 0 owns the barriers and the B half-tile
       int stage = 0;
@@ -189,6 +189,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
           if (p.a_mode == SVDX_A_ROWS) {
             // rows past the end of the group (t >= tiles_per_group) are out of bounds -> zero
             tma2_load_3d(&p.tma, full, dA, kc, t * BLOCK_M + p.tap_d0[tap], g);
+          } else if (p.wtiles) {
+            // wide images: 128 consecutive pixels of one image row (see tapgemm.cu)
+            const int row = t / p.wtiles;
+            const int w0 = (t - row * p.wtiles) * BLOCK_M;
+            const int n = row / p.H;
+            const int h = row - n * p.H;
+            tma2_load_4d(&p.tma, full, dA, kc, w0 + p.tap_d0[tap], h + p.tap_d1[tap], (n < p.nimg) ? n + p.tap_d2[tap] : (1 << 28));
           } else {
             const int R = BLOCK_M / p.W;
             const int dw = p.tap_d0[tap], dh = p.tap_d1[tap], dn = p.tap_d2[tap];

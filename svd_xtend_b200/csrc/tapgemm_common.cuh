@@ -32,6 +32,7 @@ struct __align__(64) TapGemmKParams {
   int a_mode, a_mn, b_mn, b_mode, kb_per_group;
   int rows_per_group, groups, tiles_per_group;
   int W, H, nimg;
+  int wtiles;          // CONV2D with W > 128 (W % 128 == 0): a tile = 128 consecutive pixels of ONE image row, wtiles = W / 128 (else 0)
   int num_taps;
   int tap_d0[SVDX_MAX_TAPS], tap_d1[SVDX_MAX_TAPS], tap_d2[SVDX_MAX_TAPS];
   int M, N, K;

@@ -570,9 +570,11 @@ class Engine:
         self.pgrad(mix).add_((acc * alpha).to(F32).view(mix.shape))
 
     def conv2d_3x3(self, x: Var, g: Geom, conv, *, rowbias: Optional[Var] = None, rowbias_div=1, res1: Optional[Var] = None,
-                   scales=None, res1_unit: bool = False, i_pad=None, n_pad=None, planes: bool = False, gn_rows: Optional[int] = None) -> Var:
+                   scales=None, res1_unit: bool = False, i_pad=None, n_pad=None, planes: bool = False, gn_rows: Optional[int] = None,
+                   planes_pad0: bool = False) -> Var:
         """3x3 conv, padding 1, on channels-last [N*H*W, Cin]. planes=True: x holds the 4 stride-2 parity planes
-        of a [N,2H,2W] image and the result is the stride-2 conv at geometry g (= output geometry)."""
+        of a [N,2H,2W] image and the result is the stride-2 conv at geometry g (= output geometry): padding 1 on all sides
+        (the UNet's Downsample2D), or with planes_pad0 the VAE encoder's form, F.pad(x, (0,1,0,1)) + conv(stride 2, padding 0)."""
         w = conv.weight
         O, I = w.shape[0], w.shape[1]
         ip = i_pad if i_pad is not None else I
@@ -583,10 +585,12 @@ class Engine:
         out = self.empty(M, n_alloc, x.data)
         if planes:
             taps = []
+            # input row 2h + kh - pad = parity plane (kh - pad) & 1 at row h + (kh - pad) // 2 — out-of-image rows read as zero
+            table = ((0, 0), (1, 0), (0, 1)) if planes_pad0 else ((1, -1), (0, 0), (1, 0))
             for kh in range(3):
                 for kw in range(3):
-                    ph, dh = ((1, -1), (0, 0), (1, 0))[kh]
-                    pw, dw = ((1, -1), (0, 0), (1, 0))[kw]
+                    ph, dh = table[kh]
+                    pw, dw = table[kw]
                     taps.append((dw, dh, (ph * 2 + pw) * nimg))
             taps = tuple(taps)
             whn = (g.W, g.H, 4 * nimg)

@@ -531,6 +531,15 @@ def geglu_bwd(pre, dout, dpre, bias_grad=None):
     return dpre
 
 
+def softmax_rows(x, y, scale=1.0):
+    rows, cols = x.shape
+    if _fam("elementwise", 0.0, 4.0 * rows * cols):
+        return y
+    check(load().svdx_softmax_rows(x.data_ptr(), _rowmajor(x, "x"), rows, cols, float(scale), y.data_ptr(), _rowmajor(y, "y"), _stream()),
+          "svdx_softmax_rows")
+    return y
+
+
 def blend_scales(mix_factor, out3):  # out3: float[8]
     check(load().svdx_blend_scales(mix_factor.data_ptr(), out3.data_ptr(), _stream()), "blend_scales")
     return out3
