@@ -611,6 +611,26 @@ def main():
             script_path = {"ms_per_step": sp_ms, "value": frames / (sp_ms / 1e3), "unit": "frames/s", "steps": n_s,
                            "what": "unet(...) inside torch.autocast + loss.backward() + torch.optim.AdamW.step() + zero_grad(set_to_none=True), "
                                    "every kernel launched eagerly from Python through the C ABI (train_svd.py:1021-1049 pattern)"}
+            # the same loop with unet.enable_cuda_graphs(): forward and backward of the autograd node replay captured graphs
+            try:
+                unet.enable_cuda_graphs(warmup=2)
+                for _ in range(5):
+                    script_step()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(n_s):
+                    script_step()
+                e1.record()
+                torch.cuda.synchronize()
+                spg_ms = e0.elapsed_time(e1) / n_s
+                script_path["graphed_ms_per_step"] = spg_ms
+                script_path["graphed_value"] = frames / (spg_ms / 1e3)
+                script_path["graphed_what"] = ("same script loop after unet.enable_cuda_graphs(): two shape-keyed graph launches (forward, backward) "
+                                               "per step + the script's own torch.optim.AdamW")
+            except Exception as e:
+                script_path["graphed_failed"] = f"{type(e).__name__}: {e}"
+            finally:
+                unet.disable_cuda_graphs()
             del topt
         except Exception as e:
             script_path = {"failed": f"{type(e).__name__}: {e}"}
@@ -632,6 +652,35 @@ def main():
     if rank != 0:
         finish()
         return
+
+    # ---- the VAE encode that precedes the UNet in every step of train_svd.py (:948, :959): frames + 1 conditioning frame
+    vae_encode = None
+    if world == 1 and args.config == 2 and not args.no_script_path:
+        try:
+            from svd_xtend_b200.vae import AutoencoderKLTemporalDecoder, tensor_to_vae_latent
+            graphed = None
+            torch.cuda.empty_cache()
+            torch.manual_seed(7)
+            with torch.device(dev):
+                vae = AutoencoderKLTemporalDecoder()
+            vae.to(dev).requires_grad_(False).eval()
+            px = (torch.randn(1, frames + 1, 3, 8 * lat_h, 8 * lat_w, device=dev) * 0.5).clamp(-1, 1)
+            for _ in range(2):
+                tensor_to_vae_latent(px, vae)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                lat = tensor_to_vae_latent(px, vae)
+            e1.record()
+            torch.cuda.synchronize()
+            v_ms = e0.elapsed_time(e1) / 3
+            vae_encode = {"ms": v_ms, "frames": frames + 1, "pixels": [8 * lat_h, 8 * lat_w], "finite": bool(torch.isfinite(lat).all()),
+                          "what": "svd_xtend_b200.vae.tensor_to_vae_latent on the clip + conditioning frame (train_svd.py:283-291, :948, :959), eager launches, "
+                                  "random-init weights; informational (SURVEY.md §8f-1)"}
+            del vae, px, lat
+            torch.cuda.empty_cache()
+        except Exception as e:
+            vae_encode = {"failed": f"{type(e).__name__}: {e}"}
 
     gpu_base = None
     if world == 1 and not args.no_gpu_baseline:
@@ -664,6 +713,7 @@ def main():
         "roofline": roofline,
         "roofline_by_family": by_family,
         "script_path": script_path,
+        "vae_encode": vae_encode,
         "gpu_eager_baseline": gpu_base,
         "cpu_baseline": cpu,
     }

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 VAE_CONFIG = dict(in_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512), layers_per_block=2, scaling_factor=0.18215)
-TINY_VAE_CONFIG = dict(in_channels=3, latent_channels=4, block_out_channels=(32, 64), layers_per_block=1, scaling_factor=0.18215)
+TINY_VAE_CONFIG = dict(in_channels=3, latent_channels=4, block_out_channels=(64, 128), layers_per_block=1, scaling_factor=0.18215)
 
 
 class ResnetBlock2D(nn.Module):

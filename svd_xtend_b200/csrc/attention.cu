@@ -777,8 +777,14 @@ static int attn_setup(const SvdxAttn* d, AttnKParams& p, bool bwd, dim3& grid) {
   return 0;
 }
 
+// attention_small.cu: CUDA-core kernels for strided short sequences (temporal attention, S <= 32) — HBM-bound work
+bool svdx_attention_small_eligible(const SvdxAttn* d);
+int svdx_attention_small_fwd(const SvdxAttn* d, cudaStream_t st);
+int svdx_attention_small_bwd(const SvdxAttn* d, cudaStream_t st);
+
 extern "C" int svdx_attention_fwd(const SvdxAttn* d, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  if (svdx_attention_small_eligible(d)) return svdx_attention_small_fwd(d, st);
   AttnKParams p;
   dim3 grid;
   int rc = attn_setup(d, p, false, grid);
@@ -797,6 +803,7 @@ extern "C" int svdx_attention_fwd(const SvdxAttn* d, void* stream_v) {
 
 extern "C" int svdx_attention_bwd(const SvdxAttn* d, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  if (svdx_attention_small_eligible(d)) return svdx_attention_small_bwd(d, st);
   AttnKParams p;
   dim3 grid;
   int rc = attn_setup(d, p, true, grid);

@@ -668,6 +668,14 @@ extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1
   int threads, rpc;
   gn_vec_config(C1 + C2, outer, rows, threads, rpc);
   const int RL = threads / ((C1 + C2) / 8);
+  {
+    // every CTA folds the slab's channel sums before streaming: give it at least 128 KB of input so that the fold (a few
+    // hundred ns .. 2 us at C = 2560) stays a small fraction of its life (measured: profiles/r2_kbench.txt)
+    const int quantum = 4 * RL;
+    int min_rows = (int)((131072 + (long long)(C1 + C2) * 2 - 1) / ((long long)(C1 + C2) * 2));
+    min_rows = ((min_rows + quantum - 1) / quantum) * quantum;
+    if (rpc < min_rows) rpc = min_rows;
+  }
   const int padded = (threads + 31) & ~31;      // whole warps: the channel fold uses full-mask shuffles
   const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
   gn_apply_fused_kernel<<<dim3((rows + rpc - 1) / rpc, outer), padded, 0, st>>>(s, rows, rpc, RL, num_groups, eps, inv, csum1, ldc1, csum2, ldc2, mean, rstd,

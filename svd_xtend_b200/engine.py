@@ -532,12 +532,7 @@ class Engine:
                 continue
             g = fused_g if p is None else self.pgrad(p).view(O, -1)
             dyp = dy[:, o0:o0 + O]
-            bn = raw.choose_block_n(O, K, mn_major=True)
-            tiles = ((O + 127) // 128) * ((K + bn - 1) // bn)
-            kb = (M + 63) // 64
-            # split the token contraction only as far as it still leaves >= 32 k-blocks per CTA and at most one wave:
-            # every split CTA pays a full-tile fp32 atomic epilogue
-            split = max(1, min(kb // 32, raw.num_sms() // max(tiles, 1)))
+            bn, split = raw.wgrad_plan(O, K, M)       # tile width and token split chosen together (L2 -> SM traffic model)
             raw.tapgemm(dyp, x, g, M=O, N=K, K=M, a_mn=True, b_mn=True, split_k=split, out_dtype=OUT_F32_ATOMIC,
                         block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
 

@@ -141,6 +141,35 @@ def choose_block_n(M: int, n_out: int, geglu: bool = False, mn_major: bool = Fal
     return 2 * best if geglu else best
 
 
+_WGRAD_L2_BYTES_PER_CLK = 6500.0     # fitted to profiles/r2_kbench.txt (weight-gradient GEMMs are L2 -> SM bound)
+
+
+def wgrad_plan(O: int, K: int, M: int):
+    """(block_n, split_k) of a weight-gradient GEMM dW[O, K] += dy[M, O]^T x[M, K] (MN-major operands, fp32 reduce-add
+    epilogue). Tile width and the split of the token contraction are chosen TOGETHER by a small model fitted to measured
+    launches (profiles/r2_kbench.txt): CTAs = tiles * split, time = waves * (k-blocks per CTA * max(tensor pipe, L2 -> SM bytes of the
+    CTAs running concurrently) + tile reduce-add). The round-1 rule picked the tile width alone from MMA efficiency and
+    chose 128-wide tiles at K = 640, twice the L2 traffic of 256-wide ones (100 us vs 62 us for O = 5120, K = 640)."""
+    sms = num_sms()
+    kb = (M + 63) // 64
+    m_tiles = (O + 127) // 128
+    best = None
+    for bn in ((192, 256, 128) if K > 64 else (64,)):     # ties go to the earlier width
+        n_tiles = (K + bn - 1) // bn
+        tiles = m_tiles * n_tiles
+        splits = {1, max(1, min(kb // 32, sms // max(tiles, 1))), max(1, min(kb // 8, -(-sms // max(tiles, 1))))}
+        for split in sorted(splits):
+            ctas = tiles * split
+            active = min(ctas, sms)
+            bytes_kb = 16384 + 128.0 * K / n_tiles            # out-of-range B columns of the last tile are not fetched
+            per = max(4.0 * max(bn / 2.0, 32.0 + bn / 4.0), bytes_kb * active / _WGRAD_L2_BYTES_PER_CLK)
+            waves = -(-ctas // sms)
+            cost = waves * ((kb / split) * per + bn * 8.0 + 3000.0)
+            if best is None or cost < best[0] * 0.97:
+                best = (cost, bn, split)
+    return best[1], best[2]
+
+
 def tapgemm(
     a: torch.Tensor,
     b: torch.Tensor,

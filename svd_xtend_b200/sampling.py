@@ -79,20 +79,22 @@ class VideoLatentSampler:
             self._st = dict(latents=torch.empty(B, num_frames, 4, h, w, device=dev, dtype=F32), cond=torch.empty_like(cond),
                             emb=torch.empty_like(emb), ids=torch.empty_like(ids), scal=torch.zeros(3, device=dev, dtype=F32),
                             gs=torch.empty(1, num_frames, 1, 1, 1, device=dev, dtype=F32), cfg=cfg)
-            self._host = torch.empty(3, dtype=F32).pin_memory()
         st = self._st
         st["latents"].copy_(noise.float() * math.sqrt(float(sigmas[0]) ** 2 + 1.0))
         st["cond"].copy_(cond)
         st["emb"].copy_(emb)
         st["ids"].copy_(ids)
         st["gs"].copy_(torch.linspace(min_guidance_scale, max_guidance_scale, num_frames, device=dev, dtype=F32).view(1, -1, 1, 1, 1))
+        # per-step scalars of ALL steps in one pinned buffer: row i is copied to the device right before step i (an async copy
+        # from a re-used 3-float buffer would race with the host writing the next step's values)
+        host = torch.empty(num_inference_steps, 3, dtype=F32).pin_memory()
+        host[:, 0], host[:, 1] = sigmas[:-1], sigmas[1:]
+        host[:, 2] = 0.25 * sigmas[:-1].log()
         was_training = self.unet.training
         self.unet.eval()
         try:
             for i in range(num_inference_steps):
-                self._host[0], self._host[1] = float(sigmas[i]), float(sigmas[i + 1])
-                self._host[2] = 0.25 * math.log(float(sigmas[i]))
-                st["scal"].copy_(self._host, non_blocking=True)
+                st["scal"].copy_(host[i], non_blocking=True)
                 if not self.use_cuda_graph:
                     self._step(st)
                     continue
@@ -112,4 +114,6 @@ class VideoLatentSampler:
                 self._graph.replay()
         finally:
             self.unet.train(was_training)
-        return st["latents"].clone()
+        out = st["latents"].clone()
+        torch.cuda.current_stream().synchronize()      # `host` must outlive the queued copies
+        return out
