@@ -157,13 +157,16 @@ int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1, const voi
                                float* mean, float* rstd, const float* gamma, const float* beta,
                                int32_t fuse_silu, void* y, int64_t ldy, void* stream);
 /* backward: dx (and optional dgamma/dbeta accumulation, fp32 atomic). workspace: float[2 * outer * groups]; it must be
- * ZERO on entry when workspace_is_zero != 0 (a slice of a pre-zeroed arena: no memset node), else it is cleared here. */
+ * ZERO on entry when workspace_is_zero != 0 (a slice of a pre-zeroed arena: no memset node), else it is cleared here.
+ * dres (optional, bf16 [outer*rows][lddres], single-source form only): a gradient already accumulated on x through its
+ * residual use; dx = GroupNorm backward + dres in the same pass (replaces a separate bf16 add over the activation). */
 int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
                        const void* dy, int64_t lddy,
                        int32_t outer, int32_t rows, int32_t num_groups,
                        const float* mean, const float* rstd, const float* gamma, const float* beta,
                        int32_t fuse_silu, void* dx, int64_t lddx, void* dx2, int64_t lddx2,
-                       float* dgamma, float* dbeta, float* workspace, int32_t workspace_is_zero, void* stream);
+                       float* dgamma, float* dbeta, float* workspace, int32_t workspace_is_zero,
+                       const void* dres, int64_t lddres, void* stream);
 
 /* LayerNorm over the last dim (C <= 2560, C % 8 == 0), replaces F.layer_norm of
  * BasicTransformerBlock.norm1-3 / TemporalBasicTransformerBlock.norm_in,norm1-3 [D].
@@ -249,6 +252,15 @@ int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t ldd
  * attention (1 head of dim 512, [D] AutoencoderKLTemporalDecoder.encoder.mid_block.attentions.0): scores = Q K^T and P V go through
  * svdx_tapgemm, the row softmax through this kernel. */
 int svdx_softmax_rows(const void* x, int64_t ldx, int64_t rows, int32_t cols, float scale, void* y, int64_t ldy, void* stream);
+/* Skinny products of the per-clip conditioning vectors ([B, C] rows: TimestepEmbedding MLPs, every resnet's time_emb_proj, the
+ * 1-key image cross-attention to_out(to_v(e)) [D], and their data gradients):  out[m][n] = sum_k a[m][k] * w[n][k] + bias[n],
+ * M <= 8 rows, bf16 operands, fp32 accumulation, bf16 (SVDX_OUT_BF16) or fp32 (SVDX_OUT_F32) output. A weight-streaming GEMV
+ * (one warp per output column): the 128-row tensor-core tiles of svdx_tapgemm would be > 99 % padding here. */
+int svdx_gemv(const void* a, int64_t lda, const void* w, int64_t ldw, int32_t M, int32_t N, int32_t K, const float* bias,
+              void* out, int64_t ldo, int32_t out_dtype, void* stream);
+/* ...and their weight gradients: g[o][k] += scale[0] * sum_{t < T} dy[t][o] * x[t][k], T <= 8 (scale NULL = 1) */
+int svdx_outer_accum(const void* dy, int64_t lddy, const void* x, int64_t ldx, int32_t T, int32_t O, int32_t K,
+                     const float* scale, float* g, int64_t ldg, void* stream);
 /* AlphaBlender epilogue scale triples from mix_factor, a = sigmoid(mix_factor); writes float[16]:
  *   out[0..3]   = {1-a, a, 1-a, 0}      transformer blend  out = a*x_spatial + (1-a)*(acc + residual)
  *   out[4..7]   = {1-a, 1, 0, a*(1-a)}  resnet blend       out = x_spatial + (1-a)*acc

@@ -1,8 +1,20 @@
 #!/bin/bash
-# N=2 data-parallel bench (run with gpurun --gpus 2)
+# N=2 data-parallel checks (run with gpurun --gpus 2): equivalence script, then the bench in both exchange modes
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/ddp_dev.log 2>&1
-NCCL_DEBUG=WARN timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2>> gpurun_out/ddp_dev.log
-cat gpurun_out/bench_n2.json >> gpurun_out/ddp_dev.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 scripts/ddp_check.py >> gpurun_out/ddp_dev.log 2>&1
-tail -c 3000 gpurun_out/ddp_dev.log
+L=gpurun_out/ddp_dev.log
+nvidia-smi -L > $L 2>&1
+echo "=== ddp_check" >> $L
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 scripts/ddp_check.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -20 >> $L
+for mode in sharded allreduce; do
+  echo "=== bench N=2 --ddp $mode" >> $L
+  NCCL_DEBUG=WARN timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 5 --warmup 3 --ddp $mode --no-families > gpurun_out/bench_n2_$mode.json 2>> $L
+  python - >> $L <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/bench_n2_$mode.json'))
+    print("$mode", "ms/step", round(d['ms_per_step'],3), "value", round(d['value'],1), "parallelism", d['config']['parallelism'], "loss", d['config']['final_loss'], "roofline", round(d['roofline']['frac'],3))
+except Exception as e:
+    print("$mode failed", e)
+PY
+done
+tail -c 2500 $L

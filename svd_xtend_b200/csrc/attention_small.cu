@@ -3,17 +3,23 @@
 //
 // Why a second kernel family: this op is HBM-bound, not tensor-bound — per (pixel, head) it does 2 x 14 x 14 x 64 MACs on
 // 3 x 14 x 128 bytes of input (0.64 GFLOP over 92 MB at the 40x64 level: 7 FLOP/byte). The tcgen05 kernel of attention.cu
-// has to pack 8 pixel sequences into one 128-row tile and mask 7/8 of the 128 x 128 scores; every CTA pays barrier set-up,
-// a TMEM allocation and three TMA round trips for 6 KB of useful data and ran at 12 % (forward) / 8 x off (backward) of
-// the HBM roofline (profiles/r2_kbench.txt: 56 us / 234 us at the 40x64 level against 14 us / 28 us of pure traffic).
-// Here one warp owns SPW sequences of one head (two when S <= 16): K and V (backward: also Q and dO) are staged once in
-// shared memory as fp32 rows, lane t is query t (forward, backward phase A) or key t (backward phase B), all arithmetic is
-// fp32 FMA, exp2 on the MUFU, no atomics, grid-stride over (sequence group, head). Token addressing follows the SvdxAttn
-// descriptor (outer / inner / token strides), so the strided "frames of one pixel" gather needs no permute.
+// packs 8 pixel sequences into one 128-row tile and masks 7/8 of the 128 x 128 scores; every CTA pays barrier set-up, a TMEM
+// allocation and three TMA round trips for 6 KB of useful data: 56 us forward / 235 us backward at the 40x64 level against
+// 14 us / 28 us of pure HBM traffic (profiles/r2_kbench_before.txt). A first CUDA-core version of this file (one lane per
+// query, K / V rows broadcast from shared memory) was shared-memory-bound and slower still (90 / 372 us).
+// This version gives each WARP one (sequence, head) and uses warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 x bf16 ->
+// fp32) on 16-row tiles: the scores of a 14-token sequence are ONE 16 x 16 tile, the whole forward is 16 MMAs, the backward 56.
+// The tiny MMA work leaves the kernel bound by its loads: Q / K / V (/ dO) head slices are staged with coalesced 16-byte loads
+// into padded bf16 shared-memory tiles, fragments come from conflict-free 32-bit loads (K-major operands) or ldmatrix.trans
+// (key-major V / K / dO / Q as the k x n operand), results go back through shared memory as full 128-byte rows.
+// Token addressing follows the SvdxAttn descriptor (outer / inner / token strides): the strided "frames of one pixel" gather
+// needs no permute. (tcgen05.mma has a 128-row minimum and needs TMEM + mbarrier plumbing per CTA; for 16-row problems the
+// warp-level MMA is the tensor-core path that fits, and the op's roofline is HBM either way.)
 //
 // forward : S = Q K^T * scale -> softmax over the S keys -> O = P V,  lse = log sum exp (natural log, as attention.cu)
-// backward: P recomputed; dP = dO V^T; delta = sum_s P dP; dS = P (dP - delta) * scale;
-//           dQ = dS K (phase A, lane = query);  dV = P^T dO, dK = dS^T Q (phase B, lane = key, P / dS through shared memory)
+// backward: P recomputed; dP = dO V^T; delta = sum_s P dP; dS = P (dP - delta) * scale; dQ = dS K;
+//           transposed tiles S^T = K Q^T, dP^T = V dO^T recomputed with the row statistics read back from shared memory:
+//           dV = P^T dO, dK = dS^T Q. No atomics.
 #include "common.cuh"
 #include "../../include/svd_xtend_b200.h"
 #include "host_util.h"
@@ -22,10 +28,11 @@
 namespace svdx {
 
 constexpr float AS_LOG2E = 1.4426950408889634f;
-constexpr int AS_PAD = 33;   // row stride of the per-warp [32][S] score scratch (conflict-free column reads)
+constexpr int AS_ROW = 72;            // bf16 elements per staged row (64 + 8 pad: conflict-free fragment loads, 16 B aligned rows)
+constexpr int AS_WARPS = 4;
 
 struct SmallAttnP {
-  const bf16 *q, *k, *v, *o, *dout;
+  const bf16 *q, *k, *v, *dout;
   bf16 *out, *dq, *dk, *dv;
   long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
   long long nseq;
@@ -35,222 +42,309 @@ struct SmallAttnP {
   float* lse;
 };
 
-SVDX_DEVINL long long as_token(const SmallAttnP& p, long long seq, int t) {
-  const long long outer = seq / p.inner;
-  const long long i = seq - outer * p.inner;
-  return outer * p.outer_stride + i * p.inner_stride + (long long)t * p.tok_stride;
+SVDX_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two transposed 8x8 b16 matrices: the (k x n) operand fragment of a [k rows][n cols] row-major shared-memory tile
+SVDX_DEVINL void ldmatrix_x2_trans(uint32_t& b0, uint32_t& b1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+}
+SVDX_DEVINL uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 
-// 8 bf16 (one 16-byte vector) -> 8 floats in shared memory
-SVDX_DEVINL void as_store8(float* dst, const uint4 u) {
-  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-  *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
-  *reinterpret_cast<float4*>(dst + 4) = make_float4(c.x, c.y, d.x, d.y);
-}
-
-// stage the [S][64] head slices of SPW sequences: row r = sq * S + t, 8 lanes per 128-byte row
-template <int SPW>
-SVDX_DEVINL void as_stage(const SmallAttnP& p, const bf16* __restrict__ src, long long ld, long long sg, int h, int lane, float* dst) {
-  const int S = p.S;
-  for (int i = lane; i < SPW * S * 8; i += 32) {
-    const int r = i >> 3, c = i & 7;
-    const int sq = r / S, t = r - sq * S;
-    const long long seq = sg * SPW + sq;
+// stage one [S][64] bf16 head slice (rows = tokens of one sequence) into a [16 * NT][AS_ROW] tile; rows >= S are zero
+template <int NT>
+SVDX_DEVINL void as_stage(const bf16* __restrict__ src, long long ld, long long tok0, long long tok_stride, int S, int lane, uint32_t tile) {
+#pragma unroll
+  for (int it = 0; it < 4 * NT; ++it) {
+    const int r = it * 4 + (lane >> 3), c = lane & 7;
     uint4 u = make_uint4(0u, 0u, 0u, 0u);
-    if (seq < p.nseq) u = __ldg(reinterpret_cast<const uint4*>(src + as_token(p, seq, t) * ld + h * 64 + c * 8));
-    as_store8(dst + r * 64 + c * 8, u);
+    if (r < S) u = __ldg(reinterpret_cast<const uint4*>(src + (tok0 + (long long)r * tok_stride) * ld + c * 8));
+    st_shared_v4(tile + (uint32_t)(r * AS_ROW + c * 8) * 2u, u.x, u.y, u.z, u.w);
+  }
+}
+// write a [16 * NT][64] bf16 result tile (staged in shared memory) back as full 128-byte rows, rows < S only
+template <int NT>
+SVDX_DEVINL void as_unstage(bf16* __restrict__ dst, long long ld, long long tok0, long long tok_stride, int S, int lane, uint32_t tile) {
+#pragma unroll
+  for (int it = 0; it < 4 * NT; ++it) {
+    const int r = it * 4 + (lane >> 3), c = lane & 7;
+    if (r < S) {
+      uint4 u;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(tile + (uint32_t)(r * AS_ROW + c * 8) * 2u));
+      *reinterpret_cast<uint4*>(dst + (tok0 + (long long)r * tok_stride) * ld + c * 8) = u;
+    }
   }
 }
 
-// one token's 64-wide head slice into registers (scaled)
-SVDX_DEVINL void as_load_row(const bf16* __restrict__ src, float (&f)[64], float s) {
+// acc[mt][nt] (16 x 8 tiles) = A[rows][64] * B[cols][64]^T for two K-major tiles (QK^T, dO V^T, K Q^T, V dO^T)
+template <int NT>
+SVDX_DEVINL void as_kmajor_product(float (&acc)[NT][2 * NT][4], uint32_t tA, uint32_t tB, int g, int tq) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + c);
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    f[8 * c] = a.x * s; f[8 * c + 1] = a.y * s; f[8 * c + 2] = b.x * s; f[8 * c + 3] = b.y * s;
-    f[8 * c + 4] = cc.x * s; f[8 * c + 5] = cc.y * s; f[8 * c + 6] = d.x * s; f[8 * c + 7] = d.y * s;
-  }
-}
-SVDX_DEVINL void as_store_row(bf16* dst, const float (&f)[64], float s) {
+  for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    reinterpret_cast<uint4*>(dst)[c] = make_uint4(pack_bf16x2(f[8 * c] * s, f[8 * c + 1] * s), pack_bf16x2(f[8 * c + 2] * s, f[8 * c + 3] * s),
-                                                  pack_bf16x2(f[8 * c + 4] * s, f[8 * c + 5] * s), pack_bf16x2(f[8 * c + 6] * s, f[8 * c + 7] * s));
-}
-// dot of a register row with a shared-memory row (broadcast reads), 4 independent chains
-SVDX_DEVINL float as_dot(const float (&f)[64], const float* __restrict__ row) {
-  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    for (int nt = 0; nt < 2 * NT; ++nt)
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float4 r = *reinterpret_cast<const float4*>(row + 4 * j);
-    d0 = fmaf(f[4 * j], r.x, d0); d1 = fmaf(f[4 * j + 1], r.y, d1); d2 = fmaf(f[4 * j + 2], r.z, d2); d3 = fmaf(f[4 * j + 3], r.w, d3);
-  }
-  return (d0 + d1) + (d2 + d3);
-}
-SVDX_DEVINL void as_axpy(float (&acc)[64], float a, const float* __restrict__ row) {
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float4 r = *reinterpret_cast<const float4*>(row + 4 * j);
-    acc[4 * j] = fmaf(a, r.x, acc[4 * j]); acc[4 * j + 1] = fmaf(a, r.y, acc[4 * j + 1]);
-    acc[4 * j + 2] = fmaf(a, r.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(a, r.w, acc[4 * j + 3]);
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t b[2 * NT][2];
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt) {
+      const uint32_t base = tB + (uint32_t)((nt * 8 + g) * AS_ROW + ks * 16 + 2 * tq) * 2u;
+      b[nt][0] = lds32(base);
+      b[nt][1] = lds32(base + 16);
+    }
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+      uint32_t a[4];
+      const uint32_t base = tA + (uint32_t)((mt * 16 + g) * AS_ROW + ks * 16 + 2 * tq) * 2u;
+      a[0] = lds32(base);
+      a[1] = lds32(base + 8 * AS_ROW * 2);
+      a[2] = lds32(base + 16);
+      a[3] = lds32(base + 8 * AS_ROW * 2 + 16);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt) mma_bf16_16816(acc[mt][nt], a, b[nt][0], b[nt][1]);
+    }
   }
 }
 
-constexpr int ASF_WARPS = 4;
-template <int SPW>
-__global__ void __launch_bounds__(ASF_WARPS * 32) attn_small_fwd_kernel(const SmallAttnP p) {
-  extern __shared__ float as_smem[];
+// out[mt][dn] (16 x 8 tiles over the 64 head dims) = P[rows][16 * NT] (fp32 accumulator layout, rounded to bf16) * B[16 * NT][64]
+// with B a row-major [k][64] tile read through ldmatrix.trans (P V, dS K, P^T dO, dS^T Q)
+template <int NT>
+SVDX_DEVINL void as_pv_product(float (&out)[NT][8][4], const float (&p)[NT][2 * NT][4], uint32_t tB, int lane) {
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[mt][dn][i] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < NT; ++kk) {
+    uint32_t a[NT][4];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+      a[mt][0] = pack_bf16x2(p[mt][2 * kk][0], p[mt][2 * kk][1]);
+      a[mt][1] = pack_bf16x2(p[mt][2 * kk][2], p[mt][2 * kk][3]);
+      a[mt][2] = pack_bf16x2(p[mt][2 * kk + 1][0], p[mt][2 * kk + 1][1]);
+      a[mt][3] = pack_bf16x2(p[mt][2 * kk + 1][2], p[mt][2 * kk + 1][3]);
+    }
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      uint32_t b0, b1;
+      // lanes 0-7: rows 16kk + 0..7 of column block dn; lanes 8-15: rows 16kk + 8..15 (the other lanes' addresses are ignored)
+      ldmatrix_x2_trans(b0, b1, tB + (uint32_t)((kk * 16 + (lane & 15)) * AS_ROW + dn * 8) * 2u);
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt) mma_bf16_16816(out[mt][dn], a[mt], b0, b1);
+    }
+  }
+}
+
+// accumulator tiles -> bf16 [rows][64] shared-memory tile (rows g / g + 8 of each 16-row block, column pairs 2 tq)
+template <int NT>
+SVDX_DEVINL void as_store_tile(uint32_t tile, const float (&o)[NT][8][4], const float (&s)[NT][2], int g, int tq) {
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      const uint32_t base = tile + (uint32_t)((mt * 16 + g) * AS_ROW + dn * 8 + 2 * tq) * 2u;
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base), "r"(pack_bf16x2(o[mt][dn][0] * s[mt][0], o[mt][dn][1] * s[mt][0])) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 8 * AS_ROW * 2), "r"(pack_bf16x2(o[mt][dn][2] * s[mt][1], o[mt][dn][3] * s[mt][1])) : "memory");
+    }
+}
+
+SVDX_DEVINL float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+SVDX_DEVINL float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// row softmax of score tiles in the accumulator layout: s[mt][nt][0..1] = row g, [2..3] = row g + 8; key = nt * 8 + 2 tq + {0, 1}.
+// On return s holds the NORMALISED probabilities; m2 (log2-domain row maximum) and l (row sum) are returned per (mt, row half).
+template <int NT>
+SVDX_DEVINL void as_softmax(float (&s)[NT][2 * NT][4], float qs, int S, int tq, float (&m2)[NT][2], float (&l)[NT][2]) {
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt) {
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool ok = nt * 8 + 2 * tq + i < S;
+        s[mt][nt][i] = ok ? s[mt][nt][i] * qs : -INFINITY;
+        s[mt][nt][2 + i] = ok ? s[mt][nt][2 + i] * qs : -INFINITY;
+        mx0 = fmaxf(mx0, s[mt][nt][i]);
+        mx1 = fmaxf(mx1, s[mt][nt][2 + i]);
+      }
+    mx0 = quad_max(mx0);
+    mx1 = quad_max(mx1);
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        s[mt][nt][i] = exp2_fast(s[mt][nt][i] - mx0);
+        s[mt][nt][2 + i] = exp2_fast(s[mt][nt][2 + i] - mx1);
+        l0 += s[mt][nt][i];
+        l1 += s[mt][nt][2 + i];
+      }
+    l0 = quad_sum(l0);
+    l1 = quad_sum(l1);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { s[mt][nt][i] *= i0; s[mt][nt][2 + i] *= i1; }
+    m2[mt][0] = mx0; m2[mt][1] = mx1; l[mt][0] = l0; l[mt][1] = l1;
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(AS_WARPS * 32) attn_small_fwd_kernel(const SmallAttnP p) {
+  extern __shared__ __align__(16) uint8_t as_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  constexpr uint32_t TILE = 16 * NT * AS_ROW * 2;
+  const uint32_t tQ = smem_u32(as_smem) + warp * 3 * TILE, tK = tQ + TILE, tV = tK + TILE;
   const int S = p.S;
-  float* sK = as_smem + warp * (2 * SPW * S * 64 + 32 * AS_PAD);
-  float* sV = sK + SPW * S * 64;
-  float* sc = sV + SPW * S * 64 + lane * AS_PAD;
-  const long long ngroups = (p.nseq + SPW - 1) / SPW;
-  const long long total = ngroups * p.heads;
+  const long long total = p.nseq * p.heads;
   const float qs = p.scale * AS_LOG2E;
-  const int sq = (SPW == 2) ? (lane >> 4) : 0;
-  const int t = (SPW == 2) ? (lane & 15) : lane;
-  for (long long pi = (long long)blockIdx.x * ASF_WARPS + warp; pi < total; pi += (long long)gridDim.x * ASF_WARPS) {
-    const long long sg = pi / p.heads;
-    const int h = (int)(pi - sg * p.heads);
-    as_stage<SPW>(p, p.k, p.ldk, sg, h, lane, sK);
-    as_stage<SPW>(p, p.v, p.ldv, sg, h, lane, sV);
+  for (long long pi = (long long)blockIdx.x * AS_WARPS + warp; pi < total; pi += (long long)gridDim.x * AS_WARPS) {
+    const long long seq = pi / p.heads;
+    const int h = (int)(pi - seq * p.heads);
+    const long long outer = seq / p.inner;
+    const long long tok0 = outer * p.outer_stride + (seq - outer * p.inner) * p.inner_stride;
+    as_stage<NT>(p.q + h * 64, p.ldq, tok0, p.tok_stride, S, lane, tQ);
+    as_stage<NT>(p.k + h * 64, p.ldk, tok0, p.tok_stride, S, lane, tK);
+    as_stage<NT>(p.v + h * 64, p.ldv, tok0, p.tok_stride, S, lane, tV);
     __syncwarp();
-    const long long seq = sg * SPW + sq;
-    const bool act = (t < S) && (seq < p.nseq);
-    const long long tok = act ? as_token(p, seq, t) : 0;
-    const float* Kq = sK + sq * S * 64;
-    const float* Vq = sV + sq * S * 64;
-    float m = -INFINITY;
-    {
-      float qf[64];
-      if (act) as_load_row(p.q + tok * p.ldq + h * 64, qf, qs);
-      else {
+    float s[NT][2 * NT][4];
+    as_kmajor_product<NT>(s, tQ, tK, g, tq);
+    float m2[NT][2], l[NT][2];
+    as_softmax<NT>(s, qs, S, tq, m2, l);
+    float o[NT][8][4];
+    as_pv_product<NT>(o, s, tV, lane);
+    __syncwarp();                                   // all fragment reads of tQ are done: reuse it for the output rows
+    float one[NT][2];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) qf[i] = 0.f;
-      }
-      for (int s = 0; s < S; ++s) {
-        const float d = as_dot(qf, Kq + s * 64);
-        sc[s] = d;
-        m = fmaxf(m, d);
-      }
-    }
-    float l = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const float e = exp2_fast(sc[s] - m);
-      sc[s] = e;
-      l += e;
-    }
-    float o[64];
+    for (int mt = 0; mt < NT; ++mt) { one[mt][0] = 1.f; one[mt][1] = 1.f; }
+    as_store_tile<NT>(tQ, o, one, g, tq);
+    if (p.lse && tq == 0) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    for (int s = 0; s < S; ++s) as_axpy(o, sc[s], Vq + s * 64);
-    if (act) {
-      as_store_row(p.out + tok * p.ldo + h * 64, o, 1.0f / l);
-      if (p.lse) p.lse[tok * p.heads + h] = m * 0.6931471805599453f + __logf(l);
+      for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int r = mt * 16 + g + 8 * hf;
+          if (r < S) p.lse[(tok0 + (long long)r * p.tok_stride) * p.heads + h] = (m2[mt][hf] + log2f(l[mt][hf])) * 0.6931471805599453f;
+        }
     }
-    __syncwarp();   // everyone is done with sK / sV before the next group overwrites them
+    __syncwarp();
+    as_unstage<NT>(p.out + h * 64, p.ldo, tok0, p.tok_stride, S, lane, tQ);
+    __syncwarp();
   }
 }
 
-constexpr int ASB_WARPS = 2;
-template <int SPW>
-__global__ void __launch_bounds__(ASB_WARPS * 32) attn_small_bwd_kernel(const SmallAttnP p) {
-  extern __shared__ float as_smem[];
+template <int NT>
+__global__ void __launch_bounds__(AS_WARPS * 32) attn_small_bwd_kernel(const SmallAttnP p) {
+  extern __shared__ __align__(16) uint8_t as_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  constexpr uint32_t TILE = 16 * NT * AS_ROW * 2;
+  constexpr uint32_t STAT = 16 * NT * 3 * 4;      // per query row: log2-domain max, 1 / l, delta
+  const uint32_t tQ = smem_u32(as_smem) + warp * (5 * TILE + STAT), tK = tQ + TILE, tV = tK + TILE, tD = tV + TILE, tO = tD + TILE;
+  float* stat = reinterpret_cast<float*>(as_smem + warp * (5 * TILE + STAT) + 5 * TILE);
   const int S = p.S;
-  const int tile = SPW * S * 64;
-  float* sK = as_smem + warp * (4 * tile + 2 * SPW * 32 * AS_PAD);
-  float* sV = sK + tile;
-  float* sQ = sV + tile;
-  float* sD = sQ + tile;
-  float* sP = sD + tile;                 // [SPW][32][AS_PAD]  probabilities P[t][s]
-  float* sS = sP + SPW * 32 * AS_PAD;    // [SPW][32][AS_PAD]  dS[t][s]
-  const long long ngroups = (p.nseq + SPW - 1) / SPW;
-  const long long total = ngroups * p.heads;
+  const long long total = p.nseq * p.heads;
   const float qs = p.scale * AS_LOG2E;
-  const int sq = (SPW == 2) ? (lane >> 4) : 0;
-  const int t = (SPW == 2) ? (lane & 15) : lane;
-  for (long long pi = (long long)blockIdx.x * ASB_WARPS + warp; pi < total; pi += (long long)gridDim.x * ASB_WARPS) {
-    const long long sg = pi / p.heads;
-    const int h = (int)(pi - sg * p.heads);
-    as_stage<SPW>(p, p.k, p.ldk, sg, h, lane, sK);
-    as_stage<SPW>(p, p.v, p.ldv, sg, h, lane, sV);
-    as_stage<SPW>(p, p.q, p.ldq, sg, h, lane, sQ);
-    as_stage<SPW>(p, p.dout, p.lddo, sg, h, lane, sD);
+  for (long long pi = (long long)blockIdx.x * AS_WARPS + warp; pi < total; pi += (long long)gridDim.x * AS_WARPS) {
+    const long long seq = pi / p.heads;
+    const int h = (int)(pi - seq * p.heads);
+    const long long outer = seq / p.inner;
+    const long long tok0 = outer * p.outer_stride + (seq - outer * p.inner) * p.inner_stride;
+    as_stage<NT>(p.q + h * 64, p.ldq, tok0, p.tok_stride, S, lane, tQ);
+    as_stage<NT>(p.k + h * 64, p.ldk, tok0, p.tok_stride, S, lane, tK);
+    as_stage<NT>(p.v + h * 64, p.ldv, tok0, p.tok_stride, S, lane, tV);
+    as_stage<NT>(p.dout + h * 64, p.lddo, tok0, p.tok_stride, S, lane, tD);
     __syncwarp();
-    const long long seq = sg * SPW + sq;
-    const bool act = (t < S) && (seq < p.nseq);
-    const long long tok = act ? as_token(p, seq, t) : 0;
-    const float* Kq = sK + sq * tile / SPW;
-    const float* Vq = sV + sq * tile / SPW;
-    const float* Qq = sQ + sq * tile / SPW;
-    const float* Dq = sD + sq * tile / SPW;
-    float* pr = sP + (sq * 32 + t) * AS_PAD;     // row t of this sequence's P
-    float* dr = sS + (sq * 32 + t) * AS_PAD;     // row t of dS
-    // ---------------- phase A: lane = query t
-    float m = -INFINITY;
+    // ---- query-major pass: P, dP, delta, dS, dQ = dS K
     {
-      float qf[64];
-      if (act) as_load_row(p.q + tok * p.ldq + h * 64, qf, qs);
-      else {
+      float s[NT][2 * NT][4], dp[NT][2 * NT][4];
+      as_kmajor_product<NT>(s, tQ, tK, g, tq);
+      float m2[NT][2], l[NT][2];
+      as_softmax<NT>(s, qs, S, tq, m2, l);
+      as_kmajor_product<NT>(dp, tD, tV, g, tq);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) qf[i] = 0.f;
-      }
-      for (int s = 0; s < S; ++s) {
-        const float d = as_dot(qf, Kq + s * 64);
-        pr[s] = d;
-        m = fmaxf(m, d);
-      }
-    }
-    {
-      float df[64];
-      if (act) as_load_row(p.dout + tok * p.lddo + h * 64, df, 1.0f);
-      else {
+      for (int mt = 0; mt < NT; ++mt) {
+        float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) df[i] = 0.f;
-      }
-      for (int s = 0; s < S; ++s) dr[s] = as_dot(df, Vq + s * 64);     // dP[t][s]
-    }
-    float l = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const float e = exp2_fast(pr[s] - m);
-      pr[s] = e;
-      l += e;
-    }
-    const float inv_l = 1.0f / l;
-    float delta = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const float pv = pr[s] * inv_l;
-      pr[s] = pv;
-      delta = fmaf(pv, dr[s], delta);
-    }
-    for (int s = 0; s < S; ++s) dr[s] = pr[s] * (dr[s] - delta) * p.scale;    // dS[t][s]
-    {
-      float dq[64];
+        for (int nt = 0; nt < 2 * NT; ++nt)
 #pragma unroll
-      for (int i = 0; i < 64; ++i) dq[i] = 0.f;
-      for (int s = 0; s < S; ++s) as_axpy(dq, dr[s], Kq + s * 64);
-      if (act) as_store_row(p.dq + tok * p.lddq + h * 64, dq, 1.0f);
+          for (int i = 0; i < 2; ++i) { d0 = fmaf(s[mt][nt][i], dp[mt][nt][i], d0); d1 = fmaf(s[mt][nt][2 + i], dp[mt][nt][2 + i], d1); }
+        d0 = quad_sum(d0);
+        d1 = quad_sum(d1);
+#pragma unroll
+        for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            s[mt][nt][i] = s[mt][nt][i] * (dp[mt][nt][i] - d0) * p.scale;              // dS (masked keys: P = 0)
+            s[mt][nt][2 + i] = s[mt][nt][2 + i] * (dp[mt][nt][2 + i] - d1) * p.scale;
+          }
+        if (tq == 0) {
+          float* st0 = stat + (mt * 16 + g) * 3;
+          st0[0] = m2[mt][0]; st0[1] = 1.0f / l[mt][0]; st0[2] = d0;
+          st0[24] = m2[mt][1]; st0[25] = 1.0f / l[mt][1]; st0[26] = d1;                   // row g + 8
+        }
+      }
+      float dq[NT][8][4];
+      as_pv_product<NT>(dq, s, tK, lane);
+      float one[NT][2];
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt) { one[mt][0] = 1.f; one[mt][1] = 1.f; }
+      as_store_tile<NT>(tO, dq, one, g, tq);
     }
     __syncwarp();
-    // ---------------- phase B: lane = key s (same (sq, t) mapping, t now indexes the key)
-    const float* pcol = sP + sq * 32 * AS_PAD + t;    // P[tq][t]  = pcol[tq * AS_PAD]
-    const float* dcol = sS + sq * 32 * AS_PAD + t;
+    as_unstage<NT>(p.dq + h * 64, p.lddq, tok0, p.tok_stride, S, lane, tO);
+    __syncwarp();
+    // ---- key-major pass: P^T, dS^T from S^T = K Q^T and dP^T = V dO^T with the per-query statistics; dV = P^T dO, dK = dS^T Q
     {
-      float dv[64];
+      float st[NT][2 * NT][4], dpt[NT][2 * NT][4];
+      as_kmajor_product<NT>(st, tK, tQ, g, tq);       // rows = keys, columns = queries
+      as_kmajor_product<NT>(dpt, tV, tD, g, tq);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) dv[i] = 0.f;
-      for (int tq = 0; tq < S; ++tq) as_axpy(dv, pcol[tq * AS_PAD], Dq + tq * 64);
-      if (act) as_store_row(p.dv + tok * p.lddv + h * 64, dv, 1.0f);
-    }
-    {
-      float dk[64];
+      for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
-      for (int i = 0; i < 64; ++i) dk[i] = 0.f;
-      for (int tq = 0; tq < S; ++tq) as_axpy(dk, dcol[tq * AS_PAD], Qq + tq * 64);
-      if (act) as_store_row(p.dk + tok * p.lddk + h * 64, dk, 1.0f);
+        for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float* sq = stat + (nt * 8 + 2 * tq + i) * 3;       // statistics of query column nt * 8 + 2 tq + i
+            const float pa = exp2_fast(st[mt][nt][i] * qs - sq[0]) * sq[1];
+            const float pb = exp2_fast(st[mt][nt][2 + i] * qs - sq[0]) * sq[1];
+            st[mt][nt][i] = pa;
+            st[mt][nt][2 + i] = pb;
+            dpt[mt][nt][i] = pa * (dpt[mt][nt][i] - sq[2]) * p.scale;
+            dpt[mt][nt][2 + i] = pb * (dpt[mt][nt][2 + i] - sq[2]) * p.scale;
+          }
+      float acc[NT][8][4];
+      float one[NT][2];
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt) { one[mt][0] = 1.f; one[mt][1] = 1.f; }
+      as_pv_product<NT>(acc, st, tD, lane);            // dV[key][d] = sum_q P^T[key][q] dO[q][d]
+      as_store_tile<NT>(tO, acc, one, g, tq);
+      __syncwarp();
+      as_unstage<NT>(p.dv + h * 64, p.lddv, tok0, p.tok_stride, S, lane, tO);
+      __syncwarp();
+      as_pv_product<NT>(acc, dpt, tQ, lane);           // dK[key][d] = sum_q dS^T[key][q] Q[q][d]
+      as_store_tile<NT>(tO, acc, one, g, tq);
+      __syncwarp();
+      as_unstage<NT>(p.dk + h * 64, p.lddk, tok0, p.tok_stride, S, lane, tO);
     }
     __syncwarp();
   }
@@ -275,7 +369,7 @@ static int small_fill(const SvdxAttn* d, SmallAttnP& p, bool bwd) {
   if (al & 15) return svdx_fail(SVDX_E_BADARG, "attention(small): operands must be 16 B aligned");
   memset(&p, 0, sizeof(p));
   p.q = reinterpret_cast<const bf16*>(d->q); p.k = reinterpret_cast<const bf16*>(d->k); p.v = reinterpret_cast<const bf16*>(d->v);
-  p.o = reinterpret_cast<const bf16*>(d->o); p.out = reinterpret_cast<bf16*>(d->o);
+  p.out = reinterpret_cast<bf16*>(d->o);
   p.ldq = d->ldq; p.ldk = d->ldk; p.ldv = d->ldv; p.ldo = d->ldo;
   p.nseq = d->nseq; p.heads = d->heads; p.S = d->S; p.inner = d->inner;
   p.outer_stride = d->outer_stride; p.inner_stride = d->inner_stride; p.tok_stride = d->tok_stride;
@@ -293,18 +387,18 @@ static int small_fill(const SvdxAttn* d, SmallAttnP& p, bool bwd) {
 }
 
 template <typename K>
-static int small_launch(K kernel, const SmallAttnP& p, int spw, int warps, size_t smem, cudaStream_t st, bool* attr_flags, const char* what) {
+static int small_launch(K kernel, const SmallAttnP& p, size_t smem, cudaStream_t st, bool* attr_flags, const char* what) {
   const int slot = svdx_device_slot();
   if (!attr_flags[slot]) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return svdx_fail_cuda(e, what);
     attr_flags[slot] = true;
   }
-  const long long total = ((p.nseq + spw - 1) / spw) * p.heads;
-  long long ctas = (total + warps - 1) / warps;
-  const long long cap = 8LL * svdx_num_sms();
+  const long long total = p.nseq * p.heads;
+  long long ctas = (total + AS_WARPS - 1) / AS_WARPS;
+  const long long cap = 16LL * svdx_num_sms();
   if (ctas > cap) ctas = cap;
-  kernel<<<(unsigned)ctas, warps * 32, smem, st>>>(p);
+  kernel<<<(unsigned)ctas, AS_WARPS * 32, smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return svdx_fail_cuda(e, what);
   return SVDX_OK;
@@ -314,50 +408,16 @@ int svdx_attention_small_fwd(const SvdxAttn* d, cudaStream_t st) {
   SmallAttnP p;
   int rc = small_fill(d, p, false);
   if (rc) return rc;
-  const int spw = d->S <= 16 ? 2 : 1;
-  const size_t smem = (size_t)ASF_WARPS * (2 * spw * d->S * 64 + 32 * AS_PAD) * sizeof(float);
-  // the dynamic shared-memory limit depends on S: keep one flag per (device, spw) and always request the S = 32 / 16 maximum
-  const size_t smem_max = (size_t)ASF_WARPS * (2 * spw * (spw == 2 ? 16 : 32) * 64 + 32 * AS_PAD) * sizeof(float);
   static bool f1[SVDX_MAX_DEVICES] = {false}, f2[SVDX_MAX_DEVICES] = {false};
-  if (spw == 2) {
-    const int slot = svdx_device_slot();
-    if (!f2[slot]) {
-      cudaError_t e = cudaFuncSetAttribute(attn_small_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-      if (e != cudaSuccess) return svdx_fail_cuda(e, "attention_fwd(small): smem attribute");
-      f2[slot] = true;
-    }
-    return small_launch(attn_small_fwd_kernel<2>, p, 2, ASF_WARPS, smem, st, f2, "attention_fwd(small)");
-  }
-  const int slot = svdx_device_slot();
-  if (!f1[slot]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_small_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-    if (e != cudaSuccess) return svdx_fail_cuda(e, "attention_fwd(small): smem attribute");
-    f1[slot] = true;
-  }
-  return small_launch(attn_small_fwd_kernel<1>, p, 1, ASF_WARPS, smem, st, f1, "attention_fwd(small)");
+  if (d->S <= 16) return small_launch(attn_small_fwd_kernel<1>, p, (size_t)AS_WARPS * 3 * 16 * AS_ROW * 2, st, f1, "attention_fwd(small)");
+  return small_launch(attn_small_fwd_kernel<2>, p, (size_t)AS_WARPS * 3 * 32 * AS_ROW * 2, st, f2, "attention_fwd(small)");
 }
 
 int svdx_attention_small_bwd(const SvdxAttn* d, cudaStream_t st) {
   SmallAttnP p;
   int rc = small_fill(d, p, true);
   if (rc) return rc;
-  const int spw = d->S <= 16 ? 2 : 1;
-  const size_t smem = (size_t)ASB_WARPS * (4 * spw * d->S * 64 + 2 * spw * 32 * AS_PAD) * sizeof(float);
-  const size_t smem_max = (size_t)ASB_WARPS * (4 * spw * (spw == 2 ? 16 : 32) * 64 + 2 * spw * 32 * AS_PAD) * sizeof(float);
   static bool f1[SVDX_MAX_DEVICES] = {false}, f2[SVDX_MAX_DEVICES] = {false};
-  const int slot = svdx_device_slot();
-  if (spw == 2) {
-    if (!f2[slot]) {
-      cudaError_t e = cudaFuncSetAttribute(attn_small_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-      if (e != cudaSuccess) return svdx_fail_cuda(e, "attention_bwd(small): smem attribute");
-      f2[slot] = true;
-    }
-    return small_launch(attn_small_bwd_kernel<2>, p, 2, ASB_WARPS, smem, st, f2, "attention_bwd(small)");
-  }
-  if (!f1[slot]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_small_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-    if (e != cudaSuccess) return svdx_fail_cuda(e, "attention_bwd(small): smem attribute");
-    f1[slot] = true;
-  }
-  return small_launch(attn_small_bwd_kernel<1>, p, 1, ASB_WARPS, smem, st, f1, "attention_bwd(small)");
+  if (d->S <= 16) return small_launch(attn_small_bwd_kernel<1>, p, (size_t)AS_WARPS * (5 * 16 * AS_ROW * 2 + 16 * 3 * 4), st, f1, "attention_bwd(small)");
+  return small_launch(attn_small_bwd_kernel<2>, p, (size_t)AS_WARPS * (5 * 32 * AS_ROW * 2 + 32 * 3 * 4), st, f2, "attention_bwd(small)");
 }

@@ -265,12 +265,35 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   }
 }
 
+// GEGLU backward without a bias gradient: one thread per 8 columns of one row (maximum memory-level parallelism)
+__global__ void geglu_bwd_plain_kernel(const bf16* __restrict__ pre, long long ldpre, const bf16* __restrict__ dout, long long lddo,
+                                       bf16* __restrict__ dpre, long long lddpre, long long rows, int h) {
+  const long long idx = gtid();
+  const int hv = h / 8;
+  if (idx >= rows * hv) return;
+  const long long r = idx / hv;
+  const int c = (int)(idx - r * hv) * 8;
+  const uint4 uv = *reinterpret_cast<const uint4*>(pre + r * ldpre + c);
+  const uint4 ug = *reinterpret_cast<const uint4*>(pre + r * ldpre + h + c);
+  const uint4 ud = *reinterpret_cast<const uint4*>(dout + r * lddo + c);
+  const uint32_t v[4] = {uv.x, uv.y, uv.z, uv.w}, g[4] = {ug.x, ug.y, ug.z, ug.w}, d[4] = {ud.x, ud.y, ud.z, ud.w};
+  uint32_t ov[4], og[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 fv = unpack_bf16x2(v[k]), fg = unpack_bf16x2(g[k]), fd = unpack_bf16x2(d[k]);
+    ov[k] = pack_bf16x2(fd.x * gelu_erf_f(fg.x), fd.y * gelu_erf_f(fg.y));
+    og[k] = pack_bf16x2(fd.x * fv.x * gelu_erf_grad_f(fg.x), fd.y * fv.y * gelu_erf_grad_f(fg.y));
+  }
+  *reinterpret_cast<uint4*>(dpre + r * lddpre + c) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+  *reinterpret_cast<uint4*>(dpre + r * lddpre + h + c) = make_uint4(og[0], og[1], og[2], og[3]);
+}
+
 // GEGLU backward. pre = [value | gate] (bf16, the saved projection), dout [rows][h]:
 //   dpre[:, :h] = dout * gelu(gate),  dpre[:, h:] = dout * value * gelu'(gate)
 // and, fused, the bias gradient of the projection = column sums of the (bf16-rounded) dpre it writes — saving the separate
 // column-sum pass over the [rows][2h] tensor (the largest activation gradient of a transformer block).
 // Block = 32 column vectors (8 columns each) x 8 row lanes, rows streamed in chunks of rows_per_cta like colsum_kernel.
-__global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__ pre, long long ldpre, const bf16* __restrict__ dout, long long lddo,
+__global__ void __launch_bounds__(256, 2) geglu_bwd_kernel(const bf16* __restrict__ pre, long long ldpre, const bf16* __restrict__ dout, long long lddo,
                                                         bf16* __restrict__ dpre, long long lddpre, long long rows, int h, long long rows_per_cta,
                                                         float* __restrict__ bias_grad) {
   __shared__ float sh[8][2][256 + 8];
@@ -282,21 +305,20 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__
 #pragma unroll
   for (int k = 0; k < 8; ++k) { av[k] = 0.f; ag[k] = 0.f; }
   if (c < h) {
-    for (long long r = r0 + rl; r < r1; r += 16) {
-      // two rows in flight per thread
-      const bool two = (r + 8 < r1);
-      uint4 uv[2], ug[2], ud[2];
-      uv[0] = *reinterpret_cast<const uint4*>(pre + r * ldpre + c);
-      ug[0] = *reinterpret_cast<const uint4*>(pre + r * ldpre + h + c);
-      ud[0] = *reinterpret_cast<const uint4*>(dout + r * lddo + c);
-      if (two) {
-        uv[1] = *reinterpret_cast<const uint4*>(pre + (r + 8) * ldpre + c);
-        ug[1] = *reinterpret_cast<const uint4*>(pre + (r + 8) * ldpre + h + c);
-        ud[1] = *reinterpret_cast<const uint4*>(dout + (r + 8) * lddo + c);
+    for (long long r = r0 + rl; r < r1; r += 32) {
+      // four rows in flight per thread (9 x 16-byte loads issued before any arithmetic)
+      uint4 uv[4], ug[4], ud[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (r + 8 * q < r1) {
+          uv[q] = *reinterpret_cast<const uint4*>(pre + (r + 8 * q) * ldpre + c);
+          ug[q] = *reinterpret_cast<const uint4*>(pre + (r + 8 * q) * ldpre + h + c);
+          ud[q] = *reinterpret_cast<const uint4*>(dout + (r + 8 * q) * lddo + c);
+        }
       }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q == 1 && !two) break;
+      for (int q = 0; q < 4; ++q) {
+        if (r + 8 * q >= r1) break;
         const uint32_t v[4] = {uv[q].x, uv[q].y, uv[q].z, uv[q].w}, g[4] = {ug[q].x, ug[q].y, ug[q].z, ug[q].w}, d[4] = {ud[q].x, ud[q].y, ud[q].z, ud[q].w};
         uint32_t ov[4], og[4];
 #pragma unroll
@@ -304,11 +326,9 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__
           const float2 fv = unpack_bf16x2(v[k]), fg = unpack_bf16x2(g[k]), fd = unpack_bf16x2(d[k]);
           ov[k] = pack_bf16x2(fd.x * gelu_erf_f(fg.x), fd.y * gelu_erf_f(fg.y));
           og[k] = pack_bf16x2(fd.x * fv.x * gelu_erf_grad_f(fg.x), fd.y * fv.y * gelu_erf_grad_f(fg.y));
-          if (bias_grad) {
-            const float2 rv = unpack_bf16x2(ov[k]), rg = unpack_bf16x2(og[k]);
-            av[2 * k] += rv.x; av[2 * k + 1] += rv.y;
-            ag[2 * k] += rg.x; ag[2 * k + 1] += rg.y;
-          }
+          const float2 rv = unpack_bf16x2(ov[k]), rg = unpack_bf16x2(og[k]);
+          av[2 * k] += rv.x; av[2 * k + 1] += rv.y;
+          ag[2 * k] += rg.x; ag[2 * k + 1] += rg.y;
         }
         const long long rr = r + 8 * q;
         *reinterpret_cast<uint4*>(dpre + rr * lddpre + c) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
@@ -316,7 +336,6 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__
       }
     }
   }
-  if (!bias_grad) return;
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sh[rl][0][cvl * 8 + k] = av[k]; sh[rl][1][cvl * 8 + k] = ag[k]; }
   __syncthreads();
@@ -537,6 +556,73 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const bf16* __restric
   }
 }
 
+// ---- skinny products of the [B, C] conditioning vectors (time-embedding MLPs, all 44 time_emb_proj at once, the 1-key image
+// cross-attention collapse to_out(to_v(e)), their gradients): M = B rows. A 128-row tensor-core tile would be > 99 % padding and the
+// launch is latency-bound (17 us for a 1 x 1280 x 1280 product on the tcgen05 kernel); these are weight-streaming GEMVs.
+// out[m][n] = sum_k a[m][k] * w[n][k] (+ bias[n]), m < MR <= 8: one warp per output column, lanes stride K in 16-byte vectors.
+template <int MR>
+__global__ void __launch_bounds__(256) gemv_kernel(const bf16* __restrict__ a, long long lda, const bf16* __restrict__ w, long long ldw, int M, int N,
+                                                   int K, const float* __restrict__ bias, void* __restrict__ out, long long ldo, int out_f32) {
+  const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[MR];
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+  const bf16* wr = w + n * ldw;
+  for (int v = lane; v < K / 8; v += 32) {
+    const uint4 uw = __ldg(reinterpret_cast<const uint4*>(wr + v * 8));
+    const uint32_t ww[4] = {uw.x, uw.y, uw.z, uw.w};
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      if (m < M) {
+        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(a + m * lda + v * 8));
+        const uint32_t aa[4] = {ua.x, ua.y, ua.z, ua.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 x = unpack_bf16x2(aa[k]), y = unpack_bf16x2(ww[k]);
+          acc[m] = fmaf(x.x, y.x, acc[m]);
+          acc[m] = fmaf(x.y, y.y, acc[m]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = warp_sum(acc[m]);
+  if (lane == 0) {
+    const float b = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      if (m < M) {
+        if (out_f32) reinterpret_cast<float*>(out)[m * ldo + n] = acc[m] + b;
+        else reinterpret_cast<bf16*>(out)[m * ldo + n] = __float2bfloat16(acc[m] + b);
+      }
+    }
+  }
+}
+
+// g[o][k] += s * sum_{t < T} dy[t][o] * x[t][k]   (T <= 8 token rows: the weight gradient of a skinny product), 4 columns per thread
+__global__ void outer_accum_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x, long long ldx, int T, int O, int K,
+                                   const float* __restrict__ scale, float* __restrict__ g, long long ldg) {
+  const long long idx = gtid();
+  const int kv = K / 4;
+  if (idx >= (long long)O * kv) return;
+  const int o = (int)(idx / kv);
+  const int k = (int)(idx - (long long)o * kv) * 4;
+  const float s = scale ? scale[0] : 1.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float d = __bfloat162float(dy[t * lddy + o]);
+    const uint2 u = *reinterpret_cast<const uint2*>(x + t * ldx + k);
+    const float2 p = unpack_bf16x2(u.x), q = unpack_bf16x2(u.y);
+    a0 = fmaf(d, p.x, a0); a1 = fmaf(d, p.y, a1); a2 = fmaf(d, q.x, a2); a3 = fmaf(d, q.y, a3);
+  }
+  float4* gp = reinterpret_cast<float4*>(g + (long long)o * ldg + k);
+  float4 cur = *gp;
+  cur.x = fmaf(s, a0, cur.x); cur.y = fmaf(s, a1, cur.y); cur.z = fmaf(s, a2, cur.z); cur.w = fmaf(s, a3, cur.w);
+  *gp = cur;
+}
+
 struct TransposeJob {
   long long src_off;   // element offset into the bf16 source arena
   bf16* dst;           // [I][O] destination
@@ -748,12 +834,18 @@ extern "C" int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, 
                               int32_t h, float* bias_grad, void* stream) {
   if (!pre || !dout || !dpre || rows <= 0 || h <= 0 || h % 8 || ldpre % 8 || lddo % 8 || lddpre % 8)
     return svdx_fail(SVDX_E_BADARG, "geglu_bwd: bad arguments");
+  if (!bias_grad) {
+    geglu_bwd_plain_kernel<<<nblocks(rows * (h / 8)), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), ldpre, reinterpret_cast<const bf16*>(dout), lddo,
+                                                                      reinterpret_cast<bf16*>(dpre), lddpre, rows, h);
+    SVDX_CHECK_LAUNCH("geglu_bwd");
+    return SVDX_OK;
+  }
   const int col_blocks = (h + 255) / 256;
-  long long chunks = (8LL * svdx_num_sms() + col_blocks - 1) / col_blocks;
+  long long chunks = (16LL * svdx_num_sms() + col_blocks - 1) / col_blocks;
   if (chunks < 1) chunks = 1;
   long long rows_per_cta = (rows + chunks - 1) / chunks;
-  rows_per_cta = (rows_per_cta + 15) / 16 * 16;
-  if (rows_per_cta < 16) rows_per_cta = 16;
+  rows_per_cta = (rows_per_cta + 31) / 32 * 32;
+  if (rows_per_cta < 32) rows_per_cta = 32;
   chunks = (rows + rows_per_cta - 1) / rows_per_cta;
   geglu_bwd_kernel<<<dim3(col_blocks, (unsigned)chunks), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(pre), ldpre, reinterpret_cast<const bf16*>(dout),
                                                                              lddo, reinterpret_cast<bf16*>(dpre), lddpre, rows, h, rows_per_cta, bias_grad);
@@ -767,6 +859,34 @@ extern "C" int svdx_softmax_rows(const void* x, int64_t ldx, int64_t rows, int32
     return svdx_fail(SVDX_E_BADARG, "softmax_rows: bad arguments (cols, ldx, ldy multiples of 8; 16 B aligned)");
   softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, cols, scale, reinterpret_cast<bf16*>(y), ldy);
   SVDX_CHECK_LAUNCH("softmax_rows");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_gemv(const void* a, int64_t lda, const void* w, int64_t ldw, int32_t M, int32_t N, int32_t K, const float* bias, void* out,
+                         int64_t ldo, int32_t out_dtype, void* stream) {
+  if (!a || !w || !out || M <= 0 || M > 8 || N <= 0 || K <= 0 || K % 8 || lda % 8 || ldw % 8 || (reinterpret_cast<uintptr_t>(a) & 15) ||
+      (reinterpret_cast<uintptr_t>(w) & 15) || (out_dtype != SVDX_OUT_BF16 && out_dtype != SVDX_OUT_F32))
+    return svdx_fail(SVDX_E_BADARG, "gemv: bad arguments (M <= 8, K, lda, ldw multiples of 8, 16 B aligned, bf16 / fp32 output)");
+  const unsigned blocks = (unsigned)(((long long)N * 32 + 255) / 256);
+  const int f32 = out_dtype == SVDX_OUT_F32;
+  const bf16* ap = reinterpret_cast<const bf16*>(a);
+  const bf16* wp = reinterpret_cast<const bf16*>(w);
+  if (M == 1) gemv_kernel<1><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32);
+  else if (M == 2) gemv_kernel<2><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32);
+  else if (M <= 4) gemv_kernel<4><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32);
+  else gemv_kernel<8><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32);
+  SVDX_CHECK_LAUNCH("gemv");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_outer_accum(const void* dy, int64_t lddy, const void* x, int64_t ldx, int32_t T, int32_t O, int32_t K, const float* scale,
+                                float* g, int64_t ldg, void* stream) {
+  if (!dy || !x || !g || T <= 0 || T > 8 || O <= 0 || K <= 0 || K % 4 || ldx % 4 || ldg % 4 || (reinterpret_cast<uintptr_t>(x) & 7) ||
+      (reinterpret_cast<uintptr_t>(g) & 15))
+    return svdx_fail(SVDX_E_BADARG, "outer_accum: bad arguments (T <= 8, K, ldx, ldg multiples of 4, aligned)");
+  outer_accum_kernel<<<nblocks((long long)O * (K / 4)), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx,
+                                                                         T, O, K, scale, g, ldg);
+  SVDX_CHECK_LAUNCH("outer_accum");
   return SVDX_OK;
 }
 

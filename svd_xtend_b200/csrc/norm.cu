@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
                                                                 int G, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
                                                                 const float* __restrict__ ws, float inv_count, bf16* __restrict__ dx, long long lddx,
-                                                                bf16* __restrict__ dx2, long long lddx2) {
+                                                                bf16* __restrict__ dx2, long long lddx2, const bf16* __restrict__ dres, long long lddres) {
   const int C = s.C1 + s.C2;
   const int CV = C / 8;
   const int cpg = C / G;
@@ -357,12 +357,13 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
   }
   const long long base = (long long)n * rows;
   for (int r = r0 + rl; r < r1; r += 4 * RL) {
-    uint4 ux[4], ug[4];
+    uint4 ux[4], ug[4], ur[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (r + q * RL < r1) {
         ux[q] = load_vec8(s, base + r + q * RL, c0);
         ug[q] = *reinterpret_cast<const uint4*>(dy + (base + r + q * RL) * lddy + c0);
+        if (dres) ur[q] = *reinterpret_cast<const uint4*>(dres + (base + r + q * RL) * lddres + c0);
       }
     }
 #pragma unroll
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
       if (r + q * RL >= r1) break;
       const long long row = base + r + q * RL;
       const uint32_t in[4] = {ux[q].x, ux[q].y, ux[q].z, ux[q].w}, din[4] = {ug[q].x, ug[q].y, ug[q].z, ug[q].w};
+      const uint32_t rin[4] = {ur[q].x, ur[q].y, ur[q].z, ur[q].w};
       uint32_t out[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -380,8 +382,10 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
           e0 *= silu_grad_f(fmaf(xh0, gm[2 * k], bt[2 * k]));
           e1 *= silu_grad_f(fmaf(xh1, gm[2 * k + 1], bt[2 * k + 1]));
         }
-        out[k] = pack_bf16x2(rs[2 * k] * (e0 * gm[2 * k] - t1[2 * k] - xh0 * t2[2 * k]),
-                             rs[2 * k + 1] * (e1 * gm[2 * k + 1] - t1[2 * k + 1] - xh1 * t2[2 * k + 1]));
+        float o0 = rs[2 * k] * (e0 * gm[2 * k] - t1[2 * k] - xh0 * t2[2 * k]);
+        float o1 = rs[2 * k + 1] * (e1 * gm[2 * k + 1] - t1[2 * k + 1] - xh1 * t2[2 * k + 1]);
+        if (dres) { const float2 rr = unpack_bf16x2(rin[k]); o0 += rr.x; o1 += rr.y; }   // gradient already accumulated on x (its residual use)
+        out[k] = pack_bf16x2(o0, o1);
       }
       bf16* qd = first ? (dx + row * lddx + c0) : (dx2 + row * lddx2 + (c0 - s.C1));
       *reinterpret_cast<uint4*>(qd) = make_uint4(out[0], out[1], out[2], out[3]);
@@ -668,14 +672,6 @@ extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1
   int threads, rpc;
   gn_vec_config(C1 + C2, outer, rows, threads, rpc);
   const int RL = threads / ((C1 + C2) / 8);
-  {
-    // every CTA folds the slab's channel sums before streaming: give it at least 128 KB of input so that the fold (a few
-    // hundred ns .. 2 us at C = 2560) stays a small fraction of its life (measured: profiles/r2_kbench.txt)
-    const int quantum = 4 * RL;
-    int min_rows = (int)((131072 + (long long)(C1 + C2) * 2 - 1) / ((long long)(C1 + C2) * 2));
-    min_rows = ((min_rows + quantum - 1) / quantum) * quantum;
-    if (rpc < min_rows) rpc = min_rows;
-  }
   const int padded = (threads + 31) & ~31;      // whole warps: the channel fold uses full-mask shuffles
   const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
   gn_apply_fused_kernel<<<dim3((rows + rpc - 1) / rpc, outer), padded, 0, st>>>(s, rows, rpc, RL, num_groups, eps, inv, csum1, ldc1, csum2, ldc2, mean, rstd,
@@ -687,10 +683,11 @@ extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1
 extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, const void* dy,
                                   int64_t lddy, int32_t outer, int32_t rows, int32_t num_groups, const float* mean, const float* rstd,
                                   const float* gamma, const float* beta, int32_t fuse_silu, void* dx, int64_t lddx, void* dx2,
-                                  int64_t lddx2, float* dgamma, float* dbeta, float* workspace, int32_t workspace_is_zero, void* stream_v) {
+                                  int64_t lddx2, float* dgamma, float* dbeta, float* workspace, int32_t workspace_is_zero, const void* dres,
+                                  int64_t lddres, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !dy || lddy % 8 || !dx || lddx % 8 || (C2 > 0 && (!dx2 || lddx2 % 8)) || !workspace ||
-      (dgamma && !dbeta))
+      (dgamma && !dbeta) || (dres && (C2 > 0 || lddres % 8 || (reinterpret_cast<uintptr_t>(dres) & 15))))
     return svdx_fail(SVDX_E_BADARG, "groupnorm_bwd: bad arguments");
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
   const int total = outer * num_groups;
@@ -706,7 +703,8 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
                                                     fuse_silu, workspace, dgamma, dbeta);
   const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
   gn_bwd_apply<<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta, fuse_silu,
-                                         workspace, inv, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dx2), lddx2);
+                                         workspace, inv, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dx2), lddx2,
+                                         reinterpret_cast<const bf16*>(dres), lddres);
   SVDX_CHECK_LAUNCH("groupnorm_bwd");
   return SVDX_OK;
 }

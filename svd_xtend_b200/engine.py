@@ -513,6 +513,15 @@ class Engine:
                         block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
             self.pgrad(p).add_(tmp[:p.shape[0], :p.shape[1]])
             return
+        if M <= 8 and pad_to is None and K % 4 == 0:
+            # conditioning vectors (B token rows): an outer-product accumulation, not a split-K tensor-core launch
+            o0 = 0
+            for p in ws:
+                O = p.shape[0]
+                if p.requires_grad:
+                    raw.outer_accum(dy[:, o0:o0 + O], x, self.pgrad(p).view(O, -1), None if scales3 is None else scales3[0:1])
+                o0 += O
+            return
         fused_g = None
         if len(ws) > 1 and self.arena is not None and all(p.requires_grad for p in ws):
             fused_g = self.arena.grad_matrix(list(ws))     # q|k|v are adjacent in the arena: ONE [3C, C] weight-gradient GEMM
@@ -748,8 +757,14 @@ class Engine:
                 dg = self.pgrad(gn.weight) if p_train else None
                 db = self.pgrad(gn.bias) if p_train else None
                 ws = self.stat_zeros(2 * outer * gn.num_groups, dy.device)
-                raw.groupnorm_bwd(x.data, None, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, None, dg, db, gn.num_groups, ws=ws)
-                self.add_grad(x, dx)
+                # x usually already carries the gradient of its residual use (conv2 / proj_out `res1`): folded into this pass
+                dres = x.grad if (x.needs_grad and x.grad is not None and x.grad.dtype == bf16 and x.grad.shape == dx.shape
+                                  and x.grad.stride(-1) == 1) else None
+                raw.groupnorm_bwd(x.data, None, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, None, dg, db, gn.num_groups, ws=ws, dres=dres)
+                if dres is not None:
+                    x.grad, x.owned = dx, True
+                else:
+                    self.add_grad(x, dx)
             self.record(bwd)
         return y
 

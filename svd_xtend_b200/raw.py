@@ -315,6 +315,11 @@ def tapgemm_auto(a, b, out, *, M, N, K, taps=((0, 0, 0),), bias=None, rowbias=No
     kw = dict(kw)
     if kw.get("block_n") is None:
         kw.pop("block_n", None)
+    if (M <= 8 and len(taps) == 1 and kw.get("mode", A_ROWS) == A_ROWS and not kw.get("geglu") and not kw.get("a_mn") and not kw.get("b_mn")
+            and rowbias is None and res1 is None and res2 is None and scales is None and gn_sum is None and kw.get("groups", 1) == 1
+            and K % 8 == 0 and a.stride(-1) == 1 and b.stride(-1) == 1 and out.dtype in (bf16, torch.float32)):
+        # conditioning vectors ([B, C] rows): a GEMV, not a 128-row tensor-core tile
+        return gemv(a, b, out, M=M, N=N, K=K, bias=bias, lda=kw.get("lda"), ldw=kw.get("ldb"))
     plan = split_plan(out.dtype == bf16, M, N, K, len(taps), kw.get("geglu"), kw.get("a_mn"), kw.get("b_mn"), kw.get("block_n"))
     if plan is not None:
         assert gn_sum is None, "fused GroupNorm statistics are not available on the split-K path"
@@ -414,8 +419,9 @@ def groupnorm_apply_fused(x, x2, outer, rows, eps, csum1, csum2, gamma, beta, si
     return mean, rstd
 
 
-def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2, dgamma=None, dbeta=None, groups=32, ws=None):
-    """ws: optional pre-ZEROED float[2 * outer * groups] workspace (a slice of a zeroed arena: no memset node)"""
+def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2, dgamma=None, dbeta=None, groups=32, ws=None, dres=None):
+    """ws: optional pre-ZEROED float[2 * outer * groups] workspace (a slice of a zeroed arena: no memset node);
+    dres: gradient already accumulated on x (bf16, same shape), added to dx in the same pass"""
     C1 = x.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     ws_zero = ws is not None
@@ -427,7 +433,8 @@ def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2
                                     dy.data_ptr(), _rowmajor(dy, "dy"), outer, rows, groups, mean.data_ptr(), rstd.data_ptr(),
                                     gamma.data_ptr(), beta.data_ptr(), int(silu), dx.data_ptr(), _rowmajor(dx, "dx"),
                                     _ptr(dx2), _rowmajor(dx2, "dx2") if dx2 is not None else 0, _ptr(dgamma), _ptr(dbeta),
-                                    ws.data_ptr(), int(ws_zero), _stream()), "svdx_groupnorm_bwd")
+                                    ws.data_ptr(), int(ws_zero), _ptr(dres), _rowmajor(dres, "dres") if dres is not None else 0, _stream()),
+          "svdx_groupnorm_bwd")
 
 
 def layernorm_fwd(x, gamma, beta, eps, y, addvec=None, add_div=1, xsum=None):
@@ -558,6 +565,27 @@ def geglu_bwd(pre, dout, dpre, bias_grad=None):
     check(load().svdx_geglu_bwd(pre.data_ptr(), _rowmajor(pre, "pre"), dout.data_ptr(), _rowmajor(dout, "dout"), dpre.data_ptr(),
                                 _rowmajor(dpre, "dpre"), rows, h2 // 2, _ptr(bias_grad), _stream()), "geglu_bwd")
     return dpre
+
+
+def gemv(a, w, out, *, M, N, K, bias=None, lda=None, ldw=None):
+    """out[m, n] = sum_k a[m, k] w[n, k] (+ bias[n]) for M <= 8 rows (conditioning vectors): weight-streaming GEMV"""
+    if _fam("linear", 2.0 * M * N * K):
+        return out
+    check(load().svdx_gemv(a.data_ptr(), lda if lda is not None else _rowmajor(a, "a"), w.data_ptr(), ldw if ldw is not None else _rowmajor(w, "w"),
+                           M, N, K, _ptr(bias), out.data_ptr(), _rowmajor(out, "out"), OUT_BF16 if out.dtype == bf16 else OUT_F32, _stream()),
+          "svdx_gemv")
+    return out
+
+
+def outer_accum(dy, x, g, scale=None):
+    """g[o, k] += scale * sum_t dy[t, o] x[t, k] for T <= 8 token rows (weight gradient of a skinny product)"""
+    T, O = dy.shape
+    K = x.shape[1]
+    if _fam("linear", 2.0 * T * O * K):
+        return g
+    check(load().svdx_outer_accum(dy.data_ptr(), _rowmajor(dy, "dy"), x.data_ptr(), _rowmajor(x, "x"), T, O, K, _ptr(scale), g.data_ptr(),
+                                  _rowmajor(g, "g"), _stream()), "svdx_outer_accum")
+    return g
 
 
 def softmax_rows(x, y, scale=1.0):

@@ -708,7 +708,7 @@ class UNetSpatioTemporalConditionModel(nn.Module):
             b_all = E.wc.get(("tembbias",) + tuple(id(p.bias) for p in projs), [p.bias for p in projs], (w_all.shape[0],),
                              lambda buf: buf.copy_(torch.cat([p.bias.detach().float() for p in projs])), dtype=F32)
             temb_all = torch.empty(B, w_all.shape[0], device=dev, dtype=F32)
-            raw.tapgemm(semb.data, w_all, temb_all, M=B, N=w_all.shape[0], K=w_all.shape[1], bias=b_all)
+            raw.tapgemm_auto(semb.data, w_all, temb_all, M=B, N=w_all.shape[0], K=w_all.shape[1], bias=b_all)
             o0 = 0
             for p in projs:
                 temb_slices[p] = Var(temb_all[:, o0:o0 + p.out_features])

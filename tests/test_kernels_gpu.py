@@ -123,6 +123,12 @@ def test_groupnorm_fwd_bwd(raw, outer, rows, C1, C2, silu):
         _close(dx2, dxr[:, C1:], what="groupnorm dx2")
     _close(dgamma, g.grad, what="groupnorm dgamma")
     _close(dbeta, b.grad, what="groupnorm dbeta")
+    if not C2:      # residual gradient folded into the same pass (single-source form)
+        dres = _rand(outer * rows, C, seed=10).to(bf16)
+        dx3 = torch.zeros_like(x1)
+        raw.groupnorm_bwd(x1, None, dy, outer, rows, mean, rstd, gamma, beta, silu, dx3, None, dres=dres)
+        torch.cuda.synchronize()
+        _close(dx3, dxr + dres.float(), what="groupnorm dx + dres")
 
 
 @pytest.mark.parametrize("rows,C", [(1000, 320), (560, 1280), (77, 64), (300, 640)])

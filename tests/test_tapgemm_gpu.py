@@ -339,3 +339,24 @@ def test_fused_groupnorm_sums_temporal_conv_grouped(raw):
         raw.tapgemm(x.view(-1, C), wk, out, M=B * T * HW, N=C, K=C, taps=taps, rows_per_group=T * HW, groups=B, gn_sum=sums, gn_rows=rows)
         torch.cuda.synchronize()
         _check_gn_sums(sums, out, rows, f"temporal conv slab {rows}")
+
+
+@pytest.mark.parametrize("M,N,K,f32", [(1, 1280, 1024, False), (2, 320, 320, True), (1, 40320, 1280, True), (5, 640, 640, False), (8, 96, 64, True)])
+def test_gemv_and_outer_accum_for_conditioning_vectors(raw, M, N, K, f32):
+    """M <= 8 rows (time-embedding MLPs, time_emb_proj, the 1-key cross-attention vectors): tapgemm_auto routes them to the
+    weight-streaming GEMV; their weight gradient is an outer-product accumulation."""
+    a = _rand(M, K, seed=1).to(bf16)
+    w = _rand(N, K, scale=K ** -0.5, seed=2).to(bf16)
+    bias = _rand(N, seed=3)
+    out = torch.full((M, N), float("nan"), device=_dev(), dtype=torch.float32 if f32 else bf16)
+    launches = raw.LAUNCHES[0]
+    raw.tapgemm_auto(a, w, out, M=M, N=N, K=K, bias=bias)
+    torch.cuda.synchronize()
+    assert raw.LAUNCHES[0] - launches == 1
+    _close(out, a.float() @ w.float().t() + bias, what=f"gemv {M}x{N}x{K}")
+    dy = _rand(M, N, seed=4).to(bf16)
+    g = torch.full((N, K), 0.25, device=_dev())
+    sc = torch.tensor([0.5], device=_dev())
+    raw.outer_accum(dy, a, g, sc)
+    torch.cuda.synchronize()
+    _close(g, 0.25 + 0.5 * dy.float().t() @ a.float(), what="outer_accum")
