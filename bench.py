@@ -163,7 +163,7 @@ def cpu_baseline(budget_s=25.0):
             "seconds": t}
 
 
-def run_reference(args):
+def run_reference(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -189,7 +189,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(out_fd, line)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -301,10 +301,25 @@ FAMILY_BOUND = {"linear": "tensor", "conv": "tensor", "attention": "tensor", "gr
                 "elementwise": "hbm"}
 
 
+def _protect_stdout():
+    """The driver reads ONE JSON line from stdout. Libraries print there at C level (NCCL's version banner with NCCL_DEBUG set):
+    fd 1 is pointed at stderr for the whole run and the line is written to the saved descriptor at the end."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line):
+    sys.stdout.flush()
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse()
+    out_fd = _protect_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, out_fd)
         return
 
     import torch.distributed as dist
@@ -635,6 +650,43 @@ def main():
         except Exception as e:
             script_path = {"failed": f"{type(e).__name__}: {e}"}
 
+    # ---- the data-parallel exchange alone (N > 1): the same collectives captured without the step around them
+    exchange = None
+    if world > 1:
+        try:
+            def ex():
+                if sharded:
+                    opt.reduce_scatter_grads()
+                    opt.all_gather_(arena.shadow)
+                else:
+                    dist.all_reduce(arena.grad)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                ex()
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            gx = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gx):
+                ex()
+            gx.replay()
+            barrier()
+            e0.record()
+            for _ in range(5):
+                gx.replay()
+            e1.record()
+            barrier()
+            tx = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+            dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+            nb = arena.numel * 4
+            exchange = {"ms": float(tx.item()), "mode": args.ddp if world > 1 else None,
+                        "payload_bytes": nb if not sharded else nb + arena.numel * 2,
+                        "what": ("reduce-scatter(fp32 gradient arena) + all-gather(bf16 operand weights)" if sharded else "all-reduce(fp32 gradient arena)")
+                                + " alone in a CUDA graph, max over ranks; in the step it runs after the backward (not overlapped)"}
+            del gx
+        except Exception as e:
+            exchange = {"failed": f"{type(e).__name__}: {e}"}
+
     def finish():
         """leave without tearing NCCL down: communicators referenced by live CUDA graphs block destroy_process_group()"""
         sys.stdout.flush()
@@ -712,12 +764,13 @@ def main():
         "gpu_launches": launches if not graph_captured else lps * args.steps,   # graph replay re-launches the captured kernels
         "roofline": roofline,
         "roofline_by_family": by_family,
+        "exchange": exchange,
         "script_path": script_path,
         "vae_encode": vae_encode,
         "gpu_eager_baseline": gpu_base,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    _emit(out_fd, line)
     finish()
 
 

@@ -270,11 +270,16 @@ SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long lon
                               long long m0, int valid_rows) {
   const float* bias = p.bias;
   const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
-  const bf16* r1 = (p.res1 && row_ok) ? p.res1 + m * p.ldr1 : nullptr;
+  // res1 (every residual add of the network) is fetched COALESCED: lane l loads the 16-byte piece l % 4 of rows l / 4 + 8 j
+  // (8 rows x 64 B = 8 cache lines per instruction instead of one line per lane: the row-per-lane form cost 32 L1 tag
+  // cycles per load and made the K = 320 / 640 residual GEMMs LSU-bound), the pieces are transposed through the staging half
+  // that is about to receive this chunk's output, and every lane reads back its own row. res2 (AlphaBlender only) stays direct.
+  const bf16* r1 = p.res1 ? p.res1 + m0 * p.ldr1 : nullptr;
   const bf16* r2 = (p.res2 && row_ok) ? p.res2 + m * p.ldr2 : nullptr;
   const bool scaled = p.scales != nullptr;
   const uint32_t row = sbase + lane * 64;
   const int sw = (lane >> 1) & 3;
+  const int prow = lane >> 2, ppc = lane & 3;
   uint32_t off = 0;
 #pragma unroll 1
   for (int c = half * 32; c < bn_out; c += 64) {
@@ -282,9 +287,11 @@ SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long lon
     if (col0 >= n_out_total) break;
     uint4 a1[4], a2[4];
     if (r1) {
-      const uint4* q = reinterpret_cast<const uint4*>(r1 + col0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) a1[k] = q[k];
+      for (int j = 0; j < 4; ++j) {
+        const int rr = prow + 8 * j;
+        a1[j] = (rr < valid_rows) ? *reinterpret_cast<const uint4*>(r1 + (long long)rr * p.ldr1 + col0 + ppc * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     if (r2) {
       const uint4* q = reinterpret_cast<const uint4*>(r2 + col0);
@@ -303,10 +310,22 @@ SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long lon
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] *= s_acc;
     }
-    if (r1) axpy_bf16x32(f, s_r1, a1);
-    if (r2) axpy_bf16x32(f, s_r2, a2);
     if (lane == 0) bulk_wait_read<1>();
     __syncwarp();
+    if (r1) {
+      // transpose the coalesced pieces through the (now free) staging half: same 64B swizzle as the output rows
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = prow + 8 * j;
+        st_shared_v4(sbase + off + rr * 64 + ((ppc ^ ((rr >> 1) & 3)) << 4), a1[j].x, a1[j].y, a1[j].z, a1[j].w);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a1[k].x), "=r"(a1[k].y), "=r"(a1[k].z), "=r"(a1[k].w) : "r"(row + off + ((k ^ sw) << 4)));
+      axpy_bf16x32(f, s_r1, a1);
+    }
+    if (r2) axpy_bf16x32(f, s_r2, a2);
     stage_row_bf16(row + off, sw, f);
     fence_proxy_async_smem();
     __syncwarp();
