@@ -253,11 +253,12 @@ int svdx_geglu_bwd(const void* pre, int64_t ldpre, const void* dout, int64_t ldd
  * svdx_tapgemm, the row softmax through this kernel. */
 int svdx_softmax_rows(const void* x, int64_t ldx, int64_t rows, int32_t cols, float scale, void* y, int64_t ldy, void* stream);
 /* Skinny products of the per-clip conditioning vectors ([B, C] rows: TimestepEmbedding MLPs, every resnet's time_emb_proj, the
- * 1-key image cross-attention to_out(to_v(e)) [D], and their data gradients):  out[m][n] = sum_k a[m][k] * w[n][k] + bias[n],
+ * 1-key image cross-attention to_out(to_v(e)) [D], their LoRA side paths and their data gradients):
+ *   out[m][n] = scale * sum_k a[m][k] * w[n][k] + bias[n]  (+ out[m][n] when accumulate != 0),
  * M <= 8 rows, bf16 operands, fp32 accumulation, bf16 (SVDX_OUT_BF16) or fp32 (SVDX_OUT_F32) output. A weight-streaming GEMV
  * (one warp per output column): the 128-row tensor-core tiles of svdx_tapgemm would be > 99 % padding here. */
 int svdx_gemv(const void* a, int64_t lda, const void* w, int64_t ldw, int32_t M, int32_t N, int32_t K, const float* bias,
-              void* out, int64_t ldo, int32_t out_dtype, void* stream);
+              void* out, int64_t ldo, int32_t out_dtype, float scale, int32_t accumulate, void* stream);
 /* ...and their weight gradients: g[o][k] += scale[0] * sum_{t < T} dy[t][o] * x[t][k], T <= 8 (scale NULL = 1) */
 int svdx_outer_accum(const void* dy, int64_t lddy, const void* x, int64_t ldx, int32_t T, int32_t O, int32_t K,
                      const float* scale, float* g, int64_t ldg, void* stream);

@@ -94,7 +94,7 @@ _PROTOS = {
     "svdx_colsum": [c_void_p, c_i64, c_i64, c_int, c_void_p, c_int, c_void_p],
     "svdx_geglu_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p],
     "svdx_softmax_rows": [c_void_p, c_i64, c_i64, c_int, c_float, c_void_p, c_i64, c_void_p],
-    "svdx_gemv": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_i64, c_int, c_void_p],
+    "svdx_gemv": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_i64, c_int, c_float, c_int, c_void_p],
     "svdx_outer_accum": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_i64, c_void_p],
     "svdx_blend_scales": [c_void_p, c_void_p, c_void_p],
     "svdx_adamw": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,

@@ -562,7 +562,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const bf16* __restric
 // out[m][n] = sum_k a[m][k] * w[n][k] (+ bias[n]), m < MR <= 8: one warp per output column, lanes stride K in 16-byte vectors.
 template <int MR>
 __global__ void __launch_bounds__(256) gemv_kernel(const bf16* __restrict__ a, long long lda, const bf16* __restrict__ w, long long ldw, int M, int N,
-                                                   int K, const float* __restrict__ bias, void* __restrict__ out, long long ldo, int out_f32) {
+                                                   int K, const float* __restrict__ bias, void* __restrict__ out, long long ldo, int out_f32,
+                                                   float scale, int accumulate) {
   const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -594,8 +595,14 @@ __global__ void __launch_bounds__(256) gemv_kernel(const bf16* __restrict__ a, l
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
       if (m < M) {
-        if (out_f32) reinterpret_cast<float*>(out)[m * ldo + n] = acc[m] + b;
-        else reinterpret_cast<bf16*>(out)[m * ldo + n] = __float2bfloat16(acc[m] + b);
+        float r = fmaf(scale, acc[m], b);
+        if (out_f32) {
+          float* o = reinterpret_cast<float*>(out) + m * ldo + n;
+          *o = accumulate ? *o + r : r;
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(out) + m * ldo + n;
+          *o = __float2bfloat16(accumulate ? __bfloat162float(*o) + r : r);
+        }
       }
     }
   }
@@ -863,7 +870,7 @@ extern "C" int svdx_softmax_rows(const void* x, int64_t ldx, int64_t rows, int32
 }
 
 extern "C" int svdx_gemv(const void* a, int64_t lda, const void* w, int64_t ldw, int32_t M, int32_t N, int32_t K, const float* bias, void* out,
-                         int64_t ldo, int32_t out_dtype, void* stream) {
+                         int64_t ldo, int32_t out_dtype, float scale, int32_t accumulate, void* stream) {
   if (!a || !w || !out || M <= 0 || M > 8 || N <= 0 || K <= 0 || K % 8 || lda % 8 || ldw % 8 || (reinterpret_cast<uintptr_t>(a) & 15) ||
       (reinterpret_cast<uintptr_t>(w) & 15) || (out_dtype != SVDX_OUT_BF16 && out_dtype != SVDX_OUT_F32))
     return svdx_fail(SVDX_E_BADARG, "gemv: bad arguments (M <= 8, K, lda, ldw multiples of 8, 16 B aligned, bf16 / fp32 output)");
@@ -871,10 +878,10 @@ extern "C" int svdx_gemv(const void* a, int64_t lda, const void* w, int64_t ldw,
   const int f32 = out_dtype == SVDX_OUT_F32;
   const bf16* ap = reinterpret_cast<const bf16*>(a);
   const bf16* wp = reinterpret_cast<const bf16*>(w);
-  if (M == 1) gemv_kernel<1><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32);
-  else if (M == 2) gemv_kernel<2><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32);
-  else if (M <= 4) gemv_kernel<4><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32);
-  else gemv_kernel<8><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32);
+  if (M == 1) gemv_kernel<1><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32, scale, accumulate);
+  else if (M == 2) gemv_kernel<2><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32, scale, accumulate);
+  else if (M <= 4) gemv_kernel<4><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32, scale, accumulate);
+  else gemv_kernel<8><<<blocks, 256, 0, ST(stream)>>>(ap, lda, wp, ldw, M, N, K, bias, out, ldo, f32, scale, accumulate);
   SVDX_CHECK_LAUNCH("gemv");
   return SVDX_OK;
 }

@@ -383,9 +383,13 @@ class Engine:
             # gradient shapes stay [r, in] / [out, r] (the reference default is --rank 4, train_svd_lora.py:551-553).
             rp = (A.shape[0] + 7) // 8 * 8
             t = self.empty(M, rp, x.data)
-            raw.tapgemm(x.data, self.w_lora(A, "A", False), t, M=M, N=rp, K=K)
             ov = out[:, off:off + n]
-            raw.tapgemm(t, self.w_lora(Bm, "B", False), ov, M=M, N=n, K=rp, res1=ov, scales=self._lora_scales(sc, out.device))
+            if M <= 8:      # the [B, C] cross-attention vectors: skinny products, not 128-row tiles
+                raw.gemv(x.data, self.w_lora(A, "A", False), t, M=M, N=rp, K=K)
+                raw.gemv(t, self.w_lora(Bm, "B", False), ov, M=M, N=n, K=rp, scale=sc, accumulate=True)
+            else:
+                raw.tapgemm(x.data, self.w_lora(A, "A", False), t, M=M, N=rp, K=K)
+                raw.tapgemm(t, self.w_lora(Bm, "B", False), ov, M=M, N=n, K=rp, res1=ov, scales=self._lora_scales(sc, out.device))
             lora_t.append(t)
         w_train = any(p.requires_grad for p in ws) or (bias is not None and bias.requires_grad) \
             or (blend is not None and blend[0].requires_grad) or any(l[2].requires_grad or l[3].requires_grad for l in lora)
@@ -429,14 +433,20 @@ class Engine:
                     dys = dyl[:, off:off + n]
                     s3 = self._lora_scales(sc, dyl.device, acc_only=True)
                     dt = self.empty(M, rp, x.data)
-                    raw.tapgemm(dys, self.w_lora(Bm, "B", True), dt, M=M, N=rp, K=n, scales=s3)   # dt = scale * dy B
+                    if M <= 8:
+                        raw.gemv(dys, self.w_lora(Bm, "B", True), dt, M=M, N=rp, K=n, scale=sc)       # dt = scale * dy B
+                    else:
+                        raw.tapgemm(dys, self.w_lora(Bm, "B", True), dt, M=M, N=rp, K=n, scales=s3)   # dt = scale * dy B
                     if Bm.requires_grad:
                         self._wgrad(dys, t, [Bm], n, rp, M, s3, pad_to=(n, rp))                  # dB += scale * dy^T t
                     if A.requires_grad:
                         self._wgrad(dt, x.data, [A], rp, K, M, None, pad_to=(rp, K))             # dA += dt^T x
                     if x.needs_grad:
                         dxl = self.empty(M, K, x.data)
-                        raw.tapgemm(dt, self.w_lora(A, "A", True), dxl, M=M, N=K, K=rp)
+                        if M <= 8:
+                            raw.gemv(dt, self.w_lora(A, "A", True), dxl, M=M, N=K, K=rp)
+                        else:
+                            raw.tapgemm(dt, self.w_lora(A, "A", True), dxl, M=M, N=K, K=rp)
                         self.add_grad(x, dxl)
             self.record(bwd)
         return y
@@ -513,7 +523,7 @@ class Engine:
                         block_n=bn, lda=dy.stride(0), ldb=x.stride(0), scales=scales3)
             self.pgrad(p).add_(tmp[:p.shape[0], :p.shape[1]])
             return
-        if M <= 8 and pad_to is None and K % 4 == 0:
+        if M <= 8 and (pad_to is None or tuple(pad_to) == tuple(ws[0].shape)) and K % 4 == 0 and dy.shape[1] >= sum(p.shape[0] for p in ws):
             # conditioning vectors (B token rows): an outer-product accumulation, not a split-K tensor-core launch
             o0 = 0
             for p in ws:

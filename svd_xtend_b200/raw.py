@@ -567,13 +567,13 @@ def geglu_bwd(pre, dout, dpre, bias_grad=None):
     return dpre
 
 
-def gemv(a, w, out, *, M, N, K, bias=None, lda=None, ldw=None):
-    """out[m, n] = sum_k a[m, k] w[n, k] (+ bias[n]) for M <= 8 rows (conditioning vectors): weight-streaming GEMV"""
+def gemv(a, w, out, *, M, N, K, bias=None, lda=None, ldw=None, scale=1.0, accumulate=False):
+    """out[m, n] = scale * sum_k a[m, k] w[n, k] (+ bias[n]) (+ out[m, n]) for M <= 8 rows (conditioning vectors): weight-streaming GEMV"""
     if _fam("linear", 2.0 * M * N * K):
         return out
     check(load().svdx_gemv(a.data_ptr(), lda if lda is not None else _rowmajor(a, "a"), w.data_ptr(), ldw if ldw is not None else _rowmajor(w, "w"),
-                           M, N, K, _ptr(bias), out.data_ptr(), _rowmajor(out, "out"), OUT_BF16 if out.dtype == bf16 else OUT_F32, _stream()),
-          "svdx_gemv")
+                           M, N, K, _ptr(bias), out.data_ptr(), _rowmajor(out, "out"), OUT_BF16 if out.dtype == bf16 else OUT_F32, float(scale),
+                           int(accumulate), _stream()), "svdx_gemv")
     return out
 
 

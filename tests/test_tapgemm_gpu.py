@@ -354,6 +354,11 @@ def test_gemv_and_outer_accum_for_conditioning_vectors(raw, M, N, K, f32):
     torch.cuda.synchronize()
     assert raw.LAUNCHES[0] - launches == 1
     _close(out, a.float() @ w.float().t() + bias, what=f"gemv {M}x{N}x{K}")
+    # LoRA side path form: out += scale * a w^T
+    prev = out.clone()
+    raw.gemv(a, w, out, M=M, N=N, K=K, scale=0.5, accumulate=True)
+    torch.cuda.synchronize()
+    _close(out, prev.float() + 0.5 * (a.float() @ w.float().t()), what="gemv accumulate")
     dy = _rand(M, N, seed=4).to(bf16)
     g = torch.full((N, K), 0.25, device=_dev())
     sc = torch.tensor([0.5], device=_dev())
