@@ -36,7 +36,7 @@ def main(rep, tags_json, out):
         return None, None
 
     tags = json.load(open(tags_json))
-    kernels = [r for r in data if re.search(r"svdx::", r[col["Kernel Name"]]) and "cast" not in r[col["Kernel Name"]]]
+    kernels = [r for r in data if "cast" not in r[col["Kernel Name"]]]      # the capture is already filtered by -k regex
     k = 0
     with open(out, "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on, one launch of each hot kernel at its config-2 shape (scripts/prof_shapes.py).\n"
@@ -52,6 +52,7 @@ def main(rep, tags_json, out):
                 name = re.sub(r"\(.*", "", r[col["Kernel Name"]])
                 dur, du = get(r, r"^gpu__time_duration\.sum$")
                 us = dur / 1e3 if du in ("ns", "nsecond") else dur * 1e3 if du in ("ms", "msecond") else dur
+                us = max(us, 1e-3)
                 tot_us += us
                 tens, _ = get(r, r"sm__pipe_tensor_cycles_active\.avg\.pct_of_peak_sustained_active")
                 if tens is None:

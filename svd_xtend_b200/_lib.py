@@ -11,7 +11,8 @@ import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libsvdx_b200.so"
+# SVDX_LIB selects an alternative build of the same library (kernel tuning experiments: svd_xtend_b200.build.build_variant)
+LIB_PATH = Path(os.environ["SVDX_LIB"]) if os.environ.get("SVDX_LIB") else PKG / "lib" / "libsvdx_b200.so"
 
 SVDX_MAX_TAPS = 27
 A_ROWS, A_CONV2D = 0, 1

@@ -47,6 +47,26 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines: list) -> Path:
+    """an alternative build of the library with extra -D flags (kernel tuning experiments, scripts/kbench.py): lands in
+    lib/alt_<name>/libsvdx_b200.so and is selected at run time with SVDX_LIB=<path>"""
+    out_dir = LIBDIR / f"alt_{name}"
+    (out_dir / "obj").mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    for src in _sources():
+        obj = out_dir / "obj" / (src.stem + ".o")
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        objs.append(obj)
+    lib = out_dir / "libsvdx_b200.so"
+    r = subprocess.run([nvcc, "-shared", "-o", str(lib), *map(str, objs), "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     OBJDIR.mkdir(exist_ok=True)

@@ -38,13 +38,25 @@ SVDX_DEVINL float2 load_pair(const GnSrc& s, long long row, int c) {
 // (C/8 channel vectors) x (row lanes). grid (row_chunks, outer). Accumulates sum / sumsq into mean[] / rstd[]
 // (pre-zeroed) through shared-memory then global fp32 atomics; finalised below.
 constexpr int GNV_MAX_THREADS = 512;
+// tuning knobs of the streaming kernels (compile-time; scripts/kbench.py A/Bs alternative builds through SVDX_LIB):
+// minimum resident CTAs per SM the register allocation must allow, and independent row loads in flight per thread
+#ifndef SVDX_GN_MINB
+#define SVDX_GN_MINB 1
+#endif
+#ifndef SVDX_LN_MINB
+#define SVDX_LN_MINB 1
+#endif
+#ifndef SVDX_GN_RIF
+#define SVDX_GN_RIF 4
+#endif
+constexpr int GN_RIF = SVDX_GN_RIF;
 
 SVDX_DEVINL uint4 load_vec8(const GnSrc& s, long long row, int c0) {
   const bf16* p = (c0 < s.C1) ? (s.x + row * s.ldx + c0) : (s.x2 + row * s.ldx2 + (c0 - s.C1));
   return *reinterpret_cast<const uint4*>(p);
 }
 
-__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_stats_partial(GnSrc s, int rows, int rows_per_cta, int G, float* sum, float* sumsq) {
+__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_stats_partial(GnSrc s, int rows, int rows_per_cta, int G, float* sum, float* sumsq) {
   __shared__ float sh_s[32 * 2];
   const int C = s.C1 + s.C2;
   const int CV = C / 8;
@@ -117,7 +129,7 @@ __global__ void gn_stats_finalize(float* mean, float* rstd, int total, float inv
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU)
 // same thread layout as the statistics kernel: a thread owns one 8-channel vector, folds mean/rstd/gamma/beta into
 // a per-channel scale and shift once, then streams rows (y = silu(x*scale + shift)), 16 B loads and stores
-__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_kernel(GnSrc s, int rows, int rows_per_cta, int G, const float* __restrict__ mean,
+__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_apply_kernel(GnSrc s, int rows, int rows_per_cta, int G, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, int fuse_silu, bf16* __restrict__ y, long long ldy) {
   const int C = s.C1 + s.C2;
@@ -139,14 +151,14 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_kernel(GnSrc s, int 
     sh[k] = beta[c0 + k] - mean[n * G + g] * sc[k];
   }
   const long long base = (long long)n * rows;
-  for (int r = r0 + rl; r < r1; r += 4 * RL) {
+  for (int r = r0 + rl; r < r1; r += GN_RIF * RL) {
     // four independent row loads in flight per thread before any math (the kernel is latency x bytes-in-flight bound)
-    uint4 u[4];
+    uint4 u[GN_RIF];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < GN_RIF; ++q)
       if (r + q * RL < r1) u[q] = load_vec8(s, base + r + q * RL, c0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < GN_RIF; ++q) {
       if (r + q * RL >= r1) break;
       const uint32_t in[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
       uint32_t out[4];
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_kernel(GnSrc s, int 
 // folds the C channel sums of its slab into the G group statistics in shared memory (C <= 2560 values from L2, a few hundred
 // ns), CTA x == 0 of the slab publishes mean / rstd for the backward, then rows are streamed exactly as in gn_apply_kernel.
 // One launch instead of memset + partial statistics + finalize + apply, and no extra pass over x for the statistics.
-__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_fused_kernel(GnSrc s, int rows, int rows_per_cta, int RL, int G, float eps, float inv_count,
+__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_apply_fused_kernel(GnSrc s, int rows, int rows_per_cta, int RL, int G, float eps, float inv_count,
                                                                          const float* __restrict__ csum1, long long ldc1,
                                                                          const float* __restrict__ csum2, long long ldc2,
                                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -227,13 +239,13 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_fused_kernel(GnSrc s
     sh[k] = beta[c0 + k] - sh_mean[g] * sc[k];
   }
   const long long base = (long long)n * rows;
-  for (int r = r0 + rl; r < r1; r += 4 * RL) {
-    uint4 u[4];
+  for (int r = r0 + rl; r < r1; r += GN_RIF * RL) {
+    uint4 u[GN_RIF];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < GN_RIF; ++q)
       if (r + q * RL < r1) u[q] = load_vec8(s, base + r + q * RL, c0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < GN_RIF; ++q) {
       if (r + q * RL >= r1) break;
       const uint32_t in[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
       uint32_t out[4];
@@ -253,7 +265,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_apply_fused_kernel(GnSrc s
 // pass 1: per (n, group) s1 = sum(g*gamma), s2 = sum(g*gamma*xhat), g = dy * silu'(z); optional dgamma/dbeta.
 // Same thread layout as gn_stats_partial (one 8-channel vector per thread, rows in flight).
 template <bool DG>
-__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
+__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_bwd_partial(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
                                                                   int G, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   int fuse_silu, float* ws, float* dgamma, float* dbeta) {
@@ -280,17 +292,17 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a1[k] = a2[k] = dg[k] = db[k] = 0.f; }
     const long long base = (long long)n * rows;
-    for (int r = r0 + rl; r < r1; r += 4 * RL) {
-      uint4 ux[4], ud[4];
+    for (int r = r0 + rl; r < r1; r += GN_RIF * RL) {
+      uint4 ux[GN_RIF], ud[GN_RIF];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < GN_RIF; ++q) {
         if (r + q * RL < r1) {
           ux[q] = load_vec8(s, base + r + q * RL, c0);
           ud[q] = *reinterpret_cast<const uint4*>(dy + (base + r + q * RL) * lddy + c0);
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < GN_RIF; ++q) {
         if (r + q * RL >= r1) break;
         const uint32_t wx[4] = {ux[q].x, ux[q].y, ux[q].z, ux[q].w}, wd[4] = {ud[q].x, ud[q].y, ud[q].z, ud[q].w};
 #pragma unroll
@@ -332,7 +344,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_partial(GnSrc s, const
 }
 
 // pass 2: dx = rstd * (g*gamma - s1/cnt - xhat * s2/cnt); per-thread channel constants, rows streamed
-__global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
+__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_bwd_apply(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
                                                                 int G, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
                                                                 const float* __restrict__ ws, float inv_count, bf16* __restrict__ dx, long long lddx,
@@ -356,10 +368,10 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
     t1[k] = ws[(n * G + g) * 2] * inv_count; t2[k] = ws[(n * G + g) * 2 + 1] * inv_count;
   }
   const long long base = (long long)n * rows;
-  for (int r = r0 + rl; r < r1; r += 4 * RL) {
-    uint4 ux[4], ug[4], ur[4];
+  for (int r = r0 + rl; r < r1; r += GN_RIF * RL) {
+    uint4 ux[GN_RIF], ug[GN_RIF], ur[GN_RIF];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < GN_RIF; ++q) {
       if (r + q * RL < r1) {
         ux[q] = load_vec8(s, base + r + q * RL, c0);
         ug[q] = *reinterpret_cast<const uint4*>(dy + (base + r + q * RL) * lddy + c0);
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < GN_RIF; ++q) {
       if (r + q * RL >= r1) break;
       const long long row = base + r + q * RL;
       const uint32_t in[4] = {ux[q].x, ux[q].y, ux[q].z, ux[q].w}, din[4] = {ug[q].x, ug[q].y, ug[q].z, ug[q].w};
@@ -399,7 +411,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS) gn_bwd_apply(GnSrc s, const b
 // and stores; all RPW rows' loads are issued before any arithmetic so that a warp keeps RPW * C * 2 bytes in flight); the
 // rows stay in registers between the two statistics passes and the normalisation
 template <int NJ, int RPW>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int rows, int C,
+__global__ void __launch_bounds__(256, SVDX_LN_MINB) ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, int rows, int C,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                      bf16* __restrict__ y, long long ldy, float* __restrict__ mean, float* __restrict__ rstd,
                                                      const float* __restrict__ addvec, int add_div, bf16* __restrict__ xsum, long long ldxs) {
@@ -490,7 +502,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 // them through shared memory before one atomic per channel.
 // dx = rstd*(gamma*dy - mean(gamma*dy) - xhat*mean(gamma*dy*xhat)) [+ dres]
 template <int NJ, bool DG>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
+__global__ void __launch_bounds__(256, SVDX_LN_MINB) ln_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ dy, long long lddy,
                                                      int rows, int C, const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, bf16* __restrict__ dx, long long lddx,
                                                      const bf16* __restrict__ dres, long long lddres, float* dgamma, float* dbeta) {
@@ -609,7 +621,7 @@ static void gn_vec_config(int C, int outer, int rows, int& threads, int& rows_pe
   long long chunks = (want_ctas + outer - 1) / outer;
   if (chunks < 1) chunks = 1;
   rows_per_cta = (int)((rows + chunks - 1) / chunks);
-  const int quantum = 4 * RL;
+  const int quantum = GN_RIF * RL;
   rows_per_cta = ((rows_per_cta + quantum - 1) / quantum) * quantum;
 }
 
