@@ -152,7 +152,37 @@ def sec_wgrad():
               f"{best[0]:7.1f} us ({fl / best[0] / 1e6:5.0f} TF/s) | all: " + " ".join(f"{b}/{s}:{t:.0f}" for t, b, s, _ in sorted(res, key=lambda r: (r[1], r[2]))), flush=True)
 
 
-SECTIONS = {"gn": sec_gn, "ln": sec_ln, "attn": sec_attn, "wgrad": sec_wgrad}
+def sec_gemm():
+    print("# forward / dgrad GEMMs and 3x3 convs: tile width (block_n) sweep, us per launch in a graph; * = raw.choose_block_n's pick")
+    cases = [("conv 10x16 C1280", 14, 10, 16, 1280, 1280, 9), ("linear M2240 N1280 K1280", 14, 10, 16, 1280, 1280, 1), ("linear M2240 N1280 K5120", 14, 10, 16, 5120, 1280, 1),
+             ("linear M2240 N5120 K1280", 14, 10, 16, 1280, 5120, 1), ("conv 20x32 C640", 14, 20, 32, 640, 640, 9), ("linear M8960 N640 K2560", 14, 20, 32, 2560, 640, 1),
+             ("linear M8960 N640 K640", 14, 20, 32, 640, 640, 1), ("conv 40x64 C320", 14, 40, 64, 320, 320, 9), ("linear M35840 N320 K1280", 14, 40, 64, 1280, 320, 1),
+             ("linear M35840 N320 K320", 14, 40, 64, 320, 320, 1), ("linear M35840 N960 K320", 14, 40, 64, 320, 960, 1)]
+    for name, T, H, W, K, N, taps in cases:
+        M = T * H * W
+        k = rot((M * K + M * N) * 2)
+        xs = [torch.randn(M, K, device=DEV).to(bf16) for _ in range(k)]
+        w = (torch.randn(N, taps * K, device=DEV) * (taps * K) ** -0.5).to(bf16)
+        outs = [torch.empty(M, N, device=DEV, dtype=bf16) for _ in range(k)]
+        bias = torch.randn(N, device=DEV)
+        pick = raw.choose_block_n(M, N)
+        res = []
+        for bn in (256, 160, 128, 96, 64):
+            if N % bn:
+                continue
+
+            def f(x, o, bn=bn):
+                if taps == 9:
+                    raw.tapgemm(x, w, o, M=M, N=N, K=K, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, T), bias=bias, block_n=bn)
+                else:
+                    raw.tapgemm(x, w, o, M=M, N=N, K=K, bias=bias, block_n=bn)
+            t = graph_time([lambda x=x, o=o: f(x, o) for x, o in zip(xs, outs)], reps=5)
+            res.append((bn, t))
+        fl = 2.0 * M * N * K * taps
+        print(f"  {name:28s}: " + "  ".join(f"{'*' if bn == pick else ''}bn{bn}: {t:6.1f} us ({fl / t / 1e6:5.0f} TF/s)" for bn, t in res), flush=True)
+
+
+SECTIONS = {"gemm": sec_gemm, "gn": sec_gn, "ln": sec_ln, "attn": sec_attn, "wgrad": sec_wgrad}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)
