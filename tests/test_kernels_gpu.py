@@ -90,7 +90,8 @@ def test_attention_temporal_fwd_bwd(raw, B, T, HW, heads):
     _close(to_seq(dqkv[:, 2 * C:]), vf.grad, tol=3e-2, what="temporal dv")
 
 
-@pytest.mark.parametrize("outer,rows,C1,C2,silu", [(14, 160, 320, 0, True), (3, 640, 1280, 640, True), (2, 14 * 40, 640, 0, False), (2, 100, 640, 320, True)])
+@pytest.mark.parametrize("outer,rows,C1,C2,silu", [(14, 160, 320, 0, True), (3, 640, 1280, 640, True), (2, 14 * 40, 640, 0, False), (2, 100, 640, 320, True),
+                                                  (1, 35841, 320, 0, True), (2, 9001, 320, 320, False)])   # long slabs: the cp.async rings wrap
 def test_groupnorm_fwd_bwd(raw, outer, rows, C1, C2, silu):
     C = C1 + C2
     x1 = _rand(outer * rows, C1, seed=5).to(bf16) + 0.5
@@ -131,7 +132,7 @@ def test_groupnorm_fwd_bwd(raw, outer, rows, C1, C2, silu):
         _close(dx3, dxr + dres.float(), what="groupnorm dx + dres")
 
 
-@pytest.mark.parametrize("rows,C", [(1000, 320), (560, 1280), (77, 64), (300, 640)])
+@pytest.mark.parametrize("rows,C", [(1000, 320), (560, 1280), (77, 64), (300, 640), (40003, 320), (30001, 640), (20011, 1280), (1500, 960)])
 def test_layernorm_fwd_bwd(raw, rows, C):
     x = (_rand(rows, C, seed=10) + 0.3).to(bf16)
     gamma = _rand(C, seed=11) * 0.2 + 1.0
@@ -155,6 +156,33 @@ def test_layernorm_fwd_bwd(raw, rows, C):
     _close(dx, xr.grad + dres.float(), what="layernorm dx")
     _close(dgamma, g.grad, what="layernorm dgamma")
     _close(dbeta, b.grad, what="layernorm dbeta")
+    # the other three instantiations: no parameter gradients and / or no residual gradient
+    dx2 = torch.empty_like(x)
+    raw.layernorm_bwd(x, dy, gamma, mean, rstd, dx2, dres)
+    torch.cuda.synchronize()
+    _close(dx2, xr.grad + dres.float(), what="layernorm dx (no dgamma)")
+    dx3 = torch.empty_like(x)
+    raw.layernorm_bwd(x, dy, gamma, mean, rstd, dx3)
+    torch.cuda.synchronize()
+    _close(dx3, xr.grad, what="layernorm dx (no dres)")
+    dx4 = torch.empty_like(x)
+    dg4 = torch.zeros(C, device=DEV)
+    db4 = torch.zeros(C, device=DEV)
+    raw.layernorm_bwd(x, dy, gamma, mean, rstd, dx4, None, dg4, db4)
+    torch.cuda.synchronize()
+    _close(dx4, xr.grad, what="layernorm dx (dgamma, no dres)")
+    _close(dg4, g.grad, what="layernorm dgamma (no dres)")
+    # x + addvec (per-frame vector, broadcast over add_div rows) rounded to bf16 is both an output and the normalised value
+    div = max(rows // 7, 1)
+    nvec = (rows + div - 1) // div
+    addvec = _rand(nvec, C, seed=15) * 0.5
+    xsum = torch.empty_like(x)
+    y2 = torch.empty_like(x)
+    raw.layernorm_fwd(x, gamma, beta, 1e-5, y2, addvec=addvec, add_div=div, xsum=xsum)
+    torch.cuda.synchronize()
+    xs_ref = (x.float() + addvec.repeat_interleave(div, 0)[:rows]).to(bf16)
+    assert torch.equal(xsum, xs_ref)
+    _close(y2, F.layer_norm(xs_ref.float(), (C,), gamma, beta, 1e-5), what="layernorm fwd (+addvec)")
 
 
 def test_prep_weight_layouts(raw):
