@@ -160,7 +160,11 @@ def sec_gemm():
     cases = [("conv 10x16 C1280", 14, 10, 16, 1280, 1280, 9), ("linear M2240 N1280 K1280", 14, 10, 16, 1280, 1280, 1), ("linear M2240 N1280 K5120", 14, 10, 16, 5120, 1280, 1),
              ("linear M2240 N5120 K1280", 14, 10, 16, 1280, 5120, 1), ("conv 20x32 C640", 14, 20, 32, 640, 640, 9), ("linear M8960 N640 K2560", 14, 20, 32, 2560, 640, 1),
              ("linear M8960 N640 K640", 14, 20, 32, 640, 640, 1), ("conv 40x64 C320", 14, 40, 64, 320, 320, 9), ("linear M35840 N320 K1280", 14, 40, 64, 1280, 320, 1),
-             ("linear M35840 N320 K320", 14, 40, 64, 320, 320, 1), ("linear M35840 N960 K320", 14, 40, 64, 320, 960, 1)]
+             ("linear M35840 N320 K320", 14, 40, 64, 320, 320, 1), ("linear M35840 N960 K320", 14, 40, 64, 320, 960, 1),
+             ("linear M35840 N320 K2560", 14, 40, 64, 2560, 320, 1), ("linear M35840 N320 K960", 14, 40, 64, 960, 320, 1),
+             ("conv 40x64 640->320", 14, 40, 64, 640, 320, 9), ("linear M8960 N640 K5120", 14, 20, 32, 5120, 640, 1),
+             ("linear M8960 N640 K1920", 14, 20, 32, 1920, 640, 1), ("linear M8960 N1920 K640", 14, 20, 32, 640, 1920, 1),
+             ("linear M2240 N1280 K10240", 14, 10, 16, 10240, 1280, 1), ("linear M35840 N1280 K320", 14, 40, 64, 320, 1280, 1)]
     for name, T, H, W, K, N, taps in cases:
         M = T * H * W
         k = rot((M * K + M * N) * 2)
@@ -170,8 +174,8 @@ def sec_gemm():
         bias = torch.randn(N, device=DEV)
         pick = raw.choose_block_n(M, N)
         res = []
-        for bn in (256, 160, 128, 96, 64):
-            if N % bn:
+        for bn in (320, 256, 160, 128, 96, 64):
+            if N % bn or (bn < 128 and N > 640):
                 continue
 
             def f(x, o, bn=bn):

@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, n0, half, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
-      else if constexpr (EPI == EPI_RES || EPI == EPI_RES_GN) epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, n0, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.row0, st.grp, lane, m0, valid_rows);
+      if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, n0, half, 0, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
+      else if constexpr (EPI == EPI_RES || EPI == EPI_RES_GN) epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, n0, half, 0, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.off, st.row0, st.grp, lane, m0, valid_rows);
       else if constexpr (EPI == EPI_GEGLU) epilogue_geglu(p, t_base, n0, half, bn_out, st.base, st.row0, st.grp, lane);
       else epilogue_tile(p, t_base, m, row_ok, n0, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
       // release the accumulator stage back to the MMA warp
@@ -347,7 +347,10 @@ using namespace svdx;
 
 int svdx_tapgemm_fill(const SvdxTapGemm* d, TapGemmKParams& p, int cg) {
   if (!d || !d->a || !d->b || !d->out) return svdx_fail(SVDX_E_BADARG, "tapgemm: null pointer");
-  if (d->block_n < 32 || d->block_n > 256 || d->block_n % 32) return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n must be a multiple of 32 in [32,256]");
+  // block_n == 320: the CTA-pair kernel's two-MMA tile (256 x 320, see tapgemm2.cu) — pair-eligible problems only
+  const bool wide320 = (cg == 2 && d->block_n == 320);
+  if (!wide320 && (d->block_n < 32 || d->block_n > 256 || d->block_n % 32))
+    return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n must be a multiple of 32 in [32,256] (or 320 for CTA-pair eligible problems)");
   if (d->b_major_mn && d->block_n % 64) return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n %% 64 for MN-major B");
   if (d->num_taps < 1 || d->num_taps > SVDX_MAX_TAPS) return svdx_fail(SVDX_E_BADARG, "tapgemm: num_taps");
   if (d->M <= 0 || d->N <= 0 || d->K <= 0) return svdx_fail(SVDX_E_BADARG, "tapgemm: empty problem");
@@ -446,7 +449,7 @@ int svdx_tapgemm_fill(const SvdxTapGemm* d, TapGemmKParams& p, int cg) {
     uint64_t dims[2] = {(uint64_t)d->K * d->num_taps, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
     // a CTA of a pair fetches half of the B tile; a GEGLU tile is already fetched as two halves (value | gate)
-    uint32_t box[2] = {64, (uint32_t)((d->geglu || cg == 2) ? d->block_n / 2 : d->block_n)};
+    uint32_t box[2] = {64, (uint32_t)(wide320 ? 80 : (d->geglu || cg == 2) ? d->block_n / 2 : d->block_n)};
     rc = svdx_make_tmap(&p.tmb, d->b, 2, dims, strides, box);
   }
   if (rc) return rc;
@@ -509,6 +512,8 @@ int svdx_tapgemm_fill(const SvdxTapGemm* d, TapGemmKParams& p, int cg) {
       p.epi_mode = d->geglu ? EPI_GEGLU : (d->res1 || d->res2 || d->scales) ? EPI_RES : EPI_FAST;
   }
   if (p.split_k > 1 && (p.bias || p.rowbias || p.res1 || p.res2 || p.geglu)) return svdx_fail(SVDX_E_BADARG, "tapgemm: split_k with epilogue operands");
+  if (wide320 && p.epi_mode != EPI_FAST && p.epi_mode != EPI_RES)
+    return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n 320 needs a bf16 output through the TMA-store epilogues (N % 320 == 0, aligned rows)");
   if (p.gn_sum) {
     if (p.epi_mode != EPI_FAST && p.epi_mode != EPI_RES)
       return svdx_fail(SVDX_E_BADARG, "tapgemm: gn_sum needs a bf16 output through the TMA-store epilogues (N % 32 == 0, aligned rows), no split-K / GEGLU");

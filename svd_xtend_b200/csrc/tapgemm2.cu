@@ -22,6 +22,15 @@ namespace svdx {
 constexpr int STAGES2 = 6;
 constexpr int B2_STAGE_BYTES = 128 * BLOCK_K * 2;  // half of a <=256-row B tile
 constexpr int SMEM2_BYTES = 1024 + STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) + NUM_EPI_WARPS * EPI_STAGE_BYTES + 256;
+// WIDE variant: a 256 x 320 tile (block_n == 320) computed as two N = 160 MMAs per k-step on the same A stage. The A tile is
+// pulled through L2 once per 320 output columns instead of once per 160 (C = 320 / 640 layers: -31 % L2 -> SM bytes per
+// FLOP, the bound of these kernels). 320 fp32 columns cannot be double-buffered in 512 TMEM columns, so the two accumulators
+// OVERLAP: even tiles use columns [0, 320), odd tiles [192, 512). The epilogue drains the shared columns [192, 320) of its
+// tile first and then releases the next tile's MMAs, which run while the remaining columns are drained.
+constexpr int STAGES2W = 5;
+constexpr int B2W_STAGE_BYTES = 160 * BLOCK_K * 2;  // this CTA's half of a 320-row B tile: rows [0,80) -> MMA 0, [80,160) -> MMA 1
+constexpr int SMEM2W_BYTES = 1024 + STAGES2W * (A_STAGE_BYTES + B2W_STAGE_BYTES) + NUM_EPI_WARPS * EPI_STAGE_BYTES + 256;
+constexpr int WIDE_ACC1 = 192;                      // TMEM column base of the odd tiles' accumulator
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
 SVDX_DEVINL uint32_t cluster_ctarank() {
@@ -81,8 +90,10 @@ SVDX_DEVINL void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
       : "memory");
 }
 
-template <int EPI>
+template <int EPI, bool WIDE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapgemm2_kernel(const __grid_constant__ TapGemmKParams p) {
+  constexpr int STAGES2 = WIDE ? svdx::STAGES2W : svdx::STAGES2;                 // shadow the namespace constants
+  constexpr int B2_STAGE_BYTES = WIDE ? svdx::B2W_STAGE_BYTES : svdx::B2_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -163,7 +174,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
           if (bx.active)
             tma2_load_4d(amap, full, sA + stage * A_STAGE_BYTES + bx.dst_off, kc, p.tap_d0[tap], bx.hh + p.tap_d1[tap],
                          bx.nvalid ? bx.n + p.tap_d2[tap] : (1 << 28));
-          if (lane == 0) tma2_load_2d(&p.tmb, full, sB + stage * B2_STAGE_BYTES, tap * p.K + kc, n0 + (int)rank * b_half_rows);
+          if (lane == 0) {
+            if constexpr (WIDE) {
+              tma2_load_2d(&p.tmb, full, sB + stage * B2_STAGE_BYTES, tap * p.K + kc, n0 + (int)rank * 80);
+              tma2_load_2d(&p.tmb, full, sB + stage * B2_STAGE_BYTES + 80 * 128, tap * p.K + kc, n0 + 160 + (int)rank * 80);
+            } else {
+              tma2_load_2d(&p.tmb, full, sB + stage * B2_STAGE_BYTES, tap * p.K + kc, n0 + (int)rank * b_half_rows);
+            }
+          }
           if (++kci == p.kb_per_tap) { kci = 0; ++tap; }
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
@@ -218,7 +236,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
           }
           // this CTA's half of the B tile: rows [rank*bn/2, +bn/2) of the tile. For GEGLU the tile is
           // [value rows | gate rows], so rank 0 fetches the value rows and rank 1 the gate rows.
-          if (p.geglu) tma2_load_2d(&p.tmb, full, dB, tap * p.K + kc, rank == 0 ? n0 : p.N / 2 + n0);
+          if constexpr (WIDE) {
+            // MMA 0 computes columns [n0, n0 + 160) from rows [0, 80) of both CTAs' halves, MMA 1 columns [n0 + 160, n0 + 320)
+            tma2_load_2d(&p.tmb, full, dB, tap * p.K + kc, n0 + (int)rank * 80);
+            tma2_load_2d(&p.tmb, full, dB + 80 * 128, tap * p.K + kc, n0 + 160 + (int)rank * 80);
+          } else if (p.geglu) tma2_load_2d(&p.tmb, full, dB, tap * p.K + kc, rank == 0 ? n0 : p.N / 2 + n0);
           else tma2_load_2d(&p.tmb, full, dB, tap * p.K + kc, n0 + (int)rank * b_half_rows);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
@@ -227,24 +249,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA only) ===========================
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, p.block_n, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, WIDE ? 160 : p.block_n, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      uint32_t wide_phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        if constexpr (WIDE) {
+          // ONE release barrier: the epilogue of the PREVIOUS tile arrives once the columns both accumulators share are
+          // drained (by then the same warps have fully drained the tile before it, which used this tile's columns)
+          mbar_wait(bar_tempty, wide_phase ^ 1);
+          wide_phase ^= 1;
+        } else {
+          mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t d_tmem = tmem_base + (WIDE ? acc * WIDE_ACC1 : acc * 256);
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t aaddr = sA + stage * A_STAGE_BYTES;
           const uint32_t baddr = sB + stage * B2_STAGE_BYTES;
           const uint64_t ad0 = make_smem_desc_sw128(aaddr, 16, 1024), bd0 = make_smem_desc_sw128(baddr, 16, 1024);
+          if constexpr (WIDE) {
+            const uint64_t bd1 = make_smem_desc_sw128(baddr + 80 * 128, 16, 1024);
 #pragma unroll
-          for (int j = 0; j < BLOCK_K / 16; ++j)   // a 16-deep k-step = +32 bytes = +2 in the start-address field
-            umma2_bf16(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < BLOCK_K / 16; ++j) {
+              umma2_bf16(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+              umma2_bf16(d_tmem + 160, ad0 + 2 * j, bd1 + 2 * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_K / 16; ++j)   // a 16-deep k-step = +32 bytes = +2 in the start-address field
+              umma2_bf16(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+          }
           umma2_commit_mc(bar_empty + 8 * stage, 3);  // frees this smem stage in both CTAs
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
@@ -276,11 +315,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
       const long long m = (long long)g * p.rows_per_group + rin;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_base = tmem_base + (WIDE ? acc * WIDE_ACC1 : acc * 256) + ((uint32_t)(q * 32) << 16);
       const long long m0 = (long long)g * p.rows_per_group + st.row0;        // fused GroupNorm statistics: first row / rows that exist
       const int valid_rows = max(0, min(32, p.rows_per_group - st.row0));
-      if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
-      else if constexpr (EPI == EPI_RES || EPI == EPI_RES_GN) epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.row0, st.grp, lane, m0, valid_rows);
+      if constexpr (WIDE) {
+        // accumulator columns shared with the next tile's accumulator first: [192, 320) of an even tile, [0, 128) of an odd one
+        const int lo1 = acc ? 0 : WIDE_ACC1, hi1 = acc ? 320 - WIDE_ACC1 : 320;
+        const int lo2 = acc ? 320 - WIDE_ACC1 : 0, hi2 = acc ? 320 : WIDE_ACC1;
+        if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, nt * bn_out, half, lo1, hi1, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
+        else epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, nt * bn_out, half, lo1, hi1, n_out_total, s_acc, s_r1, s_r2, st.base, st.off, st.row0, st.grp, lane, m0, valid_rows);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(bar_tempty, 0);
+        if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, nt * bn_out, half, lo2, hi2, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
+        else epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, nt * bn_out, half, lo2, hi2, n_out_total, s_acc, s_r1, s_r2, st.base, st.off, st.row0, st.grp, lane, m0, valid_rows);
+        tc_fence_before();
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, nt * bn_out, half, 0, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
+      else if constexpr (EPI == EPI_RES || EPI == EPI_RES_GN) epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, nt * bn_out, half, 0, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.off, st.row0, st.grp, lane, m0, valid_rows);
       else if constexpr (EPI == EPI_GEGLU) epilogue_geglu(p, t_base, nt * bn_out, half, bn_out, st.base, st.row0, st.grp, lane);
       else epilogue_tile(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
       tc_fence_before();
@@ -315,7 +369,8 @@ static int pair_mode() {
 bool svdx_tapgemm2_eligible(const SvdxTapGemm* d) {
   if (!pair_mode() || !d) return false;
   if (d->a_major_mn || d->b_major_mn || d->b_mode != 0 || d->split_k != 1) return false;
-  if (d->block_n < 64 || d->block_n % 32 || (d->block_n / 2) % 8) return false;
+  if (d->block_n == 320) return !d->geglu && d->N % 320 == 0 && d->M >= 512 && d->out_dtype == SVDX_OUT_BF16;   // WIDE tile
+  if (d->block_n < 64 || d->block_n > 256 || d->block_n % 32 || (d->block_n / 2) % 8) return false;
   if (d->geglu && d->block_n % 64) return false;
   if (d->M < 512) return false;                       // small problems: keep the finer 128-row tiling
   const int n_out = d->geglu ? d->N / 2 : d->N;
@@ -334,12 +389,26 @@ int svdx_tapgemm2_launch(const TapGemmKParams& p, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2W_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2W_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST_GN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2W_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES_GN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2W_BYTES);
     if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm2: set smem attribute");
     attr_done[slot] = true;
   }
   const int total_tiles = p.pair_m_tiles * p.n_tiles;
   int clusters = svdx_num_sms() / 2;
   if (clusters > total_tiles) clusters = total_tiles;
+  if (p.block_n == 320) {
+    if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm2_kernel<EPI_FAST_GN, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
+    else if (p.epi_mode == EPI_RES && p.gn_sum) tapgemm2_kernel<EPI_RES_GN, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
+    else if (p.epi_mode == EPI_FAST) tapgemm2_kernel<EPI_FAST, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
+    else if (p.epi_mode == EPI_RES) tapgemm2_kernel<EPI_RES, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
+    else return svdx_fail(SVDX_E_BADARG, "tapgemm2: block_n 320 needs the bf16 TMA-store epilogues");
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return svdx_fail_cuda(e2, "tapgemm2: launch (wide)");
+    return SVDX_OK;
+  }
   if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm2_kernel<EPI_FAST_GN><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_RES && p.gn_sum) tapgemm2_kernel<EPI_RES_GN><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_FAST) tapgemm2_kernel<EPI_FAST><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);

@@ -223,18 +223,18 @@ SVDX_DEVINL void stage_row_bf16(uint32_t row, int sw, const float (&f)[32]) {
 // plain epilogue (bias / row-bias only): two 32-column chunks per round (both staging halves), one proxy fence and one
 // bulk group per round.
 template <bool GN>
-SVDX_DEVINL void epilogue_fast(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int bn_out,
+SVDX_DEVINL void epilogue_fast(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int c_lo, int c_hi,
                                int n_out_total, uint32_t sbase, int row0, int grp, int lane, long long m0, int valid_rows) {
   const float* bias = p.bias;
   const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
   const uint32_t rowX = sbase + lane * 64, rowY = rowX + 2048;
   const int sw = (lane >> 1) & 3;
 #pragma unroll 1
-  for (int c = half * 32; c < bn_out; c += 128) {
+  for (int c = c_lo + half * 32; c < c_hi; c += 128) {           // accumulator columns [c_lo, c_hi) of the tile
     const int colA = n0 + c;
     if (colA >= n_out_total) break;
     const int colB = colA + 64;
-    const bool hasB = (c + 64 < bn_out) && (colB < n_out_total);   // warp-uniform
+    const bool hasB = (c + 64 < c_hi) && (colB < n_out_total);     // warp-uniform
     uint32_t va[32], vb[32];
     tmem_ld32(t_base + c, va);
     if (hasB) tmem_ld32(t_base + c + 64, vb);
@@ -265,8 +265,8 @@ SVDX_DEVINL void epilogue_fast(const TapGemmKParams& p, uint32_t t_base, long lo
 // residual / AlphaBlender epilogue: out = s_acc*(acc + bias + rowbias) + s_r1*res1 + s_r2*res2; one chunk per round,
 // alternating staging halves; the residual rows are requested before the TMEM wait.
 template <bool GN>
-SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int bn_out,
-                              int n_out_total, float s_acc, float s_r1, float s_r2, uint32_t sbase, int row0, int grp, int lane,
+SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int c_lo, int c_hi,
+                              int n_out_total, float s_acc, float s_r1, float s_r2, uint32_t sbase, uint32_t& off, int row0, int grp, int lane,
                               long long m0, int valid_rows) {
   const float* bias = p.bias;
   const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
@@ -280,9 +280,10 @@ SVDX_DEVINL void epilogue_res(const TapGemmKParams& p, uint32_t t_base, long lon
   const uint32_t row = sbase + lane * 64;
   const int sw = (lane >> 1) & 3;
   const int prow = lane >> 2, ppc = lane & 3;
-  uint32_t off = 0;
+  // `off` (which staging half comes next) lives in the caller across tiles: bulk_wait_read<1> only guarantees that the
+  // half written TWO stores ago has been read out
 #pragma unroll 1
-  for (int c = half * 32; c < bn_out; c += 64) {
+  for (int c = c_lo + half * 32; c < c_hi; c += 64) {
     const int col0 = n0 + c;
     if (col0 >= n_out_total) break;
     uint4 a1[4], a2[4];

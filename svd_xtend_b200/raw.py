@@ -141,6 +141,29 @@ def choose_block_n(M: int, n_out: int, geglu: bool = False, mn_major: bool = Fal
     return 2 * best if geglu else best
 
 
+WIDE_TILE = os.environ.get("SVDX_WIDE", "1") != "0"
+WIDE_MIN_K = int(os.environ.get("SVDX_WIDE_MIN_K", "640"))
+
+
+def _wide_tile_ok(M, N, k_total, out, ldo, geglu, a_mn, b_mn, b_mode, split_k, out_dtype, bias, rowbias) -> bool:
+    """256 x 320 CTA-pair tiles (svdx_tapgemm block_n = 320: the A tile crosses L2 once per 320 output columns instead of
+    once per 160) for the C = 320 / 640 / 960 layers when the contraction is long enough to hide the partly exposed epilogue
+    of the overlapping accumulators. Mirrors the library's conditions for the wide form (CTA-pair kernel, bf16 TMA-store
+    epilogues); anything else keeps choose_block_n's width."""
+    if not WIDE_TILE or geglu or a_mn or b_mn or b_mode != 0 or split_k != 1 or N % 320 or M < 512 or k_total < WIDE_MIN_K:
+        return False
+    if out.dtype != bf16 or (out_dtype is not None and out_dtype != OUT_BF16):
+        return False
+    ld = ldo if ldo is not None else out.stride(0)
+    if ld % 8 or out.data_ptr() % 16:
+        return False
+    if bias is not None and bias.data_ptr() % 16:
+        return False
+    if rowbias is not None and (rowbias.data_ptr() % 16 or rowbias.stride(0) % 4):
+        return False
+    return True
+
+
 _WGRAD_L2_BYTES_PER_CLK = 6500.0     # fitted to profiles/r2_kbench.txt (weight-gradient GEMMs are L2 -> SM bound)
 
 
@@ -235,6 +258,8 @@ def tapgemm(
     n_out = N // 2 if geglu else N
     if block_n is None:
         block_n = choose_block_n(M, n_out, geglu, b_mn)
+        if _wide_tile_ok(M, N, K * len(taps), out, ldo, geglu, a_mn, b_mn, b_mode, split_k, out_dtype, bias, rowbias):
+            block_n = 320
     d.block_n = block_n
     d.split_k = split_k
     d.out = out.data_ptr()

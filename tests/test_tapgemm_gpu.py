@@ -365,3 +365,54 @@ def test_gemv_and_outer_accum_for_conditioning_vectors(raw, M, N, K, f32):
     raw.outer_accum(dy, a, g, sc)
     torch.cuda.synchronize()
     _close(g, 0.25 + 0.5 * dy.float().t() @ a.float(), what="outer_accum")
+
+
+# ---- 256 x 320 CTA-pair tiles (block_n = 320): two N = 160 MMAs per k-step, overlapping TMEM accumulators
+@pytest.mark.parametrize("M,N,K", [(35840, 320, 320), (2560, 640, 1280), (8960, 640, 2560), (1000, 320, 192), (70000, 960, 64)])
+@pytest.mark.parametrize("res,gn", [(False, False), (True, False), (False, True), (True, True)])
+def test_wide_tile_linear(raw, M, N, K, res, gn):
+    a = _rand(M, K, seed=1).to(bf16)
+    w = _rand(N, K, scale=K ** -0.5, seed=2).to(bf16)
+    bias = _rand(N, seed=3)
+    r1 = _rand(M, N, seed=4).to(bf16) if res else None
+    out = torch.full((M, N), float("nan"), device=_dev(), dtype=bf16)
+    rows = M // 5 if M % 5 == 0 else M
+    sums = torch.zeros(M // rows, 2, N, device=_dev()) if gn else None
+    raw.tapgemm(a, w, out, M=M, N=N, K=K, bias=bias, res1=r1, block_n=320, **({"gn_sum": sums, "gn_rows": rows} if gn else {}))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias + (r1.float() if res else 0)
+    _close(out, ref, what=f"wide linear {M}x{N}x{K} res {res}")
+    if gn:
+        _check_gn_sums(sums, out, rows, f"wide linear {M}x{N}x{K} rows {rows} res {res}")
+    # the same problem through the 160-wide tiles must give the same values (same k order, same epilogue arithmetic)
+    out2 = torch.empty_like(out)
+    raw.tapgemm(a, w, out2, M=M, N=N, K=K, bias=bias, res1=r1, block_n=160)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(14, 40, 64, 320, 320), (14, 20, 32, 640, 640), (3, 40, 64, 64, 320), (14, 10, 16, 128, 640)])
+def test_wide_tile_conv3x3(raw, N, H, W, Cin, Cout):
+    x = _rand(N, H, W, Cin, seed=20).to(bf16)
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=21).to(bf16)
+    bias = _rand(Cout, seed=22)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9 * Cin)
+    out = torch.full((N * H * W, Cout), float("nan"), device=_dev(), dtype=bf16)
+    sums = torch.zeros(N, 2, Cout, device=_dev())
+    raw.tapgemm(x.view(-1, Cin), wk, out, M=N * H * W, N=Cout, K=Cin, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS,
+                conv_whn=(W, H, N), bias=bias, gn_sum=sums, gn_rows=H * W, block_n=320)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    _close(out, ref, what="wide conv3x3")
+    _check_gn_sums(sums, out, H * W, f"wide conv {N}x{H}x{W} {Cin}->{Cout}")
+
+
+def test_wide_tile_rejected_where_unsupported(raw):
+    a = _rand(1024, 64, seed=1).to(bf16)
+    w = _rand(640, 64, seed=2).to(bf16)
+    with pytest.raises(RuntimeError):      # (SvdxError is a RuntimeError) fp32 output: the generic epilogue has no wide form
+        raw.tapgemm(a, w, torch.zeros(1024, 640, device=_dev()), M=1024, N=640, K=64, block_n=320)
+    with pytest.raises(RuntimeError):      # N not a multiple of 320
+        raw.tapgemm(a, w[:480], torch.empty(1024, 480, device=_dev(), dtype=bf16), M=1024, N=480, K=64, block_n=320)
+    with pytest.raises(RuntimeError):      # small M: 1-CTA kernel
+        raw.tapgemm(a[:256], w, torch.empty(256, 640, device=_dev(), dtype=bf16), M=256, N=640, K=64, block_n=320)
