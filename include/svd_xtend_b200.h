@@ -85,7 +85,8 @@ typedef struct SvdxTapGemm {
                               group, zero outside (dW of a (3,1,1) temporal conv tap) */
   /* problem */
   int32_t M, N, K;      /* M output rows, N = B rows (before GEGLU halving), K = contraction per tap */
-  int32_t block_n;      /* multiple of 32, <= 256 (multiple of 64 when b_major_mn) */
+  int32_t block_n;      /* multiple of 32, <= 256 (multiple of 64 when b_major_mn); 320 = the CTA-pair kernel's 256 x 320 tile
+                           (two N = 160 MMAs per k-step on one A stage): M >= 512, N % 320 == 0, bf16 TMA-store epilogues only */
   int32_t split_k;      /* >= 1; > 1 requires SVDX_OUT_F32_ATOMIC */
   /* epilogue */
   void* out;
@@ -113,6 +114,23 @@ typedef struct SvdxTapGemm {
   float* gn_sum;
   int64_t gn_ld;        /* floats per (slab, moment) row, >= N */
   int32_t gn_rows;
+  /* GroupNorm BACKWARD statistics fused into the epilogue (pass 1 of F.group_norm's backward): set on the GEMM / conv that
+   * WRITES dy = dL/d(GroupNorm output) — the data gradient of the conv that consumed the normalised tensor. gnb_x (channels
+   * [0, gnb_c1)) and gnb_x2 (the rest; NULL = single source) are the GroupNorm's bf16 INPUT, gnb_ab[(2*s + 0) * N + n] /
+   * [(2*s + 1) * N + n] the forward scale / shift of channel n in statistics slab s = m / gnb_rows (written by
+   * svdx_groupnorm_apply*, y = act(x * scale + shift); only read when gnb_silu). The epilogue accumulates
+   *   gnb_sum[(2*s + 0) * N + n] += e,  gnb_sum[(2*s + 1) * N + n] += e * x[m][n],   e = dy[m][n] * act'(x * scale + shift)
+   * on the bf16 values it stores (buffer zero on entry); svdx_groupnorm_bwd_fused turns them into dx / dgamma / dbeta with ONE
+   * pass over x and dy. Requires the plain bf16 TMA-store epilogue (no residual / scales / GEGLU / split-K / gn_sum), N even. */
+  const void* gnb_x;
+  int64_t gnb_ldx;
+  const void* gnb_x2;
+  int64_t gnb_ldx2;
+  int32_t gnb_c1;
+  const float* gnb_ab;
+  float* gnb_sum;
+  int32_t gnb_rows;
+  int32_t gnb_silu;
 } SvdxTapGemm;
 
 int svdx_tapgemm(const SvdxTapGemm* desc, void* stream);
@@ -146,8 +164,12 @@ int svdx_groupnorm_stats(const void* x, int64_t ldx, int32_t C1, const void* x2,
 int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
                          int32_t outer, int32_t rows, int32_t num_groups,
                          const float* mean, const float* rstd, const float* gamma, const float* beta,
-                         int32_t fuse_silu, void* y, int64_t ldy, void* stream);
-/* GroupNorm(+SiLU) apply from per-CHANNEL sums produced by the svdx_tapgemm epilogues (gn_sum above): csum1 / csum2 are the
+                         int32_t fuse_silu, void* y, int64_t ldy, float* ab_out, void* stream);
+/* ab_out (optional, both apply forms): fp32 [outer][2][C], receives the per-channel scale / shift of every slab
+ * (y = act(x * scale + shift)) — the gnb_ab table of the GroupNorm-backward sums fused into svdx_tapgemm's epilogue.
+ * gamma / beta must be 16-byte aligned.
+ *
+ * GroupNorm(+SiLU) apply from per-CHANNEL sums produced by the svdx_tapgemm epilogues (gn_sum above): csum1 / csum2 are the
  * [outer][2][ld] fp32 sum / sum-of-squares arrays of the two channel-concatenated sources (csum2 NULL when C2 == 0). Every
  * CTA first folds the channels of its slab into the 32 group statistics (shared memory), the CTA with blockIdx.x == 0 of
  * each slab also writes mean / rstd [outer][groups] for the backward. Replaces stats + finalize + apply by ONE launch. */
@@ -155,7 +177,7 @@ int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1, const voi
                                int32_t outer, int32_t rows, int32_t num_groups, float eps,
                                const float* csum1, int64_t ldc1, const float* csum2, int64_t ldc2,
                                float* mean, float* rstd, const float* gamma, const float* beta,
-                               int32_t fuse_silu, void* y, int64_t ldy, void* stream);
+                               int32_t fuse_silu, void* y, int64_t ldy, float* ab_out, void* stream);
 /* backward: dx (and optional dgamma/dbeta accumulation, fp32 atomic). workspace: float[2 * outer * groups]; it must be
  * ZERO on entry when workspace_is_zero != 0 (a slice of a pre-zeroed arena: no memset node), else it is cleared here.
  * dres (optional, bf16 [outer*rows][lddres], single-source form only): a gradient already accumulated on x through its
@@ -167,6 +189,14 @@ int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const void* x2, i
                        int32_t fuse_silu, void* dx, int64_t lddx, void* dx2, int64_t lddx2,
                        float* dgamma, float* dbeta, float* workspace, int32_t workspace_is_zero,
                        const void* dres, int64_t lddres, void* stream);
+/* backward when pass 1 already ran inside the epilogue that produced dy (svdx_tapgemm gnb_sum): csum = that [outer][2][C]
+ * buffer (sum e, sum e*x per slab and channel). One launch, one pass over x and dy: every CTA folds the channel sums into the
+ * group sums, dgamma / dbeta (optional, accumulated) come straight from the channel sums. Other arguments as svdx_groupnorm_bwd. */
+int svdx_groupnorm_bwd_fused(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                             const void* dy, int64_t lddy, int32_t outer, int32_t rows, int32_t num_groups,
+                             const float* mean, const float* rstd, const float* gamma, const float* beta,
+                             int32_t fuse_silu, const float* csum, void* dx, int64_t lddx, void* dx2, int64_t lddx2,
+                             float* dgamma, float* dbeta, const void* dres, int64_t lddres, void* stream);
 
 /* LayerNorm over the last dim (C <= 2560, C % 8 == 0), replaces F.layer_norm of
  * BasicTransformerBlock.norm1-3 / TemporalBasicTransformerBlock.norm_in,norm1-3 [D].

@@ -36,6 +36,8 @@ class SvdxTapGemm(C.Structure):
         ("res1", c_void_p), ("ldr1", c_i64), ("res2", c_void_p), ("ldr2", c_i64),
         ("scales", c_void_p), ("pre", c_void_p), ("ldpre", c_i64),
         ("gn_sum", c_void_p), ("gn_ld", c_i64), ("gn_rows", c_int),
+        ("gnb_x", c_void_p), ("gnb_ldx", c_i64), ("gnb_x2", c_void_p), ("gnb_ldx2", c_i64), ("gnb_c1", c_int),
+        ("gnb_ab", c_void_p), ("gnb_sum", c_void_p), ("gnb_rows", c_int), ("gnb_silu", c_int),
     ]
 
 
@@ -62,9 +64,13 @@ _PROTOS = {
     "svdx_groupnorm_stats": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_float,
                              c_void_p, c_void_p, c_void_p],
     "svdx_groupnorm_apply": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int,
-                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p],
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p, c_void_p],
     "svdx_groupnorm_apply_fused": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_float,
-                                   c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p],
+                                   c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p,
+                                   c_void_p],
+    "svdx_groupnorm_bwd_fused": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_void_p, c_i64,
+                                 c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
     "svdx_groupnorm_bwd": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p, c_i64,
                            c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p],

@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS, 2) gn_apply_ring(GnSrc s, int
                                                                      const float* __restrict__ csum1, long long ldc1,
                                                                      const float* __restrict__ csum2, long long ldc2, float* mean, float* rstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                     int fuse_silu, bf16* __restrict__ y, long long ldy) {
+                                                                     int fuse_silu, bf16* __restrict__ y, long long ldy, float* __restrict__ ab_out) {
   __shared__ float sh_sum[32], sh_sq[32], sh_mean[32], sh_rstd[32];
   const int C = s.C1 + s.C2;
   const int CV = C / 8;
@@ -523,6 +523,14 @@ __global__ void __launch_bounds__(GNV_MAX_THREADS, 2) gn_apply_ring(GnSrc s, int
     const int g = (c0 + k) / cpg;
     sc[k] = sh_rstd[g] * gm[k];
     sh[k] = bt[k] - sh_mean[g] * sc[k];
+  }
+  if (ab_out && blockIdx.x == 0 && rl == 0) {
+    // the per-channel scale / shift of this slab, for the backward sums fused into the consumer's dgrad epilogue (gnb_ab)
+    float* a = ab_out + (2LL * n) * C + c0;
+    *reinterpret_cast<float4*>(a) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+    *reinterpret_cast<float4*>(a + 4) = make_float4(sc[4], sc[5], sc[6], sc[7]);
+    *reinterpret_cast<float4*>(a + C) = make_float4(sh[0], sh[1], sh[2], sh[3]);
+    *reinterpret_cast<float4*>(a + C + 4) = make_float4(sh[4], sh[5], sh[6], sh[7]);
   }
   bf16* py = y + (base + rr) * ldy + c0;
   const long long ystep = (long long)RL * ldy;
@@ -926,6 +934,131 @@ __global__ void __launch_bounds__(256, SVDX_LN_MINB) ln_bwd_kernel(const bf16* _
   }
 }
 
+// backward pass 2 when pass 1 ran inside the dgrad epilogue (svdx_tapgemm gnb_sum): every CTA folds the per-channel sums
+// S_c = sum e, SX_c = sum e*x of its slab into s1_g = sum_c gamma_c S_c and sx_g = sum_c gamma_c SX_c (C values from L2), then
+// streams rows exactly as gn_bwd_apply_ring. CTA x == 0 of a slab also emits dgamma_c += rstd (SX_c - mean S_c), dbeta_c += S_c.
+template <bool DRES>
+__global__ void __launch_bounds__(GNV_MAX_THREADS, 1) gn_bwd_fused_ring(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
+                                                                         int RL, int G, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                         const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
+                                                                         const float* __restrict__ csum, float inv_count, bf16* __restrict__ dx,
+                                                                         long long lddx, bf16* __restrict__ dx2, long long lddx2,
+                                                                         const bf16* __restrict__ dres, long long lddres, float* dgamma, float* dbeta) {
+  __shared__ float sh_s1[32], sh_sx[32];
+  const int C = s.C1 + s.C2;
+  const int CV = C / 8;
+  const int cpg = C / G;
+  const int n = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, rows);
+  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+  const int c0 = cv * 8;
+  const int bd = blockDim.x;
+  const int rr = r0 + rl;
+  const int nit = (rl < RL && rr < r1) ? (r1 - rr + RL - 1) / RL : 0;
+  uint4* ringx = gn_ring_smem + threadIdx.x;
+  uint4* ringd = ringx + GN_RING * bd;
+  uint4* ringr = ringd + GN_RING * bd;
+  const long long base = (long long)n * rows;
+  const bool first = c0 < s.C1;
+  const long long ld = first ? s.ldx : s.ldx2;
+  const bf16* px = (first ? (s.x + c0) : (s.x2 + (c0 - s.C1))) + (base + rr) * ld;
+  const bf16* pd = dy + (base + rr) * lddy + c0;
+  const bf16* pr = DRES ? dres + (base + rr) * lddres + c0 : nullptr;
+  const long long step = (long long)RL * ld, dstep = (long long)RL * lddy, rstep = (long long)RL * lddres;
+#pragma unroll
+  for (int d = 0; d < GN_RING; ++d) {
+    if (d < nit) {
+      cp_async16(&ringx[d * bd], px + d * step);
+      cp_async16(&ringd[d * bd], pd + d * dstep);
+      if (DRES) cp_async16(&ringr[d * bd], pr + d * rstep);
+    }
+    cp_async_commit();
+  }
+  // ---- fold the channel sums of this slab (weighted by gamma) into the G groups
+  if (threadIdx.x < 32) { sh_s1[threadIdx.x] = 0.f; sh_sx[threadIdx.x] = 0.f; }
+  __syncthreads();
+  {
+    const int lane = threadIdx.x & 31;
+    const float* cs = csum + (2LL * n) * C;
+    constexpr int NI = 4;
+    for (int cb = (threadIdx.x & ~31); cb < C; cb += NI * bd) {
+      float a[NI], b[NI], w[NI];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int c = cb + i * bd + lane;
+        a[i] = 0.f; b[i] = 0.f; w[i] = 0.f;
+        if (c < C) { a[i] = cs[c]; b[i] = cs[C + c]; w[i] = gamma[c]; }
+      }
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int c = cb + i * bd + lane;
+        if (cb + i * bd >= C) break;               // warp-uniform
+        const int g = (c < C) ? c / cpg : -1;
+        if (dgamma && blockIdx.x == 0 && c < C) {
+          const float mu = mean[n * G + g], rs = rstd[n * G + g];
+          atomicAdd(&dgamma[c], rs * (b[i] - mu * a[i]));
+          atomicAdd(&dbeta[c], a[i]);
+        }
+        float av = a[i] * w[i], bv = b[i] * w[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float a2 = __shfl_down_sync(0xffffffffu, av, o), b2 = __shfl_down_sync(0xffffffffu, bv, o);
+          const int g2 = __shfl_down_sync(0xffffffffu, g, o);
+          if (lane + o < 32 && g2 == g) { av += a2; bv += b2; }
+        }
+        const int gprev = __shfl_up_sync(0xffffffffu, g, 1);
+        if (g >= 0 && (lane == 0 || gprev != g)) { atomicAdd(&sh_s1[g], av); atomicAdd(&sh_sx[g], bv); }
+      }
+    }
+  }
+  __syncthreads();
+  if (nit == 0) return;
+  float A[8], B[8], P[8], Q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int g = (c0 + k) / cpg;
+    const float mu = mean[n * G + g], rs = rstd[n * G + g];
+    const float t1 = sh_s1[g] * inv_count, t2 = rs * (sh_sx[g] - mu * sh_s1[g]) * inv_count;
+    A[k] = rs * gamma[c0 + k];
+    B[k] = beta[c0 + k] - mu * A[k];
+    P[k] = rs * rs * t2;
+    Q[k] = mu * P[k] - rs * t1;
+  }
+  const long long ols = first ? lddx : lddx2;
+  bf16* po = (first ? (dx + c0) : (dx2 + (c0 - s.C1))) + (base + rr) * ols;
+  const long long ostep = (long long)RL * ols;
+  for (int i = 0; i < nit; ++i) {
+    cp_async_wait<GN_RING - 1>();
+    const int slot = (i & (GN_RING - 1)) * bd;
+    const uint4 ux = ringx[slot], ud = ringd[slot];
+    uint4 ur = make_uint4(0u, 0u, 0u, 0u);
+    if (DRES) ur = ringr[slot];
+    const uint32_t in[4] = {ux.x, ux.y, ux.z, ux.w}, din[4] = {ud.x, ud.y, ud.z, ud.w}, rin[4] = {ur.x, ur.y, ur.z, ur.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 v = unpack_bf16x2(in[k]), d = unpack_bf16x2(din[k]);
+      float e0 = d.x, e1 = d.y;
+      if (fuse_silu) {
+        e0 *= silu_grad_f(fmaf(v.x, A[2 * k], B[2 * k]));
+        e1 *= silu_grad_f(fmaf(v.y, A[2 * k + 1], B[2 * k + 1]));
+      }
+      float o0 = fmaf(e0, A[2 * k], fmaf(-v.x, P[2 * k], Q[2 * k]));
+      float o1 = fmaf(e1, A[2 * k + 1], fmaf(-v.y, P[2 * k + 1], Q[2 * k + 1]));
+      if (DRES) { const float2 r2 = unpack_bf16x2(rin[k]); o0 += r2.x; o1 += r2.y; }
+      out[k] = pack_bf16x2(o0, o1);
+    }
+    *reinterpret_cast<uint4*>(po + i * ostep) = make_uint4(out[0], out[1], out[2], out[3]);
+    if (i + GN_RING < nit) {
+      cp_async16(&ringx[slot], px + (i + GN_RING) * step);
+      cp_async16(&ringd[slot], pd + (i + GN_RING) * dstep);
+      if (DRES) cp_async16(&ringr[slot], pr + (i + GN_RING) * rstep);
+    }
+    cp_async_commit();
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm, cp.async ring variants
 // A warp streams its rows (grid-stride) through a private ring of D row slots per tensor in shared memory, filled by
 // cp.async; lane l copies and later reads the 16-byte vectors l, l + 32, ... of a row, so the x / dy / dres rings need no
@@ -1231,7 +1364,7 @@ static void gn_ring_config(int C, int outer, int rows, int& threads, int& RL, in
   if (RL < 1) RL = 1;
   threads = (CV * RL + 31) & ~31;
   static int cps = 0;
-  if (cps == 0) { const char* e = getenv("SVDX_GN_RING_CPS"); cps = (e && atoi(e) > 0) ? atoi(e) : 4; }
+  if (cps == 0) { const char* e = getenv("SVDX_GN_RING_CPS"); cps = (e && atoi(e) > 0) ? atoi(e) : 2; }   // in-step A/B (same box): 2 <= 3 < 1 < 4 < 6
   const long long want_ctas = (long long)cps * svdx_num_sms();
   long long chunks = (want_ctas + outer - 1) / outer;
   if (chunks < 1) chunks = 1;
@@ -1280,9 +1413,10 @@ extern "C" int svdx_groupnorm_stats(const void* x, int64_t ldx, int32_t C1, cons
 
 extern "C" int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, int32_t outer,
                                     int32_t rows, int32_t num_groups, const float* mean, const float* rstd, const float* gamma,
-                                    const float* beta, int32_t fuse_silu, void* y, int64_t ldy, void* stream_v) {
+                                    const float* beta, int32_t fuse_silu, void* y, int64_t ldy, float* ab_out, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
-  if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !y || ldy % 8 || (reinterpret_cast<uintptr_t>(y) & 15) || !mean || !rstd || !gamma || !beta)
+  if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !y || ldy % 8 || (reinterpret_cast<uintptr_t>(y) & 15) || !mean || !rstd || !gamma || !beta ||
+      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15) || (ab_out && ((reinterpret_cast<uintptr_t>(ab_out) & 15) || !gn_ring_enabled())))
     return svdx_fail(SVDX_E_BADARG, "groupnorm_apply: bad arguments");
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
   int threads, rpc;
@@ -1294,7 +1428,7 @@ extern "C" int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, cons
     const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
     gn_apply_ring<false><<<dim3((rows + rpc - 1) / rpc, outer), threads, (size_t)GN_RING * threads * 16, st>>>(
         s, rows, rpc, RL, num_groups, 0.f, inv, nullptr, 0, nullptr, 0, const_cast<float*>(mean), const_cast<float*>(rstd), gamma, beta, fuse_silu,
-        reinterpret_cast<bf16*>(y), ldy);
+        reinterpret_cast<bf16*>(y), ldy, ab_out);
     SVDX_CHECK_LAUNCH("groupnorm_apply");
     return SVDX_OK;
   }
@@ -1308,9 +1442,10 @@ extern "C" int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, cons
 extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, int32_t outer,
                                           int32_t rows, int32_t num_groups, float eps, const float* csum1, int64_t ldc1,
                                           const float* csum2, int64_t ldc2, float* mean, float* rstd, const float* gamma,
-                                          const float* beta, int32_t fuse_silu, void* y, int64_t ldy, void* stream_v) {
+                                          const float* beta, int32_t fuse_silu, void* y, int64_t ldy, float* ab_out, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !y || ldy % 8 || (reinterpret_cast<uintptr_t>(y) & 15) || !mean || !rstd || !gamma || !beta ||
+      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15) || (ab_out && ((reinterpret_cast<uintptr_t>(ab_out) & 15) || !gn_ring_enabled())) ||
       !csum1 || ldc1 < C1 || (C2 > 0 && (!csum2 || ldc2 < C2)) || outer <= 0 || rows <= 0)
     return svdx_fail(SVDX_E_BADARG, "groupnorm_apply_fused: bad arguments");
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
@@ -1322,7 +1457,7 @@ extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1
     gn_ring_config(C1 + C2, outer, rows, threads, RLr, rpc);
     const float invr = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
     gn_apply_ring<true><<<dim3((rows + rpc - 1) / rpc, outer), threads, (size_t)GN_RING * threads * 16, st>>>(
-        s, rows, rpc, RLr, num_groups, eps, invr, csum1, ldc1, csum2, ldc2, mean, rstd, gamma, beta, fuse_silu, reinterpret_cast<bf16*>(y), ldy);
+        s, rows, rpc, RLr, num_groups, eps, invr, csum1, ldc1, csum2, ldc2, mean, rstd, gamma, beta, fuse_silu, reinterpret_cast<bf16*>(y), ldy, ab_out);
     SVDX_CHECK_LAUNCH("groupnorm_apply_fused");
     return SVDX_OK;
   }
@@ -1393,6 +1528,38 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
   return SVDX_OK;
 }
 
+extern "C" int svdx_groupnorm_bwd_fused(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, const void* dy,
+                                        int64_t lddy, int32_t outer, int32_t rows, int32_t num_groups, const float* mean, const float* rstd,
+                                        const float* gamma, const float* beta, int32_t fuse_silu, const float* csum, void* dx, int64_t lddx,
+                                        void* dx2, int64_t lddx2, float* dgamma, float* dbeta, const void* dres, int64_t lddres,
+                                        void* stream_v) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !dy || lddy % 8 || (reinterpret_cast<uintptr_t>(dy) & 15) || !dx || lddx % 8 ||
+      (reinterpret_cast<uintptr_t>(dx) & 15) || (C2 > 0 && (!dx2 || lddx2 % 8 || (reinterpret_cast<uintptr_t>(dx2) & 15))) || !csum || !mean || !rstd ||
+      !gamma || !beta || (dgamma && !dbeta) || (dres && (C2 > 0 || lddres % 8 || (reinterpret_cast<uintptr_t>(dres) & 15))) || outer <= 0 || rows <= 0)
+    return svdx_fail(SVDX_E_BADARG, "groupnorm_bwd_fused: bad arguments");
+  GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
+  static bool a1[SVDX_MAX_DEVICES] = {false}, a2[SVDX_MAX_DEVICES] = {false};
+  gn_ring_attr(gn_bwd_fused_ring<true>, a1);
+  gn_ring_attr(gn_bwd_fused_ring<false>, a2);
+  int threads, RL, rpc;
+  gn_ring_config(C1 + C2, outer, rows, threads, RL, rpc);
+  dim3 grid((rows + rpc - 1) / rpc, outer);
+  const size_t slab = (size_t)GN_RING * threads * 16;
+  const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
+  const bf16* dyb = reinterpret_cast<const bf16*>(dy);
+  if (dres)
+    gn_bwd_fused_ring<true><<<grid, threads, 3 * slab, st>>>(s, dyb, lddy, rows, rpc, RL, num_groups, mean, rstd, gamma, beta, fuse_silu, csum, inv,
+                                                             reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dx2), lddx2,
+                                                             reinterpret_cast<const bf16*>(dres), lddres, dgamma, dbeta);
+  else
+    gn_bwd_fused_ring<false><<<grid, threads, 2 * slab, st>>>(s, dyb, lddy, rows, rpc, RL, num_groups, mean, rstd, gamma, beta, fuse_silu, csum, inv,
+                                                              reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dx2), lddx2, nullptr, 0, dgamma,
+                                                              dbeta);
+  SVDX_CHECK_LAUNCH("groupnorm_bwd_fused");
+  return SVDX_OK;
+}
+
 template <int NJ, int RPW>
 static void ln_fwd_launch(const void* x, int64_t ldx, int rows, int C, const float* g, const float* b, float eps, void* y, int64_t ldy,
                           float* mean, float* rstd, const float* addvec, int add_div, void* xsum, int64_t ldxs, cudaStream_t st) {
@@ -1418,7 +1585,7 @@ static void ln_fwd_ring_launch(const void* x, int64_t ldx, int rows, int C, cons
                                float* mean, float* rstd, const float* addvec, int add_div, void* xsum, int64_t ldxs, cudaStream_t st) {
   static bool attr[SVDX_MAX_DEVICES] = {false};
   gn_ring_attr(ln_fwd_ring<NJ>, attr);
-  static int cps = ln_ring_cps("SVDX_LN_RING_CPS", 2);
+  static int cps = ln_ring_cps("SVDX_LN_RING_CPS", 3);
   int ctas = (rows + 7) / 8;
   const int cap = svdx_num_sms() * cps;
   if (ctas > cap) ctas = cap;

@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_kernel(const __grid_co
       if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, n0, half, 0, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
       else if constexpr (EPI == EPI_RES || EPI == EPI_RES_GN) epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, n0, half, 0, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.off, st.row0, st.grp, lane, m0, valid_rows);
       else if constexpr (EPI == EPI_GEGLU) epilogue_geglu(p, t_base, n0, half, bn_out, st.base, st.row0, st.grp, lane);
+      else if constexpr (EPI == EPI_FAST_GNB) epilogue_fast_gnb(p, t_base, m, row_ok, n0, half, 0, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
       else epilogue_tile(p, t_base, m, row_ok, n0, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
@@ -474,6 +475,9 @@ int svdx_tapgemm_fill(const SvdxTapGemm* d, TapGemmKParams& p, int cg) {
   p.res2 = reinterpret_cast<const bf16*>(d->res2); p.ldr2 = d->ldr2;
   p.scales = d->scales; p.pre = reinterpret_cast<bf16*>(d->pre); p.ldpre = d->ldpre;
   p.gn_sum = d->gn_sum; p.gn_ld = d->gn_ld; p.gn_rows = d->gn_rows;
+  p.gnb_x = reinterpret_cast<const bf16*>(d->gnb_x); p.gnb_ldx = d->gnb_ldx; p.gnb_c1 = d->gnb_x2 ? d->gnb_c1 : d->N;
+  p.gnb_x2 = reinterpret_cast<const bf16*>(d->gnb_x2); p.gnb_ldx2 = d->gnb_ldx2;
+  p.gnb_ab = d->gnb_ab; p.gnb_sum = d->gnb_sum; p.gnb_rows = d->gnb_rows; p.gnb_silu = d->gnb_silu;
   {
     static int probe = -1;
     if (probe < 0) { const char* e = getenv("SVDX_EPI_PROBE"); probe = e ? atoi(e) : 0; }
@@ -512,7 +516,16 @@ int svdx_tapgemm_fill(const SvdxTapGemm* d, TapGemmKParams& p, int cg) {
       p.epi_mode = d->geglu ? EPI_GEGLU : (d->res1 || d->res2 || d->scales) ? EPI_RES : EPI_FAST;
   }
   if (p.split_k > 1 && (p.bias || p.rowbias || p.res1 || p.res2 || p.geglu)) return svdx_fail(SVDX_E_BADARG, "tapgemm: split_k with epilogue operands");
-  if (wide320 && p.epi_mode != EPI_FAST && p.epi_mode != EPI_RES)
+  if (p.gnb_sum) {
+    if (p.epi_mode != EPI_FAST || p.gn_sum)
+      return svdx_fail(SVDX_E_BADARG, "tapgemm: gnb_sum needs the plain bf16 TMA-store epilogue (no residual / scales / GEGLU / split-K / gn_sum)");
+    if (!p.gnb_x || p.gnb_rows <= 0 || (p.gnb_silu && !p.gnb_ab) || (d->N & 1) || (p.gnb_ldx % 8) || (reinterpret_cast<uintptr_t>(p.gnb_x) & 15) ||
+        (reinterpret_cast<uintptr_t>(p.gnb_sum) & 7) || (p.gnb_ab && (reinterpret_cast<uintptr_t>(p.gnb_ab) & 7)) ||
+        (p.gnb_x2 && (p.gnb_c1 <= 0 || p.gnb_c1 >= d->N || p.gnb_c1 % 32 || (p.gnb_ldx2 % 8) || (reinterpret_cast<uintptr_t>(p.gnb_x2) & 15))))
+      return svdx_fail(SVDX_E_BADARG, "tapgemm: gnb operands (x rows 16-byte aligned, gnb_rows > 0, scale/shift table for SiLU, concat split % 32)");
+    p.epi_mode = EPI_FAST_GNB;
+  }
+  if (wide320 && p.epi_mode != EPI_FAST && p.epi_mode != EPI_RES && p.epi_mode != EPI_FAST_GNB)
     return svdx_fail(SVDX_E_BADARG, "tapgemm: block_n 320 needs a bf16 output through the TMA-store epilogues (N % 320 == 0, aligned rows)");
   if (p.gn_sum) {
     if (p.epi_mode != EPI_FAST && p.epi_mode != EPI_RES)
@@ -549,13 +562,15 @@ extern "C" int svdx_tapgemm(const SvdxTapGemm* d, void* stream_v) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<EPI_FAST_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<EPI_RES_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_kernel<EPI_FAST_GNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return svdx_fail_cuda(e, "tapgemm: set smem attribute");
     attr_done[slot] = true;
   }
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
   int grid = svdx_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm_kernel<EPI_FAST_GN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  if (p.epi_mode == EPI_FAST_GNB) tapgemm_kernel<EPI_FAST_GNB><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  else if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm_kernel<EPI_FAST_GN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_RES && p.gn_sum) tapgemm_kernel<EPI_RES_GN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_FAST) tapgemm_kernel<EPI_FAST><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_GEGLU) tapgemm_kernel<EPI_GEGLU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);

@@ -323,11 +323,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
         const int lo1 = acc ? 0 : WIDE_ACC1, hi1 = acc ? 320 - WIDE_ACC1 : 320;
         const int lo2 = acc ? 320 - WIDE_ACC1 : 0, hi2 = acc ? 320 : WIDE_ACC1;
         if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, nt * bn_out, half, lo1, hi1, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
+        else if constexpr (EPI == EPI_FAST_GNB) epilogue_fast_gnb(p, t_base, m, row_ok, nt * bn_out, half, lo1, hi1, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
         else epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, nt * bn_out, half, lo1, hi1, n_out_total, s_acc, s_r1, s_r2, st.base, st.off, st.row0, st.grp, lane, m0, valid_rows);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(bar_tempty, 0);
         if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, nt * bn_out, half, lo2, hi2, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
+        else if constexpr (EPI == EPI_FAST_GNB) epilogue_fast_gnb(p, t_base, m, row_ok, nt * bn_out, half, lo2, hi2, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
         else epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, nt * bn_out, half, lo2, hi2, n_out_total, s_acc, s_r1, s_r2, st.base, st.off, st.row0, st.grp, lane, m0, valid_rows);
         tc_fence_before();
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -336,6 +338,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
       if constexpr (EPI == EPI_FAST || EPI == EPI_FAST_GN) epilogue_fast<EPI == EPI_FAST_GN>(p, t_base, m, row_ok, nt * bn_out, half, 0, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
       else if constexpr (EPI == EPI_RES || EPI == EPI_RES_GN) epilogue_res<EPI == EPI_RES_GN>(p, t_base, m, row_ok, nt * bn_out, half, 0, bn_out, n_out_total, s_acc, s_r1, s_r2, st.base, st.off, st.row0, st.grp, lane, m0, valid_rows);
       else if constexpr (EPI == EPI_GEGLU) epilogue_geglu(p, t_base, nt * bn_out, half, bn_out, st.base, st.row0, st.grp, lane);
+      else if constexpr (EPI == EPI_FAST_GNB) epilogue_fast_gnb(p, t_base, m, row_ok, nt * bn_out, half, 0, bn_out, n_out_total, st.base, st.row0, st.grp, lane, m0, valid_rows);
       else epilogue_tile(p, t_base, m, row_ok, nt * bn_out, half, bn_out, n_out_total, s_acc, s_r1, s_r2, st, lane);
       tc_fence_before();
       __syncwarp();
@@ -389,6 +392,8 @@ int svdx_tapgemm2_launch(const TapGemmKParams& p, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES_GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST_GNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST_GNB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2W_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2W_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_RES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2W_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm2_kernel<EPI_FAST_GN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2W_BYTES);
@@ -400,7 +405,8 @@ int svdx_tapgemm2_launch(const TapGemmKParams& p, cudaStream_t stream) {
   int clusters = svdx_num_sms() / 2;
   if (clusters > total_tiles) clusters = total_tiles;
   if (p.block_n == 320) {
-    if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm2_kernel<EPI_FAST_GN, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
+    if (p.epi_mode == EPI_FAST_GNB) tapgemm2_kernel<EPI_FAST_GNB, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
+    else if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm2_kernel<EPI_FAST_GN, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
     else if (p.epi_mode == EPI_RES && p.gn_sum) tapgemm2_kernel<EPI_RES_GN, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
     else if (p.epi_mode == EPI_FAST) tapgemm2_kernel<EPI_FAST, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
     else if (p.epi_mode == EPI_RES) tapgemm2_kernel<EPI_RES, true><<<2 * clusters, NUM_THREADS, SMEM2W_BYTES, stream>>>(p);
@@ -409,7 +415,8 @@ int svdx_tapgemm2_launch(const TapGemmKParams& p, cudaStream_t stream) {
     if (e2 != cudaSuccess) return svdx_fail_cuda(e2, "tapgemm2: launch (wide)");
     return SVDX_OK;
   }
-  if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm2_kernel<EPI_FAST_GN><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  if (p.epi_mode == EPI_FAST_GNB) tapgemm2_kernel<EPI_FAST_GNB><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
+  else if (p.epi_mode == EPI_FAST && p.gn_sum) tapgemm2_kernel<EPI_FAST_GN><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_RES && p.gn_sum) tapgemm2_kernel<EPI_RES_GN><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_FAST) tapgemm2_kernel<EPI_FAST><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);
   else if (p.epi_mode == EPI_GEGLU) tapgemm2_kernel<EPI_GEGLU><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(p);

@@ -58,6 +58,15 @@ struct __align__(64) TapGemmKParams {
   float* gn_sum;       // fused GroupNorm statistics of the output (per slab m / gn_rows, per channel): [slab][2][gn_ld]
   long long gn_ld;
   int gn_rows;
+  // GroupNorm BACKWARD statistics fused into the epilogue of the GEMM / conv that writes dy = dL/d(GroupNorm output)
+  const bf16* gnb_x;   // the GroupNorm's INPUT (channels [0, gnb_c1)), and gnb_x2 the concatenated second source
+  long long gnb_ldx;
+  const bf16* gnb_x2;
+  long long gnb_ldx2;
+  int gnb_c1;
+  const float* gnb_ab; // [slab][2][N]: forward scale / shift per channel (y = act(x * scale + shift))
+  float* gnb_sum;      // [slab][2][N], zero on entry: sum(e), sum(e * x), e = dy * act'(x * scale + shift)
+  int gnb_rows, gnb_silu;
   int tma_store;       // epilogue stores through shared memory + TMA (tmo / tmpre valid)
   int epi_mode;        // EPI_GENERIC / EPI_FAST / EPI_GEGLU / EPI_RES: which kernel instantiation runs
   int probe;   // dev switch SVDX_EPI_PROBE: 1 = epilogue without global stores, 2 = no epilogue work at all
@@ -195,6 +204,8 @@ SVDX_DEVINL void gn_chunk_sums(const TapGemmKParams& p, uint32_t buf, int lane, 
 constexpr int EPI_GENERIC = 0, EPI_FAST = 1, EPI_GEGLU = 2, EPI_RES = 3;
 // + fused GroupNorm statistics of the output (separate instantiations: the plain ones keep their register budget)
 constexpr int EPI_FAST_GN = 4, EPI_RES_GN = 5;
+// + fused GroupNorm BACKWARD sums (the output is the gradient of a GroupNorm's output)
+constexpr int EPI_FAST_GNB = 6;
 
 SVDX_DEVINL void add_vec32(float (&f)[32], const float* __restrict__ src) {
   const float4* bp = reinterpret_cast<const float4*>(src);
@@ -259,6 +270,101 @@ SVDX_DEVINL void epilogue_fast(const TapGemmKParams& p, uint32_t t_base, long lo
       gn_chunk_sums(p, sbase, lane, colA, n_out_total, m0, valid_rows);
       if (hasB) gn_chunk_sums(p, sbase + 2048, lane, colB, n_out_total, m0, valid_rows);
     }
+  }
+}
+
+// ---- GroupNorm backward, pass 1, fused into the epilogue that WRITES dy (the dgrad conv / GEMM whose input was the
+// GroupNorm(+SiLU) output): per (slab, channel) S = sum_rows e and SX = sum_rows e * x with e = dy * act'(x * scale + shift),
+// from the staged bf16 dy chunk (exactly the values stored) and the matching 32 x 32 chunk of the GroupNorm input x staged
+// beside it. The consumer (svdx_groupnorm_bwd_fused) folds channels into groups: s1 = sum_c gamma_c S_c,
+// s2 = rstd * (sum_c gamma_c SX_c - mean * s1); dgamma_c = rstd * (SX_c - mean * S_c), dbeta_c = S_c. Same lane layout as
+// gn_chunk_sums (lane = column pair x row parity), slabs walked segment by segment.
+SVDX_DEVINL void gnb_chunk_sums(const TapGemmKParams& p, uint32_t buf_dy, uint32_t buf_x, int lane, int col0, int n_out_total, long long m0,
+                                int valid_rows) {
+  const int pr = lane & 15, h = lane >> 4;
+  const uint32_t in_chunk = (uint32_t)(pr & 3) * 4u;
+  const int jch = pr >> 2;
+  long long slab = m0 / p.gnb_rows;
+  int left = p.gnb_rows - (int)(m0 - slab * p.gnb_rows);
+  const int col = col0 + 2 * pr;
+  const bool col_ok = col < n_out_total;
+  int r = 0;
+  while (r < valid_rows) {                                     // warp-uniform trip count
+    const int seg_end = min(valid_rows, r + left);
+    float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);
+    if (col_ok && p.gnb_silu) {
+      A = *reinterpret_cast<const float2*>(p.gnb_ab + (2 * slab) * p.N + col);
+      B = *reinterpret_cast<const float2*>(p.gnb_ab + (2 * slab + 1) * p.N + col);
+    }
+    float s0 = 0.f, s1 = 0.f, x0 = 0.f, x1 = 0.f;
+    for (int rr = r + ((h ^ r) & 1); rr < seg_end; rr += 2) {
+      const uint32_t off = rr * 64 + ((uint32_t)(jch ^ ((rr >> 1) & 3)) << 4) + in_chunk;
+      uint32_t wd, wx;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd) : "r"(buf_dy + off));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wx) : "r"(buf_x + off));
+      const float2 d = unpack_bf16x2(wd), xv = unpack_bf16x2(wx);
+      float e0 = d.x, e1 = d.y;
+      if (p.gnb_silu) {
+        e0 *= silu_grad_f(fmaf(xv.x, A.x, B.x));
+        e1 *= silu_grad_f(fmaf(xv.y, A.y, B.y));
+      }
+      s0 += e0; s1 += e1;
+      x0 = fmaf(e0, xv.x, x0); x1 = fmaf(e1, xv.y, x1);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    x0 += __shfl_xor_sync(0xffffffffu, x0, 16); x1 += __shfl_xor_sync(0xffffffffu, x1, 16);
+    if (h == 0 && col_ok) {
+      float* d = p.gnb_sum + (2 * slab) * p.N + col;
+      asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d), "f"(s0), "f"(s1) : "memory");
+      asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d + p.N), "f"(x0), "f"(x1) : "memory");
+    }
+    r = seg_end; ++slab; left = p.gnb_rows;
+  }
+}
+
+// plain epilogue + gnb_chunk_sums: one chunk per round, staging half X = the dy chunk (TMA-store source), half Y = the x chunk
+SVDX_DEVINL void epilogue_fast_gnb(const TapGemmKParams& p, uint32_t t_base, long long m, bool row_ok, int n0, int half, int c_lo, int c_hi,
+                                   int n_out_total, uint32_t sbase, int row0, int grp, int lane, long long m0, int valid_rows) {
+  const float* bias = p.bias;
+  const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rowbias_div) * p.ldrb : nullptr;
+  const uint32_t rowX = sbase + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  const int prow = lane >> 2, ppc = lane & 3;
+#pragma unroll 1
+  for (int c = c_lo + half * 32; c < c_hi; c += 64) {
+    const int col0 = n0 + c;
+    if (col0 >= n_out_total) break;
+    // the matching chunk of the GroupNorm input, fetched coalesced (8 rows x 64 B per instruction) before the TMEM wait
+    const bool src1 = col0 < p.gnb_c1;
+    const long long xld = src1 ? p.gnb_ldx : p.gnb_ldx2;
+    const bf16* xs = (src1 ? p.gnb_x + col0 : p.gnb_x2 + (col0 - p.gnb_c1)) + m0 * xld + ppc * 8;
+    uint4 xa[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = prow + 8 * j;
+      xa[j] = (rr < valid_rows) ? *reinterpret_cast<const uint4*>(xs + (long long)rr * xld) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint32_t v[32];
+    tmem_ld32(t_base + c, v);
+    tc_wait_ld();
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    if (bias) add_vec32(f, bias + col0);
+    if (rb) add_vec32(f, rb + col0);
+    if (lane == 0) bulk_wait_read<0>();   // the previous round's store has drained half X
+    __syncwarp();
+    stage_row_bf16(rowX, sw, f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = prow + 8 * j;
+      st_shared_v4(sbase + 2048 + rr * 64 + ((ppc ^ ((rr >> 1) & 3)) << 4), xa[j].x, xa[j].y, xa[j].z, xa[j].w);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_3d(&p.tmo, sbase, col0, row0, grp); bulk_commit(); }
+    gnb_chunk_sums(p, sbase, sbase + 2048, lane, col0, n_out_total, m0, valid_rows);
+    __syncwarp();                          // all lanes are done with half Y before the next round overwrites it
   }
 }
 

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 
 from . import raw
@@ -26,7 +28,7 @@ F32 = torch.float32
 class Var:
     """An activation on the tape: bf16 ``[rows, C]`` data plus (lazily) its gradient."""
 
-    __slots__ = ("data", "grad", "needs_grad", "owned", "csum")
+    __slots__ = ("data", "grad", "needs_grad", "owned", "csum", "gnb", "gnb_sums")
 
     def __init__(self, data: torch.Tensor, needs_grad: bool = False):
         self.data = data
@@ -36,6 +38,10 @@ class Var:
         # fused GroupNorm statistics of this tensor, produced by the GEMM / conv epilogue that wrote it:
         # (rows per statistics slab, [(fp32 [slabs, 2, C_i] channel sums, C_i), ...]) — several parts after a channel concat
         self.csum = None
+        # set on a GroupNorm OUTPUT: what the dgrad epilogue of its consumer needs to accumulate the GroupNorm-backward sums
+        # (dict x / x2 / ab / rows / silu); gnb_sums = (fp32 [slabs, 2, C] sums, the gradient tensor they were computed on)
+        self.gnb = None
+        self.gnb_sums = None
 
     def take_grad(self) -> Optional[torch.Tensor]:
         g, self.grad, self.owned = self.grad, None, False
@@ -138,6 +144,7 @@ class Engine:
         self._stat_arena: Optional[torch.Tensor] = None
         self._stat_ptr = 0
         self.fuse_gn_stats = True
+        self.fuse_gn_bwd = os.environ.get("SVDX_GN_BWD_FUSE", "1") != "0"
 
     # ------------------------------------------------------------------ tape
     def begin(self, recording: bool):
@@ -171,6 +178,18 @@ class Engine:
         if raw.split_plan(True, M, N, K, ntaps) is not None:
             return None
         return self.stat_zeros((M // gn_rows) * 2 * N, device).view(M // gn_rows, 2, N)
+
+    def _gnb_for(self, x: Var, M: int, N: int, K: int, ntaps: int, scales, device):
+        """tapgemm(gnb=...) arguments when x is a GroupNorm output and the data-gradient launch about to run is the first
+        writer of its gradient: the epilogue then also accumulates pass 1 of the GroupNorm backward (per-channel sums), and
+        the GroupNorm's backward is ONE launch with one pass over x and dy. None when the launch cannot carry them."""
+        ctx = x.gnb
+        if ctx is None or not self.fuse_gn_bwd or scales is not None or x.grad is not None or N % 32 or M % ctx["rows"] or N != ctx["C"]:
+            return None
+        if raw.split_plan(True, M, N, K, ntaps) is not None:
+            return None
+        sums = self.stat_zeros((M // ctx["rows"]) * 2 * N, device).view(M // ctx["rows"], 2, N)
+        return dict(x=ctx["x"], x2=ctx["x2"], ab=ctx["ab"], rows=ctx["rows"], silu=ctx["silu"], sum=sums)
 
     def detach_tape(self) -> List[Callable[[], None]]:
         """hand the recorded tape to the caller (the autograd node of this forward) and stop recording"""
@@ -233,6 +252,7 @@ class Engine:
         kept and later overwritten in place); pass owned=False when g aliases another Var's gradient."""
         if not v.needs_grad:
             return
+        v.gnb_sums = None        # sums fused into an earlier producer of this gradient no longer describe it
         if v.grad is None:
             v.grad, v.owned = g, owned
         elif v.grad.dtype != bf16:
@@ -637,10 +657,12 @@ class Engine:
                 if x.needs_grad:
                     wt = self.w_conv(w, True)  # [I, 9*Opad]
                     Op = wt.shape[1] // 9
+                    gnb = None
                     if not planes:
                         dx = self.empty(M, I, x.data)
+                        gnb = self._gnb_for(x, M, I, Op, 9, sc, dy.device)
                         raw.tapgemm_auto(dy, wt, dx, M=M, N=I, K=Op, mode=A_CONV2D, taps=_neg_taps(CONV3x3_TAPS),
-                                         conv_whn=(g.W, g.H, nimg), scales=sc)
+                                         conv_whn=(g.W, g.H, nimg), scales=sc, **({} if gnb is None else {"gnb": gnb}))
                     else:
                         # gradient w.r.t. each parity plane: the taps that read that plane, shifts negated
                         dx = self.empty(4 * M, I, x.data)
@@ -653,6 +675,8 @@ class Engine:
                             raw.tapgemm(dy, wsub, dx[pl * M:(pl + 1) * M], M=M, N=I, K=O, mode=A_CONV2D, taps=tp,
                                         conv_whn=(g.W, g.H, nimg), scales=sc)
                     self.add_grad(x, dx)
+                    if gnb is not None:
+                        x.gnb_sums = (gnb["sum"], dx)
             self.record(bwd)
         return y
 
@@ -693,8 +717,12 @@ class Engine:
                 if x.needs_grad:
                     wt = self.w_conv(w, True)
                     dx = self.empty(M, I, x.data)
-                    raw.tapgemm_auto(dy, wt, dx, M=M, N=I, K=O, taps=_neg_taps(taps), rows_per_group=g.T * HW, groups=g.B, scales=sc)
+                    gnb = self._gnb_for(x, M, I, O, 3, sc, dy.device)
+                    raw.tapgemm_auto(dy, wt, dx, M=M, N=I, K=O, taps=_neg_taps(taps), rows_per_group=g.T * HW, groups=g.B, scales=sc,
+                                     **({} if gnb is None else {"gnb": gnb}))
                     self.add_grad(x, dx)
+                    if gnb is not None:
+                        x.gnb_sums = (gnb["sum"], dx)
             self.record(bwd)
         return y
 
@@ -745,32 +773,43 @@ class Engine:
         gamma, beta = self.vec_f32(gn.weight), self.vec_f32(gn.bias)
         out = self.empty(x.rows, C, x.data)
         cs = x.csum
+        p_train = gn.weight.requires_grad
+        need = x.needs_grad or p_train
+        # per-channel scale / shift table for the backward sums fused into the consumer's dgrad epilogue (see _gnb_for)
+        ab = torch.empty(outer, 2, C, device=out.device, dtype=F32) if (need and self.recording and self.fuse_gn_bwd) else None
         if cs is not None and cs[0] == rows and len(cs[1]) <= 2 and sum(c for _, c in cs[1]) == C and all(t.shape[0] == outer for t, _ in cs[1]):
             parts = cs[1]
             C1 = parts[0][1]
             x1 = x.data if len(parts) == 1 else x.data[:, :C1]
             x2 = None if len(parts) == 1 else x.data[:, C1:]
             mean, rstd = raw.groupnorm_apply_fused(x1, x2, outer, rows, gn.eps, parts[0][0], None if len(parts) == 1 else parts[1][0],
-                                                   gamma, beta, silu, out, gn.num_groups)
+                                                   gamma, beta, silu, out, gn.num_groups, ab=ab)
         else:
             mean, rstd = raw.groupnorm_stats(x.data, None, outer, rows, gn.eps, gn.num_groups)
-            raw.groupnorm_apply(x.data, None, outer, rows, mean, rstd, gamma, beta, silu, out, gn.num_groups)
-        p_train = gn.weight.requires_grad
-        need = x.needs_grad or p_train
+            raw.groupnorm_apply(x.data, None, outer, rows, mean, rstd, gamma, beta, silu, out, gn.num_groups, ab=ab)
         y = Var(out, need)
+        if ab is not None:
+            y.gnb = dict(x=x.data, x2=None, ab=ab, rows=rows, silu=silu, C=C)   # x.data is the (already concatenated) [M, C] tensor
         if need and self.recording:
             def bwd():
+                fused = y.gnb_sums
                 dy = y.take_grad()
+                y.gnb_sums = None
                 if dy is None:
                     return
                 dx = self.empty(x.rows, C, x.data)
                 dg = self.pgrad(gn.weight) if p_train else None
                 db = self.pgrad(gn.bias) if p_train else None
-                ws = self.stat_zeros(2 * outer * gn.num_groups, dy.device)
                 # x usually already carries the gradient of its residual use (conv2 / proj_out `res1`): folded into this pass
                 dres = x.grad if (x.needs_grad and x.grad is not None and x.grad.dtype == bf16 and x.grad.shape == dx.shape
                                   and x.grad.stride(-1) == 1) else None
-                raw.groupnorm_bwd(x.data, None, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, None, dg, db, gn.num_groups, ws=ws, dres=dres)
+                if fused is not None and fused[1] is dy:
+                    # pass 1 ran inside the dgrad epilogue that wrote dy: one launch, one pass over x and dy
+                    raw.groupnorm_bwd_fused(x.data, None, dy, outer, rows, mean, rstd, gamma, beta, silu, fused[0], dx, None, dg, db,
+                                            gn.num_groups, dres=dres)
+                else:
+                    ws = self.stat_zeros(2 * outer * gn.num_groups, dy.device)
+                    raw.groupnorm_bwd(x.data, None, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, None, dg, db, gn.num_groups, ws=ws, dres=dres)
                 if dres is not None:
                     x.grad, x.owned = dx, True
                 else:

@@ -142,7 +142,7 @@ def choose_block_n(M: int, n_out: int, geglu: bool = False, mn_major: bool = Fal
 
 
 WIDE_TILE = os.environ.get("SVDX_WIDE", "1") != "0"
-WIDE_MIN_K = int(os.environ.get("SVDX_WIDE_MIN_K", "640"))
+WIDE_MIN_K = int(os.environ.get("SVDX_WIDE_MIN_K", "960"))
 
 
 def _wide_tile_ok(M, N, k_total, out, ldo, geglu, a_mn, b_mn, b_mode, split_k, out_dtype, bias, rowbias) -> bool:
@@ -150,7 +150,10 @@ def _wide_tile_ok(M, N, k_total, out, ldo, geglu, a_mn, b_mn, b_mode, split_k, o
     once per 160) for the C = 320 / 640 / 960 layers when the contraction is long enough to hide the partly exposed epilogue
     of the overlapping accumulators. Mirrors the library's conditions for the wide form (CTA-pair kernel, bf16 TMA-store
     epilogues); anything else keeps choose_block_n's width."""
-    if not WIDE_TILE or geglu or a_mn or b_mn or b_mode != 0 or split_k != 1 or N % 320 or M < 512 or k_total < WIDE_MIN_K:
+    # measured (scripts/kbench.py gemm, profiles/r2_kbench_gemm.txt): wins 8-25 % where the alternative is 160-wide tiles and
+    # K * taps >= 960 (convs at C = 320 / 640: 1.06 -> 1.30-1.43 PFLOP/s); loses against 256-wide tiles (N % 256 == 0) and
+    # at short K, where the partly exposed epilogue costs more than the A traffic saved
+    if not WIDE_TILE or geglu or a_mn or b_mn or b_mode != 0 or split_k != 1 or N % 320 or N % 256 == 0 or M < 512 or k_total < WIDE_MIN_K:
         return False
     if out.dtype != bf16 or (out_dtype is not None and out_dtype != OUT_BF16):
         return False
@@ -225,6 +228,7 @@ def tapgemm(
     pre: Optional[torch.Tensor] = None,
     gn_sum: Optional[torch.Tensor] = None,
     gn_rows: int = 0,
+    gnb: Optional[dict] = None,
 ) -> torch.Tensor:
     """Launch svdx_tapgemm on the current stream. All tensors are CUDA; a/b/res/pre are bf16.
     gn_sum: zeroed fp32 [slabs, 2, C] buffer that receives the per-channel sum / sum of squares of the output (fused
@@ -296,6 +300,21 @@ def tapgemm(
         d.gn_sum = gn_sum.data_ptr()
         d.gn_ld = gn_sum.shape[2]
         d.gn_rows = gn_rows
+    if gnb is not None:
+        # GroupNorm-backward sums of the output (= dL/d(GroupNorm output)): x / x2 the GroupNorm input, ab its forward
+        # scale / shift table, sum the zeroed fp32 [slabs, 2, N] accumulator, rows per slab, silu flag
+        gx, gx2 = gnb["x"], gnb.get("x2")
+        assert gx.dtype == bf16 and gnb["sum"].dtype == torch.float32 and gnb["sum"].is_contiguous() and gnb["sum"].shape[-1] == N
+        d.gnb_x = gx.data_ptr()
+        d.gnb_ldx = _rowmajor(gx, "gnb x")
+        if gx2 is not None:
+            d.gnb_x2 = gx2.data_ptr()
+            d.gnb_ldx2 = _rowmajor(gx2, "gnb x2")
+            d.gnb_c1 = gx.shape[-1]
+        d.gnb_ab = _ptr(gnb.get("ab"))
+        d.gnb_sum = gnb["sum"].data_ptr()
+        d.gnb_rows = gnb["rows"]
+        d.gnb_silu = int(gnb["silu"])
     check(load().svdx_tapgemm(C.byref(d), _stream()), "svdx_tapgemm")
     return out
 
@@ -417,19 +436,20 @@ def groupnorm_stats(x, x2, outer, rows, eps, groups=32):
     return mean, rstd
 
 
-def groupnorm_apply(x, x2, outer, rows, mean, rstd, gamma, beta, silu, y, groups=32):
+def groupnorm_apply(x, x2, outer, rows, mean, rstd, gamma, beta, silu, y, groups=32, ab=None):
     C1 = x.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     if _fam("groupnorm", 0.0, 4.0 * x.shape[0] * (C1 + C2)):
         return y
     check(load().svdx_groupnorm_apply(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0,
                                       C2, outer, rows, groups, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                      int(silu), y.data_ptr(), _rowmajor(y, "y"), _stream()), "groupnorm_apply")
+                                      int(silu), y.data_ptr(), _rowmajor(y, "y"), _ptr(ab), _stream()), "groupnorm_apply")
     return y
 
 
-def groupnorm_apply_fused(x, x2, outer, rows, eps, csum1, csum2, gamma, beta, silu, y, groups=32):
-    """GroupNorm(+SiLU) from the per-channel sums of the producing epilogues; returns (mean, rstd) [outer*groups] for backward"""
+def groupnorm_apply_fused(x, x2, outer, rows, eps, csum1, csum2, gamma, beta, silu, y, groups=32, ab=None):
+    """GroupNorm(+SiLU) from the per-channel sums of the producing epilogues; returns (mean, rstd) [outer*groups] for backward.
+    ab: optional fp32 [outer, 2, C] that receives the per-channel scale / shift (for tapgemm's gnb_* backward sums)"""
     C1 = x.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     stats = torch.empty(2, outer * groups, device=x.device, dtype=torch.float32)
@@ -439,7 +459,7 @@ def groupnorm_apply_fused(x, x2, outer, rows, eps, csum1, csum2, gamma, beta, si
     check(load().svdx_groupnorm_apply_fused(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0, C2,
                                             outer, rows, groups, eps, csum1.data_ptr(), csum1.shape[2],
                                             _ptr(csum2), csum2.shape[2] if csum2 is not None else 0, mean.data_ptr(), rstd.data_ptr(),
-                                            gamma.data_ptr(), beta.data_ptr(), int(silu), y.data_ptr(), _rowmajor(y, "y"), _stream()),
+                                            gamma.data_ptr(), beta.data_ptr(), int(silu), y.data_ptr(), _rowmajor(y, "y"), _ptr(ab), _stream()),
           "svdx_groupnorm_apply_fused")
     return mean, rstd
 
@@ -460,6 +480,20 @@ def groupnorm_bwd(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, dx, dx2
                                     _ptr(dx2), _rowmajor(dx2, "dx2") if dx2 is not None else 0, _ptr(dgamma), _ptr(dbeta),
                                     ws.data_ptr(), int(ws_zero), _ptr(dres), _rowmajor(dres, "dres") if dres is not None else 0, _stream()),
           "svdx_groupnorm_bwd")
+
+
+def groupnorm_bwd_fused(x, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, csum, dx, dx2, dgamma=None, dbeta=None, groups=32, dres=None):
+    """GroupNorm backward from the per-channel sums the dgrad epilogue accumulated (tapgemm gnb_sum): one launch, one pass"""
+    C1 = x.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    if _fam("groupnorm", 0.0, 6.0 * x.shape[0] * (C1 + C2)):
+        return
+    check(load().svdx_groupnorm_bwd_fused(x.data_ptr(), _rowmajor(x, "x"), C1, _ptr(x2), _rowmajor(x2, "x2") if x2 is not None else 0, C2,
+                                          dy.data_ptr(), _rowmajor(dy, "dy"), outer, rows, groups, mean.data_ptr(), rstd.data_ptr(),
+                                          gamma.data_ptr(), beta.data_ptr(), int(silu), csum.data_ptr(), dx.data_ptr(), _rowmajor(dx, "dx"),
+                                          _ptr(dx2), _rowmajor(dx2, "dx2") if dx2 is not None else 0, _ptr(dgamma), _ptr(dbeta),
+                                          _ptr(dres), _rowmajor(dres, "dres") if dres is not None else 0, _stream()),
+          "svdx_groupnorm_bwd_fused")
 
 
 def layernorm_fwd(x, gamma, beta, eps, y, addvec=None, add_div=1, xsum=None):

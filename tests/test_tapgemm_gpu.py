@@ -416,3 +416,90 @@ def test_wide_tile_rejected_where_unsupported(raw):
         raw.tapgemm(a, w[:480], torch.empty(1024, 480, device=_dev(), dtype=bf16), M=1024, N=480, K=64, block_n=320)
     with pytest.raises(RuntimeError):      # small M: 1-CTA kernel
         raw.tapgemm(a[:256], w, torch.empty(256, 640, device=_dev(), dtype=bf16), M=256, N=640, K=64, block_n=320)
+
+
+# ---- GroupNorm backward, pass 1 fused into the epilogue that writes dy (gnb_*), + svdx_groupnorm_bwd_fused
+def _gnb_reference(x, dy, outer, rows, gamma, beta, silu):
+    C = x.shape[1]
+    xr = x.float().reshape(outer, rows, C).permute(0, 2, 1).requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    b = beta.clone().requires_grad_(True)
+    ref = F.group_norm(xr, 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref.backward(dy.float().view(outer, rows, C).permute(0, 2, 1))
+    return xr.grad.permute(0, 2, 1).reshape(outer * rows, C), g.grad, b.grad
+
+
+@pytest.mark.parametrize("M,N,K,rows,bn", [(35840, 320, 640, 2560, 320), (35840, 320, 640, 2560, 160), (2240, 640, 1280, 160, None),
+                                           (560, 1280, 64, 40, None), (280, 320, 128, 40, None), (4480, 1280, 320, 2240, None)])
+@pytest.mark.parametrize("silu,concat", [(True, False), (False, False), (True, True)])
+def test_groupnorm_backward_sums_fused_into_the_dgrad_epilogue(raw, M, N, K, rows, bn, silu, concat):
+    """the GEMM writes dy (the gradient of a GroupNorm output) and accumulates sum e, sum e*x per (slab, channel); the fused
+    backward kernel turns them into dx / dgamma / dbeta: compared with F.group_norm's backward on the bf16 dy it stored"""
+    outer = M // rows
+    a = _rand(M, K, seed=1).to(bf16)
+    w = _rand(N, K, scale=K ** -0.5, seed=2).to(bf16)
+    x = (_rand(M, N, seed=5) + 0.5).to(bf16)                      # the GroupNorm input
+    gamma = _rand(N, seed=7) * 0.2 + 1.0
+    beta = _rand(N, seed=8) * 0.1
+    C1 = N // 2 if concat else N
+    x1 = x[:, :C1] if concat else x
+    x2 = x[:, C1:] if concat else None
+    mean, rstd = raw.groupnorm_stats(x1, x2, outer, rows, 1e-5)
+    y = torch.empty(M, N, device=_dev(), dtype=bf16)
+    ab = torch.empty(outer, 2, N, device=_dev())
+    raw.groupnorm_apply(x1, x2, outer, rows, mean, rstd, gamma, beta, silu, y, ab=ab)
+    torch.cuda.synchronize()
+    cpg = N // 32
+    scale = rstd.view(outer, 32).repeat_interleave(cpg, 1) * gamma
+    shift = beta - mean.view(outer, 32).repeat_interleave(cpg, 1) * scale
+    assert torch.allclose(ab[:, 0], scale, rtol=1e-5, atol=1e-6) and torch.allclose(ab[:, 1], shift, rtol=1e-5, atol=1e-5)
+    dy = torch.full((M, N), float("nan"), device=_dev(), dtype=bf16)
+    sums = torch.zeros(outer, 2, N, device=_dev())
+    raw.tapgemm(a, w, dy, M=M, N=N, K=K, block_n=bn, gnb=dict(x=x1, x2=x2, ab=ab, rows=rows, silu=silu, sum=sums))
+    torch.cuda.synchronize()
+    _close(dy, a.float() @ w.float().t(), what="dy")
+    # the sums against fp32 math on the stored bf16 dy
+    z = x.float() * scale.repeat_interleave(rows, 0) + shift.repeat_interleave(rows, 0)
+    e = dy.float() * ((torch.sigmoid(z) * (1 + z * (1 - torch.sigmoid(z)))) if silu else 1.0)
+    S = e.view(outer, rows, N).sum(1)
+    SX = (e * x.float()).view(outer, rows, N).sum(1)
+    tol = 2e-3 * (e.abs().view(outer, rows, N).sum(1).max().item())
+    assert (sums[:, 0] - S).abs().max().item() < tol and (sums[:, 1] - SX).abs().max().item() < 2 * tol
+    dx = torch.full((M, N), float("nan"), device=_dev(), dtype=bf16)
+    dgamma = torch.zeros(N, device=_dev())
+    dbeta = torch.zeros(N, device=_dev())
+    dres = _rand(M, N, seed=10).to(bf16) if not concat else None
+    raw.groupnorm_bwd_fused(x1, x2, dy, outer, rows, mean, rstd, gamma, beta, silu, sums, dx[:, :C1] if concat else dx,
+                            dx[:, C1:] if concat else None, dgamma, dbeta, dres=dres)
+    torch.cuda.synchronize()
+    dxr, dgr, dbr = _gnb_reference(x, dy, outer, rows, gamma, beta, silu)
+    _close(dx, dxr + (dres.float() if dres is not None else 0), what="fused groupnorm dx")
+    _close(dgamma, dgr, what="fused groupnorm dgamma")
+    _close(dbeta, dbr, what="fused groupnorm dbeta")
+
+
+def test_groupnorm_backward_sums_conv3x3(raw):
+    Nimg, H, W, Cin, Cout = 14, 20, 32, 128, 640
+    M = Nimg * H * W
+    g = _rand(Nimg, H, W, Cin, seed=20).to(bf16)
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=21).to(bf16)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9 * Cin)
+    x = (_rand(M, Cout, seed=5) + 0.3).to(bf16)
+    gamma = _rand(Cout, seed=7) * 0.2 + 1.0
+    beta = _rand(Cout, seed=8) * 0.1
+    rows = H * W
+    mean, rstd = raw.groupnorm_stats(x, None, Nimg, rows, 1e-5)
+    y = torch.empty(M, Cout, device=_dev(), dtype=bf16)
+    ab = torch.empty(Nimg, 2, Cout, device=_dev())
+    raw.groupnorm_apply(x, None, Nimg, rows, mean, rstd, gamma, beta, True, y, ab=ab)
+    dy = torch.empty(M, Cout, device=_dev(), dtype=bf16)
+    sums = torch.zeros(Nimg, 2, Cout, device=_dev())
+    raw.tapgemm(g.view(-1, Cin), wk, dy, M=M, N=Cout, K=Cin, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, Nimg),
+                gnb=dict(x=x, x2=None, ab=ab, rows=rows, silu=True, sum=sums))
+    dx = torch.empty(M, Cout, device=_dev(), dtype=bf16)
+    raw.groupnorm_bwd_fused(x, None, dy, Nimg, rows, mean, rstd, gamma, beta, True, sums, dx, None)
+    torch.cuda.synchronize()
+    dxr, _, _ = _gnb_reference(x, dy, Nimg, rows, gamma, beta, True)
+    _close(dx, dxr, what="conv dgrad + fused groupnorm backward")
