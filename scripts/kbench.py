@@ -189,7 +189,47 @@ def sec_gemm():
         print(f"  {name:28s}: " + "  ".join(f"{'*' if bn == pick else ''}bn{bn}: {t:6.1f} us ({fl / t / 1e6:5.0f} TF/s)" for bn, t in res), flush=True)
 
 
-SECTIONS = {"gemm": sec_gemm, "gn": sec_gn, "ln": sec_ln, "attn": sec_attn, "wgrad": sec_wgrad}
+def sec_gnb():
+    print("# GroupNorm backward: pass 1 inside the dgrad epilogue (gnb) vs the separate partial kernel; us per launch in a graph")
+    for name, T, H, W, C, taps in [("conv3x3 40x64 C320", 14, 40, 64, 320, 9), ("conv3x3 20x32 C640", 14, 20, 32, 640, 9),
+                                   ("conv(3,1,1) 40x64 C320", 14, 40, 64, 320, 3), ("conv(3,1,1) 20x32 C640", 14, 20, 32, 640, 3),
+                                   ("linear 40x64 C320", 14, 40, 64, 320, 1)]:
+        M = T * H * W
+        rows = H * W
+        k = rot(M * C * 2 * 4)
+        gs = [torch.randn(M, C, device=DEV).to(bf16) for _ in range(k)]          # upstream gradient (A operand of the dgrad)
+        xs = [torch.randn(M, C, device=DEV).to(bf16) for _ in range(k)]          # GroupNorm input
+        dys = [torch.empty(M, C, device=DEV, dtype=bf16) for _ in range(k)]
+        dxs = [torch.empty(M, C, device=DEV, dtype=bf16) for _ in range(k)]
+        w = (torch.randn(C, taps * C, device=DEV) * (taps * C) ** -0.5).to(bf16)
+        gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+        st = [raw.groupnorm_stats(x, None, T, rows, 1e-5) for x in xs]
+        abs_ = [torch.empty(T, 2, C, device=DEV) for _ in range(k)]
+        for x, s_, ab, y in zip(xs, st, abs_, dys):
+            raw.groupnorm_apply(x, None, T, rows, s_[0], s_[1], gamma, beta, True, y, ab=ab)
+        sums = torch.zeros(T, 2, C, device=DEV)
+        ws = torch.zeros(2 * T * 32, device=DEV)
+
+        def dgrad(g, dy, gnb):
+            kw = {} if gnb is None else {"gnb": gnb}
+            if taps == 9:
+                raw.tapgemm(g, w, dy, M=M, N=C, K=C, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, T), **kw)
+            elif taps == 3:
+                raw.tapgemm(g, w, dy, M=M, N=C, K=C, taps=((-rows, 0, 0), (0, 0, 0), (rows, 0, 0)), rows_per_group=M, groups=1, **kw)
+            else:
+                raw.tapgemm(g, w, dy, M=M, N=C, K=C, **kw)
+        t_plain = graph_time([lambda g=g, dy=dy: dgrad(g, dy, None) for g, dy in zip(gs, dys)], reps=5)
+        t_gnb = graph_time([lambda g=g, dy=dy, x=x, ab=ab: dgrad(g, dy, dict(x=x, x2=None, ab=ab, rows=rows, silu=True, sum=sums))
+                            for g, dy, x, ab in zip(gs, dys, xs, abs_)], reps=5)
+        t_two = graph_time([lambda x=x, dy=dy, dx=dx, s_=s_: raw.groupnorm_bwd(x, None, dy, T, rows, s_[0], s_[1], gamma, beta, True, dx, None, ws=ws)
+                            for x, dy, dx, s_ in zip(xs, dys, dxs, st)], reps=5)
+        t_one = graph_time([lambda x=x, dy=dy, dx=dx, s_=s_: raw.groupnorm_bwd_fused(x, None, dy, T, rows, s_[0], s_[1], gamma, beta, True, sums, dx, None)
+                            for x, dy, dx, s_ in zip(xs, dys, dxs, st)], reps=5)
+        print(f"  {name:26s}: dgrad {t_plain:6.1f} us, with gnb sums {t_gnb:6.1f} us (+{t_gnb - t_plain:5.1f}) | GroupNorm bwd two kernels {t_two:6.1f} us, "
+              f"fused one kernel {t_one:6.1f} us (-{t_two - t_one:5.1f}) | net {t_gnb - t_plain - (t_two - t_one):+6.1f} us", flush=True)
+
+
+SECTIONS = {"gnb": sec_gnb, "gemm": sec_gemm, "gn": sec_gn, "ln": sec_ln, "attn": sec_attn, "wgrad": sec_wgrad}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)

@@ -184,7 +184,7 @@ class Engine:
         writer of its gradient: the epilogue then also accumulates pass 1 of the GroupNorm backward (per-channel sums), and
         the GroupNorm's backward is ONE launch with one pass over x and dy. None when the launch cannot carry them."""
         ctx = x.gnb
-        if ctx is None or not self.fuse_gn_bwd or scales is not None or x.grad is not None or N % 32 or M % ctx["rows"] or N != ctx["C"]:
+        if ctx is None or not self.fuse_gn_bwd or scales is not None or x.grad is not None or N % 32 or M % ctx["rows"] or N != ctx["C"] or M <= 8:
             return None
         if raw.split_plan(True, M, N, K, ntaps) is not None:
             return None
@@ -441,8 +441,12 @@ class Engine:
                 if x.needs_grad:
                     wt = self.w_lin_cat(ws, True) if fused is not None else self.w_lin(weight, True)
                     dx = self.empty(M, K, x.data)
-                    raw.tapgemm_auto(dyl, wt, dx, M=M, N=K, K=N, scales=sc3)
+                    # x a GroupNorm output (the transformers' proj_in): pass 1 of its backward rides in this epilogue
+                    gnb = None if lora else self._gnb_for(x, M, K, N, 1, sc3, dyl.device)
+                    raw.tapgemm_auto(dyl, wt, dx, M=M, N=K, K=N, scales=sc3, **({} if gnb is None else {"gnb": gnb}))
                     self.add_grad(x, dx)
+                    if gnb is not None:
+                        x.gnb_sums = (gnb["sum"], dx)
                 if any(p.requires_grad for p in ws):
                     self._wgrad(dyl, x.data, ws, N, K, M, sc3)
                 if bias is not None and bias.requires_grad and not bias_done:
