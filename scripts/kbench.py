@@ -229,7 +229,31 @@ def sec_gnb():
               f"fused one kernel {t_one:6.1f} us (-{t_two - t_one:5.1f}) | net {t_gnb - t_plain - (t_two - t_one):+6.1f} us", flush=True)
 
 
-SECTIONS = {"gnb": sec_gnb, "gemm": sec_gemm, "gn": sec_gn, "ln": sec_ln, "attn": sec_attn, "wgrad": sec_wgrad}
+def sec_res():
+    print("# GEMMs / convs with the residual epilogue (+res1, cold residual), us per launch in a graph, default tile width")
+    for name, T, H, W, K, N, taps in [("linear M35840 N320 K320", 14, 40, 64, 320, 320, 1), ("linear M35840 N320 K1280", 14, 40, 64, 1280, 320, 1),
+                                      ("conv 40x64 C320", 14, 40, 64, 320, 320, 9), ("linear M8960 N640 K640", 14, 20, 32, 640, 640, 1),
+                                      ("linear M8960 N640 K2560", 14, 20, 32, 2560, 640, 1), ("conv 20x32 C640", 14, 20, 32, 640, 640, 9),
+                                      ("linear M2240 N1280 K1280", 14, 10, 16, 1280, 1280, 1), ("linear M2240 N1280 K5120", 14, 10, 16, 5120, 1280, 1)]:
+        M = T * H * W
+        k = rot((M * K + 2 * M * N) * 2)
+        xs = [torch.randn(M, K, device=DEV).to(bf16) for _ in range(k)]
+        rs = [torch.randn(M, N, device=DEV).to(bf16) for _ in range(k)]
+        w = (torch.randn(N, taps * K, device=DEV) * (taps * K) ** -0.5).to(bf16)
+        outs = [torch.empty(M, N, device=DEV, dtype=bf16) for _ in range(k)]
+        bias = torch.randn(N, device=DEV)
+
+        def f(x, o, r):
+            if taps == 9:
+                raw.tapgemm(x, w, o, M=M, N=N, K=K, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, T), bias=bias, res1=r)
+            else:
+                raw.tapgemm(x, w, o, M=M, N=N, K=K, bias=bias, res1=r)
+        t0 = graph_time([lambda x=x, o=o: f(x, o, None) for x, o in zip(xs, outs)], reps=5)
+        t1 = graph_time([lambda x=x, o=o, r=r: f(x, o, r) for x, o, r in zip(xs, outs, rs)], reps=5)
+        print(f"  {name:28s}: plain {t0:6.1f} us | +res1 {t1:6.1f} us (+{t1 - t0:5.1f})", flush=True)
+
+
+SECTIONS = {"gnb": sec_gnb, "res": sec_res, "gemm": sec_gemm, "gn": sec_gn, "ln": sec_ln, "attn": sec_attn, "wgrad": sec_wgrad}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)

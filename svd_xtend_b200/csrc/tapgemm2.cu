@@ -313,11 +313,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) tapg
       const int rin = t * BLOCK_M + q * 32 + lane;
       const bool row_ok = rin < p.rows_per_group;
       const long long m = (long long)g * p.rows_per_group + rin;
+      const long long m0 = (long long)g * p.rows_per_group + st.row0;        // fused GroupNorm statistics: first row / rows that exist
+      const int valid_rows = max(0, min(32, p.rows_per_group - st.row0));
+      if constexpr (EPI == EPI_RES || EPI == EPI_RES_GN || EPI == EPI_FAST_GNB)
+        prefetch_epilogue_operands(p, EPI, m0, valid_rows, nt * bn_out, bn_out, n_out_total, lane, half);
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (WIDE ? acc * WIDE_ACC1 : acc * 256) + ((uint32_t)(q * 32) << 16);
-      const long long m0 = (long long)g * p.rows_per_group + st.row0;        // fused GroupNorm statistics: first row / rows that exist
-      const int valid_rows = max(0, min(32, p.rows_per_group - st.row0));
       if constexpr (WIDE) {
         // accumulator columns shared with the next tile's accumulator first: [192, 320) of an even tile, [0, 128) of an odd one
         const int lo1 = acc ? 0 : WIDE_ACC1, hi1 = acc ? 320 - WIDE_ACC1 : 320;

@@ -231,6 +231,33 @@ SVDX_DEVINL void stage_row_bf16(uint32_t row, int sw, const float (&f)[32]) {
                  pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
 }
 
+// Epilogue operands that are read per chunk (the residual of EPI_RES, the GroupNorm input of EPI_FAST_GNB) are usually not in L2
+// any more; a warp has ONE chunk's loads in flight, so the fetch was latency-bound (+12 us on a 15 us K = 320 residual GEMM,
+// +20 us on a conv dgrad with the backward sums). Each epilogue warp therefore requests its 32 rows x bn columns of the tile
+// into L2 BEFORE it waits for the accumulator: the lines arrive during the main loop. Lane = row; the two warps of a lane
+// quarter take alternate 128-byte lines.
+SVDX_DEVINL void prefetch_rows_l2(const bf16* base, long long ld, long long m0, int valid_rows, int col0, int ncols, int lane, int half) {
+  if (!base || lane >= valid_rows) return;
+  const char* row = reinterpret_cast<const char*>(base + (m0 + lane) * ld + col0);
+  const int bytes = ncols * 2;
+  for (int b = half * 128; b < bytes; b += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+}
+SVDX_DEVINL void prefetch_epilogue_operands(const TapGemmKParams& p, int epi, long long m0, int valid_rows, int n0, int bn_out, int n_out_total,
+                                            int lane, int half) {
+  const int ncols = min(bn_out, n_out_total - n0);
+  if (ncols <= 0) return;
+  if (epi == EPI_RES || epi == EPI_RES_GN) {
+    prefetch_rows_l2(p.res1, p.ldr1, m0, valid_rows, n0, ncols, lane, half);
+    prefetch_rows_l2(p.res2, p.ldr2, m0, valid_rows, n0, ncols, lane, half);
+  } else if (epi == EPI_FAST_GNB) {
+    if (n0 < p.gnb_c1) prefetch_rows_l2(p.gnb_x, p.gnb_ldx, m0, valid_rows, n0, min(ncols, p.gnb_c1 - n0), lane, half);
+    if (n0 + ncols > p.gnb_c1) {
+      const int c0 = max(n0, p.gnb_c1);
+      prefetch_rows_l2(p.gnb_x2, p.gnb_ldx2, m0, valid_rows, c0 - p.gnb_c1, n0 + ncols - c0, lane, half);
+    }
+  }
+}
+
 // plain epilogue (bias / row-bias only): two 32-column chunks per round (both staging halves), one proxy fence and one
 // bulk group per round.
 template <bool GN>
