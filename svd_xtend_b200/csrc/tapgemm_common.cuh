@@ -324,19 +324,51 @@ SVDX_DEVINL void gnb_chunk_sums(const TapGemmKParams& p, uint32_t buf_dy, uint32
       B = *reinterpret_cast<const float2*>(p.gnb_ab + (2 * slab + 1) * p.N + col);
     }
     float s0 = 0.f, s1 = 0.f, x0 = 0.f, x1 = 0.f;
-    for (int rr = r + ((h ^ r) & 1); rr < seg_end; rr += 2) {
-      const uint32_t off = rr * 64 + ((uint32_t)(jch ^ ((rr >> 1) & 3)) << 4) + in_chunk;
-      uint32_t wd, wx;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd) : "r"(buf_dy + off));
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wx) : "r"(buf_x + off));
-      const float2 d = unpack_bf16x2(wd), xv = unpack_bf16x2(wx);
-      float e0 = d.x, e1 = d.y;
-      if (p.gnb_silu) {
-        e0 *= silu_grad_f(fmaf(xv.x, A.x, B.x));
-        e1 *= silu_grad_f(fmaf(xv.y, A.y, B.y));
+    if (r == 0 && seg_end == 32) {
+      // the common case (a whole 32-row chunk inside one slab): rows h, h + 2, ... in two unrolled batches of 8 so that the
+      // sigmoid chains (ex2 -> rcp) of different rows overlap; the rolled loop below ran one dependent chain at a time
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        uint32_t wd[8], wx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = h + 2 * (8 * b + i);
+          const uint32_t off = rr * 64 + ((uint32_t)(jch ^ ((rr >> 1) & 3)) << 4) + in_chunk;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd[i]) : "r"(buf_dy + off));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wx[i]) : "r"(buf_x + off));
+        }
+        float e0[8], e1[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 d = unpack_bf16x2(wd[i]), xv = unpack_bf16x2(wx[i]);
+          e0[i] = d.x; e1[i] = d.y;
+          if (p.gnb_silu) {
+            e0[i] *= silu_grad_f(fmaf(xv.x, A.x, B.x));
+            e1[i] *= silu_grad_f(fmaf(xv.y, A.y, B.y));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 xv = unpack_bf16x2(wx[i]);
+          s0 += e0[i]; s1 += e1[i];
+          x0 = fmaf(e0[i], xv.x, x0); x1 = fmaf(e1[i], xv.y, x1);
+        }
       }
-      s0 += e0; s1 += e1;
-      x0 = fmaf(e0, xv.x, x0); x1 = fmaf(e1, xv.y, x1);
+    } else {
+      for (int rr = r + ((h ^ r) & 1); rr < seg_end; rr += 2) {
+        const uint32_t off = rr * 64 + ((uint32_t)(jch ^ ((rr >> 1) & 3)) << 4) + in_chunk;
+        uint32_t wd, wx;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd) : "r"(buf_dy + off));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wx) : "r"(buf_x + off));
+        const float2 d = unpack_bf16x2(wd), xv = unpack_bf16x2(wx);
+        float e0 = d.x, e1 = d.y;
+        if (p.gnb_silu) {
+          e0 *= silu_grad_f(fmaf(xv.x, A.x, B.x));
+          e1 *= silu_grad_f(fmaf(xv.y, A.y, B.y));
+        }
+        s0 += e0; s1 += e1;
+        x0 = fmaf(e0, xv.x, x0); x1 = fmaf(e1, xv.y, x1);
+      }
     }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
     x0 += __shfl_xor_sync(0xffffffffu, x0, 16); x1 += __shfl_xor_sync(0xffffffffu, x1, 16);
