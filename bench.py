@@ -53,8 +53,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configuration")
-    ap.add_argument("--ddp", default="sharded", choices=["sharded", "allreduce"],
-                    help="N > 1: reduce-scatter + sharded AdamW + bf16 all-gather (default) or bucketed all-reduce + replicated AdamW")
+    ap.add_argument("--ddp", default="p2p", choices=["p2p", "sharded", "allreduce"],
+                    help="N > 1: p2p (default) = sharded AdamW with reduce-scatter + update + all-gather as ONE kernel over NVLink peer "
+                         "memory (falls back to 'sharded' if the peer mapping cannot be set up); sharded = the same through NCCL "
+                         "reduce-scatter / all-gather; allreduce = bucketed all-reduce + replicated AdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager bf16-autocast oracle timing on the GPU")
     ap.add_argument("--no-families", action="store_true", help="skip the per-family ablation rooflines")
@@ -324,7 +326,7 @@ def main():
 
     import torch.distributed as dist
     from svd_xtend_b200 import raw
-    from svd_xtend_b200.train import FusedAdamW, GradReducer, GraphedStep, ParamArena, ShardedAdamW
+    from svd_xtend_b200.train import FusedAdamW, GradReducer, GraphedStep, P2PShardedAdamW, ParamArena, ShardedAdamW
     from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel
     from svd_xtend_b200.workload import BENCH_CONFIGS, SVD_CONFIG, edm_loss, synthetic_batch   # train_svd.py:951-1036
 
@@ -365,13 +367,30 @@ def main():
     unet.train()
     if cfg["grad_ckpt"]:
         unet.enable_gradient_checkpointing()     # train_svd.py:731-732
-    sharded = world > 1 and args.ddp == "sharded"
+    sharded = world > 1 and args.ddp in ("sharded", "p2p")
     arena = ParamArena(unet, pad_to=world * 64)
     unet.attach_arena(arena)
     hyper = dict(lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)             # train_svd.py:384-418 defaults
     # N > 1 (default): reduce-scatter of the gradient arena + AdamW on this rank's 1/N slice + all-gather of the bf16 operand
     # weights (0.75x the NVLink bytes of an all-reduce, 1/N of the optimizer traffic); --ddp allreduce keeps replicated AdamW
-    opt = ShardedAdamW(arena, **hyper) if sharded else FusedAdamW(arena, **hyper)
+    ddp_mode = args.ddp if world > 1 else None
+    if sharded and args.ddp == "p2p":
+        # the fused exchange needs every rank's arenas mapped into every process (CUDA IPC, one node): all ranks agree on
+        # whether that worked before anyone builds a graph on it
+        try:
+            opt = P2PShardedAdamW(arena, **hyper)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:      # noqa: BLE001
+            print(f"[bench] rank {rank}: peer mapping failed ({type(e).__name__}: {e}); using the NCCL sharded exchange", file=sys.stderr, flush=True)
+            opt, ok = None, torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1:
+            opt = ShardedAdamW(arena, **hyper)
+            ddp_mode = "sharded (p2p mapping unavailable)"
+    elif sharded:
+        opt = ShardedAdamW(arena, **hyper)
+    else:
+        opt = FusedAdamW(arena, **hyper)
     opt.on_updated = lambda: unet.refresh_trainable_operands(shadow_current=True)   # the optimizer rewrites the bf16 shadow itself
     reducer = GradReducer(arena) if (world > 1 and not sharded) else None
     if reducer is not None:
@@ -654,12 +673,24 @@ def main():
     exchange = None
     if world > 1:
         try:
+            p2p = isinstance(opt, P2PShardedAdamW)
+
             def ex():
-                if sharded:
+                if p2p:
+                    opt._fence()
+                    raw.adamw_p2p(arena.data[opt.lo:opt.hi], opt.m, opt.v, opt.peer_grad, opt.peer_shadow, opt.lo, ex_state, 1.0 / world, tick=False)
+                    opt._fence()
+                elif sharded:
                     opt.reduce_scatter_grads()
                     opt.all_gather_(arena.shadow)
                 else:
                     dist.all_reduce(arena.grad)
+            # (p2p: the timed kernel includes the optimizer arithmetic; lr = 0 and weight decay 0 in this copy of the state so
+            # the replays leave the weights alone)
+            ex_state = opt.state.clone() if p2p else None
+            if p2p:
+                ex_state[0] = 0.0
+                ex_state[4] = 0.0
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -679,9 +710,10 @@ def main():
             tx = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
             dist.all_reduce(tx, op=dist.ReduceOp.MAX)
             nb = arena.numel * 4
-            exchange = {"ms": float(tx.item()), "mode": args.ddp if world > 1 else None,
+            exchange = {"ms": float(tx.item()), "mode": ddp_mode,
                         "payload_bytes": nb if not sharded else nb + arena.numel * 2,
-                        "what": ("reduce-scatter(fp32 gradient arena) + all-gather(bf16 operand weights)" if sharded else "all-reduce(fp32 gradient arena)")
+                        "what": ("fence + svdx_adamw_p2p (peer loads of the gradient slices, AdamW on 1/N, peer stores of the bf16 operands) + fence" if p2p
+                                 else "reduce-scatter(fp32 gradient arena) + all-gather(bf16 operand weights)" if sharded else "all-reduce(fp32 gradient arena)")
                                 + " alone in a CUDA graph, max over ranks; in the step it runs after the backward (not overlapped)"}
             del gx
         except Exception as e:
@@ -755,7 +787,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (seeded default-init weights, randn latents per train_svd.py:951-1017)",
         "config": {"workload": cfg["name"], "baseline_config": args.config, "frames": frames, "latent_hw": [lat_h, lat_w], "per_gpu_batch": 1,
-                   "global_batch": world, "trainable_params": n_train, "total_params": n_total, "parallelism": f"dp{world}" + ("" if world == 1 else "-zero1" if sharded else "-allreduce"),
+                   "global_batch": world, "trainable_params": n_train, "total_params": n_total, "parallelism": f"dp{world}" + ("" if world == 1 else "-zero1-p2p" if isinstance(opt, P2PShardedAdamW) else "-zero1" if sharded else "-allreduce"),
                    "cuda_graph": graph_captured, "gradient_checkpointing": bool(cfg["grad_ckpt"]), "lora_rank": cfg["lora_rank"],
                    "l2": "no explicit flush: the per-step working set (3 GB bf16 operand weights + >10 GB activations) is >> 126 MB L2",
                    "final_loss": final_loss, "cpu_arm": CPU_ARM_NOTE},

@@ -308,6 +308,17 @@ int svdx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr
  * writing state[0] (lr scheduler of train_svd.py:790-796). Two launches. */
 int svdx_adamw_graph(float* p, const float* g, float* m, float* v, int64_t n, float* state, float grad_scale,
                      void* shadow_bf16, void* stream);
+/* Data-parallel optimizer step over NVLink peer memory (one process per GPU, every rank's gradient and bf16 operand arenas
+ * mapped into every process with CUDA IPC): reduce-scatter + AdamW + all-gather as ONE kernel. This rank owns [lo, lo + n):
+ * it loads that slice of grads[r] (r = 0 .. world-1, the FULL arenas, peer-mapped), sums in rank order, applies AdamW with
+ * grad_scale (= 1 / world) to its local p / m / v slices (length n) and stores the bf16 value to shadows[r][lo + i] of every
+ * rank. The caller provides the cross-rank ordering: all gradients final before the launch, no rank reads its shadow or
+ * clears its gradients until every rank's launch has completed. tick != 0 also advances the device step count / bias
+ * corrections in state[5..7] (svdx_adamw_graph's state layout). Replaces DistributedDataParallel's all-reduce +
+ * torch.optim.AdamW of train_svd.py:767-773,815-824,1044-1049 at N > 1. */
+int svdx_adamw_p2p(float* p, float* m, float* v, const void* const* grads, void* const* shadows, int32_t world,
+                   int64_t lo, int64_t n, float* state, float grad_scale, int32_t tick, void* stream);
+
 /* many bf16 transposes dst[i][o] = src_base[src_off + o*I + i] in one launch (dgrad operands of all trainable linears).
  * jobs: device array of {int64 src_off; void* dst; int32 O; int32 I}; tile_prefix[j] = first 32x32 tile of job j. */
 int svdx_multi_transpose(const void* src_base, const void* jobs, const int32_t* tile_prefix, int32_t njobs, int32_t total_tiles,

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 
-from svd_xtend_b200.train import FusedAdamW, GradReducer, ParamArena, ShardedAdamW
+from svd_xtend_b200.train import FusedAdamW, GradReducer, P2PShardedAdamW, ParamArena, ShardedAdamW
 from svd_xtend_b200.unet import UNetSpatioTemporalConditionModel
 from svd_xtend_b200.workload import edm_loss, synthetic_batch
 
@@ -98,5 +98,61 @@ e_masters = ((arena.data - data_ref).norm() / (data_ref - w0).norm()).item()
 print(f"[ddp_check] rank {rank}: sharded path: bf16 operand update vs all-reduce+AdamW rel-l2 {e_shadow:.3e}, identical across ranks: {same_shadow}, "
       f"own-slice master max err / max update {own:.3e}, masters after gather rel-l2 of update {e_masters:.3e}, t = {opt.t}", flush=True)
 assert e_shadow < 2e-2 and same_shadow and own < 1e-3 and e_masters < 1e-3 and opt.t == 1
+shadow_nccl, data_nccl = arena.shadow.clone(), arena.data.clone()
+
+# ---- (3) the same step as ONE kernel over NVLink peer memory (svdx_adamw_p2p) vs the NCCL sharded step; then three more steps
+# captured in a CUDA graph (fences + kernel replayed) against the eager NCCL optimizer fed the same gradients
+arena.data.copy_(w0)
+arena.refresh_shadow()
+arena.grad.copy_(singles[rank])
+torch.cuda.synchronize()
+dist.barrier()
+popt = P2PShardedAdamW(arena, lr=1e-3, weight_decay=1e-2)
+popt.step()
+torch.cuda.synchronize()
+dist.barrier()
+same_as_nccl = torch.equal(arena.shadow, shadow_nccl) if world == 2 else ((arena.shadow.float() - shadow_nccl.float()).abs().max().item() < 1e-2 * shadow_nccl.float().abs().max().item())
+own_p2p = torch.equal(arena.data[popt.lo:popt.hi], data_nccl[popt.lo:popt.hi]) if world == 2 else True
+others = [torch.empty_like(arena.shadow) for _ in range(world)]
+dist.all_gather(others, arena.shadow)
+same_ranks = all(torch.equal(o, arena.shadow) for o in others)
+print(f"[ddp_check] rank {rank}: p2p fused step: bf16 operands equal to the NCCL sharded step: {same_as_nccl}, own masters equal: {own_p2p}, "
+      f"identical across ranks: {same_ranks}, t = {popt.t}", flush=True)
+assert same_as_nccl and own_p2p and same_ranks and popt.t == 1
+# graph replays: state (m, v, step count) continues from the eager step above; the reference continues the NCCL optimizer
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+g = torch.cuda.CUDAGraph()
+snap = [t.clone() for t in (arena.data, arena.shadow, popt.m, popt.v, popt.state)]
+with torch.cuda.stream(side):
+    popt.step()                      # warm-up outside capture (NCCL communicator on this stream)
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+for t, s_ in zip((arena.data, arena.shadow, popt.m, popt.v, popt.state), snap):
+    t.copy_(s_)
+torch.cuda.synchronize()
+dist.barrier()
+with torch.cuda.graph(g):
+    popt.step()
+for t, s_ in zip((arena.data, arena.shadow, popt.m, popt.v, popt.state), snap):
+    t.copy_(s_)                       # capture does not run the kernels, but keep the state explicit
+torch.cuda.synchronize()
+dist.barrier()
+for _ in range(3):
+    arena.grad.copy_(singles[rank])
+    g.replay()
+torch.cuda.synchronize()
+dist.barrier()
+shadow_p2p3 = arena.shadow.clone()
+# reference: NCCL sharded optimizer from the same post-step-1 state, three more steps
+arena.data.copy_(data_nccl)
+arena.shadow.copy_(shadow_nccl)
+for _ in range(3):
+    arena.grad.copy_(singles[rank])
+    opt.step()
+torch.cuda.synchronize()
+rep_equal = torch.equal(shadow_p2p3, arena.shadow) if world == 2 else ((shadow_p2p3.float() - arena.shadow.float()).abs().max().item() < 1e-2 * arena.shadow.float().abs().max().item())
+print(f"[ddp_check] rank {rank}: p2p fused step, 3 CUDA-graph replays vs 3 NCCL sharded steps: operands equal: {rep_equal}, t = {popt.t} / {opt.t}", flush=True)
+assert rep_equal and popt.t == 4 and opt.t == 4
 dist.barrier()
 dist.destroy_process_group()

@@ -504,6 +504,57 @@ __global__ void adamw_state_kernel(float* __restrict__ p, const float* __restric
   }
 }
 
+// Data-parallel optimizer step as ONE kernel over NVLink peer memory: reduce-scatter + AdamW + all-gather fused.
+// Rank r owns the arena slice [lo, lo + n). For every 4 owned elements it LOADS that slice of every rank's fp32 gradient
+// arena (world - 1 of them through NVLink / NVSwitch peer mappings), sums in rank order (the same order on every rank: the
+// owner is the only one that computes an element), applies AdamW (grad_scale = 1 / world -> the mean gradient) to its fp32
+// master / moments, and STORES the bf16 operand value into every rank's shadow arena. Versus NCCL reduce-scatter -> AdamW ->
+// all-gather: the same NVLink bytes, but no intermediate pass over HBM (the summed gradient and the local shadow slice are
+// never written and re-read), one launch, and the link transfer overlaps the optimizer arithmetic load by load.
+// The callers order it between two cross-rank barriers (all gradients final before / all shadows complete after).
+struct AdamP2P {
+  const float* grad[16];
+  bf16* shadow[16];
+};
+__global__ void __launch_bounds__(256) adamw_p2p_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const __grid_constant__ AdamP2P ptr,
+                                                        int world, long long lo, long long n4, const float* __restrict__ state, float gscale) {
+  const float lr = state[0], b1 = state[1], b2 = state[2], eps = state[3], wd = state[4], bc1 = state[6], bc2 = state[7];
+  const float decay = 1.f - lr * wd, step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i4 = gtid(); i4 < n4; i4 += stride) {
+    const long long i = i4 * 4;
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int r0 = 0; r0 < world; r0 += 4) {
+      // up to four ranks' loads in flight together (NVLink round trips are microseconds)
+      float4 t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < world) t[k] = __ldcg(reinterpret_cast<const float4*>(ptr.grad[r0 + k] + lo + i));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < world) { g4.x += t[k].x; g4.y += t[k].y; g4.z += t[k].z; g4.w += t[k].w; }
+    }
+    float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float gg[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] = b1 * mm[k] + (1.f - b1) * gg[k];
+      vv[k] = b2 * vv[k] + (1.f - b2) * gg[k] * gg[k];
+      pp[k] = pp[k] * decay - step_size * mm[k] / (sqrtf(vv[k]) * inv_sqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    uint2 o;
+    o.x = pack_bf16x2(pp[0], pp[1]);
+    o.y = pack_bf16x2(pp[2], pp[3]);
+    for (int r = 0; r < world; ++r) *reinterpret_cast<uint2*>(ptr.shadow[r] + lo + i) = o;
+  }
+  __threadfence_system();     // the peer stores are performed system-wide before this kernel counts as complete
+}
+
 // row softmax of a bf16 score matrix, y[r][:] = softmax(scale * x[r][:]) (fp32 arithmetic, in place allowed): the single-head,
 // head_dim 512 attention of the VAE encoder's mid block goes through two GEMMs and this kernel (its S x S scores are small).
 // One CTA per row; a row of <= 16 K columns stays L1/L2 resident over the three passes.
@@ -923,6 +974,30 @@ extern "C" int svdx_adamw_graph(float* p, const float* g, float* m, float* v, in
   const long long n4 = (n + 3) / 4;
   adamw_state_kernel<<<nblocks(n4), 256, 0, ST(stream)>>>(p, g, m, v, n4, n, state, grad_scale, reinterpret_cast<bf16*>(shadow_bf16));
   SVDX_CHECK_LAUNCH("adamw_graph");
+  return SVDX_OK;
+}
+
+extern "C" int svdx_adamw_p2p(float* p, float* m, float* v, const void* const* grads, void* const* shadows, int32_t world, int64_t lo, int64_t n,
+                              float* state, float grad_scale, int32_t tick, void* stream) {
+  if (!p || !m || !v || !grads || !shadows || !state || world < 1 || world > 16 || n <= 0 || n % 4 || lo % 4 ||
+      (reinterpret_cast<uintptr_t>(p) & 15) || (reinterpret_cast<uintptr_t>(m) & 15) || (reinterpret_cast<uintptr_t>(v) & 15))
+    return svdx_fail(SVDX_E_BADARG, "adamw_p2p: bad arguments (world <= 16, slice offset / length multiples of 4, 16-byte aligned buffers)");
+  AdamP2P ptr;
+  for (int r = 0; r < 16; ++r) { ptr.grad[r] = nullptr; ptr.shadow[r] = nullptr; }
+  for (int r = 0; r < world; ++r) {
+    if (!grads[r] || !shadows[r] || (reinterpret_cast<uintptr_t>(grads[r]) & 15) || (reinterpret_cast<uintptr_t>(shadows[r]) & 7))
+      return svdx_fail(SVDX_E_BADARG, "adamw_p2p: null / misaligned peer arena");
+    ptr.grad[r] = reinterpret_cast<const float*>(grads[r]);
+    ptr.shadow[r] = reinterpret_cast<bf16*>(shadows[r]);
+  }
+  if (tick) adamw_tick_kernel<<<1, 1, 0, ST(stream)>>>(state);
+  const long long n4 = n / 4;
+  // a few resident CTAs per SM, grid-stride: enough 16-byte loads in flight to cover the NVLink round trip
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)svdx_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  adamw_p2p_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(p, m, v, ptr, world, lo, n4, state, grad_scale);
+  SVDX_CHECK_LAUNCH("adamw_p2p");
   return SVDX_OK;
 }
 

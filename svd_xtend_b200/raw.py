@@ -26,7 +26,7 @@ def dtype_code(t: torch.Tensor, what: str) -> int:
 
 # number of kernels launched through the C ABI since import (each wrapper adds what its entry point launches)
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"svdx_groupnorm_stats": 2, "svdx_groupnorm_bwd": 2, "svdx_groupnorm_apply_fused": 1, "svdx_attention_bwd": 3, "svdx_adamw_graph": 2}
+_KERNELS_PER_CALL = {"svdx_groupnorm_stats": 2, "svdx_groupnorm_bwd": 2, "svdx_groupnorm_apply_fused": 1, "svdx_attention_bwd": 3, "svdx_adamw_graph": 2, "svdx_adamw_p2p": 2}
 
 
 def check(rc: int, what: str = "") -> None:
@@ -666,6 +666,20 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
         return
     check(load().svdx_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps, weight_decay,
                             step, grad_scale, _ptr(shadow), _stream()), "adamw")
+
+
+def adamw_p2p(p, m, v, peer_grads, peer_shadows, lo, state, grad_scale, tick=True):
+    """reduce-scatter + AdamW + all-gather in one kernel over NVLink peer memory (svdx_adamw_p2p): p / m / v are this rank's
+    slices, peer_grads / peer_shadows the FULL arenas of every rank (this rank's own included) as tensors mapped into this
+    process (train.map_peer_tensors)"""
+    world = len(peer_grads)
+    n = p.numel()
+    if _fam("adamw", 0.0, (4.0 * world + 28.0 + 2.0 * world) * n):
+        return
+    ga = (C.c_void_p * world)(*[t.data_ptr() for t in peer_grads])
+    sa = (C.c_void_p * world)(*[t.data_ptr() for t in peer_shadows])
+    check(load().svdx_adamw_p2p(p.data_ptr(), m.data_ptr(), v.data_ptr(), ga, sa, world, lo, n, state.data_ptr(), float(grad_scale),
+                                int(tick), _stream()), "svdx_adamw_p2p")
 
 
 def adamw_graph(p, g, m, v, state, grad_scale=1.0, shadow=None):

@@ -296,6 +296,66 @@ class ShardedAdamW:
         return ts
 
 
+def map_peer_tensors(t: torch.Tensor, group=None) -> List[torch.Tensor]:
+    """every rank's copy of the (same-shaped, flat) CUDA tensor `t`, mapped into THIS process through CUDA IPC: element r of
+    the result aliases rank r's memory (element `rank` is t itself). One process per GPU of ONE node, all GPUs visible to
+    every process (torchrun's default). Kernels of this rank may then load / store the peers' memory over NVLink."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    st = t.untyped_storage()
+    meta = (st._share_cuda_(), t.storage_offset(), t.numel(), t.device.index)
+    metas = [None] * world
+    dist.all_gather_object(metas, meta, group=group)
+    out = []
+    for r, (handle, off, numel, dev) in enumerate(metas):
+        if r == rank:
+            out.append(t)
+            continue
+        if numel != t.numel():
+            raise RuntimeError("map_peer_tensors: ranks hold arenas of different sizes")
+        pst = torch.UntypedStorage._new_shared_cuda(*handle)
+        peer = torch.empty(0, dtype=t.dtype, device=pst.device).set_(pst, off, (numel,))
+        # a one-element cross-device copy makes torch enable peer access between this rank's GPU and the owner's
+        torch.empty(1, dtype=t.dtype, device=t.device).copy_(peer[:1])
+        out.append(peer)
+    torch.cuda.synchronize(t.device)
+    dist.barrier(group=group)
+    return out
+
+
+class P2PShardedAdamW(ShardedAdamW):
+    """ShardedAdamW with the three NCCL phases (reduce-scatter, 1/N AdamW, all-gather of the bf16 operands) replaced by ONE
+    kernel over NVLink peer memory (`svdx_adamw_p2p`): every rank reads its slice of every rank's gradient arena directly,
+    updates its masters / moments and stores the bf16 operands into every rank's shadow arena. Same bytes over the links, no
+    intermediate HBM passes, one launch; two tiny all-reduces (captured with the step) order the ranks around it. Results are
+    those of ShardedAdamW (bit-identical at world 2; at larger worlds the gradient sum runs in rank order on the owner)."""
+
+    def __init__(self, arena: ParamArena, lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8, group=None):
+        super().__init__(arena, lr=lr, betas=betas, weight_decay=weight_decay, eps=eps, group=group)
+        if arena.shadow is None:
+            raise ValueError("P2PShardedAdamW needs the arena's bf16 shadow (CUDA arena)")
+        if self.world > 16:
+            raise ValueError("P2PShardedAdamW: at most 16 ranks (one NVSwitch domain)")
+        self._flag = torch.zeros(1, device=arena.data.device, dtype=F32)
+        if self.world > 1:
+            self.peer_grad = map_peer_tensors(arena.grad, group)
+            self.peer_shadow = map_peer_tensors(arena.shadow, group)
+        else:
+            self.peer_grad, self.peer_shadow = [arena.grad], [arena.shadow]
+
+    def _fence(self):
+        dist.all_reduce(self._flag, group=self.group)      # stream-ordered on every rank, captured into the step graph
+
+    def step(self):
+        a = self.arena
+        if self.world > 1:
+            self._fence()                                   # every rank's gradients are final
+        raw.adamw_p2p(a.data[self.lo:self.hi], self.m, self.v, self.peer_grad, self.peer_shadow, self.lo, self.state, 1.0 / self.world)
+        if self.world > 1:
+            self._fence()                                   # every shadow is complete, nobody still reads this rank's gradients
+        if self.on_updated is not None:
+            self.on_updated()
+
+
 class GradReducer:
     """Bucketed gradient all-reduce (mean) over the flat gradient arena on a side stream.
 
