@@ -146,6 +146,9 @@ int svdx_splitk_epilogue(float* ws, int64_t ldw, void* out, int64_t ldo, int64_t
 
 /* number of SMs the persistent kernels size their grids to (queried once) */
 int svdx_num_sms(void);
+/* enable peer access from the current device to peer_device (needed before svdx_adamw_p2p dereferences arenas that live on,
+ * or were IPC-mapped from, that GPU); idempotent; fails when the GPUs have no P2P path */
+int svdx_enable_peer_access(int32_t peer_device);
 /* sizeof(SvdxTapGemm) (which==0) / sizeof(SvdxAttn) (which==1): lets bindings verify their struct layout */
 int svdx_struct_size(int which);
 /* human-readable last error of this thread */

@@ -3,9 +3,11 @@
 mkdir -p gpurun_out
 L=gpurun_out/ddp_dev.log
 nvidia-smi -L > $L 2>&1
+echo "=== kernel unit test (one device)" >> $L
+timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu --no-header -p no:cacheprovider -k adamw_p2p 2>&1 | grep -v "^$" | tail -5 >> $L
 echo "=== ddp_check" >> $L
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 scripts/ddp_check.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -30 >> $L
-for mode in p2p sharded; do
+for mode in p2p; do
   echo "=== bench N=2 --ddp $mode" >> $L
   NCCL_DEBUG=WARN timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 --ddp $mode --no-families --no-script-path --no-gpu-baseline --no-cpu-baseline > gpurun_out/bench_n2_$mode.json 2>> $L
   python - >> $L <<PY

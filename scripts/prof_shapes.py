@@ -37,10 +37,10 @@ def main():
     out = torch.empty(M, C, device=DEV, dtype=bf16)
     bias = torch.randn(C, device=DEV)
     sums = torch.zeros(T, 2, C, device=DEV)
-    tag("conv3x3 L0 320->320 (+bias, fused GN stats) pair kernel", 2.0 * M * C * 9 * C)
+    tag("conv3x3 L0 320->320 (+bias, fused GN stats) CTA-pair kernel, 256x320 tile", 2.0 * M * C * 9 * C)
     raw.tapgemm(x, w9, out, M=M, N=C, K=C, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, T), bias=bias, gn_sum=sums, gn_rows=H * W)
     res = rnd(M, C)
-    tag("conv3x3 L0 320->320 (+bias +residual) pair kernel", 2.0 * M * C * 9 * C)
+    tag("conv3x3 L0 320->320 (+bias +residual) CTA-pair kernel, 256x320 tile", 2.0 * M * C * 9 * C)
     raw.tapgemm(x, w9, out, M=M, N=C, K=C, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, T), bias=bias, res1=res)
     w3 = rnd(C, 3 * C, scale=(3 * C) ** -0.5)
     tag("temporal conv (3,1,1) L0 320->320", 2.0 * M * C * 3 * C)
@@ -108,6 +108,17 @@ def main():
     ws = torch.zeros(2 * T * 32, device=DEV)
     tag("GroupNorm+SiLU backward L0 (partial sums + apply, + residual gradient)", 0.0, 8.0 * M * C, launches=2)
     raw.groupnorm_bwd(out, None, res, T, H * W, mean, rstd, gamma, beta, True, y, None, ws=ws, dres=x)
+    ab = torch.empty(T, 2, C, device=DEV)
+    raw.groupnorm_apply(out, None, T, H * W, mean, rstd, gamma, beta, True, y, ab=ab)      # (captured too: plain apply)
+    TAGS.insert(len(TAGS), dict(name="GroupNorm+SiLU apply L0 (stand-alone statistics given)", flops=0.0, bytes=4.0 * M * C, launches=1))
+    print("TAG GroupNorm+SiLU apply L0 (stand-alone statistics given)", flush=True)
+    gsum = torch.zeros(T, 2, C, device=DEV)
+    dyb = torch.empty(M, C, device=DEV, dtype=bf16)
+    tag("conv3x3 dgrad L0 320->320 + GroupNorm-backward sums in the epilogue (256x320 tile)", 2.0 * M * C * 9 * C)
+    raw.tapgemm(x, w9, dyb, M=M, N=C, K=C, mode=raw.A_CONV2D, taps=raw.CONV3x3_TAPS, conv_whn=(W, H, T),
+                gnb=dict(x=out, x2=None, ab=ab, rows=H * W, silu=True, sum=gsum))
+    tag("GroupNorm+SiLU backward L0 from the epilogue sums (one launch, + residual gradient)", 0.0, 8.0 * M * C)
+    raw.groupnorm_bwd_fused(out, None, dyb, T, H * W, mean, rstd, gamma, beta, True, gsum, y, None, dres=x)
     tag("LayerNorm forward L0", 0.0, 4.0 * M * C)
     lm, lr = raw.layernorm_fwd(x, gamma, beta, 1e-5, y)
     tag("LayerNorm backward L0 (+ residual gradient)", 0.0, 8.0 * M * C)

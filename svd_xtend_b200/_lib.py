@@ -60,6 +60,7 @@ _PROTOS = {
     "svdx_splitk_epilogue": [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_int, c_i64, c_void_p, c_i64,
                              c_void_p, c_i64, c_void_p, c_void_p],
     "svdx_num_sms": [],
+    "svdx_enable_peer_access": [c_int],
     "svdx_struct_size": [c_int],
     "svdx_groupnorm_stats": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_float,
                              c_void_p, c_void_p, c_void_p],

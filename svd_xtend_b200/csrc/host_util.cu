@@ -33,6 +33,23 @@ extern "C" int svdx_num_sms(void) {
   return n[slot];
 }
 
+// kernels of the CURRENT device may dereference memory of `peer_device` (its allocations, or another process's allocations on
+// it mapped here through CUDA IPC) once peer access is enabled on the current device's context; idempotent
+extern "C" int svdx_enable_peer_access(int32_t peer_device) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return svdx_fail_cuda(e, "enable_peer_access: cudaGetDevice");
+  if (dev == peer_device) return SVDX_OK;
+  int can = 0;
+  e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+  if (e != cudaSuccess) return svdx_fail_cuda(e, "enable_peer_access: cudaDeviceCanAccessPeer");
+  if (!can) return svdx_fail(SVDX_E_BADARG, "enable_peer_access: the two GPUs are not peer-capable (no NVLink / PCIe P2P path)");
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return SVDX_OK; }
+  if (e != cudaSuccess) return svdx_fail_cuda(e, "enable_peer_access: cudaDeviceEnablePeerAccess");
+  return SVDX_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

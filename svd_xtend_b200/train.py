@@ -312,10 +312,11 @@ def map_peer_tensors(t: torch.Tensor, group=None) -> List[torch.Tensor]:
             continue
         if numel != t.numel():
             raise RuntimeError("map_peer_tensors: ranks hold arenas of different sizes")
-        pst = torch.UntypedStorage._new_shared_cuda(*handle)
+        pst = torch.UntypedStorage._new_shared_cuda(*handle)       # cudaIpcOpenMemHandle under the owner's device index
         peer = torch.empty(0, dtype=t.dtype, device=pst.device).set_(pst, off, (numel,))
-        # a one-element cross-device copy makes torch enable peer access between this rank's GPU and the owner's
-        torch.empty(1, dtype=t.dtype, device=t.device).copy_(peer[:1])
+        # kernels of THIS rank's GPU dereference the mapping: peer access from the current device to the owner's
+        with torch.cuda.device(t.device):
+            raw._lib.check(raw.load().svdx_enable_peer_access(int(dev)), "svdx_enable_peer_access")
         out.append(peer)
     torch.cuda.synchronize(t.device)
     dist.barrier(group=group)

@@ -367,3 +367,34 @@ def test_groupnorm_apply_fused_from_channel_sums(raw, outer, rows, C1, C2, silu)
     _close(dx1, dxr[:, :C1], what="groupnorm dx (fused stats)")
     if C2:
         _close(dx2, dxr[:, C1:], what="groupnorm dx2 (fused stats)")
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (2, 1), (3, 1), (8, 5)])
+def test_adamw_p2p_kernel_matches_reduce_scatter_adamw_all_gather(raw, world, rank):
+    """svdx_adamw_p2p on one device (the 'peer' arenas are local tensors): slice [lo, hi) of the summed gradients goes through
+    AdamW and lands as bf16 in EVERY shadow arena; everything outside the slice stays untouched. Reference: svdx_adamw_graph on
+    the summed gradient slice (what reduce-scatter -> AdamW -> all-gather computes)."""
+    n_total = 4096 * world
+    n = n_total // world
+    lo = rank * n
+    grads = [_rand(n_total, seed=30 + r) for r in range(world)]
+    shadows = [torch.full((n_total,), 7.0, device=DEV, dtype=bf16) for _ in range(world)]
+    data = _rand(n_total, seed=50)
+    p = data[lo:lo + n].clone()
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    state = torch.tensor([1e-2, 0.9, 0.999, 1e-8, 1e-2, 0.0, 1.0, 1.0], device=DEV)
+    p_ref, m_ref, v_ref, state_ref = p.clone(), m.clone(), v.clone(), state.clone()
+    sh_ref = torch.empty(n, device=DEV, dtype=bf16)
+    for _ in range(3):
+        raw.adamw_p2p(p, m, v, grads, shadows, lo, state, 1.0 / world)
+        gsum = grads[0][lo:lo + n].clone()
+        for r in range(1, world):
+            gsum += grads[r][lo:lo + n]
+        raw.adamw_graph(p_ref, gsum, m_ref, v_ref, state_ref, 1.0 / world, shadow=sh_ref)
+    torch.cuda.synchronize()
+    assert torch.equal(p, p_ref) and torch.equal(m, m_ref) and torch.equal(v, v_ref) and torch.equal(state, state_ref)
+    for r in range(world):
+        assert torch.equal(shadows[r][lo:lo + n], sh_ref)
+        rest = torch.cat([shadows[r][:lo], shadows[r][lo + n:]])
+        assert bool((rest == 7.0).all())
