@@ -149,6 +149,12 @@ int svdx_num_sms(void);
 /* enable peer access from the current device to peer_device (needed before svdx_adamw_p2p dereferences arenas that live on,
  * or were IPC-mapped from, that GPU); idempotent; fails when the GPUs have no P2P path */
 int svdx_enable_peer_access(int32_t peer_device);
+/* CUDA IPC of a device buffer between the processes of one node (one process per GPU). export: the 64-byte handle of the
+ * allocation that contains ptr + ptr's byte offset inside it. import (call it with the CONSUMING GPU current): maps the
+ * allocation into this process for that GPU (peer access enabled lazily) and returns the address corresponding to ptr. An
+ * allocation can be imported once per process; the mapping lives until the process exits. */
+int svdx_ipc_export(const void* ptr, void* handle64_out, int64_t* offset_out);
+int svdx_ipc_import(const void* handle64, int64_t offset, void** ptr_out);
 /* sizeof(SvdxTapGemm) (which==0) / sizeof(SvdxAttn) (which==1): lets bindings verify their struct layout */
 int svdx_struct_size(int which);
 /* human-readable last error of this thread */

@@ -61,6 +61,8 @@ _PROTOS = {
                              c_void_p, c_i64, c_void_p, c_void_p],
     "svdx_num_sms": [],
     "svdx_enable_peer_access": [c_int],
+    "svdx_ipc_export": [c_void_p, c_void_p, c_void_p],
+    "svdx_ipc_import": [c_void_p, c_i64, c_void_p],
     "svdx_struct_size": [c_int],
     "svdx_groupnorm_stats": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_float,
                              c_void_p, c_void_p, c_void_p],

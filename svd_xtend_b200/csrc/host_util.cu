@@ -50,6 +50,42 @@ extern "C" int svdx_enable_peer_access(int32_t peer_device) {
   return SVDX_OK;
 }
 
+// ---- CUDA IPC of a device buffer between the ranks of one node (one process per GPU): the owner exports the handle of the
+// allocation that contains `ptr` plus ptr's byte offset inside it; a consumer opens it WITH ITS OWN DEVICE CURRENT, so the
+// mapping is made for (and peer access lazily enabled from) the GPU whose kernels will dereference it.
+typedef CUresult (*AddrRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+extern "C" int svdx_ipc_export(const void* ptr, void* handle_out, int64_t* offset_out) {
+  if (!ptr || !handle_out || !offset_out) return svdx_fail(SVDX_E_BADARG, "ipc_export: null argument");
+  static AddrRangeFn range = nullptr;
+  if (!range) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) return svdx_fail(SVDX_E_NODRIVER, "ipc_export: cuMemGetAddressRange unavailable");
+    range = reinterpret_cast<AddrRangeFn>(p);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return svdx_fail(SVDX_E_BADARG, "ipc_export: not a device allocation");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
+  if (e != cudaSuccess) return svdx_fail_cuda(e, "ipc_export: cudaIpcGetMemHandle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out, &h, 64);
+  *offset_out = (int64_t)(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return SVDX_OK;
+}
+extern "C" int svdx_ipc_import(const void* handle, int64_t offset, void** ptr_out) {
+  if (!handle || !ptr_out || offset < 0) return svdx_fail(SVDX_E_BADARG, "ipc_import: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* base = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return svdx_fail_cuda(e, "ipc_import: cudaIpcOpenMemHandle");
+  *ptr_out = static_cast<char*>(base) + offset;
+  return SVDX_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

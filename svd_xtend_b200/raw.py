@@ -671,13 +671,13 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
 def adamw_p2p(p, m, v, peer_grads, peer_shadows, lo, state, grad_scale, tick=True):
     """reduce-scatter + AdamW + all-gather in one kernel over NVLink peer memory (svdx_adamw_p2p): p / m / v are this rank's
     slices, peer_grads / peer_shadows the FULL arenas of every rank (this rank's own included) as tensors mapped into this
-    process (train.map_peer_tensors)"""
+    process (train.map_peer_buffers)"""
     world = len(peer_grads)
     n = p.numel()
     if _fam("adamw", 0.0, (4.0 * world + 28.0 + 2.0 * world) * n):
         return
-    ga = (C.c_void_p * world)(*[t.data_ptr() for t in peer_grads])
-    sa = (C.c_void_p * world)(*[t.data_ptr() for t in peer_shadows])
+    ga = (C.c_void_p * world)(*[t if isinstance(t, int) else t.data_ptr() for t in peer_grads])       # tensors or mapped addresses
+    sa = (C.c_void_p * world)(*[t if isinstance(t, int) else t.data_ptr() for t in peer_shadows])
     check(load().svdx_adamw_p2p(p.data_ptr(), m.data_ptr(), v.data_ptr(), ga, sa, world, lo, n, state.data_ptr(), float(grad_scale),
                                 int(tick), _stream()), "svdx_adamw_p2p")
 

@@ -296,31 +296,42 @@ class ShardedAdamW:
         return ts
 
 
-def map_peer_tensors(t: torch.Tensor, group=None) -> List[torch.Tensor]:
-    """every rank's copy of the (same-shaped, flat) CUDA tensor `t`, mapped into THIS process through CUDA IPC: element r of
-    the result aliases rank r's memory (element `rank` is t itself). One process per GPU of ONE node, all GPUs visible to
-    every process (torchrun's default). Kernels of this rank may then load / store the peers' memory over NVLink."""
+def map_peer_buffers(t: torch.Tensor, group=None) -> List[int]:
+    """device addresses, valid in THIS process for kernels of THIS rank's GPU, of every rank's copy of the (same-shaped, flat)
+    CUDA tensor `t`: element r is rank r's buffer (element `rank` is t's own address). The owners export CUDA-IPC handles
+    (`svdx_ipc_export`), the handles travel through torch.distributed, and every rank opens its peers' handles with its own
+    GPU current (`svdx_ipc_import`), so the mappings are made for the GPU that will dereference them. One process per GPU of
+    ONE node; peers sharing one allocation (caching-allocator segment) are opened once."""
+    import ctypes as C
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    st = t.untyped_storage()
-    meta = (st._share_cuda_(), t.storage_offset(), t.numel(), t.device.index)
+    lib = raw.load()
+    handle = (C.c_ubyte * 64)()
+    off = C.c_int64(0)
+    with torch.cuda.device(t.device):
+        raw._lib.check(lib.svdx_ipc_export(t.data_ptr(), handle, C.byref(off)), "svdx_ipc_export")
     metas = [None] * world
-    dist.all_gather_object(metas, meta, group=group)
+    dist.all_gather_object(metas, (bytes(handle), int(off.value), t.numel(), t.element_size()), group=group)
     out = []
-    for r, (handle, off, numel, dev) in enumerate(metas):
+    for r, (hb, o, numel, esz) in enumerate(metas):
         if r == rank:
-            out.append(t)
+            out.append(t.data_ptr())
             continue
-        if numel != t.numel():
-            raise RuntimeError("map_peer_tensors: ranks hold arenas of different sizes")
-        pst = torch.UntypedStorage._new_shared_cuda(*handle)       # cudaIpcOpenMemHandle under the owner's device index
-        peer = torch.empty(0, dtype=t.dtype, device=pst.device).set_(pst, off, (numel,))
-        # kernels of THIS rank's GPU dereference the mapping: peer access from the current device to the owner's
-        with torch.cuda.device(t.device):
-            raw._lib.check(raw.load().svdx_enable_peer_access(int(dev)), "svdx_enable_peer_access")
-        out.append(peer)
+        if numel != t.numel() or esz != t.element_size():
+            raise RuntimeError("map_peer_buffers: ranks hold arenas of different sizes")
+        base = _IPC_OPEN.get(hb)
+        if base is None:
+            p = C.c_void_p()
+            with torch.cuda.device(t.device):
+                raw._lib.check(lib.svdx_ipc_import((C.c_ubyte * 64).from_buffer_copy(hb), 0, C.byref(p)), "svdx_ipc_import")
+            base = int(p.value)
+            _IPC_OPEN[hb] = base
+        out.append(base + o)
     torch.cuda.synchronize(t.device)
     dist.barrier(group=group)
     return out
+
+
+_IPC_OPEN: Dict[bytes, int] = {}      # allocation handle -> base address of its mapping in this process
 
 
 class P2PShardedAdamW(ShardedAdamW):
@@ -338,10 +349,10 @@ class P2PShardedAdamW(ShardedAdamW):
             raise ValueError("P2PShardedAdamW: at most 16 ranks (one NVSwitch domain)")
         self._flag = torch.zeros(1, device=arena.data.device, dtype=F32)
         if self.world > 1:
-            self.peer_grad = map_peer_tensors(arena.grad, group)
-            self.peer_shadow = map_peer_tensors(arena.shadow, group)
+            self.peer_grad = map_peer_buffers(arena.grad, group)
+            self.peer_shadow = map_peer_buffers(arena.shadow, group)
         else:
-            self.peer_grad, self.peer_shadow = [arena.grad], [arena.shadow]
+            self.peer_grad, self.peer_shadow = [arena.grad.data_ptr()], [arena.shadow.data_ptr()]
 
     def _fence(self):
         dist.all_reduce(self._flag, group=self.group)      # stream-ordered on every rank, captured into the step graph
