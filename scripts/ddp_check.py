@@ -155,4 +155,8 @@ rep_equal = torch.equal(shadow_p2p3, arena.shadow) if world == 2 else ((shadow_p
 print(f"[ddp_check] rank {rank}: p2p fused step, 3 CUDA-graph replays vs 3 NCCL sharded steps: operands equal: {rep_equal}, t = {popt.t} / {opt.t}", flush=True)
 assert rep_equal and popt.t == 4 and opt.t == 4
 dist.barrier()
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(0)      # destroy_process_group() blocks while a CUDA graph that captured NCCL kernels is alive
+dist.barrier()
 dist.destroy_process_group()
