@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configuration")
-    ap.add_argument("--ddp", default="sharded", choices=["p2p", "sharded", "allreduce"],
+    ap.add_argument("--ddp", default="p2p", choices=["p2p", "sharded", "allreduce"],
                     help="N > 1: p2p (default) = sharded AdamW with reduce-scatter + update + all-gather as ONE kernel over NVLink peer "
                          "memory (falls back to 'sharded' if the peer mapping cannot be set up); sharded = the same through NCCL "
                          "reduce-scatter / all-gather; allreduce = bucketed all-reduce + replicated AdamW")
