@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical A/B: the register-array GroupNorm / LayerNorm kernels selected by SVDX_GN_RING=0 / SVDX_LN_RING=0 / SVDX_LIB alt builds were removed after this comparison)
 mkdir -p gpurun_out
 L=gpurun_out/r2g.log
 : > $L

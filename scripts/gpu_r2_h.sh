@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical A/B: the register-array GroupNorm / LayerNorm kernels selected by SVDX_GN_RING=0 / SVDX_LN_RING=0 / SVDX_LIB alt builds were removed after this comparison)
 # cp.async ring norm kernels: correctness, A/B against the register-array kernels, CTAs-per-SM sweep; gemm block_n sweep; quick bench
 mkdir -p gpurun_out
 L=gpurun_out/r2h.log

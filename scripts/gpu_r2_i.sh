@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical A/B: the register-array GroupNorm / LayerNorm kernels selected by SVDX_GN_RING=0 / SVDX_LN_RING=0 / SVDX_LIB alt builds were removed after this comparison)
 # in-step A/B of the ring norm kernels (same box): whole-step time per variant, warm-L2 kbench, ncu launch list without cache flushes
 mkdir -p gpurun_out
 L=gpurun_out/r2i.log

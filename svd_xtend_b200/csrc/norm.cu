@@ -1,7 +1,7 @@
 // GroupNorm(32)(+SiLU) and LayerNorm, forward and backward, over channels-last bf16 activations.
-// HBM-bound CUDA-core kernels: coalesced bf16x2 row reads (one warp per row, lanes stride the
-// channel axis), fp32 statistics, warp-shuffle / shared-memory reductions, fp32 atomics for the
-// cross-CTA partial sums.
+// HBM-bound CUDA-core kernels: 16-byte vector accesses, fp32 statistics, warp-shuffle / shared-memory reductions, fp32
+// atomics for the cross-CTA partial sums. The row-streaming kernels (GroupNorm apply / backward, LayerNorm forward /
+// backward) keep their loads in flight through cp.async rings in shared memory instead of registers.
 //
 // Replaces F.group_norm + F.silu of ResnetBlock2D / TemporalResnetBlock / TransformerSpatioTemporalModel
 // [D: diffusers models/resnet.py, transformer_temporal.py] and conv_norm_out
@@ -14,11 +14,6 @@
 
 namespace svdx {
 
-constexpr int GN_THREADS = 256;
-constexpr int GN_WARPS = GN_THREADS / 32;
-constexpr int GN_ROWS_PER_CTA = 64;
-constexpr int MAX_C = 2560;  // channel pairs are kept in smem accumulators: 2 * MAX_C floats
-
 struct GnSrc {
   const bf16* x;
   long long ldx;
@@ -28,35 +23,22 @@ struct GnSrc {
   int C2;
 };
 
-SVDX_DEVINL float2 load_pair(const GnSrc& s, long long row, int c) {
-  const bf16* p = (c < s.C1) ? (s.x + row * s.ldx + c) : (s.x2 + row * s.ldx2 + (c - s.C1));
-  return unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p));
-}
-
 // ------------------------------------------------------------------ GroupNorm statistics
 // Vectorised: a thread owns ONE 8-channel vector (16 B) and walks rows, keeping 4 loads in flight; the block is
 // (C/8 channel vectors) x (row lanes). grid (row_chunks, outer). Accumulates sum / sumsq into mean[] / rstd[]
 // (pre-zeroed) through shared-memory then global fp32 atomics; finalised below.
 constexpr int GNV_MAX_THREADS = 512;
-// tuning knobs of the streaming kernels (compile-time; scripts/kbench.py A/Bs alternative builds through SVDX_LIB):
-// minimum resident CTAs per SM the register allocation must allow, and independent row loads in flight per thread
-#ifndef SVDX_GN_MINB
-#define SVDX_GN_MINB 1
-#endif
+constexpr int GN_RIF = 4;            // independent row loads per thread of the statistics kernel
 #ifndef SVDX_LN_MINB
-#define SVDX_LN_MINB 1
+#define SVDX_LN_MINB 1               // register-array LayerNorm kernels (C > 1280 only): minimum resident CTAs per SM
 #endif
-#ifndef SVDX_GN_RIF
-#define SVDX_GN_RIF 4
-#endif
-constexpr int GN_RIF = SVDX_GN_RIF;
 
 SVDX_DEVINL uint4 load_vec8(const GnSrc& s, long long row, int c0) {
   const bf16* p = (c0 < s.C1) ? (s.x + row * s.ldx + c0) : (s.x2 + row * s.ldx2 + (c0 - s.C1));
   return *reinterpret_cast<const uint4*>(p);
 }
 
-__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_stats_partial(GnSrc s, int rows, int rows_per_cta, int G, float* sum, float* sumsq) {
+__global__ void __launch_bounds__(GNV_MAX_THREADS, 1) gn_stats_partial(GnSrc s, int rows, int rows_per_cta, int G, float* sum, float* sumsq) {
   __shared__ float sh_s[32 * 2];
   const int C = s.C1 + s.C2;
   const int CV = C / 8;
@@ -126,289 +108,10 @@ __global__ void gn_stats_finalize(float* mean, float* rstd, int total, float inv
   rstd[i] = rsqrtf(var + eps);
 }
 
-// ------------------------------------------------------------------ GroupNorm apply (+SiLU)
-// same thread layout as the statistics kernel: a thread owns one 8-channel vector, folds mean/rstd/gamma/beta into
-// a per-channel scale and shift once, then streams rows (y = silu(x*scale + shift)), 16 B loads and stores
-__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_apply_kernel(GnSrc s, int rows, int rows_per_cta, int G, const float* __restrict__ mean,
-                                                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                                   const float* __restrict__ beta, int fuse_silu, bf16* __restrict__ y, long long ldy) {
-  const int C = s.C1 + s.C2;
-  const int CV = C / 8;
-  const int cpg = C / G;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, rows);
-  const int RL = blockDim.x / CV;
-  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (rl >= RL) return;
-  const int c0 = cv * 8;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int g = (c0 + k) / cpg;
-    const float rs = rstd[n * G + g];
-    sc[k] = rs * gamma[c0 + k];
-    sh[k] = beta[c0 + k] - mean[n * G + g] * sc[k];
-  }
-  const long long base = (long long)n * rows;
-  for (int r = r0 + rl; r < r1; r += GN_RIF * RL) {
-    // four independent row loads in flight per thread before any math (the kernel is latency x bytes-in-flight bound)
-    uint4 u[GN_RIF];
-#pragma unroll
-    for (int q = 0; q < GN_RIF; ++q)
-      if (r + q * RL < r1) u[q] = load_vec8(s, base + r + q * RL, c0);
-#pragma unroll
-    for (int q = 0; q < GN_RIF; ++q) {
-      if (r + q * RL >= r1) break;
-      const uint32_t in[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
-      uint32_t out[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 v = unpack_bf16x2(in[k]);
-        float a = fmaf(v.x, sc[2 * k], sh[2 * k]), b = fmaf(v.y, sc[2 * k + 1], sh[2 * k + 1]);
-        if (fuse_silu) { a = silu_f(a); b = silu_f(b); }
-        out[k] = pack_bf16x2(a, b);
-      }
-      *reinterpret_cast<uint4*>(y + (base + r + q * RL) * ldy + c0) = make_uint4(out[0], out[1], out[2], out[3]);
-    }
-  }
-}
-
-// GroupNorm apply straight from the per-channel sums the producing svdx_tapgemm epilogue accumulated (gn_sum): every CTA
-// folds the C channel sums of its slab into the G group statistics in shared memory (C <= 2560 values from L2, a few hundred
-// ns), CTA x == 0 of the slab publishes mean / rstd for the backward, then rows are streamed exactly as in gn_apply_kernel.
-// One launch instead of memset + partial statistics + finalize + apply, and no extra pass over x for the statistics.
-__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_apply_fused_kernel(GnSrc s, int rows, int rows_per_cta, int RL, int G, float eps, float inv_count,
-                                                                         const float* __restrict__ csum1, long long ldc1,
-                                                                         const float* __restrict__ csum2, long long ldc2,
-                                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                         int fuse_silu, bf16* __restrict__ y, long long ldy) {
-  __shared__ float sh_sum[32], sh_sq[32], sh_mean[32], sh_rstd[32];
-  const int C = s.C1 + s.C2;
-  const int CV = C / 8;
-  const int cpg = C / G;
-  const int n = blockIdx.y;
-  if (threadIdx.x < 32) { sh_sum[threadIdx.x] = 0.f; sh_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
-  {
-    // a warp's 32 consecutive channels fall into at most 1 + 31 / cpg groups: reduce runs of equal group with shuffles,
-    // one shared-memory atomic per run
-    const int lane = threadIdx.x & 31;
-    for (int c0 = (threadIdx.x & ~31); c0 < C; c0 += blockDim.x) {
-      const int c = c0 + lane;
-      float a = 0.f, b = 0.f;
-      int g = -1;
-      if (c < C) {
-        const float* base = (c < s.C1) ? (csum1 + (2LL * n) * ldc1 + c) : (csum2 + (2LL * n) * ldc2 + (c - s.C1));
-        a = base[0];
-        b = base[(c < s.C1) ? ldc1 : ldc2];
-        g = c / cpg;
-      }
-      // segmented inclusive suffix sum over equal-g runs (g is non-decreasing across lanes)
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float a2 = __shfl_down_sync(0xffffffffu, a, o), b2 = __shfl_down_sync(0xffffffffu, b, o);
-        const int g2 = __shfl_down_sync(0xffffffffu, g, o);
-        if (lane + o < 32 && g2 == g) { a += a2; b += b2; }
-      }
-      const int gprev = __shfl_up_sync(0xffffffffu, g, 1);
-      if (g >= 0 && (lane == 0 || gprev != g)) { atomicAdd(&sh_sum[g], a); atomicAdd(&sh_sq[g], b); }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < G) {
-    const float m = sh_sum[threadIdx.x] * inv_count;
-    const float var = fmaxf(sh_sq[threadIdx.x] * inv_count - m * m, 0.f);
-    const float rs = rsqrtf(var + eps);
-    sh_mean[threadIdx.x] = m;
-    sh_rstd[threadIdx.x] = rs;
-    if (blockIdx.x == 0) { mean_out[n * G + threadIdx.x] = m; rstd_out[n * G + threadIdx.x] = rs; }
-  }
-  __syncthreads();
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, rows);
-  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;      // the block is padded to whole warps: lanes past CV * RL only folded
-  if (rl >= RL) return;
-  const int c0 = cv * 8;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int g = (c0 + k) / cpg;
-    sc[k] = sh_rstd[g] * gamma[c0 + k];
-    sh[k] = beta[c0 + k] - sh_mean[g] * sc[k];
-  }
-  const long long base = (long long)n * rows;
-  for (int r = r0 + rl; r < r1; r += GN_RIF * RL) {
-    uint4 u[GN_RIF];
-#pragma unroll
-    for (int q = 0; q < GN_RIF; ++q)
-      if (r + q * RL < r1) u[q] = load_vec8(s, base + r + q * RL, c0);
-#pragma unroll
-    for (int q = 0; q < GN_RIF; ++q) {
-      if (r + q * RL >= r1) break;
-      const uint32_t in[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
-      uint32_t out[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 v = unpack_bf16x2(in[k]);
-        float a = fmaf(v.x, sc[2 * k], sh[2 * k]), b = fmaf(v.y, sc[2 * k + 1], sh[2 * k + 1]);
-        if (fuse_silu) { a = silu_f(a); b = silu_f(b); }
-        out[k] = pack_bf16x2(a, b);
-      }
-      *reinterpret_cast<uint4*>(y + (base + r + q * RL) * ldy + c0) = make_uint4(out[0], out[1], out[2], out[3]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------ GroupNorm backward
-// pass 1: per (n, group) s1 = sum(g*gamma), s2 = sum(g*gamma*xhat), g = dy * silu'(z); optional dgamma/dbeta.
-// Same thread layout as gn_stats_partial (one 8-channel vector per thread, rows in flight).
-template <bool DG>
-__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_bwd_partial(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
-                                                                  int G, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  int fuse_silu, float* ws, float* dgamma, float* dbeta) {
-  __shared__ float sh_s[32 * 2];
-  const int C = s.C1 + s.C2;
-  const int CV = C / 8;
-  const int cpg = C / G;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, rows);
-  const int RL = blockDim.x / CV;
-  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh_s[i] = 0.f;
-  __syncthreads();
-  if (rl < RL) {
-    const int c0 = cv * 8;
-    float gm[8], bt[8], mu[8], rs[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int g = (c0 + k) / cpg;
-      gm[k] = gamma[c0 + k]; bt[k] = beta[c0 + k]; mu[k] = mean[n * G + g]; rs[k] = rstd[n * G + g];
-    }
-    float a1[8], a2[8], dg[8], db[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { a1[k] = a2[k] = dg[k] = db[k] = 0.f; }
-    const long long base = (long long)n * rows;
-    for (int r = r0 + rl; r < r1; r += GN_RIF * RL) {
-      uint4 ux[GN_RIF], ud[GN_RIF];
-#pragma unroll
-      for (int q = 0; q < GN_RIF; ++q) {
-        if (r + q * RL < r1) {
-          ux[q] = load_vec8(s, base + r + q * RL, c0);
-          ud[q] = *reinterpret_cast<const uint4*>(dy + (base + r + q * RL) * lddy + c0);
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < GN_RIF; ++q) {
-        if (r + q * RL >= r1) break;
-        const uint32_t wx[4] = {ux[q].x, ux[q].y, ux[q].z, ux[q].w}, wd[4] = {ud[q].x, ud[q].y, ud[q].z, ud[q].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 v = unpack_bf16x2(wx[k]), d = unpack_bf16x2(wd[k]);
-          const float xh0 = (v.x - mu[2 * k]) * rs[2 * k], xh1 = (v.y - mu[2 * k + 1]) * rs[2 * k + 1];
-          float e0 = d.x, e1 = d.y;
-          if (fuse_silu) {
-            e0 *= silu_grad_f(xh0 * gm[2 * k] + bt[2 * k]);
-            e1 *= silu_grad_f(xh1 * gm[2 * k + 1] + bt[2 * k + 1]);
-          }
-          a1[2 * k] += e0 * gm[2 * k]; a1[2 * k + 1] += e1 * gm[2 * k + 1];
-          a2[2 * k] += e0 * gm[2 * k] * xh0; a2[2 * k + 1] += e1 * gm[2 * k + 1] * xh1;
-          if (DG) {
-            dg[2 * k] += e0 * xh0; dg[2 * k + 1] += e1 * xh1;
-            db[2 * k] += e0; db[2 * k + 1] += e1;
-          }
-        }
-      }
-    }
-    int g = c0 / cpg, left = cpg - (c0 - g * cpg);
-    float sa = 0.f, sb = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (left == 0) { atomicAdd(&sh_s[g], sa); atomicAdd(&sh_s[G + g], sb); sa = sb = 0.f; ++g; left = cpg; }
-      sa += a1[k]; sb += a2[k]; --left;
-    }
-    atomicAdd(&sh_s[g], sa); atomicAdd(&sh_s[G + g], sb);
-    if (DG) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { atomicAdd(&dgamma[c0 + k], dg[k]); atomicAdd(&dbeta[c0 + k], db[k]); }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < G; i += blockDim.x) {
-    atomicAdd(&ws[(n * G + i) * 2 + 0], sh_s[i]);
-    atomicAdd(&ws[(n * G + i) * 2 + 1], sh_s[G + i]);
-  }
-}
-
-// pass 2: dx = rstd * (g*gamma - s1/cnt - xhat * s2/cnt); per-thread channel constants, rows streamed
-__global__ void __launch_bounds__(GNV_MAX_THREADS, SVDX_GN_MINB) gn_bwd_apply(GnSrc s, const bf16* __restrict__ dy, long long lddy, int rows, int rows_per_cta,
-                                                                int G, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
-                                                                const float* __restrict__ ws, float inv_count, bf16* __restrict__ dx, long long lddx,
-                                                                bf16* __restrict__ dx2, long long lddx2, const bf16* __restrict__ dres, long long lddres) {
-  const int C = s.C1 + s.C2;
-  const int CV = C / 8;
-  const int cpg = C / G;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, rows);
-  const int RL = blockDim.x / CV;
-  const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (rl >= RL) return;
-  const int c0 = cv * 8;
-  const bool first = c0 < s.C1;
-  float gm[8], bt[8], mu[8], rs[8], t1[8], t2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int g = (c0 + k) / cpg;
-    gm[k] = gamma[c0 + k]; bt[k] = beta[c0 + k]; mu[k] = mean[n * G + g]; rs[k] = rstd[n * G + g];
-    t1[k] = ws[(n * G + g) * 2] * inv_count; t2[k] = ws[(n * G + g) * 2 + 1] * inv_count;
-  }
-  const long long base = (long long)n * rows;
-  for (int r = r0 + rl; r < r1; r += GN_RIF * RL) {
-    uint4 ux[GN_RIF], ug[GN_RIF], ur[GN_RIF];
-#pragma unroll
-    for (int q = 0; q < GN_RIF; ++q) {
-      if (r + q * RL < r1) {
-        ux[q] = load_vec8(s, base + r + q * RL, c0);
-        ug[q] = *reinterpret_cast<const uint4*>(dy + (base + r + q * RL) * lddy + c0);
-        if (dres) ur[q] = *reinterpret_cast<const uint4*>(dres + (base + r + q * RL) * lddres + c0);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < GN_RIF; ++q) {
-      if (r + q * RL >= r1) break;
-      const long long row = base + r + q * RL;
-      const uint32_t in[4] = {ux[q].x, ux[q].y, ux[q].z, ux[q].w}, din[4] = {ug[q].x, ug[q].y, ug[q].z, ug[q].w};
-      const uint32_t rin[4] = {ur[q].x, ur[q].y, ur[q].z, ur[q].w};
-      uint32_t out[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 v = unpack_bf16x2(in[k]), d = unpack_bf16x2(din[k]);
-        const float xh0 = (v.x - mu[2 * k]) * rs[2 * k], xh1 = (v.y - mu[2 * k + 1]) * rs[2 * k + 1];
-        float e0 = d.x, e1 = d.y;
-        if (fuse_silu) {
-          e0 *= silu_grad_f(fmaf(xh0, gm[2 * k], bt[2 * k]));
-          e1 *= silu_grad_f(fmaf(xh1, gm[2 * k + 1], bt[2 * k + 1]));
-        }
-        float o0 = rs[2 * k] * (e0 * gm[2 * k] - t1[2 * k] - xh0 * t2[2 * k]);
-        float o1 = rs[2 * k + 1] * (e1 * gm[2 * k + 1] - t1[2 * k + 1] - xh1 * t2[2 * k + 1]);
-        if (dres) { const float2 rr = unpack_bf16x2(rin[k]); o0 += rr.x; o1 += rr.y; }   // gradient already accumulated on x (its residual use)
-        out[k] = pack_bf16x2(o0, o1);
-      }
-      bf16* qd = first ? (dx + row * lddx + c0) : (dx2 + row * lddx2 + (c0 - s.C1));
-      *reinterpret_cast<uint4*>(qd) = make_uint4(out[0], out[1], out[2], out[3]);
-    }
-  }
-}
-
 // ------------------------------------------------------------------ GroupNorm, cp.async ring variants
-// The register-array kernels above keep GN_RIF 16-byte loads per tensor in flight per thread and then stall on them;
-// with 84-128 registers a thread only 15-30 warps are resident, so an SM has a load burst in flight a fraction of the time.
-// Here every thread streams its rows through a private GN_RING-deep ring of 16-byte shared-memory slots filled by
+// GroupNorm apply (+SiLU) and backward. Round 1-2's first versions kept 4 x 16-byte loads per tensor in flight per thread in
+// REGISTERS and then stalled on them; with 84-128 registers a thread only 15-30 warps were resident, so an SM had a load burst
+// in flight a fraction of the time (1-2.6 TB/s, profiles/r2_kbench_before.txt). Here every thread streams its rows through a private GN_RING-deep ring of 16-byte shared-memory slots filled by
 // cp.async (LDGSTS): GN_RING rows per tensor stay in flight per thread continuously, no registers are tied up by loads in
 // flight, and the first GN_RING rows are requested BEFORE the statistics prologue so its L2 round trips overlap the first
 // HBM round trip. A thread only ever reads slots it filled itself: cp.async.wait_group is the only synchronisation.
@@ -1353,11 +1056,6 @@ static void gn_vec_config(int C, int outer, int rows, int& threads, int& rows_pe
 
 // ring kernels: block = RL x CV threads padded to whole warps, ~SVDX_GN_RING_CPS CTAs per SM (each thread then walks
 // enough rows to amortise the ring fill), dynamic shared memory GN_RING slots x 16 B x threads per streamed tensor
-static bool gn_ring_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("SVDX_GN_RING"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on == 1;
-}
 static void gn_ring_config(int C, int outer, int rows, int& threads, int& RL, int& rows_per_cta) {
   const int CV = C / 8;
   RL = 256 / CV;
@@ -1416,11 +1114,11 @@ extern "C" int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, cons
                                     const float* beta, int32_t fuse_silu, void* y, int64_t ldy, float* ab_out, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !y || ldy % 8 || (reinterpret_cast<uintptr_t>(y) & 15) || !mean || !rstd || !gamma || !beta ||
-      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15) || (ab_out && ((reinterpret_cast<uintptr_t>(ab_out) & 15) || !gn_ring_enabled())))
+      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15) || (ab_out && ((reinterpret_cast<uintptr_t>(ab_out) & 15))))
     return svdx_fail(SVDX_E_BADARG, "groupnorm_apply: bad arguments");
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
   int threads, rpc;
-  if (gn_ring_enabled()) {
+  {
     static bool attr[SVDX_MAX_DEVICES] = {false};
     gn_ring_attr(gn_apply_ring<false>, attr);
     int RL;
@@ -1432,11 +1130,6 @@ extern "C" int svdx_groupnorm_apply(const void* x, int64_t ldx, int32_t C1, cons
     SVDX_CHECK_LAUNCH("groupnorm_apply");
     return SVDX_OK;
   }
-  gn_vec_config(C1 + C2, outer, rows, threads, rpc);
-  gn_apply_kernel<<<dim3((rows + rpc - 1) / rpc, outer), threads, 0, st>>>(s, rows, rpc, num_groups, mean, rstd, gamma, beta, fuse_silu,
-                                                                          reinterpret_cast<bf16*>(y), ldy);
-  SVDX_CHECK_LAUNCH("groupnorm_apply");
-  return SVDX_OK;
 }
 
 extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, int32_t outer,
@@ -1445,12 +1138,12 @@ extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1
                                           const float* beta, int32_t fuse_silu, void* y, int64_t ldy, float* ab_out, void* stream_v) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   if (gn_check(C1, C2, num_groups, ldx, ldx2, x, x2) || !y || ldy % 8 || (reinterpret_cast<uintptr_t>(y) & 15) || !mean || !rstd || !gamma || !beta ||
-      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15) || (ab_out && ((reinterpret_cast<uintptr_t>(ab_out) & 15) || !gn_ring_enabled())) ||
+      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15) || (ab_out && ((reinterpret_cast<uintptr_t>(ab_out) & 15))) ||
       !csum1 || ldc1 < C1 || (C2 > 0 && (!csum2 || ldc2 < C2)) || outer <= 0 || rows <= 0)
     return svdx_fail(SVDX_E_BADARG, "groupnorm_apply_fused: bad arguments");
   GnSrc s{reinterpret_cast<const bf16*>(x), ldx, C1, reinterpret_cast<const bf16*>(x2), ldx2, C2};
   int threads, rpc;
-  if (gn_ring_enabled()) {
+  {
     static bool attr[SVDX_MAX_DEVICES] = {false};
     gn_ring_attr(gn_apply_ring<true>, attr);
     int RLr;
@@ -1461,14 +1154,6 @@ extern "C" int svdx_groupnorm_apply_fused(const void* x, int64_t ldx, int32_t C1
     SVDX_CHECK_LAUNCH("groupnorm_apply_fused");
     return SVDX_OK;
   }
-  gn_vec_config(C1 + C2, outer, rows, threads, rpc);
-  const int RL = threads / ((C1 + C2) / 8);
-  const int padded = (threads + 31) & ~31;      // whole warps: the channel fold uses full-mask shuffles
-  const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
-  gn_apply_fused_kernel<<<dim3((rows + rpc - 1) / rpc, outer), padded, 0, st>>>(s, rows, rpc, RL, num_groups, eps, inv, csum1, ldc1, csum2, ldc2, mean, rstd,
-                                                                               gamma, beta, fuse_silu, reinterpret_cast<bf16*>(y), ldy);
-  SVDX_CHECK_LAUNCH("groupnorm_apply_fused");
-  return SVDX_OK;
 }
 
 extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, const void* dy,
@@ -1484,7 +1169,7 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
   const int total = outer * num_groups;
   if (!workspace_is_zero) cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * total, st);
   int threads, rpc;
-  if (gn_ring_enabled()) {
+  {
     static bool a1[SVDX_MAX_DEVICES] = {false}, a2[SVDX_MAX_DEVICES] = {false}, a3[SVDX_MAX_DEVICES] = {false}, a4[SVDX_MAX_DEVICES] = {false};
     gn_ring_attr(gn_bwd_partial_ring<true>, a1);
     gn_ring_attr(gn_bwd_partial_ring<false>, a2);
@@ -1512,20 +1197,6 @@ extern "C" int svdx_groupnorm_bwd(const void* x, int64_t ldx, int32_t C1, const 
     SVDX_CHECK_LAUNCH("groupnorm_bwd");
     return SVDX_OK;
   }
-  gn_vec_config(C1 + C2, outer, rows, threads, rpc);
-  dim3 grid((rows + rpc - 1) / rpc, outer);
-  if (dgamma)
-    gn_bwd_partial<true><<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta,
-                                                   fuse_silu, workspace, dgamma, dbeta);
-  else
-    gn_bwd_partial<false><<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta,
-                                                    fuse_silu, workspace, dgamma, dbeta);
-  const float inv = 1.0f / ((float)rows * (float)((C1 + C2) / num_groups));
-  gn_bwd_apply<<<grid, threads, 0, st>>>(s, reinterpret_cast<const bf16*>(dy), lddy, rows, rpc, num_groups, mean, rstd, gamma, beta, fuse_silu,
-                                         workspace, inv, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dx2), lddx2,
-                                         reinterpret_cast<const bf16*>(dres), lddres);
-  SVDX_CHECK_LAUNCH("groupnorm_bwd");
-  return SVDX_OK;
 }
 
 extern "C" int svdx_groupnorm_bwd_fused(const void* x, int64_t ldx, int32_t C1, const void* x2, int64_t ldx2, int32_t C2, const void* dy,
@@ -1570,11 +1241,6 @@ static void ln_fwd_launch(const void* x, int64_t ldx, int rows, int C, const flo
                                           addvec, add_div, reinterpret_cast<bf16*>(xsum), ldxs);
 }
 
-static bool ln_ring_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("SVDX_LN_RING"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on == 1;
-}
 static int ln_ring_cps(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && atoi(e) > 0) ? atoi(e) : dflt;
@@ -1632,7 +1298,7 @@ extern "C" int svdx_layernorm_fwd(const void* x, int64_t ldx, int32_t rows, int3
       (addvec && (!xsum || add_div <= 0 || ldxs % 8 || (reinterpret_cast<uintptr_t>(addvec) & 15) || (reinterpret_cast<uintptr_t>(xsum) & 15))))
     return svdx_fail(SVDX_E_BADARG, "layernorm_fwd: bad arguments (C %% 8, C <= 2560, 16-byte aligned rows and vectors)");
   const int nj = (C / 8 + 31) / 32;
-  if (ln_ring_enabled() && nj <= 5) {
+  if (nj <= 5) {
     if (nj <= 1) ln_fwd_ring_launch<1>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
     else if (nj <= 2) ln_fwd_ring_launch<2>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
     else if (nj <= 3) ln_fwd_ring_launch<3>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
@@ -1640,11 +1306,7 @@ extern "C" int svdx_layernorm_fwd(const void* x, int64_t ldx, int32_t rows, int3
     SVDX_CHECK_LAUNCH("layernorm_fwd");
     return SVDX_OK;
   }
-  if (nj <= 1) ln_fwd_launch<1, 4>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
-  else if (nj <= 2) ln_fwd_launch<2, 2>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
-  else if (nj <= 3) ln_fwd_launch<3, 2>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
-  else if (nj <= 5) ln_fwd_launch<5, 1>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
-  else ln_fwd_launch<10, 1>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);
+  ln_fwd_launch<10, 1>(x, ldx, rows, C, gamma, beta, eps, y, ldy, mean, rstd, addvec, add_div, xsum, ldxs, st);   // 1280 < C <= 2560: rows in registers
   SVDX_CHECK_LAUNCH("layernorm_fwd");
   return SVDX_OK;
 }
@@ -1674,8 +1336,10 @@ extern "C" int svdx_layernorm_bwd(const void* x, int64_t ldx, const void* dy, in
       (dgamma && !dbeta) || (dres && lddres % 8))
     return svdx_fail(SVDX_E_BADARG, "layernorm_bwd: bad arguments (C %% 8, C <= 2560, 16-byte aligned rows)");
   const int nj = (C / 8 + 31) / 32;
-  if (ln_ring_enabled() && nj <= 5 && !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(dy) & 15) &&
-      !(dres && (reinterpret_cast<uintptr_t>(dres) & 15))) {
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15) ||
+      (dres && (reinterpret_cast<uintptr_t>(dres) & 15)))
+    return svdx_fail(SVDX_E_BADARG, "layernorm_bwd: x / dy / dx / dres must be 16-byte aligned");
+  if (nj <= 5) {
     if (nj <= 1) ln_bwd_ring_launch<1>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
     else if (nj <= 2) ln_bwd_ring_launch<2>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
     else if (nj <= 3) ln_bwd_ring_launch<3>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
@@ -1683,11 +1347,7 @@ extern "C" int svdx_layernorm_bwd(const void* x, int64_t ldx, const void* dy, in
     SVDX_CHECK_LAUNCH("layernorm_bwd");
     return SVDX_OK;
   }
-  if (nj <= 1) ln_bwd_launch<1>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
-  else if (nj <= 2) ln_bwd_launch<2>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
-  else if (nj <= 3) ln_bwd_launch<3>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
-  else if (nj <= 5) ln_bwd_launch<5>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
-  else ln_bwd_launch<10>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);
+  ln_bwd_launch<10>(x, ldx, dy, lddy, rows, C, gamma, mean, rstd, dx, lddx, dres, lddres, dgamma, dbeta, st);   // 1280 < C <= 2560
   SVDX_CHECK_LAUNCH("layernorm_bwd");
   return SVDX_OK;
 }

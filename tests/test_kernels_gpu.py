@@ -132,7 +132,7 @@ def test_groupnorm_fwd_bwd(raw, outer, rows, C1, C2, silu):
         _close(dx3, dxr + dres.float(), what="groupnorm dx + dres")
 
 
-@pytest.mark.parametrize("rows,C", [(1000, 320), (560, 1280), (77, 64), (300, 640), (40003, 320), (30001, 640), (20011, 1280), (1500, 960)])
+@pytest.mark.parametrize("rows,C", [(1000, 320), (560, 1280), (77, 64), (300, 640), (40003, 320), (30001, 640), (20011, 1280), (1500, 960), (130, 2048)])   # C > 1280: the register-array kernels
 def test_layernorm_fwd_bwd(raw, rows, C):
     x = (_rand(rows, C, seed=10) + 0.3).to(bf16)
     gamma = _rand(C, seed=11) * 0.2 + 1.0
