@@ -119,3 +119,60 @@ def test_shim_fails_loudly_without_diffusers(monkeypatch):
     monkeypatch.setitem(sys.modules, "diffusers", None)      # import diffusers -> ModuleNotFoundError
     with pytest.raises(RuntimeError, match="diffusers"):
         shim.install()
+
+
+def test_wide_tile_rule():
+    """256x320 CTA-pair tiles: only where the alternative is 160-wide tiles, the contraction is long, and the launch has the
+    bf16 TMA-store epilogue (raw._wide_tile_ok mirrors the library's conditions; profiles/r2_kbench_gemm.txt)"""
+    from svd_xtend_b200 import raw
+    bf16 = torch.bfloat16
+    out = torch.empty(1024, 640, dtype=bf16)
+    common = dict(ldo=None, geglu=False, a_mn=False, b_mn=False, b_mode=0, split_k=1, out_dtype=None, bias=None, rowbias=None)
+    assert raw._wide_tile_ok(1024, 640, 2560, out, **common)
+    assert raw._wide_tile_ok(35840, 320, 2880, torch.empty(8, 320, dtype=bf16), **common)
+    assert not raw._wide_tile_ok(1024, 640, 640, out, **common)                       # short contraction
+    assert not raw._wide_tile_ok(1024, 1280, 5120, torch.empty(8, 1280, dtype=bf16), **common)   # 256-wide tiles divide N
+    assert not raw._wide_tile_ok(256, 640, 2560, out, **common)                        # small M: 1-CTA kernel
+    assert not raw._wide_tile_ok(1024, 480, 2560, torch.empty(8, 480, dtype=bf16), **common)     # N % 320
+    assert not raw._wide_tile_ok(1024, 640, 2560, torch.empty(8, 640), **common)       # fp32 output
+    assert not raw._wide_tile_ok(1024, 640, 2560, out, **{**common, "geglu": True})
+    assert not raw._wide_tile_ok(1024, 640, 2560, out, **{**common, "split_k": 4})
+    assert not raw._wide_tile_ok(1024, 640, 2560, out, **{**common, "a_mn": True, "b_mn": True})
+
+
+def test_groupnorm_backward_fusion_is_decided_per_launch():
+    """Engine._gnb_for: the dgrad epilogue carries the GroupNorm-backward sums only when it is the first writer of that
+    gradient, has the plain epilogue (no scales), the widths match and the launch is not split-K"""
+    from svd_xtend_b200 import raw
+    from svd_xtend_b200.engine import Engine, Var
+    E = Engine()
+    E.fuse_gn_bwd = True
+    M, rows = 35840, 2560
+    x = torch.zeros(M, 320, dtype=torch.bfloat16)
+    y = Var(torch.zeros(M, 320, dtype=torch.bfloat16), needs_grad=True)
+    y.gnb = dict(x=x, x2=None, ab=torch.zeros(M // rows, 2, 320), rows=rows, silu=True, C=320)
+    E._stat_arena = torch.zeros(1 << 16)
+    g = E._gnb_for(y, M, 320, 320, 9, None, "cpu")
+    assert g is not None and g["sum"].shape == (M // rows, 2, 320) and g["rows"] == rows and g["x"] is x
+    assert E._gnb_for(y, M, 320, 320, 9, torch.ones(3), "cpu") is None                 # scaled accumulation (LoRA / blend)
+    assert E._gnb_for(y, M, 640, 320, 9, None, "cpu") is None                          # not this GroupNorm's width
+    assert E._gnb_for(y, M - 64, 320, 320, 9, None, "cpu") is None                     # rows do not tile into slabs
+    y.grad = torch.zeros(8, 320, dtype=torch.bfloat16)
+    assert E._gnb_for(y, M, 320, 320, 9, None, "cpu") is None                          # somebody already wrote this gradient
+    y.grad = None
+    assert E._gnb_for(Var(x, True), M, 320, 320, 9, None, "cpu") is None               # not a GroupNorm output
+    # small levels run split-K (fp32 workspace + epilogue kernel): no fused sums there
+    small = Var(torch.zeros(2560, 320, dtype=torch.bfloat16), needs_grad=True)
+    small.gnb = dict(x=x[:2560], x2=None, ab=torch.zeros(2, 2, 320), rows=1280, silu=True, C=320)
+    assert raw.split_plan(True, 2560, 320, 320, 9) is not None and E._gnb_for(small, 2560, 320, 320, 9, None, "cpu") is None
+    # a second accumulation invalidates sums computed for the first
+    y.gnb_sums = (g["sum"], torch.zeros(1))
+    E.add_grad(y, torch.zeros(8, 320, dtype=torch.bfloat16))
+    assert y.gnb_sums is None
+
+
+def test_peer_memory_optimizer_api_exists():
+    from svd_xtend_b200 import _lib, train
+    assert issubclass(train.P2PShardedAdamW, train.ShardedAdamW)
+    for name in ("svdx_adamw_p2p", "svdx_ipc_export", "svdx_ipc_import", "svdx_enable_peer_access"):
+        assert name in _lib._PROTOS
