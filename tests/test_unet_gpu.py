@@ -30,7 +30,11 @@ def _build(cfg, seed=0):
                 p.add_(0.05 * torch.randn_like(p))
             if n.endswith("mix_factor"):
                 p.add_(0.3 * torch.randn_like(p))
-    ours = Ours(**cfg).to(DEV)
+    # constructed on the device: its own initial values are overwritten on the next line, and a second 1.5 B-parameter random
+    # init on the host cores is what made the suite slow on busy hosts (bench.py builds the model the same way)
+    with torch.device(DEV):
+        ours = Ours(**cfg)
+    ours = ours.to(DEV)
     ours.load_state_dict(oracle.state_dict())
     return oracle, ours
 
